@@ -1,0 +1,211 @@
+/*
+ * w2c.h — C ABI of the B200-native When2com forward hot path (libw2c.so).
+ *
+ * The reference (GT-RIPL/MultiAgentPerception) has no FFI layer: its hot path is torch.nn modules called from
+ * ptsemseg/models/agent.py.  Every entry point below replaces one group of reference module calls; the
+ * reference file:line each one stands in for is cited on the declaration.  The Python host side
+ * (multiagentperception_b200/) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in _host;
+ *  - the caller owns every buffer (no allocation inside, no hidden global state);
+ *  - every call enqueues work on the given CUDA stream and returns without synchronising (graph-capturable);
+ *  - return value: 0 = W2C_OK, negative = error; w2c_last_error() gives a thread-local message.
+ *  - activations are NHWC.  "act" selects the storage:  W2C_ACT_BF16 = one bf16 plane per pixel;
+ *    W2C_ACT_BF16X2 = two bf16 planes per pixel [hi(C) | lo(C)] with value = hi + lo (the "bf16x3" parity
+ *    precision: every product is evaluated as hi*hi + hi*lo + lo*hi on the tensor cores, fp32 accumulate).
+ */
+#ifndef W2C_H_
+#define W2C_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* w2c_stream_t; /* a cudaStream_t / CUstream */
+
+enum {
+  W2C_OK = 0,
+  W2C_ERR_INVALID = -1,     /* bad argument (null pointer, shape not supported by the layout rules) */
+  W2C_ERR_UNSUPPORTED = -2, /* valid request the library has no kernel for */
+  W2C_ERR_CUDA = -3,        /* CUDA runtime error while launching */
+  W2C_ERR_DRIVER = -4       /* driver entry point (tensor-map encode) unavailable */
+};
+
+enum { W2C_ACT_BF16 = 0, W2C_ACT_BF16X2 = 1 };
+enum { W2C_OUT_NHWC = 0, W2C_OUT_NCHW_F32 = 1 };
+enum { W2C_IMPL_TCGEN05 = 0, W2C_IMPL_SIMT = 1 };
+enum {
+  W2C_CONV3X3_S1 = 0,   /* Conv2d k3 s1 p1                       */
+  W2C_CONV3X3_S2 = 1,   /* Conv2d k3 s2 p1   (H, W even)         */
+  W2C_DECONV3X3_S2 = 2, /* ConvTranspose2d k3 s2 p1 output_padding 1 */
+  W2C_CONV1X1_S1 = 3,   /* Conv2d k1 s1 p0                       */
+  W2C_CONV1X1_S2 = 4    /* Conv2d k1 s2 p0   (resnet downsample) */
+};
+
+/* Library / build identification. */
+int w2c_version(void);
+const char* w2c_last_error(void);
+/* Number of kernel launches this process has enqueued through the library (all entry points). */
+uint64_t w2c_launch_count(void);
+
+/*
+ * Fused  conv (or transposed conv) -> per-channel affine (folded eval-mode BatchNorm + conv bias) -> [+residual]
+ * -> [ReLU].   Replaces conv2DBatchNormRelu.forward (ptsemseg/models/utils.py:87-120) and
+ * deconv2DBatchNormRelu.forward (utils.py:148-168) as used by n_segnet_encoder/decoder (backbone.py:41-55,
+ * 126-140), img_encoder.squeezer (agent.py:54-60), policy_net4 (agent.py:126-142); with residual it is the
+ * BasicBlock tail of the resnet18 trunk used by resnet_encoder (backbone.py:72-96), and with scale = 1,
+ * shift = bias it is the plain Conv2d(+ReLU) of simple_decoder.pred (backbone.py:150-154).
+ *
+ *   y[n, oh, ow, co] = act( scale[co] * sum_{tap,ci} x[n, ih, iw, ci] * w[co, tap, ci] + shift[co] (+ res) )
+ *
+ * x        NHWC, n x h_in x w_in pixels, each pixel x_cstride channels per plane; the conv reads channels
+ *          [x_coffset, x_coffset + cin).  cin must be a multiple of 64.
+ * w        packed by w2c_pack_conv_weight: bf16 [planes][cout_pad][ntaps*cin], k = tap*cin + ci.
+ * scale, shift   fp32 [cout].
+ * residual NHWC like y (same act, pixel stride y_cstride, offset y_coffset) or NULL.
+ * y        W2C_OUT_NHWC: NHWC in the same act storage, pixel stride y_cstride, written at channel y_coffset;
+ *          W2C_OUT_NCHW_F32: fp32 [n][cout][h_out][w_out] (the logits layout the reference returns).
+ */
+typedef struct w2c_conv_args {
+  const void* x;
+  const void* w;
+  const float* scale;
+  const float* shift;
+  const void* residual;
+  void* y;
+  int32_t n, h_in, w_in;
+  int32_t cin, cout;
+  int32_t x_cstride, x_coffset;
+  int32_t y_cstride, y_coffset;
+  int32_t kind;     /* W2C_CONV3X3_S1 ... */
+  int32_t relu;     /* 0 / 1 */
+  int32_t act;      /* W2C_ACT_* (storage of x, residual, and of y when out_fmt = NHWC) */
+  int32_t out_fmt;  /* W2C_OUT_* */
+  int32_t impl;     /* W2C_IMPL_TCGEN05 (product) or W2C_IMPL_SIMT (on-GPU cross-check, tests only) */
+  int32_t block_n;  /* 0 = auto; else 16/32/64/128/256 */
+} w2c_conv_args;
+
+int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream);
+
+/* cout rounded up to the row padding the packed weight layout uses. */
+int32_t w2c_cout_pad(int32_t cout);
+/* Bytes of the packed weight buffer for a conv of the given geometry. */
+size_t w2c_packed_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t act);
+
+/*
+ * Pack a PyTorch-layout fp32 conv weight into the K-major bf16 layout the conv kernels read.
+ *   transposed = 0: w is Conv2d.weight          [cout][cin_real][kh][kw]
+ *   transposed = 1: w is ConvTranspose2d.weight [cin_real][cout][kh][kw]
+ * cin_real <= cin (extra input channels are zero-filled); ntaps = kh*kw (9 or 1).
+ * act = W2C_ACT_BF16X2 additionally writes the low-order plane (w - bf16(w)).
+ */
+int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
+                         int32_t transposed, int32_t act, void* packed, w2c_stream_t stream);
+
+/*
+ * Fold eval-mode BatchNorm2d (+ the conv bias) into the per-channel affine the conv epilogue applies
+ * (nn.BatchNorm2d inside cbr_unit / dcbr_unit, utils.py:110-114,152-164):
+ *   scale = gamma / sqrt(var + eps);  shift = beta + (bias - mean) * scale.
+ * Any of gamma/beta/mean/var may be NULL together (no BN): scale = 1, shift = bias.  bias may be NULL.
+ */
+int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, const float* mean,
+                const float* var, float eps, int32_t cout, float* scale, float* shift, w2c_stream_t stream);
+
+/*
+ * First encoder layer: Conv2d(3 -> cout, k3 s1 p1) + BN + ReLU reading the caller's fp32 NCHW batch directly.
+ * Replaces divide_inputs + cat (agent.py:1088-1108) and n_segnet_encoder.conv1 (backbone.py:19,42).
+ *   x     fp32 [b][3*n_agents][h][w]  (views concatenated on the channel axis, trainer.py:651)
+ *   w     fp32 [cout][27]  (k = ci*9 + kh*3 + kw, i.e. Conv2d.weight flattened), scale/shift fp32 [cout]
+ *   y     NHWC [(n_agents*b)][h][w][cout], image index = agent*b + batch ("agent-major", agent.py:1103-1108)
+ * cout must be a multiple of 8 and <= 128.
+ */
+int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
+                         int32_t b, int32_t n_agents, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                         w2c_stream_t stream);
+
+/*
+ * Key / query heads: flatten -> Linear -> ReLU -> Linear -> ReLU -> Linear.  Replaces km_generator.forward and
+ * linear.forward (agent.py:145-178).  feat is the NHWC policy feature map [m][s][s][256]; w0 must already be
+ * permuted to NHWC flatten order (the reference flattens NCHW, agent.py:158).
+ *   out fp32 [m][out_dim].  ws: fp32 scratch of m*(256+128) floats.
+ */
+int w2c_kq_mlp_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const float* w0, const float* b0,
+                   const float* w1, const float* b1, const float* w2, const float* b2, int32_t out_dim,
+                   float* out, float* ws, w2c_stream_t stream);
+
+/*
+ * Communication graph + fusion.  Replaces MIMOGeneralDotProductAttention.forward (agent.py:252-286),
+ * GeneralDotProductAttention / ScaledDotProductAttention (agent.py:194-213,345-368), the +0.001*I bias
+ * (agent.py:1164-1167), activated_select / argmax_select (agent.py:1036-1078) and agents2batch (1080-1086).
+ *
+ *   qt[b,j,:] = Wq * query[b,j,:] + bq      (skipped when wq == NULL: qt = query, needs q_dim == k_dim)
+ *   S[b,i,j]  = <key[b,i,:], qt[b,j,:]> / temperature
+ *   P[b,:,j]  = softmax_i S   (or sparsemax_i when sparse != 0; MIMOcomWho: mask_self removes i == j)
+ *   prob_out  = P + diag_bias * I
+ *   coef      = P                                   (mode SOFTMAX: fuse with the un-biased P)
+ *             = prob_out * [prob_out > thresh]      (mode ACTIVATED)
+ *             = onehot_i(argmax_i prob_out)         (mode ARGMAX)
+ *   fused[j*b_sz + b] = sum_i coef[b,i,j] * val[i*b_sz + b]          (agent-major images, NHWC)
+ *   action[b,j] = argmax_i coef'   (coef' = prob_out for SOFTMAX, coef otherwise), int64
+ *   connect[0] += #{(b,i,j): i != j, coef != 0}     (int32 counter; caller zeroes it)
+ *
+ * keys fp32 [n_k*b_sz][k_dim] and queries fp32 [n_q*b_sz][q_dim] are agent-major like the images.
+ * val   NHWC [(n_k*b_sz)][hw][c] in `act` storage;  fused the same with n_q images.
+ * prob_out fp32 [b_sz][n_k][n_q];  coef_out fp32 [b_sz][n_k][n_q] (may be NULL);  action int64 [b_sz][n_q].
+ * n_k, n_q <= 8.
+ */
+enum { W2C_FUSE_SOFTMAX = 0, W2C_FUSE_ACTIVATED = 1, W2C_FUSE_ARGMAX = 2 };
+typedef struct w2c_attn_args {
+  const float* keys;
+  const float* queries;
+  const float* wq;
+  const float* bq;
+  const void* val;
+  void* fused;
+  float* prob_out;
+  float* coef_out;
+  int64_t* action;
+  int32_t* connect;
+  int32_t b_sz, n_k, n_q;
+  int32_t k_dim, q_dim;
+  int32_t hw, c; /* pixels per image, channels per plane */
+  int32_t fused_cstride, fused_coffset; /* pixel stride / channel offset of `fused` (concat buffers) */
+  int32_t act;
+  int32_t mode;      /* W2C_FUSE_* */
+  int32_t sparse;    /* 0 softmax, 1 sparsemax */
+  int32_t mask_self; /* 1: drop i == j before the softmax (MIMOcomWho, agent.py:306-343) */
+  float temperature; /* 1 for the "general" attention, sqrt(128) for ScaledDotProductAttention */
+  float diag_bias;   /* 0.001 for MIMOcom, 0 otherwise */
+  float thresh;      /* 0.2 */
+} w2c_attn_args;
+
+int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream);
+
+/* ---- resnet18 trunk / simple_decoder specifics (backbone.py:58-96,143-164) ------------------------- */
+
+/* Conv2d(3 -> 64, k7 s2 p3, no bias) + BN + ReLU on the fp32 NCHW batch; same input convention as the stem. */
+int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
+                           int32_t b, int32_t n_agents, int32_t h, int32_t w_px, int32_t act,
+                           w2c_stream_t stream);
+/* MaxPool2d(k3 s2 p1) on NHWC. */
+int w2c_maxpool3x3s2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t act,
+                         w2c_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False) by an integer factor, fp32 NCHW in -> fp32 NCHW out. */
+int w2c_bilinear_up_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
+                        w2c_stream_t stream);
+
+/* ---- layout helpers --------------------------------------------------------------------------------- */
+/* NHWC activation (act storage) -> fp32 NCHW, and back.  Used at module boundaries and by the tests. */
+int w2c_nhwc_to_nchw_f32(const void* x, float* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,
+                         int32_t coffset, int32_t act, w2c_stream_t stream);
+int w2c_nchw_f32_to_nhwc(const float* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,
+                         int32_t coffset, int32_t act, w2c_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2C_H_ */

@@ -1,0 +1,106 @@
+"""ctypes binding of libw2c.so — the C ABI declared in include/w2c.h.
+
+There is no fallback: if the library is missing it is built with nvcc; if that fails, or a call returns an error,
+an exception is raised. Nothing here computes on the CPU.
+"""
+import ctypes
+import os
+import threading
+
+from . import build as _build
+
+c_i32 = ctypes.c_int32
+c_f32 = ctypes.c_float
+c_vp = ctypes.c_void_p
+
+ACT_BF16, ACT_BF16X2 = 0, 1
+OUT_NHWC, OUT_NCHW_F32 = 0, 1
+IMPL_TCGEN05, IMPL_SIMT = 0, 1
+CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2 = 0, 1, 2, 3, 4
+FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX = 0, 1, 2
+
+
+class ConvArgs(ctypes.Structure):
+    """struct w2c_conv_args (include/w2c.h)."""
+    _fields_ = [
+        ("x", c_vp), ("w", c_vp), ("scale", c_vp), ("shift", c_vp), ("residual", c_vp), ("y", c_vp),
+        ("n", c_i32), ("h_in", c_i32), ("w_in", c_i32),
+        ("cin", c_i32), ("cout", c_i32),
+        ("x_cstride", c_i32), ("x_coffset", c_i32),
+        ("y_cstride", c_i32), ("y_coffset", c_i32),
+        ("kind", c_i32), ("relu", c_i32), ("act", c_i32), ("out_fmt", c_i32), ("impl", c_i32), ("block_n", c_i32),
+    ]
+
+
+class AttnArgs(ctypes.Structure):
+    """struct w2c_attn_args (include/w2c.h)."""
+    _fields_ = [
+        ("keys", c_vp), ("queries", c_vp), ("wq", c_vp), ("bq", c_vp), ("val", c_vp), ("fused", c_vp),
+        ("prob_out", c_vp), ("coef_out", c_vp), ("action", c_vp), ("connect", c_vp),
+        ("b_sz", c_i32), ("n_k", c_i32), ("n_q", c_i32),
+        ("k_dim", c_i32), ("q_dim", c_i32),
+        ("hw", c_i32), ("c", c_i32),
+        ("fused_cstride", c_i32), ("fused_coffset", c_i32),
+        ("act", c_i32), ("mode", c_i32), ("sparse", c_i32), ("mask_self", c_i32),
+        ("temperature", c_f32), ("diag_bias", c_f32), ("thresh", c_f32),
+    ]
+
+
+# symbol -> (restype, argtypes); every symbol include/w2c.h declares must be listed here (tests check both ways)
+_SIGNATURES = {
+    "w2c_version": (ctypes.c_int, []),
+    "w2c_last_error": (ctypes.c_char_p, []),
+    "w2c_launch_count": (ctypes.c_uint64, []),
+    "w2c_conv_bnrelu_fwd": (ctypes.c_int, [ctypes.POINTER(ConvArgs), c_vp]),
+    "w2c_cout_pad": (c_i32, [c_i32]),
+    "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
+    "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "w2c_fold_bn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp]),
+    "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "w2c_attn_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs), c_vp]),
+    "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_maxpool3x3s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_bilinear_up_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_nhwc_to_nchw_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_nchw_f32_to_nhwc": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+class W2CError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load (building first if needed) libw2c.so and bind every entry point. Raises if that is impossible."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        path = _build.LIB_PATH
+        if not os.path.exists(path) or os.environ.get("W2C_REBUILD") == "1":
+            path = _build.build()
+        lib = ctypes.CDLL(path)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError = the .so is stale / incomplete: fail loudly
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+        return _lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().w2c_last_error()
+        raise W2CError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))

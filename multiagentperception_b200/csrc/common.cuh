@@ -1,0 +1,45 @@
+// Internal helpers shared by the libw2c translation units: error reporting, launch accounting, activation
+// load/store in the two storage formats (bf16 and bf16 hi|lo planes).
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/w2c.h"
+
+namespace w2c {
+
+int set_error(int code, const char* fmt, ...);
+void count_launch(unsigned n = 1);
+
+#define W2C_CHECK_ARG(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::w2c::set_error(W2C_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define W2C_CHECK_LAUNCH(what)                                                                  \
+  do {                                                                                          \
+    cudaError_t e__ = cudaGetLastError();                                                       \
+    if (e__ != cudaSuccess)                                                                     \
+      return ::w2c::set_error(W2C_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e__));           \
+    ::w2c::count_launch();                                                                      \
+  } while (0)
+
+// value = hi (+ lo).  Pixel layout for BF16X2: [hi: cstride channels][lo: cstride channels].
+__device__ __forceinline__ float act_load(const __nv_bfloat16* pix, int c, int cstride, int act) {
+  float v = __bfloat162float(pix[c]);
+  if (act == W2C_ACT_BF16X2) v += __bfloat162float(pix[cstride + c]);
+  return v;
+}
+__device__ __forceinline__ void act_store(__nv_bfloat16* pix, int c, int cstride, int act, float v) {
+  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  pix[c] = hi;
+  if (act == W2C_ACT_BF16X2) pix[cstride + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+__host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace w2c

@@ -1,0 +1,411 @@
+// Small HBM-bound kernels around the tensor-core convs: weight packing, BN folding, the 3-channel stems that read
+// the caller's fp32 NCHW batch, max-pool, bilinear up-sampling, layout conversion, and library bookkeeping.
+#include <cstring>
+
+#include "common.cuh"
+
+namespace w2c {
+
+// ------------------------------------------------------------------------------------------ bookkeeping
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+namespace {
+
+inline int grid_for(size_t total, int threads, int max_blocks = 148 * 32) {
+  size_t b = (total + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > static_cast<size_t>(max_blocks)) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int ntaps,
+                                   int transposed, int planes, int cout_pad, __nv_bfloat16* __restrict__ out) {
+  const size_t ktot = static_cast<size_t>(ntaps) * cin;
+  const size_t total = static_cast<size_t>(cout_pad) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = idx / ktot;
+    const int k = idx % ktot;
+    const int tap = k / cin, ci = k % cin;
+    float v = 0.f;
+    if (co < cout && ci < cin_real) {
+      // Conv2d.weight [co][ci][tap];  ConvTranspose2d.weight [ci][co][tap]
+      v = transposed ? w[(static_cast<size_t>(ci) * cout + co) * ntaps + tap]
+                     : w[(static_cast<size_t>(co) * cin_real + ci) * ntaps + tap];
+    }
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[idx] = hi;
+    if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
+__global__ void fold_bn_kernel(const float* bias, const float* gamma, const float* beta, const float* mean,
+                               const float* var, float eps, int cout, float* scale, float* shift) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  const float b = bias ? bias[c] : 0.f;
+  if (gamma) {
+    // same association as F.batch_norm's eval formula: (x - mean) / sqrt(var + eps) * gamma + beta
+    const float s = gamma[c] / sqrtf(var[c] + eps);
+    scale[c] = s;
+    shift[c] = beta[c] + (b - mean[c]) * s;
+  } else {
+    scale[c] = 1.f;
+    shift[c] = b;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ 3-channel stems
+// Conv2d(3->cout, k3 s1 p1) + affine + ReLU. One thread per output pixel; the 27 inputs live in registers, the
+// weights in shared memory as [27][cout] so the per-k reads are warp-wide broadcasts of float4.
+template <int GROUP>
+__global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                                                      int b_sz, int n_agents, int h, int wpx, int cout, int act) {
+  extern __shared__ float sm[];
+  float* s_w = sm;                // [27][cout]
+  float* s_scale = sm + 27 * cout;
+  float* s_shift = s_scale + cout;
+  for (int i = threadIdx.x; i < 27 * cout; i += blockDim.x) {
+    const int k = i / cout, co = i % cout;
+    s_w[i] = w[co * 27 + k];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_scale[i] = scale[i], s_shift[i] = shift[i];
+  __syncthreads();
+
+  const size_t plane = static_cast<size_t>(h) * wpx;
+  const size_t total = static_cast<size_t>(b_sz) * n_agents * plane;
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = idx % wpx;
+    const int oh = (idx / wpx) % h;
+    const int img = idx / plane;  // agent-major: img = agent * b_sz + batch
+    const int agent = img / b_sz, bat = img % b_sz;
+    const float* xin = x + (static_cast<size_t>(bat) * 3 * n_agents + 3 * agent) * plane;
+    float in[27];
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int ih = oh + kh - 1, iw = ow + kw - 1;
+          in[ci * 9 + kh * 3 + kw] =
+              (ih >= 0 && ih < h && iw >= 0 && iw < wpx) ? __ldg(xin + ci * plane + static_cast<size_t>(ih) * wpx + iw) : 0.f;
+        }
+    __nv_bfloat16* ypix = y + idx * (static_cast<size_t>(cout) * planes);
+    for (int g = 0; g < cout; g += GROUP) {
+      float acc[GROUP];
+#pragma unroll
+      for (int j = 0; j < GROUP; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 27; ++k) {
+        const float4* wr = reinterpret_cast<const float4*>(s_w + k * cout + g);
+#pragma unroll
+        for (int j4 = 0; j4 < GROUP / 4; ++j4) {
+          const float4 wv = wr[j4];
+          acc[4 * j4 + 0] = fmaf(in[k], wv.x, acc[4 * j4 + 0]);
+          acc[4 * j4 + 1] = fmaf(in[k], wv.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(in[k], wv.z, acc[4 * j4 + 2]);
+          acc[4 * j4 + 3] = fmaf(in[k], wv.w, acc[4 * j4 + 3]);
+        }
+      }
+#pragma unroll
+      for (int j8 = 0; j8 < GROUP / 8; ++j8) {
+        uint4 hv, lv;
+        __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
+        __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = g + j8 * 8 + 2 * j;
+          const float a = fmaxf(fmaf(acc[j8 * 8 + 2 * j], s_scale[c], s_shift[c]), 0.f);
+          const float b = fmaxf(fmaf(acc[j8 * 8 + 2 * j + 1], s_scale[c + 1], s_shift[c + 1]), 0.f);
+          hb[j] = __floats2bfloat162_rn(a, b);
+          const float2 hf = __bfloat1622float2(hb[j]);
+          lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+        }
+        *reinterpret_cast<uint4*>(ypix + g + j8 * 8) = hv;
+        if (planes == 2) *reinterpret_cast<uint4*>(ypix + cout + g + j8 * 8) = lv;
+      }
+    }
+  }
+}
+
+// Conv2d(3->64, k7 s2 p3) + affine + ReLU (resnet18 conv1/bn1/relu). One thread per output pixel, 32 output
+// channels per pass; weights in shared memory as [147][64].
+__global__ void __launch_bounds__(128) stem7x7_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                      const float* __restrict__ scale,
+                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
+                                                      int b_sz, int n_agents, int h, int wpx, int act) {
+  constexpr int COUT = 64, K = 147;
+  extern __shared__ float sm[];
+  float* s_w = sm;  // [147][64]
+  float* s_scale = sm + K * COUT;
+  float* s_shift = s_scale + COUT;
+  for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
+    const int k = i / COUT, co = i % COUT;
+    s_w[i] = w[co * K + k];
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_scale[i] = scale[i], s_shift[i] = shift[i];
+  __syncthreads();
+  const int ho = h / 2, wo = wpx / 2;
+  const size_t plane = static_cast<size_t>(h) * wpx;
+  const size_t total = static_cast<size_t>(b_sz) * n_agents * ho * wo;
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = idx % wo;
+    const int oh = (idx / wo) % ho;
+    const int img = idx / (static_cast<size_t>(ho) * wo);
+    const int agent = img / b_sz, bat = img % b_sz;
+    const float* xin = x + (static_cast<size_t>(bat) * 3 * n_agents + 3 * agent) * plane;
+    __nv_bfloat16* ypix = y + idx * (static_cast<size_t>(COUT) * planes);
+    for (int g = 0; g < COUT; g += 32) {
+      float acc[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+      for (int ci = 0; ci < 3; ++ci)
+        for (int kh = 0; kh < 7; ++kh) {
+          const int ih = oh * 2 + kh - 3;
+          if (ih < 0 || ih >= h) continue;
+#pragma unroll
+          for (int kw = 0; kw < 7; ++kw) {
+            const int iw = ow * 2 + kw - 3;
+            const float v = (iw >= 0 && iw < wpx) ? __ldg(xin + ci * plane + static_cast<size_t>(ih) * wpx + iw) : 0.f;
+            const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 49 + kh * 7 + kw) * COUT + g);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const float4 wv = wr[j4];
+              acc[4 * j4 + 0] = fmaf(v, wv.x, acc[4 * j4 + 0]);
+              acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
+              acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
+              acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
+            }
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float v = fmaxf(fmaf(acc[j], s_scale[g + j], s_shift[g + j]), 0.f);
+        act_store(ypix, g + j, COUT, act, v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ pool / upsample
+__global__ void maxpool3x3s2_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h,
+                                    int wpx, int c, int act) {
+  const int ho = h / 2, wo = wpx / 2;
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t total = static_cast<size_t>(n) * ho * wo * c;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = idx % c;
+    size_t t = idx / c;
+    const int ow = t % wo;
+    t /= wo;
+    const int oh = t % ho;
+    const int img = t / ho;
+    float m = -INFINITY;
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh * 2 + kh - 1;
+      if (ih < 0 || ih >= h) continue;
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow * 2 + kw - 1;
+        if (iw < 0 || iw >= wpx) continue;
+        const __nv_bfloat16* pix = x + ((static_cast<size_t>(img) * h + ih) * wpx + iw) * (static_cast<size_t>(c) * planes);
+        m = fmaxf(m, act_load(pix, ch, c, act));
+      }
+    }
+    act_store(y + (idx / c) * (static_cast<size_t>(c) * planes), ch, c, act, m);
+  }
+}
+
+// F.interpolate(..., mode='bilinear', align_corners=False) with an integer up-scale factor (area_pixel source index).
+__global__ void bilinear_up_kernel(const float* __restrict__ x, float* __restrict__ y, int nc, int h, int wpx,
+                                   int factor) {
+  const int ho = h * factor, wo = wpx * factor;
+  const float rs = 1.f / static_cast<float>(factor);
+  const size_t total = static_cast<size_t>(nc) * ho * wo;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = idx % wo;
+    const int oh = (idx / wo) % ho;
+    const size_t pl = idx / (static_cast<size_t>(ho) * wo);
+    float sh = (oh + 0.5f) * rs - 0.5f;
+    float sw = (ow + 0.5f) * rs - 0.5f;
+    sh = sh < 0.f ? 0.f : sh;
+    sw = sw < 0.f ? 0.f : sw;
+    const int h0 = static_cast<int>(sh), w0 = static_cast<int>(sw);
+    const int h1 = h0 + (h0 < h - 1 ? 1 : 0), w1 = w0 + (w0 < wpx - 1 ? 1 : 0);
+    const float lh = sh - h0, lw = sw - w0;
+    const float* xp = x + pl * static_cast<size_t>(h) * wpx;
+    const float v00 = __ldg(xp + h0 * wpx + w0), v01 = __ldg(xp + h0 * wpx + w1);
+    const float v10 = __ldg(xp + h1 * wpx + w0), v11 = __ldg(xp + h1 * wpx + w1);
+    // same evaluation order as ATen's upsample_bilinear2d: h0lambda*(w0lambda*v00 + w1lambda*v01) + h1lambda*(...)
+    y[idx] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ layout helpers
+__global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int h, int wpx,
+                                    int c, int cstride, int coffset, int act) {
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t total = static_cast<size_t>(n) * c * h * wpx;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = idx % wpx;
+    size_t t = idx / wpx;
+    const int oh = t % h;
+    t /= h;
+    const int ch = t % c;
+    const int img = t / c;
+    const __nv_bfloat16* pix = x + ((static_cast<size_t>(img) * h + oh) * wpx + ow) * (static_cast<size_t>(cstride) * planes) + coffset;
+    y[idx] = act_load(pix, ch, cstride, act);
+  }
+}
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int wpx,
+                                    int c, int cstride, int coffset, int act) {
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t total = static_cast<size_t>(n) * c * h * wpx;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ch = idx % c;
+    size_t t = idx / c;
+    const int ow = t % wpx;
+    t /= wpx;
+    const int oh = t % h;
+    const int img = t / h;
+    const float v = x[((static_cast<size_t>(img) * c + ch) * h + oh) * wpx + ow];
+    __nv_bfloat16* pix = y + ((static_cast<size_t>(img) * h + oh) * wpx + ow) * (static_cast<size_t>(cstride) * planes) + coffset;
+    act_store(pix, ch, cstride, act, v);
+  }
+}
+
+}  // namespace
+}  // namespace w2c
+
+using namespace w2c;
+
+extern "C" {
+
+int w2c_version(void) { return 100; }
+const char* w2c_last_error(void) { return g_err; }
+uint64_t w2c_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int32_t w2c_cout_pad(int32_t cout) { return (cout + 15) / 16 * 16; }
+size_t w2c_packed_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t act) {
+  return static_cast<size_t>(w2c_cout_pad(cout)) * ntaps * cin * 2 * (act == W2C_ACT_BF16X2 ? 2 : 1);
+}
+
+int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
+                         int32_t transposed, int32_t act, void* packed, w2c_stream_t stream) {
+  W2C_CHECK_ARG(w && packed, "pack: null pointer");
+  W2C_CHECK_ARG(cout > 0 && cin_real > 0 && cin >= cin_real && cin % 64 == 0, "pack: bad channels %d/%d/%d", cout,
+                cin_real, cin);
+  W2C_CHECK_ARG(ntaps == 9 || ntaps == 1, "pack: ntaps must be 9 or 1");
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int cout_pad = w2c_cout_pad(cout);
+  const size_t total = static_cast<size_t>(cout_pad) * ntaps * cin;
+  pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin_real, cin, ntaps, transposed, planes, cout_pad, static_cast<__nv_bfloat16*>(packed));
+  W2C_CHECK_LAUNCH("pack_weight_kernel");
+  return W2C_OK;
+}
+
+int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,
+                float eps, int32_t cout, float* scale, float* shift, w2c_stream_t stream) {
+  W2C_CHECK_ARG(scale && shift && cout > 0, "fold_bn: bad arguments");
+  const bool any = gamma || beta || mean || var;
+  W2C_CHECK_ARG(!any || (gamma && beta && mean && var), "fold_bn: BN tensors must be all present or all NULL");
+  fold_bn_kernel<<<ceil_div(cout, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(conv_bias, gamma, beta, mean, var,
+                                                                                     eps, cout, scale, shift);
+  W2C_CHECK_LAUNCH("fold_bn_kernel");
+  return W2C_OK;
+}
+
+int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
+                         int32_t n_agents, int32_t h, int32_t w_px, int32_t cout, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && w && scale && shift && y, "stem3x3: null pointer");
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3: bad extent");
+  W2C_CHECK_ARG(cout % 32 == 0 && cout <= 128, "stem3x3: cout=%d must be a multiple of 32 and <= 128", cout);
+  const size_t total = static_cast<size_t>(b) * n_agents * h * w_px;
+  const size_t smem = (27 * cout + 2 * cout) * sizeof(float);
+  stem3x3_kernel<32><<<grid_for(total, 256, 148 * 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, h, w_px, cout, act);
+  W2C_CHECK_LAUNCH("stem3x3_kernel");
+  return W2C_OK;
+}
+
+int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
+                           int32_t n_agents, int32_t h, int32_t w_px, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && w && scale && shift && y, "stem7x7: null pointer");
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0, "stem7x7: bad extent");
+  const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (w_px / 2);
+  const size_t smem = (147 * 64 + 128) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(stem7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    attr = true;
+  }
+  stem7x7_kernel<<<grid_for(total, 128, 148 * 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, h, w_px, act);
+  W2C_CHECK_LAUNCH("stem7x7_kernel");
+  return W2C_OK;
+}
+
+int w2c_maxpool3x3s2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t act,
+                         w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && y && n > 0 && h > 0 && w_px > 0 && c > 0 && h % 2 == 0 && w_px % 2 == 0, "maxpool: bad arguments");
+  const size_t total = static_cast<size_t>(n) * (h / 2) * (w_px / 2) * c;
+  maxpool3x3s2_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(y), n, h, w_px, c, act);
+  W2C_CHECK_LAUNCH("maxpool3x3s2_kernel");
+  return W2C_OK;
+}
+
+int w2c_bilinear_up_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
+                        w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && y && n > 0 && c > 0 && h > 0 && w_px > 0 && factor >= 1, "bilinear: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h * factor * w_px * factor;
+  bilinear_up_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n * c, h, w_px, factor);
+  W2C_CHECK_LAUNCH("bilinear_up_kernel");
+  return W2C_OK;
+}
+
+int w2c_nhwc_to_nchw_f32(const void* x, float* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,
+                         int32_t coffset, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && y && n > 0 && h > 0 && w_px > 0 && c > 0, "nhwc_to_nchw: bad arguments");
+  if (cstride <= 0) cstride = c;
+  const size_t total = static_cast<size_t>(n) * c * h * w_px;
+  nhwc_to_nchw_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), y, n, h, w_px, c, cstride, coffset, act);
+  W2C_CHECK_LAUNCH("nhwc_to_nchw_kernel");
+  return W2C_OK;
+}
+
+int w2c_nchw_f32_to_nhwc(const float* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,
+                         int32_t coffset, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && y && n > 0 && h > 0 && w_px > 0 && c > 0, "nchw_to_nhwc: bad arguments");
+  if (cstride <= 0) cstride = c;
+  const size_t total = static_cast<size_t>(n) * c * h * w_px;
+  nchw_to_nhwc_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<__nv_bfloat16*>(y), n, h, w_px, c, cstride, coffset, act);
+  W2C_CHECK_LAUNCH("nchw_to_nhwc_kernel");
+  return W2C_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+"""Torch-tensor front end of the C ABI: each function takes CUDA tensors, passes raw device pointers + sizes and the
+current CUDA stream to libw2c.so, and returns the (caller-visible) output tensor. PyTorch is used for device memory
+and streams only; all arithmetic happens in the hand-written kernels.
+
+Activation maps are NHWC bf16 tensors of shape [n, h, w, planes * c] (planes = 2 for the hi|lo "bf16x3" parity
+precision, see include/w2c.h).
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_BF16, ACT_BF16X2, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, CONV3X3_S1, CONV3X3_S2,
+                   DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("libw2c operates on CUDA tensors only (got a %s tensor)" % t.device)
+    if not t.is_contiguous():
+        raise ValueError("libw2c needs contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def planes_of(act):
+    return 2 if act == ACT_BF16X2 else 1
+
+
+def launch_count():
+    return int(_lib.load().w2c_launch_count())
+
+
+def cout_pad(cout):
+    return int(_lib.load().w2c_cout_pad(cout))
+
+
+def new_act(n, h, w, c, act, device):
+    return torch.empty((n, h, w, planes_of(act) * c), dtype=torch.bfloat16, device=device)
+
+
+# ------------------------------------------------------------------------------------------------ setup-time ops
+def fold_bn(conv_bias, bn_weight, bn_bias, bn_mean, bn_var, eps, cout, device):
+    """scale/shift of the fused epilogue from an eval-mode BatchNorm2d and the conv bias (utils.py:110-114)."""
+    lib = _lib.load()
+    scale = torch.empty(cout, dtype=torch.float32, device=device)
+    shift = torch.empty(cout, dtype=torch.float32, device=device)
+    f32 = lambda t: None if t is None else t.detach().to(device=device, dtype=torch.float32).contiguous()
+    cb, g, b, m, v = f32(conv_bias), f32(bn_weight), f32(bn_bias), f32(bn_mean), f32(bn_var)
+    _lib.check(lib.w2c_fold_bn(_ptr(cb), _ptr(g), _ptr(b), _ptr(m), _ptr(v), float(eps), cout, _ptr(scale),
+                               _ptr(shift), _stream()), "w2c_fold_bn")
+    return scale, shift
+
+
+def pack_conv_weight(w, cin_pad, transposed, act):
+    """Conv2d.weight [co,ci,kh,kw] (or ConvTranspose2d.weight [ci,co,kh,kw]) -> packed bf16 K-major operand."""
+    lib = _lib.load()
+    w = w.detach().to(dtype=torch.float32).contiguous()
+    if transposed:
+        cin_real, cout = w.shape[0], w.shape[1]
+    else:
+        cout, cin_real = w.shape[0], w.shape[1]
+    ntaps = w.shape[2] * w.shape[3]
+    nbytes = lib.w2c_packed_weight_bytes(cout, cin_pad, ntaps, act)
+    packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.w2c_pack_conv_weight(_ptr(w), cout, cin_real, cin_pad, ntaps, int(bool(transposed)), act,
+                                        _ptr(packed), _stream()), "w2c_pack_conv_weight")
+    return packed
+
+
+# ------------------------------------------------------------------------------------------------ hot-path ops
+def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind, relu, act, out_fmt=OUT_NHWC,
+                residual=None, x_cstride=0, x_coffset=0, y_cstride=0, y_coffset=0, impl=IMPL_TCGEN05, block_n=0):
+    lib = _lib.load()
+    a = _lib.ConvArgs(x=_ptr(x), w=_ptr(w_packed), scale=_ptr(scale), shift=_ptr(shift), residual=_ptr(residual),
+                      y=_ptr(y), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout, x_cstride=x_cstride,
+                      x_coffset=x_coffset, y_cstride=y_cstride, y_coffset=y_coffset, kind=kind, relu=int(relu),
+                      act=act, out_fmt=out_fmt, impl=impl, block_n=block_n)
+    _lib.check(lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), _stream()), "w2c_conv_bnrelu_fwd")
+    return y
+
+
+def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act):
+    lib = _lib.load()
+    _lib.check(lib.w2c_stem_conv3x3_fwd(_ptr(x_nchw), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents, h,
+                                        w, cout, act, _stream()), "w2c_stem_conv3x3_fwd")
+    return y
+
+
+def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act):
+    lib = _lib.load()
+    _lib.check(lib.w2c_stem_conv7x7s2_fwd(_ptr(x_nchw), _ptr(w147), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,
+                                          h, w, act, _stream()), "w2c_stem_conv7x7s2_fwd")
+    return y
+
+
+def maxpool3x3s2(x, y, *, n, h, w, c, act):
+    lib = _lib.load()
+    _lib.check(lib.w2c_maxpool3x3s2_fwd(_ptr(x), _ptr(y), n, h, w, c, act, _stream()), "w2c_maxpool3x3s2_fwd")
+    return y
+
+
+def bilinear_up(x, y, *, n, c, h, w, factor):
+    lib = _lib.load()
+    _lib.check(lib.w2c_bilinear_up_fwd(_ptr(x), _ptr(y), n, c, h, w, factor, _stream()), "w2c_bilinear_up_fwd")
+    return y
+
+
+def kq_mlp(feat, act, m, n_feat, w0, b0, w1, b1, w2, b2, out_dim, out, ws):
+    lib = _lib.load()
+    _lib.check(lib.w2c_kq_mlp_fwd(_ptr(feat), act, m, n_feat, _ptr(w0), _ptr(b0), _ptr(w1), _ptr(b1), _ptr(w2),
+                                  _ptr(b2), out_dim, _ptr(out), _ptr(ws), _stream()), "w2c_kq_mlp_fwd")
+    return out
+
+
+def attn_fuse(keys, queries, wq, bq, val, fused, prob_out, coef_out, action, connect, *, b_sz, n_k, n_q, k_dim,
+              q_dim, hw, c, act, mode, sparse=False, mask_self=False, temperature=1.0, diag_bias=0.0, thresh=0.2,
+              fused_cstride=0, fused_coffset=0):
+    lib = _lib.load()
+    a = _lib.AttnArgs(keys=_ptr(keys), queries=_ptr(queries), wq=_ptr(wq), bq=_ptr(bq), val=_ptr(val),
+                      fused=_ptr(fused), prob_out=_ptr(prob_out), coef_out=_ptr(coef_out), action=_ptr(action),
+                      connect=_ptr(connect), b_sz=b_sz, n_k=n_k, n_q=n_q, k_dim=k_dim, q_dim=q_dim, hw=hw, c=c,
+                      fused_cstride=fused_cstride, fused_coffset=fused_coffset, act=act, mode=mode,
+                      sparse=int(bool(sparse)), mask_self=int(bool(mask_self)), temperature=float(temperature),
+                      diag_bias=float(diag_bias), thresh=float(thresh))
+    _lib.check(lib.w2c_attn_fuse_fwd(ctypes.byref(a), _stream()), "w2c_attn_fuse_fwd")
+
+
+# ------------------------------------------------------------------------------------------------ layout helpers
+def nchw_to_act(x_nchw, act, cstride=0, coffset=0, out=None):
+    lib = _lib.load()
+    n, c, h, w = x_nchw.shape
+    cs = cstride if cstride > 0 else c
+    if out is None:
+        out = torch.zeros((n, h, w, planes_of(act) * cs), dtype=torch.bfloat16, device=x_nchw.device)
+    x32 = x_nchw.to(torch.float32).contiguous()
+    _lib.check(lib.w2c_nchw_f32_to_nhwc(_ptr(x32), _ptr(out), n, h, w, c, cs, coffset, act, _stream()),
+               "w2c_nchw_f32_to_nhwc")
+    return out
+
+
+def act_to_nchw(x_act, c, act, cstride=0, coffset=0):
+    lib = _lib.load()
+    n, h, w, _ = x_act.shape
+    cs = cstride if cstride > 0 else c
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x_act.device)
+    _lib.check(lib.w2c_nhwc_to_nchw_f32(_ptr(x_act), _ptr(out), n, h, w, c, cs, coffset, act, _stream()),
+               "w2c_nhwc_to_nchw_f32")
+    return out

@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""Kernel-by-kernel bring-up check on a real B200: every libw2c entry point against a float64 torch evaluation of
+the same op. Each case runs in its own subprocess under a timeout, so a hung kernel (e.g. a dead mbarrier pipeline)
+costs one case, not the whole GPU call. Results go to gpurun_out/kernel_check.jsonl.
+
+    python tools/gpu_kernel_check.py            # run all cases
+    python tools/gpu_kernel_check.py --case X   # run one case in-process
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _imports():
+    import torch
+    import torch.nn.functional as F
+    from multiagentperception_b200 import ops
+    return torch, F, ops
+
+
+def _bf16_round(t):
+    import torch
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+def _quant(t, act):
+    """What the kernels see of an fp32 tensor in the given activation storage (as float64)."""
+    import torch
+    hi = t.to(torch.bfloat16)
+    if act == 0:
+        return hi.to(torch.float64)
+    lo = (t - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi.to(torch.float64) + lo.to(torch.float64)
+
+
+def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw_out=False, impl=0, block_n=0,
+               cin_real=None, seed=0, x_cs=0, x_co=0, y_cs=0, y_co=0):
+    torch, F, ops = _imports()
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    cin_real = cin_real or cin
+    ksz = 1 if kind in (ops.CONV1X1_S1, ops.CONV1X1_S2) else 3
+    x = torch.randn(n, cin_real, h, w, generator=g)
+    transposed = kind == ops.DECONV3X3_S2
+    wshape = (cin_real, cout, ksz, ksz) if transposed else (cout, cin_real, ksz, ksz)
+    wt = torch.randn(*wshape, generator=g) / (cin_real * ksz * ksz) ** 0.5
+    scale = torch.rand(cout, generator=g) + 0.5
+    shift = torch.randn(cout, generator=g) * 0.1
+    x, wt, scale, shift = x.to(dev), wt.to(dev), scale.to(dev), shift.to(dev)
+
+    x_cs_eff = x_cs if x_cs else cin
+    xa = ops.nchw_to_act(x, act, cstride=x_cs_eff, coffset=x_co)      # zero-filled outside the slice
+    if cin_real < cin or x_cs:
+        pass  # padded channels are zero in xa by construction (nchw_to_act zero-initialises)
+    wp = ops.pack_conv_weight(wt, cin, transposed, act)
+    xq, wq = _quant(x, act), _quant(wt, act)
+    if kind == ops.CONV3X3_S1:
+        ref = F.conv2d(xq, wq, padding=1)
+    elif kind == ops.CONV3X3_S2:
+        ref = F.conv2d(xq, wq, padding=1, stride=2)
+    elif kind == ops.DECONV3X3_S2:
+        ref = F.conv_transpose2d(xq, wq, stride=2, padding=1, output_padding=1)
+    elif kind == ops.CONV1X1_S1:
+        ref = F.conv2d(xq, wq)
+    else:
+        ref = F.conv2d(xq, wq, stride=2)
+    ref = ref * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+    ho, wo = ref.shape[2], ref.shape[3]
+    res_act = None
+    y_cs_eff = y_cs if y_cs else cout
+    if residual:
+        r = torch.randn(n, cout, ho, wo, generator=g).to(dev)
+        res_act = ops.nchw_to_act(r, act, cstride=y_cs_eff, coffset=y_co)
+        ref = ref + _quant(r, act)
+    if relu:
+        ref = ref.clamp_min(0)
+    if nchw_out:
+        y = torch.full((n, cout, ho, wo), float("nan"), dtype=torch.float32, device=dev)
+    else:
+        y = torch.zeros((n, ho, wo, ops.planes_of(act) * y_cs_eff), dtype=torch.bfloat16, device=dev)
+    ops.conv_bnrelu(xa, wp, scale, shift, y, n=n, h_in=h, w_in=w, cin=cin, cout=cout, kind=kind, relu=relu, act=act,
+                    out_fmt=ops.OUT_NCHW_F32 if nchw_out else ops.OUT_NHWC, residual=res_act, x_cstride=x_cs,
+                    x_coffset=x_co, y_cstride=y_cs, y_coffset=y_co, impl=impl, block_n=block_n)
+    torch.cuda.synchronize()
+    got = y.double() if nchw_out else ops.act_to_nchw(y, cout, act, cstride=y_cs_eff, coffset=y_co).double()
+    err = (got - ref).abs().max().item()
+    mag = ref.abs().max().item()
+    # bf16 output rounding: 2^-9 relative per element; bf16x2 / fp32 outputs: ~1e-5
+    tol = (6e-3 if (act == 0 and not nchw_out) else 2e-4) * max(mag, 1.0)
+    return {"max_err": err, "ref_max": mag, "tol": tol, "ok": bool(err <= tol) and bool(torch.isfinite(got).all())}
+
+
+def case_layout():
+    torch, F, ops = _imports()
+    out = {}
+    ok = True
+    for act in (0, 1):
+        x = torch.randn(2, 24, 5, 7, device="cuda:0")
+        a = ops.nchw_to_act(x, act, cstride=32, coffset=8)
+        back = ops.act_to_nchw(a, 24, act, cstride=32, coffset=8)
+        err = (back.double() - _quant(x, act)).abs().max().item()
+        out["act%d" % act] = err
+        ok &= err == 0.0
+    out["ok"] = ok
+    return out
+
+
+CONV_CASES = {
+    # name: (kind, n, h, w, cin, cout, act, kwargs)
+    "simt_s1": (0, 2, 9, 11, 64, 24, 0, dict(impl=1)),
+    "simt_s2": (1, 2, 8, 12, 64, 32, 1, dict(impl=1)),
+    "simt_deconv": (2, 2, 5, 6, 64, 16, 0, dict(impl=1)),
+    "simt_1x1s2_res": (4, 1, 8, 8, 64, 64, 1, dict(impl=1, residual=True, relu=True)),
+    "tc_s1_min": (0, 1, 8, 16, 64, 64, 0, dict()),
+    "tc_s1_multi": (0, 3, 24, 40, 128, 128, 0, dict()),
+    "tc_s1_bn256": (0, 2, 16, 16, 256, 256, 0, dict(block_n=256)),
+    "tc_s1_bn64_k512": (0, 2, 16, 16, 512, 192, 0, dict(block_n=64)),
+    "tc_s1_x2": (0, 2, 16, 16, 128, 64, 1, dict()),
+    "tc_s2": (1, 2, 32, 32, 64, 128, 0, dict()),
+    "tc_s2_x2": (1, 1, 16, 48, 128, 64, 1, dict()),
+    "tc_deconv": (2, 2, 16, 16, 128, 128, 0, dict()),
+    "tc_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict()),
+    "tc_1x1": (3, 2, 16, 16, 128, 64, 0, dict(relu=False)),
+    "tc_1x1s2_res": (4, 2, 16, 16, 64, 128, 0, dict(residual=True)),
+    "tc_small_8x8": (0, 5, 8, 8, 256, 256, 0, dict()),
+    "tc_small_4x4": (1, 5, 8, 8, 256, 256, 0, dict()),
+    "tc_nchw_c11": (0, 2, 32, 32, 64, 11, 0, dict(nchw_out=True)),
+    "tc_nchw_c11_x2": (0, 2, 16, 32, 64, 11, 1, dict(nchw_out=True, relu=False)),
+    "tc_slices": (0, 2, 16, 16, 64, 64, 0, dict(x_cs=128, x_co=64, y_cs=192, y_co=64)),
+    "tc_cinpad": (0, 2, 16, 16, 64, 64, 0, dict(cin_real=40)),
+    "tc_ragged": (0, 3, 13, 21, 64, 72, 0, dict()),
+}
+
+
+def case_stem():
+    torch, F, ops = _imports()
+    dev = "cuda:0"
+    out, ok = {}, True
+    for act in (0, 1):
+        b, na, h, w, cout = 2, 3, 20, 28, 64
+        x = torch.randn(b, 3 * na, h, w, device=dev)
+        wt = torch.randn(cout, 3, 3, 3, device=dev) * 0.2
+        scale = torch.rand(cout, device=dev) + 0.5
+        shift = torch.randn(cout, device=dev) * 0.1
+        y = ops.new_act(b * na, h, w, cout, act, dev)
+        ops.stem_conv3x3(x, wt.reshape(cout, 27).contiguous(), scale, shift, y, b=b, n_agents=na, h=h, w=w, cout=cout,
+                         act=act)
+        xs = torch.cat([x[:, 3 * i:3 * i + 3] for i in range(na)], 0).double()
+        ref = F.conv2d(xs, wt.double(), padding=1) * scale.double().view(1, -1, 1, 1) + shift.double().view(1, -1, 1, 1)
+        ref = ref.clamp_min(0)
+        got = ops.act_to_nchw(y, cout, act).double()
+        err = (got - ref).abs().max().item()
+        tol = (6e-3 if act == 0 else 1e-4) * max(1.0, ref.abs().max().item())
+        out["stem3x3_act%d" % act] = err
+        ok &= err <= tol
+        # 7x7 s2 + maxpool
+        h2, w2 = 32, 48
+        x = torch.randn(b, 3 * na, h2, w2, device=dev)
+        wt7 = torch.randn(64, 3, 7, 7, device=dev) * 0.08
+        y7 = ops.new_act(b * na, h2 // 2, w2 // 2, 64, act, dev)
+        ops.stem_conv7x7s2(x, wt7.reshape(64, 147).contiguous(), scale, shift, y7, b=b, n_agents=na, h=h2, w=w2, act=act)
+        xs = torch.cat([x[:, 3 * i:3 * i + 3] for i in range(na)], 0).double()
+        ref7 = (F.conv2d(xs, wt7.double(), padding=3, stride=2) * scale.double().view(1, -1, 1, 1)
+                + shift.double().view(1, -1, 1, 1)).clamp_min(0)
+        got7 = ops.act_to_nchw(y7, 64, act).double()
+        err7 = (got7 - ref7).abs().max().item()
+        out["stem7x7_act%d" % act] = err7
+        ok &= err7 <= (6e-3 if act == 0 else 1e-4) * max(1.0, ref7.abs().max().item())
+        yp = ops.new_act(b * na, h2 // 4, w2 // 4, 64, act, dev)
+        ops.maxpool3x3s2(y7, yp, n=b * na, h=h2 // 2, w=w2 // 2, c=64, act=act)
+        refp = F.max_pool2d(got7, 3, 2, 1)
+        errp = (ops.act_to_nchw(yp, 64, act).double() - refp).abs().max().item()
+        out["maxpool_act%d" % act] = errp
+        ok &= errp <= 1e-6
+    xb = torch.randn(3, 11, 4, 6, device=dev)
+    yb = torch.empty(3, 11, 4 * 32, 6 * 32, device=dev)
+    ops.bilinear_up(xb, yb, n=3, c=11, h=4, w=6, factor=32)
+    refb = F.interpolate(xb.double(), size=(128, 192), mode="bilinear", align_corners=False)
+    errb = (yb.double() - refb).abs().max().item()
+    out["bilinear"] = errb
+    ok &= errb <= 1e-5
+    out["ok"] = bool(ok)
+    return out
+
+
+def _attn_ref(keys, queries, wq, bq, val, b_sz, n_k, n_q, mode, sparse, mask_self, temperature, diag_bias, thresh):
+    import torch
+    k = keys.double().view(n_k, b_sz, -1).transpose(0, 1)       # (B, n_k, kd)
+    q = queries.double().view(n_q, b_sz, -1).transpose(0, 1)    # (B, n_q, qd)
+    qt = q @ wq.double().t() + bq.double() if wq is not None else q
+    S = torch.bmm(k, qt.transpose(1, 2)) / temperature          # (B, n_k, n_q)
+    if mask_self:
+        eye = torch.eye(n_k, n_q, dtype=torch.bool, device=S.device)
+        S = S.masked_fill(eye, float("-inf"))
+    if sparse:
+        z = S - S.max(dim=1, keepdim=True)[0]
+        zs = torch.sort(z, dim=1, descending=True)[0]
+        rng = torch.arange(1, n_k + 1, device=S.device, dtype=torch.float64).view(1, -1, 1)
+        is_gt = (1 + rng * zs > zs.cumsum(1)).double()
+        kk = (is_gt * rng).max(dim=1, keepdim=True)[0]
+        tau = ((is_gt * zs).sum(1, keepdim=True) - 1) / kk
+        P = (z - tau).clamp_min(0)
+    else:
+        P = torch.softmax(S, dim=1)
+    Pb = P + diag_bias * torch.eye(n_k, n_q, dtype=torch.float64, device=S.device)
+    if mode == 0:
+        coef, act_src = P, Pb
+    elif mode == 1:
+        coef = Pb * (Pb > thresh).double()
+        act_src = coef
+    else:
+        coef = torch.nn.functional.one_hot(Pb.argmax(dim=1), n_k).double().transpose(1, 2)
+        act_src = coef
+    V = val.double()                                            # (n_k*B, C, h, w) agent-major
+    Vb = V.view(n_k, b_sz, *V.shape[1:]).transpose(0, 1)        # (B, n_k, C, h, w)
+    fused = torch.einsum("bij,bichw->bjchw", coef, Vb)          # (B, n_q, C, h, w)
+    fused = fused.transpose(0, 1).reshape(n_q * b_sz, *V.shape[1:])
+    off = ~torch.eye(n_k, n_q, dtype=torch.bool, device=S.device)
+    connect = int(((coef != 0) & off).sum().item())
+    return Pb, coef, act_src.argmax(dim=1), fused, connect
+
+
+def case_attn():
+    torch, F, ops = _imports()
+    dev = "cuda:0"
+    out, ok = {}, True
+    cfgs = [
+        dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=0, act=0, diag=0.001),
+        dict(b_sz=3, n_k=5, n_q=5, kd=1024, qd=32, mode=1, act=1, diag=0.001),
+        dict(b_sz=2, n_k=6, n_q=6, kd=1024, qd=32, mode=2, act=0, diag=0.001),
+        dict(b_sz=2, n_k=8, n_q=8, kd=1024, qd=32, mode=1, act=0, diag=0.001),
+        dict(b_sz=2, n_k=5, n_q=1, kd=128, qd=128, mode=1, act=0, diag=0.0, sparse=True, wq=False, temp=128 ** 0.5),
+        dict(b_sz=2, n_k=5, n_q=1, kd=1024, qd=32, mode=2, act=1, diag=0.0),
+        dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=0, act=0, diag=0.0, mask_self=True),
+    ]
+    for ci, cf in enumerate(cfgs):
+        b_sz, n_k, n_q, kd, qd = cf["b_sz"], cf["n_k"], cf["n_q"], cf["kd"], cf["qd"]
+        C, hh, ww = 512, 4, 4
+        act = cf["act"]
+        keys = torch.randn(n_k * b_sz, kd, device=dev) * 0.3
+        queries = torch.randn(n_q * b_sz, qd, device=dev) * 0.3
+        use_wq = cf.get("wq", True)
+        wq = torch.randn(kd, qd, device=dev) * 0.2 if use_wq else None
+        bq = torch.randn(kd, device=dev) * 0.1 if use_wq else None
+        val = torch.randn(n_k * b_sz, C, hh, ww, device=dev)
+        va = ops.nchw_to_act(val, act)
+        fused = ops.new_act(n_q * b_sz, hh, ww, C, act, dev)
+        prob = torch.empty(b_sz, n_k, n_q, device=dev)
+        coef = torch.empty(b_sz, n_k, n_q, device=dev)
+        action = torch.empty(b_sz, n_q, dtype=torch.int64, device=dev)
+        connect = torch.zeros(1, dtype=torch.int32, device=dev)
+        ops.attn_fuse(keys, queries, wq, bq, va, fused, prob, coef, action, connect, b_sz=b_sz, n_k=n_k, n_q=n_q,
+                      k_dim=kd, q_dim=qd, hw=hh * ww, c=C, act=act, mode=cf["mode"], sparse=cf.get("sparse", False),
+                      mask_self=cf.get("mask_self", False), temperature=cf.get("temp", 1.0), diag_bias=cf["diag"],
+                      thresh=0.2)
+        torch.cuda.synchronize()
+        Pb, cref, aref, fref, nconn = _attn_ref(keys, queries, wq, bq, _quant(val, act), b_sz, n_k, n_q, cf["mode"],
+                                                cf.get("sparse", False), cf.get("mask_self", False),
+                                                cf.get("temp", 1.0), cf["diag"], 0.2)
+        e_p = (prob.double() - Pb).abs().max().item()
+        e_c = (coef.double() - cref).abs().max().item()
+        e_f = (ops.act_to_nchw(fused, C, act).double() - fref).abs().max().item()
+        a_ok = bool((action == aref).all().item())
+        c_ok = (int(connect.item()) == nconn) if cf["mode"] != 0 else True
+        tol_f = (6e-3 if act == 0 else 1e-4) * max(1.0, fref.abs().max().item())
+        good = e_p < 1e-5 and e_c < 1e-5 and e_f <= tol_f and a_ok and c_ok
+        out["cfg%d" % ci] = dict(e_prob=e_p, e_coef=e_c, e_fused=e_f, action_ok=a_ok, connect_ok=c_ok, ok=good)
+        ok &= good
+    out["ok"] = bool(ok)
+    return out
+
+
+def case_mlp():
+    torch, F, ops = _imports()
+    dev = "cuda:0"
+    out, ok = {}, True
+    for act in (0, 1):
+        for (m, s, od) in ((5, 4, 1024), (10, 1, 32), (13, 2, 128)):
+            n_feat = 256 * s * s
+            feat = torch.randn(m, 256, s, s, device=dev)
+            fa = ops.nchw_to_act(feat, act)
+            w0 = torch.randn(256, n_feat, device=dev) / n_feat ** 0.5
+            b0 = torch.randn(256, device=dev) * 0.1
+            w1 = torch.randn(128, 256, device=dev) / 16
+            b1 = torch.randn(128, device=dev) * 0.1
+            w2 = torch.randn(od, 128, device=dev) / 11
+            b2 = torch.randn(od, device=dev) * 0.1
+            # reference flattens NCHW (agent.py:158); the kernel reads NHWC, so permute w0's input axis
+            w0_nhwc = w0.view(256, 256, s, s).permute(0, 2, 3, 1).reshape(256, n_feat).contiguous()
+            res = torch.empty(m, od, device=dev)
+            ws = torch.empty(m * 384, device=dev)
+            ops.kq_mlp(fa, act, m, n_feat, w0_nhwc, b0, w1, b1, w2, b2, od, res, ws)
+            x = _quant(feat, act).reshape(m, n_feat)
+            h = (x @ w0.double().t() + b0.double()).clamp_min(0)
+            h = (h @ w1.double().t() + b1.double()).clamp_min(0)
+            ref = h @ w2.double().t() + b2.double()
+            err = (res.double() - ref).abs().max().item()
+            out["act%d_m%d_s%d" % (act, m, s)] = err
+            ok &= err < 2e-5 * max(1.0, ref.abs().max().item())
+    out["ok"] = bool(ok)
+    return out
+
+
+def run_case(name):
+    t0 = time.time()
+    if name == "layout":
+        r = case_layout()
+    elif name == "stem":
+        r = case_stem()
+    elif name == "attn":
+        r = case_attn()
+    elif name == "mlp":
+        r = case_mlp()
+    elif name in CONV_CASES:
+        kind, n, h, w, cin, cout, act, kw = CONV_CASES[name]
+        r = _conv_case(kind, n, h, w, cin, cout, act, **kw)
+    else:
+        raise SystemExit("unknown case " + name)
+    r["case"] = name
+    r["seconds"] = round(time.time() - t0, 2)
+    return r
+
+
+def all_cases():
+    return ["layout"] + list(CONV_CASES) + ["stem", "mlp", "attn"]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--case")
+    ap.add_argument("--timeout", type=int, default=180)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "kernel_check.jsonl"))
+    args = ap.parse_args()
+    if args.case:
+        print(json.dumps(run_case(args.case)))
+        return 0
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    n_bad = 0
+    with open(args.out, "w") as f:
+        for name in all_cases():
+            try:
+                p = subprocess.run([sys.executable, os.path.abspath(__file__), "--case", name], capture_output=True,
+                                   text=True, timeout=args.timeout)
+                line = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else ""
+                try:
+                    rec = json.loads(line)
+                except Exception:
+                    rec = {"case": name, "ok": False, "rc": p.returncode, "stderr": p.stderr[-1500:], "stdout": p.stdout[-500:]}
+            except subprocess.TimeoutExpired:
+                rec = {"case": name, "ok": False, "timeout": True}
+            n_bad += 0 if rec.get("ok") else 1
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            print(json.dumps(rec), flush=True)
+    print("kernel_check: %d failing case(s)" % n_bad)
+    return 1 if n_bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
