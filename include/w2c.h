@@ -118,14 +118,15 @@ int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, c
 /*
  * First encoder layer: Conv2d(3 -> cout, k3 s1 p1) + BN + ReLU reading the caller's fp32 NCHW batch directly.
  * Replaces divide_inputs + cat (agent.py:1088-1108) and n_segnet_encoder.conv1 (backbone.py:19,42).
- *   x     fp32 [b][3*n_agents][h][w]  (views concatenated on the channel axis, trainer.py:651)
+ *   x     fp32 [b][c_total][h][w]  (views concatenated on the channel axis, trainer.py:651); agent a reads
+ *         channels [c_first + 3a, c_first + 3a + 3)
  *   w     fp32 [cout][27]  (k = ci*9 + kh*3 + kw, i.e. Conv2d.weight flattened), scale/shift fp32 [cout]
  *   y     NHWC [(n_agents*b)][h][w][cout], image index = agent*b + batch ("agent-major", agent.py:1103-1108)
- * cout must be a multiple of 8 and <= 128.
+ * cout must be a multiple of 32 and <= 128.
  */
 int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
-                         int32_t b, int32_t n_agents, int32_t h, int32_t w_px, int32_t cout, int32_t act,
-                         w2c_stream_t stream);
+                         int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
+                         int32_t cout, int32_t act, w2c_stream_t stream);
 
 /*
  * Key / query heads: flatten -> Linear -> ReLU -> Linear -> ReLU -> Linear.  Replaces km_generator.forward and
@@ -181,6 +182,14 @@ typedef struct w2c_attn_args {
   float temperature; /* 1 for the "general" attention, sqrt(128) for ScaledDotProductAttention */
   float diag_bias;   /* 0.001 for MIMOcom, 0 otherwise */
   float thresh;      /* 0.2 */
+  /* Agent sharding (one process per GPU): the score matrix is always computed for all n_k x n_q pairs, but only
+   * queries [q_first, q_first + q_count) are fused and written, as images 0..q_count*b_sz of `fused`
+   * (q_count = 0: all n_q).  keys / queries / val may point into an all-gathered buffer in which every rank
+   * contributed agents_per_rank agents: agent i is row-block (i % agents_per_rank) of rank segment
+   * (i / agents_per_rank), segments *_rank_stride ELEMENTS apart (agents_per_rank = 0: dense agent-major). */
+  int32_t q_first, q_count;
+  int32_t agents_per_rank;
+  int64_t keys_rank_stride, queries_rank_stride, val_rank_stride;
 } w2c_attn_args;
 
 int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream);
@@ -189,8 +198,8 @@ int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream);
 
 /* Conv2d(3 -> 64, k7 s2 p3, no bias) + BN + ReLU on the fp32 NCHW batch; same input convention as the stem. */
 int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
-                           int32_t b, int32_t n_agents, int32_t h, int32_t w_px, int32_t act,
-                           w2c_stream_t stream);
+                           int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
+                           int32_t act, w2c_stream_t stream);
 /* MaxPool2d(k3 s2 p1) on NHWC. */
 int w2c_maxpool3x3s2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t act,
                          w2c_stream_t stream);

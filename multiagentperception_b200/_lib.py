@@ -43,6 +43,9 @@ class AttnArgs(ctypes.Structure):
         ("fused_cstride", c_i32), ("fused_coffset", c_i32),
         ("act", c_i32), ("mode", c_i32), ("sparse", c_i32), ("mask_self", c_i32),
         ("temperature", c_f32), ("diag_bias", c_f32), ("thresh", c_f32),
+        ("q_first", c_i32), ("q_count", c_i32), ("agents_per_rank", c_i32),
+        ("keys_rank_stride", ctypes.c_int64), ("queries_rank_stride", ctypes.c_int64),
+        ("val_rank_stride", ctypes.c_int64),
     ]
 
 
@@ -56,10 +59,10 @@ _SIGNATURES = {
     "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "w2c_fold_bn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp]),
-    "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 8 + [c_vp]),
     "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "w2c_attn_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs), c_vp]),
-    "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 7 + [c_vp]),
     "w2c_maxpool3x3s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_bilinear_up_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_nhwc_to_nchw_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),

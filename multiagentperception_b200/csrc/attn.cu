@@ -76,6 +76,14 @@ struct AttnParams {
   int slabs;  // CTAs per scene
 };
 
+// Row (agent i, scene) of a per-agent array that may live in an all-gathered buffer: agents are grouped
+// agents_per_rank at a time, one group per rank segment, segments rank_stride elements apart.
+__device__ __forceinline__ size_t agent_row(const w2c_attn_args& a, int i, int scene, int64_t rank_stride) {
+  const int apr = a.agents_per_rank > 0 ? a.agents_per_rank : a.n_k;
+  return static_cast<size_t>(i / apr) * static_cast<size_t>(rank_stride) +
+         static_cast<size_t>((i % apr) * a.b_sz + scene);
+}
+
 // shared memory: [mbarrier 8B pad to 16][qt: n_q*k_dim f32][q: n_q*q_dim f32][S/P/coef: 3*64 f32][V slab]
 __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
   const w2c_attn_args& a = p.a;
@@ -109,8 +117,10 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
     // producer: one bulk copy per supporting agent (image index = agent * b_sz + scene)
     ptx::mbar_arrive_expect_tx(bar, slab_bytes * a.n_k);
     for (int i = 0; i < a.n_k; ++i) {
-      const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.val) +
-                                 (static_cast<size_t>(i * a.b_sz + scene) * a.hw + pix0) * vpix;
+      const size_t img = agent_row(a, i, scene, 0);
+      const size_t seg = static_cast<size_t>(i / (a.agents_per_rank > 0 ? a.agents_per_rank : a.n_k)) *
+                         static_cast<size_t>(a.val_rank_stride);
+      const __nv_bfloat16* src = static_cast<const __nv_bfloat16*>(a.val) + seg + (img * a.hw + pix0) * vpix;
       ptx::bulk_load_1d(s_V + static_cast<size_t>(i) * p.pix_per_cta * vpix, src, slab_bytes, bar);
     }
   }
@@ -118,7 +128,9 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
   // ---- scores (all warps; overlaps the copies above)
   for (int i = threadIdx.x; i < a.n_q * a.q_dim; i += blockDim.x) {
     const int j = i / a.q_dim, e = i % a.q_dim;
-    s_q[i] = a.queries[static_cast<size_t>(j * a.b_sz + scene) * a.q_dim + e];
+    const int apr = a.agents_per_rank > 0 ? a.agents_per_rank : a.n_k;
+    s_q[i] = a.queries[static_cast<size_t>(j / apr) * a.queries_rank_stride +
+                       static_cast<size_t>((j % apr) * a.b_sz + scene) * a.q_dim + e];
   }
   __syncthreads();
   if (a.wq) {
@@ -135,7 +147,9 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
   __syncthreads();
   for (int pair = warp; pair < a.n_k * a.n_q; pair += nwarps) {
     const int i = pair / a.n_q, j = pair % a.n_q;
-    const float* kr = a.keys + static_cast<size_t>(i * a.b_sz + scene) * a.k_dim;
+    const int apr = a.agents_per_rank > 0 ? a.agents_per_rank : a.n_k;
+    const float* kr = a.keys + static_cast<size_t>(i / apr) * a.keys_rank_stride +
+                      static_cast<size_t>((i % apr) * a.b_sz + scene) * a.k_dim;
     float acc = 0.f;
     for (int d = lane; d < a.k_dim; d += 32) acc = fmaf(__ldg(kr + d), s_qt[j * a.k_dim + d], acc);
     acc = warp_sum(acc);
@@ -240,7 +254,8 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
         }
       }
     }
-    for (int j = 0; j < a.n_q; ++j) {
+    const int j_end = a.q_count > 0 ? a.q_first + a.q_count : a.n_q;
+    for (int j = a.q_first; j < j_end; ++j) {
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = 0.f;
@@ -262,7 +277,7 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
         lb[e] = __floats2bfloat162_rn(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
       }
       __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(a.fused) +
-                           (static_cast<size_t>(j * a.b_sz + scene) * a.hw + pix0 + px) * fpix + a.fused_coffset + g * 8;
+                           (static_cast<size_t>((j - a.q_first) * a.b_sz + scene) * a.hw + pix0 + px) * fpix + a.fused_coffset + g * 8;
       *reinterpret_cast<uint4*>(dst) = hv;
       if (planes == 2) *reinterpret_cast<uint4*>(dst + a.fused_cstride) = lv;
     }
@@ -304,6 +319,10 @@ extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream)
   W2C_CHECK_ARG(a.mode >= W2C_FUSE_SOFTMAX && a.mode <= W2C_FUSE_ARGMAX, "attn: bad mode %d", a.mode);
   W2C_CHECK_ARG(a.temperature != 0.f, "attn: temperature must be non-zero");
   W2C_CHECK_ARG(!a.mask_self || a.n_k > 1, "attn: mask_self needs at least two supporting agents");
+  W2C_CHECK_ARG(a.q_first >= 0 && a.q_count >= 0 && a.q_first + a.q_count <= a.n_q, "attn: fused query window "
+                "[%d, %d) outside n_q=%d", a.q_first, a.q_first + a.q_count, a.n_q);
+  W2C_CHECK_ARG(a.agents_per_rank >= 0 && (a.agents_per_rank == 0 || a.n_k % a.agents_per_rank == 0),
+                "attn: agents_per_rank=%d must divide n_k=%d", a.agents_per_rank, a.n_k);
   AttnParams p;
   p.a = a;
   if (p.a.fused_cstride <= 0) p.a.fused_cstride = a.c;

@@ -73,7 +73,8 @@ template <int GROUP>
 __global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ scale,
                                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-                                                      int b_sz, int n_agents, int h, int wpx, int cout, int act) {
+                                                      int b_sz, int n_agents, int c_total, int c_first, int h,
+                                                      int wpx, int cout, int act) {
   extern __shared__ float sm[];
   float* s_w = sm;                // [27][cout]
   float* s_scale = sm + 27 * cout;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ 
     const int oh = (idx / wpx) % h;
     const int img = idx / plane;  // agent-major: img = agent * b_sz + batch
     const int agent = img / b_sz, bat = img % b_sz;
-    const float* xin = x + (static_cast<size_t>(bat) * 3 * n_agents + 3 * agent) * plane;
+    const float* xin = x + (static_cast<size_t>(bat) * c_total + c_first + 3 * agent) * plane;
     float in[27];
 #pragma unroll
     for (int ci = 0; ci < 3; ++ci)
@@ -149,7 +150,8 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(128) stem7x7_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                       const float* __restrict__ scale,
                                                       const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-                                                      int b_sz, int n_agents, int h, int wpx, int act) {
+                                                      int b_sz, int n_agents, int c_total, int c_first, int h,
+                                                      int wpx, int act) {
   constexpr int COUT = 64, K = 147;
   extern __shared__ float sm[];
   float* s_w = sm;  // [147][64]
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(128) stem7x7_kernel(const float* __restrict__ 
     const int oh = (idx / wo) % ho;
     const int img = idx / (static_cast<size_t>(ho) * wo);
     const int agent = img / b_sz, bat = img % b_sz;
-    const float* xin = x + (static_cast<size_t>(bat) * 3 * n_agents + 3 * agent) * plane;
+    const float* xin = x + (static_cast<size_t>(bat) * c_total + c_first + 3 * agent) * plane;
     __nv_bfloat16* ypix = y + idx * (static_cast<size_t>(COUT) * planes);
     for (int g = 0; g < COUT; g += 32) {
       float acc[32];
@@ -338,21 +340,26 @@ int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, c
 }
 
 int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
-                         int32_t n_agents, int32_t h, int32_t w_px, int32_t cout, int32_t act, w2c_stream_t stream) {
+                         int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout,
+                         int32_t act, w2c_stream_t stream) {
   W2C_CHECK_ARG(x && w && scale && shift && y, "stem3x3: null pointer");
   W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3: bad extent");
+  W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem3x3: channel window [%d, %d) outside %d",
+                c_first, c_first + 3 * n_agents, c_total);
   W2C_CHECK_ARG(cout % 32 == 0 && cout <= 128, "stem3x3: cout=%d must be a multiple of 32 and <= 128", cout);
   const size_t total = static_cast<size_t>(b) * n_agents * h * w_px;
   const size_t smem = (27 * cout + 2 * cout) * sizeof(float);
   stem3x3_kernel<32><<<grid_for(total, 256, 148 * 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, h, w_px, cout, act);
+      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, c_total, c_first, h, w_px, cout, act);
   W2C_CHECK_LAUNCH("stem3x3_kernel");
   return W2C_OK;
 }
 
 int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
-                           int32_t n_agents, int32_t h, int32_t w_px, int32_t act, w2c_stream_t stream) {
+                           int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t act,
+                           w2c_stream_t stream) {
   W2C_CHECK_ARG(x && w && scale && shift && y, "stem7x7: null pointer");
+  W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem7x7: channel window outside the input");
   W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0, "stem7x7: bad extent");
   const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (w_px / 2);
   const size_t smem = (147 * 64 + 128) * sizeof(float);
@@ -362,7 +369,7 @@ int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, c
     attr = true;
   }
   stem7x7_kernel<<<grid_for(total, 128, 148 * 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, h, w_px, act);
+      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, c_total, c_first, h, w_px, act);
   W2C_CHECK_LAUNCH("stem7x7_kernel");
   return W2C_OK;
 }

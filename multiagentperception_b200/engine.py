@@ -1,0 +1,327 @@
+"""Host-side execution engine of the accelerated forward path.
+
+A model (models/agents.py) describes its forward once per (batch, height, width) as a straight-line *program* of
+libw2c launches over preallocated NHWC buffers; the engine
+  * folds BatchNorm + bias and packs conv weights once per weight version (setup-time, on device),
+  * records every launch as a pre-bound ctypes call (no per-step Python tensor work),
+  * optionally captures the whole program in a CUDA graph and replays it per step.
+PyTorch supplies device memory, streams and graphs only.
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib, ops
+
+PRECISIONS = {"bf16": ops.ACT_BF16, "bf16x3": ops.ACT_BF16X2}
+BN_EPS_DEFAULT = 1e-5
+
+
+def default_precision():
+    p = os.environ.get("W2C_PRECISION", "bf16")
+    if p not in PRECISIONS:
+        raise ValueError("W2C_PRECISION must be one of %s (got %r)" % (sorted(PRECISIONS), p))
+    return p
+
+
+def use_graphs_default():
+    return os.environ.get("W2C_CUDA_GRAPH", "1") != "0"
+
+
+class ActMap:
+    """Handle of an NHWC activation map living in (a channel slice of) a bf16 buffer."""
+    __slots__ = ("buf", "n", "h", "w", "c", "cstride", "coffset")
+
+    def __init__(self, buf, n, h, w, c, cstride=None, coffset=0):
+        self.buf, self.n, self.h, self.w, self.c = buf, n, h, w, c
+        self.cstride = cstride if cstride is not None else c
+        self.coffset = coffset
+
+    def slice(self, coffset, c):
+        return ActMap(self.buf, self.n, self.h, self.w, c, self.cstride, self.coffset + coffset)
+
+    def images(self, first, count):
+        """Sub-range of images [first, first+count) as a view (agent-major layouts make agents contiguous)."""
+        return ActMap(self.buf[first:first + count], count, self.h, self.w, self.c, self.cstride, self.coffset)
+
+
+class PackedConv:
+    __slots__ = ("w", "scale", "shift", "cin", "cout", "kind", "relu")
+
+
+class WeightCache:
+    """Device-side packed operands for one (model, device, precision). Rebuilt when the model invalidates it."""
+
+    def __init__(self, device, act):
+        self.device = device
+        self.act = act
+        self._convs = {}
+        self._misc = {}
+
+    # conv / transposed conv (+ optional BatchNorm) -> packed bf16 weight + fp32 scale/shift
+    def conv(self, conv, bn, relu, key=None):
+        key = key or id(conv)
+        pc = self._convs.get(key)
+        if pc is not None:
+            return pc
+        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        w = conv.weight.detach().to(self.device, torch.float32)
+        cin_real = conv.in_channels
+        cin = (cin_real + 63) // 64 * 64
+        kh, kw = conv.kernel_size
+        stride = conv.stride[0]
+        if transposed:
+            kind = ops.DECONV3X3_S2
+        elif (kh, kw) == (3, 3):
+            kind = {1: ops.CONV3X3_S1, 2: ops.CONV3X3_S2}.get(stride)
+        elif (kh, kw) == (1, 1):
+            kind = {1: ops.CONV1X1_S1, 2: ops.CONV1X1_S2}.get(stride)
+        else:
+            kind = None
+        if kind is None:
+            raise NotImplementedError("no sm_100a kernel for conv k=%s stride=%s" % ((kh, kw), stride))
+        pc = PackedConv()
+        pc.w = ops.pack_conv_weight(w, cin, transposed, self.act)
+        pc.cin, pc.cout, pc.kind, pc.relu = cin, conv.out_channels, kind, bool(relu)
+        pc.scale, pc.shift = self._fold(conv, bn)
+        self._convs[key] = pc
+        return pc
+
+    def _fold(self, conv, bn):
+        if bn is not None:
+            return ops.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                               conv.out_channels, self.device)
+        return ops.fold_bn(conv.bias, None, None, None, None, BN_EPS_DEFAULT, conv.out_channels, self.device)
+
+    # 3-input-channel stem: fp32 [cout][k] weight + scale/shift
+    def stem(self, conv, bn):
+        key = ("stem", id(conv))
+        st = self._misc.get(key)
+        if st is None:
+            w = conv.weight.detach().to(self.device, torch.float32).reshape(conv.out_channels, -1).contiguous()
+            scale, shift = self._fold(conv, bn)
+            st = (w, scale, shift)
+            self._misc[key] = st
+        return st
+
+    # key/query head: fc.0 permuted to NHWC flatten order
+    def mlp(self, fc, spatial):
+        key = ("mlp", id(fc))
+        m = self._misc.get(key)
+        if m is None:
+            f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
+            w0 = fc[0].weight.detach().to(self.device, torch.float32)
+            n_feat = w0.shape[1]
+            if n_feat != 256 * spatial * spatial:
+                raise ValueError("key/query head expects %d input features, the policy map provides %d"
+                                 % (n_feat, 256 * spatial * spatial))
+            w0 = w0.view(256, 256, spatial, spatial).permute(0, 2, 3, 1).reshape(256, n_feat).contiguous()
+            m = (w0, f32(fc[0].bias), f32(fc[2].weight), f32(fc[2].bias), f32(fc[4].weight), f32(fc[4].bias))
+            self._misc[key] = m
+        return m
+
+    def tensor(self, t, key):
+        v = self._misc.get(key)
+        if v is None:
+            v = t.detach().to(self.device, torch.float32).contiguous()
+            self._misc[key] = v
+        return v
+
+
+class Program:
+    """A recorded straight-line sequence of libw2c launches for one input shape."""
+
+    def __init__(self, weights, device, act):
+        self.weights = weights
+        self.device = device
+        self.act = act
+        self.planes = ops.planes_of(act)
+        self.calls = []      # (fn, args tuple) with the stream appended at run time
+        self.keep = []       # keeps ctypes structs / tensors alive
+        self.graph = None
+        self.n_launches = 0  # kernel launches per run (counted from the library's counter)
+        self._lib = _lib.load()
+
+    # ---- buffers
+    def act_buf(self, n, h, w, c):
+        t = torch.empty((n, h, w, self.planes * c), dtype=torch.bfloat16, device=self.device)
+        self.keep.append(t)
+        return ActMap(t, n, h, w, c)
+
+    def f32_buf(self, *shape, dtype=torch.float32, zero=False):
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+        self.keep.append(t)
+        return t
+
+    # ---- recorded launches
+    def _record(self, fn, *args):
+        self.calls.append((fn, args))
+
+    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0):
+        """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given)."""
+        if x.c != pc.cin:
+            raise ValueError("conv expects %d input channels, got %d" % (pc.cin, x.c))
+        if pc.kind in (ops.CONV3X3_S2, ops.CONV1X1_S2):
+            ho, wo = x.h // 2, x.w // 2
+        elif pc.kind == ops.DECONV3X3_S2:
+            ho, wo = x.h * 2, x.w * 2
+        else:
+            ho, wo = x.h, x.w
+        if nchw_out is not None:
+            y_ptr, out_fmt, ycs, yco, ret = nchw_out.data_ptr(), ops.OUT_NCHW_F32, 0, 0, nchw_out
+        else:
+            if out is None:
+                out = self.act_buf(x.n, ho, wo, pc.cout)
+            y_ptr, out_fmt, ycs, yco, ret = out.buf.data_ptr(), ops.OUT_NHWC, out.cstride, out.coffset, out
+        a = _lib.ConvArgs(x=x.buf.data_ptr(), w=pc.w.data_ptr(), scale=pc.scale.data_ptr(), shift=pc.shift.data_ptr(),
+                          residual=residual.buf.data_ptr() if residual is not None else None, y=y_ptr, n=x.n,
+                          h_in=x.h, w_in=x.w, cin=pc.cin, cout=pc.cout, x_cstride=x.cstride, x_coffset=x.coffset,
+                          y_cstride=ycs, y_coffset=yco, kind=pc.kind, relu=int(pc.relu), act=self.act,
+                          out_fmt=out_fmt, impl=ops.IMPL_TCGEN05, block_n=block_n)
+        self.keep.append(a)
+        self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
+        return ret
+
+    def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0):
+        wt, scale, shift = st
+        cout = wt.shape[0]
+        out = self.act_buf(b * n_agents, h, w, cout)
+        self._record(self._lib.w2c_stem_conv3x3_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
+                     shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act)
+        return out
+
+    def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0):
+        wt, scale, shift = st
+        out = self.act_buf(b * n_agents, h // 2, w // 2, 64)
+        self._record(self._lib.w2c_stem_conv7x7s2_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
+                     shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1], c_first, h, w, self.act)
+        return out
+
+    def maxpool(self, x):
+        out = self.act_buf(x.n, x.h // 2, x.w // 2, x.c)
+        self._record(self._lib.w2c_maxpool3x3s2_fwd, x.buf.data_ptr(), out.buf.data_ptr(), x.n, x.h, x.w, x.c, self.act)
+        return out
+
+    def bilinear(self, x_nchw, factor):
+        n, c, h, w = x_nchw.shape
+        out = self.f32_buf(n, c, h * factor, w * factor)
+        self._record(self._lib.w2c_bilinear_up_fwd, x_nchw.data_ptr(), out.data_ptr(), n, c, h, w, factor)
+        return out
+
+    def kq_mlp(self, feat, mlp, out_dim, out=None):
+        w0, b0, w1, b1, w2, b2 = mlp
+        m = feat.n
+        n_feat = feat.h * feat.w * feat.c
+        if out is None:
+            out = self.f32_buf(m, out_dim)
+        elif tuple(out.shape) != (m, out_dim) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("kq_mlp: out must be a contiguous fp32 [%d, %d] tensor" % (m, out_dim))
+        ws = self.f32_buf(m * 384)
+        self._record(self._lib.w2c_kq_mlp_fwd, feat.buf.data_ptr(), self.act, m, n_feat, w0.data_ptr(), b0.data_ptr(),
+                     w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, out.data_ptr(), ws.data_ptr())
+        return out
+
+    def attn(self, keys, queries, wq, bq, val, fused, prob, coef, action, connect, *, b_sz, n_k, n_q, k_dim, q_dim,
+             mode, sparse=False, mask_self=False, temperature=1.0, diag_bias=0.0, thresh=0.2, q_first=0, q_count=0,
+             agents_per_rank=0, keys_rank_stride=0, queries_rank_stride=0, val_rank_stride=0):
+        p = lambda t: t.data_ptr() if t is not None else None
+        a = _lib.AttnArgs(keys=p(keys), queries=p(queries), wq=p(wq), bq=p(bq), val=val.buf.data_ptr(),
+                          fused=fused.buf.data_ptr(), prob_out=p(prob), coef_out=p(coef), action=p(action),
+                          connect=p(connect), b_sz=b_sz, n_k=n_k, n_q=n_q, k_dim=k_dim, q_dim=q_dim,
+                          hw=val.h * val.w, c=val.c, fused_cstride=fused.cstride, fused_coffset=fused.coffset,
+                          act=self.act, mode=mode, sparse=int(bool(sparse)), mask_self=int(bool(mask_self)),
+                          temperature=float(temperature), diag_bias=float(diag_bias), thresh=float(thresh),
+                          q_first=q_first, q_count=q_count, agents_per_rank=agents_per_rank,
+                          keys_rank_stride=keys_rank_stride, queries_rank_stride=queries_rank_stride,
+                          val_rank_stride=val_rank_stride)
+        if val.cstride != val.c or val.coffset != 0:
+            raise ValueError("attention values must be a dense NHWC map")
+        self.keep.append(a)
+        self._record(self._lib.w2c_attn_fuse_fwd, ctypes.byref(a))
+
+    def host_op(self, fn):
+        """A step that must run outside CUDA-graph capture (a torch.distributed collective): splits the program
+        into separately captured segments around it. fn() is called on the current stream at run time."""
+        self.calls.append((None, fn))
+
+    def copy_channels(self, src, dst):
+        """dst[..., slice] = src (device-to-device strided copy through torch; used for concat inputs only)."""
+        def run(_stream):
+            for pl in range(self.planes):
+                d = dst.buf[..., pl * dst.cstride + dst.coffset: pl * dst.cstride + dst.coffset + dst.c]
+                s = src.buf[..., pl * src.cstride + src.coffset: pl * src.cstride + src.coffset + src.c]
+                d.copy_(s)
+            return 0
+        self.calls.append((run, None))
+
+    def memset(self, t):
+        def run(_stream):
+            t.zero_()
+            return 0
+        self.calls.append((run, None))
+
+    # ---- execution
+    def _segments(self):
+        """Split the call list at host ops: [(calls, host_fn_or_None), ...]."""
+        segs, cur = [], []
+        for fn, args in self.calls:
+            if fn is None:
+                segs.append((cur, args))
+                cur = []
+            else:
+                cur.append((fn, args))
+        segs.append((cur, None))
+        return segs
+
+    def _run_calls(self, calls):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        for fn, args in calls:
+            rc = fn(stream) if args is None else fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, getattr(fn, "__name__", "launch"))
+
+    def _run_eager(self):
+        for calls, host in self._segments():
+            self._run_calls(calls)
+            if host is not None:
+                host()
+
+    def run(self, use_graph):
+        if not use_graph:
+            if not self.n_launches:
+                before = ops.launch_count()
+                self._run_eager()
+                self.n_launches = ops.launch_count() - before
+            else:
+                self._run_eager()
+            return
+        if self.graph is None:
+            # first run eagerly (sets kernel attributes, surfaces errors), then capture each segment
+            before = ops.launch_count()
+            self._run_eager()
+            self.n_launches = ops.launch_count() - before
+            torch.cuda.synchronize(self.device)
+            graphs = []
+            for calls, host in self._segments():
+                g = None
+                if calls:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run_calls(calls)
+                graphs.append((g, host))
+            self.graph = graphs
+            return  # results of the eager pass are already in the buffers
+        for g, host in self.graph:
+            if g is not None:
+                g.replay()
+            if host is not None:
+                host()
+
+    def conv_only_program(self):
+        """A program replaying just the tensor-core conv launches of this one (same buffers): used by bench.py to
+        time the dominant kernel in isolation from the stems / attention / layout kernels."""
+        sub = Program(self.weights, self.device, self.act)
+        sub.keep = self.keep
+        sub.calls = [(fn, args) for fn, args in self.calls if fn is self._lib.w2c_conv_bnrelu_fwd]
+        return sub

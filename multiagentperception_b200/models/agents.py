@@ -1,0 +1,682 @@
+"""The When2com model family behind the reference's constructor / forward() signatures.
+
+Each class mirrors one model of ptsemseg/models/agent.py: same constructor keywords, same state_dict keys, same
+forward arguments and return tuples. forward() in eval mode compiles (once per input shape) a program of sm_100a
+kernel launches through engine.Program and runs it; there is no eager PyTorch path.
+
+  Single_agent      agent.py:375-395        All_agents        agent.py:399-469
+  LearnWho2Com      agent.py:472-673        LearnWhen2Com     agent.py:676-889
+  MIMO_All_agents   agent.py:892-981        MIMOcom           agent.py:983-1204
+  MIMOcomWho        agent.py:1207-1423
+"""
+import torch
+import torch.nn as nn
+
+from .. import engine, ops
+from .layers import (_Container, conv2DBatchNormRelu, deconv2DBatchNormRelu, get_decoder, get_encoder,
+                     n_segnet_decoder, n_segnet_encoder, resnet_encoder, simple_decoder)
+
+FEATURE_CHANNELS = 512
+
+
+# ------------------------------------------------------------------------------------------- sub-module containers
+class img_encoder(_Container):
+    """agent.py:39-60: backbone + squeezer conv (stride by feat_squeezer)."""
+
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1,
+                 enc_backbone="n_segnet_encoder"):
+        super().__init__()
+        self.feature_backbone = get_encoder(enc_backbone)(n_classes=n_classes, in_channels=in_channels)
+        self.feat_squeezer = feat_squeezer
+        stride = {2: 2, 4: 4}.get(feat_squeezer, 1)
+        self.squeezer = conv2DBatchNormRelu(512, feat_channel, 3, stride, 1)
+
+
+class img_decoder(_Container):
+    """agent.py:63-89."""
+
+    def __init__(self, n_classes=21, in_channels=512, agent_num=5, feat_squeezer=-1, dec_backbone="n_segnet_decoder"):
+        super().__init__()
+        self.feat_squeezer = feat_squeezer
+        dec = get_decoder(dec_backbone)
+        if feat_squeezer == 2:
+            self.desqueezer = deconv2DBatchNormRelu(in_channels, in_channels)
+            self.output_decoder = dec(n_classes=n_classes, in_channels=in_channels)
+        elif feat_squeezer == 4:
+            self.desqueezer1 = deconv2DBatchNormRelu(in_channels, 512)
+            self.desqueezer2 = deconv2DBatchNormRelu(512, 512)
+            self.output_decoder = dec(n_classes=n_classes, in_channels=512)
+        else:
+            self.output_decoder = dec(n_classes=n_classes, in_channels=in_channels)
+
+
+class policy_net4(_Container):
+    """agent.py:114-142: a private img_encoder followed by five conv-BN-ReLU (strides 1,1,2,1,2)."""
+    SPEC = ((512, 512, 1), (512, 256, 1), (256, 256, 2), (256, 256, 1), (256, 256, 2))
+
+    def __init__(self, n_classes=21, in_channels=512, input_feat_sz=32, enc_backbone="n_segnet_encoder"):
+        super().__init__()
+        self.img_encoder = img_encoder(n_classes=n_classes, in_channels=in_channels, enc_backbone=enc_backbone)
+        for i, (cin, cout, stride) in enumerate(self.SPEC, 1):
+            setattr(self, "conv%d" % i, conv2DBatchNormRelu(cin, cout, 3, stride, 1))
+
+
+class km_generator(_Container):
+    """agent.py:145-159 (and the identical `linear`, agent.py:162-178): 3-layer MLP head."""
+
+    def __init__(self, out_size=128, input_feat_sz=32):
+        super().__init__()
+        side = input_feat_sz // 4
+        self.n_feat = int(256 * side * side)
+        self.fc = nn.Sequential(nn.Linear(self.n_feat, 256), nn.ReLU(inplace=True), nn.Linear(256, 128),
+                                nn.ReLU(inplace=True), nn.Linear(128, out_size))
+
+
+linear = km_generator
+
+
+class _DotAttention(_Container):
+    """Parameter holder of the *GeneralDotProductAttention modules (agent.py:242-368): one Linear(query -> key)."""
+
+    def __init__(self, query_size, key_size):
+        super().__init__()
+        self.linear = nn.Linear(query_size, key_size)
+
+
+class _ScaledAttention(_Container):
+    """ScaledDotProductAttention, agent.py:194-213: parameter-free, temperature 128**0.5 (agent.py:523,725)."""
+
+    def __init__(self, temperature):
+        super().__init__()
+        self.temperature = temperature
+
+
+def _make_attention(attention, query_size, key_size):
+    if attention == "general":
+        return _DotAttention(query_size, key_size)
+    if attention == "additive":
+        raise NotImplementedError("AdditiveAttentin (agent.py:215-240) has no accelerated kernel; no shipped "
+                                  "config selects it")
+    return _ScaledAttention(128 ** 0.5)
+
+
+# ------------------------------------------------------------------------------------------- program builders
+def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=None):
+    """img_encoder.forward (agent.py:56-60) on agents [c_first/3, ...) of the fp32 NCHW batch -> ActMap."""
+    wc = prog.weights
+    bb = enc.feature_backbone
+    if isinstance(bb, n_segnet_encoder):
+        if h % 32 or w % 32:
+            raise ValueError("n_segnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
+        units = bb.units()
+        a = prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h, w, c_first)
+        for i, u in enumerate(units[1:], 2):
+            a = prog.conv(a, wc.conv(u.conv, u.bn, True))
+    elif isinstance(bb, resnet_encoder):
+        if h % 32 or w % 32:
+            raise ValueError("resnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
+        fb = bb.feature_backbone
+        a = prog.stem7x7(x_nchw, wc.stem(fb.conv1, fb.bn1), b, n_agents, h, w, c_first)
+        a = prog.maxpool(a)
+        for li in range(1, 5):
+            for blk in getattr(fb, "layer%d" % li):
+                idt = a
+                if blk.downsample is not None:
+                    idt = prog.conv(a, wc.conv(blk.downsample[0], blk.downsample[1], False))
+                y = prog.conv(a, wc.conv(blk.conv1, blk.bn1, True))
+                a = prog.conv(y, wc.conv(blk.conv2, blk.bn2, True), residual=idt)
+    else:
+        raise ValueError("unknown encoder backbone %r" % type(bb).__name__)
+    if enc.feat_squeezer == 4:
+        raise NotImplementedError("feat_squeezer=4 (stride-4 squeezer, agent.py:51-52) has no accelerated kernel")
+    return prog.conv(a, wc.conv(enc.squeezer.conv, enc.squeezer.bn, True), out=out)
+
+
+def _build_decoder(prog, dec, a):
+    """img_decoder.forward (agent.py:80-89) -> fp32 NCHW logits tensor."""
+    wc = prog.weights
+    if dec.feat_squeezer == 2:
+        a = prog.conv(a, wc.conv(dec.desqueezer.conv, dec.desqueezer.bn, True))
+    elif dec.feat_squeezer == 4:
+        a = prog.conv(a, wc.conv(dec.desqueezer1.conv, dec.desqueezer1.bn, True))
+        a = prog.conv(a, wc.conv(dec.desqueezer2.conv, dec.desqueezer2.bn, True))
+    od = dec.output_decoder
+    if isinstance(od, n_segnet_decoder):
+        units = od.units()
+        for u in units[:-1]:
+            a = prog.conv(a, wc.conv(u.conv, u.bn, True))
+        last = units[-1]
+        logits = prog.f32_buf(a.n, last.conv.out_channels, a.h, a.w)
+        prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out=logits)  # logits pass BN+ReLU too, backbone.py:124
+        return logits
+    if isinstance(od, simple_decoder):
+        y = prog.conv(a, wc.conv(od.pred[0], None, True))
+        small = prog.f32_buf(a.n, od.pred[2].out_channels, a.h, a.w)
+        prog.conv(y, wc.conv(od.pred[2], None, False), nchw_out=small)
+        return prog.bilinear(small, 32)
+    raise ValueError("unknown decoder backbone %r" % type(od).__name__)
+
+
+def _build_policy(prog, pol, x_nchw, b, n_agents, h, w):
+    """policy_net4.forward (agent.py:134-142) -> ActMap (n_agents*b, s, s, 256)."""
+    a = _build_encoder(prog, pol.img_encoder, "img_encoder", x_nchw, b, n_agents, h, w)
+    if a.h % 4 or a.w % 4:
+        raise ValueError("policy_net4 needs the %dx%d feature map divisible by 4" % (a.h, a.w))
+    for i in range(1, 6):
+        u = getattr(pol, "conv%d" % i)
+        a = prog.conv(a, prog.weights.conv(u.conv, u.bn, True))
+    return a
+
+
+class _Compiled:
+    """One compiled forward: the program, its static input and its output buffers."""
+    __slots__ = ("prog", "x", "out")
+
+
+# ------------------------------------------------------------------------------------------- model base
+class _W2CModel(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self._w2c = {"precision": engine.default_precision(), "graphs": engine.use_graphs_default(),
+                     "programs": {}, "weights": {}, "clone_outputs": True}
+
+    # ---- configuration
+    def set_precision(self, name):
+        """'bf16' (throughput) or 'bf16x3' (fp32-grade parity precision on the same tensor-core kernels)."""
+        if name not in engine.PRECISIONS:
+            raise ValueError("precision must be one of %s" % sorted(engine.PRECISIONS))
+        self._w2c["precision"] = name
+        return self
+
+    def set_cuda_graphs(self, enabled):
+        self._w2c["graphs"] = bool(enabled)
+        self._w2c["programs"].clear()
+        return self
+
+    def set_clone_outputs(self, enabled):
+        """False returns views of the engine's static output buffers (valid until the next forward)."""
+        self._w2c["clone_outputs"] = bool(enabled)
+        return self
+
+    def invalidate(self):
+        """Drop packed weights and compiled programs (call after mutating parameters in place)."""
+        self._w2c["programs"].clear()
+        self._w2c["weights"].clear()
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        self.invalidate()
+        return r
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        if "_w2c" in self.__dict__:
+            self.invalidate()
+        return r
+
+    def kernel_launches_per_forward(self):
+        """Launches of libw2c kernels in the most recently compiled programs (for bench accounting)."""
+        return {k: c.prog.n_launches for k, c in self._w2c["programs"].items()}
+
+    # ---- compile / run
+    def _compiled(self, inputs, tag, builder):
+        if self.training:
+            raise RuntimeError(
+                "%s: the B200 path implements the eval-mode forward only (BatchNorm folded from running statistics, "
+                "no autograd). Call model.eval() first; training stays on the reference implementation."
+                % type(self).__name__)
+        if not (torch.is_tensor(inputs) and inputs.is_cuda):
+            raise RuntimeError("%s.forward needs a CUDA tensor: there is no CPU fallback" % type(self).__name__)
+        if inputs.dim() != 4:
+            raise ValueError("expected (B, 3*N, H, W) input, got shape %s" % (tuple(inputs.shape),))
+        dev = inputs.device
+        act = engine.PRECISIONS[self._w2c["precision"]]
+        key = (dev, act, tuple(inputs.shape), tag)
+        c = self._w2c["programs"].get(key)
+        if c is None:
+            wkey = (dev, act)
+            wc = self._w2c["weights"].get(wkey)
+            if wc is None:
+                wc = engine.WeightCache(dev, act)
+                self._w2c["weights"][wkey] = wc
+            with torch.cuda.device(dev), torch.no_grad():
+                prog = engine.Program(wc, dev, act)
+                c = _Compiled()
+                c.prog = prog
+                c.x = prog.f32_buf(*inputs.shape)
+                c.out = builder(prog, c.x)
+            self._w2c["programs"][key] = c
+        with torch.cuda.device(dev), torch.no_grad():
+            c.x.copy_(inputs)
+            c.prog.run(self._w2c["graphs"])
+        return c
+
+    def _ret(self, t):
+        return t.clone() if self._w2c["clone_outputs"] else t
+
+
+def _check_views(inputs, n_agents):
+    if inputs.shape[1] != 3 * n_agents:
+        raise ValueError("expected %d channels (3 per agent x %d agents), got %d" % (3 * n_agents, n_agents,
+                                                                                      inputs.shape[1]))
+
+
+# ------------------------------------------------------------------------------------------- models
+class Single_agent(_W2CModel):
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, enc_backbone="n_segnet_encoder",
+                 dec_backbone="n_segnet_decoder", feat_squeezer=-1):
+        super().__init__()
+        self.in_channels = in_channels
+        self.encoder = img_encoder(n_classes=n_classes, in_channels=in_channels, feat_channel=feat_channel,
+                                   feat_squeezer=feat_squeezer, enc_backbone=enc_backbone)
+        self.decoder = img_decoder(n_classes=n_classes, in_channels=feat_channel, feat_squeezer=feat_squeezer,
+                                   dec_backbone=dec_backbone)
+
+    def forward(self, inputs):
+        _check_views(inputs, 1)
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            feat = _build_encoder(prog, self.encoder, "encoder", x, b, 1, h, w)
+            return {"pred": _build_decoder(prog, self.decoder, feat)}
+
+        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+
+
+class _AttentionModel(_W2CModel):
+    """Shared constructor plumbing of the four learned-communication models."""
+
+    def _init_common(self, n_classes, in_channels, feat_channel, feat_squeezer, attention, has_query, sparse,
+                     shared_img_encoder, image_size, key_size, query_size, enc_backbone, dec_backbone, head_cls,
+                     attention_module, decoder_in):
+        self.in_channels = in_channels
+        self.feature_map_channel = FEATURE_CHANNELS
+        self.key_size = key_size
+        self.query_size = query_size
+        self.shared_img_encoder = shared_img_encoder
+        self.has_query = has_query
+        self.sparse = sparse
+        self.attention = attention
+        self.image_size = image_size
+        if shared_img_encoder != "unified":
+            raise NotImplementedError(
+                "only shared_img_encoder='unified' (every shipped config) is on the accelerated path; got %r"
+                % (shared_img_encoder,))
+        self.u_encoder = img_encoder(n_classes=n_classes, in_channels=in_channels, feat_channel=feat_channel,
+                                     feat_squeezer=feat_squeezer, enc_backbone=enc_backbone)
+        self.key_net = head_cls(out_size=key_size, input_feat_sz=image_size / 32)
+        self.attention_net = attention_module
+        self.query_key_net = policy_net4(n_classes=n_classes, in_channels=in_channels, enc_backbone=enc_backbone)
+        if has_query:
+            self.query_net = head_cls(out_size=query_size, input_feat_sz=image_size / 32)
+        self.decoder = img_decoder(n_classes=n_classes, in_channels=decoder_in, feat_squeezer=feat_squeezer,
+                                   dec_backbone=dec_backbone)
+
+    # parameter groups the reference trainers read (agent.py:1017-1030)
+    @property
+    def attention_paras(self):
+        return list(self.attention_net.parameters())
+
+    @property
+    def img_net_paras(self):
+        extra = list(self.argmax_decoder.parameters()) if hasattr(self, "argmax_decoder") else []
+        return list(self.u_encoder.parameters()) + list(self.decoder.parameters()) + extra
+
+    @property
+    def policy_net_paras(self):
+        p = list(self.query_key_net.parameters()) + list(self.key_net.parameters()) + self.attention_paras
+        if self.has_query:
+            p = p + list(self.query_net.parameters())
+        return p
+
+    @property
+    def all_paras(self):
+        return self.img_net_paras + self.policy_net_paras
+
+    def _attn_weights(self, prog):
+        if isinstance(self.attention_net, _DotAttention):
+            wq = prog.weights.tensor(self.attention_net.linear.weight, ("attn_w", id(self.attention_net)))
+            bq = prog.weights.tensor(self.attention_net.linear.bias, ("attn_b", id(self.attention_net)))
+            return wq, bq, 1.0
+        return None, None, float(self.attention_net.temperature)
+
+    def _keys_queries(self, prog, x, b, n, h, w, dst=None):
+        """u_encoder features, key and query vectors for the n agents in x (agent.py:1111-1148). dst = (keys,
+        queries, val) tensors to write into (the rank's slot of the exchange buffer when agents are sharded)."""
+        val_out = None
+        if dst is not None:
+            val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], FEATURE_CHANNELS)
+        val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out)
+        qk = _build_policy(prog, self.query_key_net, x, b, n, h, w)
+        if qk.h != qk.w:
+            raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
+        keys = prog.kq_mlp(qk, prog.weights.mlp(self.key_net.fc, qk.h), self.key_size,
+                           out=None if dst is None else dst[0])
+        if self.has_query:
+            queries = prog.kq_mlp(qk, prog.weights.mlp(self.query_net.fc, qk.h), self.query_size,
+                                  out=None if dst is None else dst[1])
+        else:
+            queries = prog.f32_buf(n * b, self.query_size) if dst is None else dst[1]
+            queries.fill_(1.0)  # torch.ones(batch, 1, query_size), agent.py:1144
+        return val, keys, queries
+
+
+_MODES = {"softmax": ops.FUSE_SOFTMAX, "activated": ops.FUSE_ACTIVATED, "argmax_test": ops.FUSE_ARGMAX}
+
+
+class MIMOcom(_AttentionModel):
+    who = False
+
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1, attention="additive",
+                 has_query=True, sparse=False, agent_num=5, shuffle_flag=False, image_size=512,
+                 shared_img_encoder=False, key_size=128, query_size=128, enc_backbone="n_segnet_encoder",
+                 dec_backbone="n_segnet_decoder"):
+        super().__init__()
+        self.agent_num = agent_num
+        self.shuffle_flag = shuffle_flag
+        if agent_num > 8:
+            raise ValueError("agent_num must be <= 8")
+        head = linear if self.who else km_generator
+        self._init_common(n_classes, in_channels, feat_channel, feat_squeezer, attention, has_query, sparse,
+                          shared_img_encoder, image_size, key_size, query_size, enc_backbone, dec_backbone, head,
+                          _DotAttention(query_size, key_size),
+                          FEATURE_CHANNELS * 2 if self.who else FEATURE_CHANNELS)
+
+    def shard_agents(self, group=None, rank=None, world=None):
+        """Shard the agents over the ranks of a torch.distributed process group (one process per GPU). After this,
+        forward() takes only this rank's views, (B, 3*agent_num/world, H, W) for agents
+        [rank*apr, (rank+1)*apr), and returns `pred` for those agents; prob_action / action / num_connect are
+        complete and identical on every rank. Pass world=1 (or call unshard_agents) to undo."""
+        import torch.distributed as dist
+        if world is None:
+            world = dist.get_world_size(group)
+        if rank is None:
+            rank = dist.get_rank(group)
+        if self.agent_num % world:
+            raise ValueError("agent_num=%d is not divisible by %d ranks" % (self.agent_num, world))
+        self._w2c["shard"] = None if world == 1 else (group, rank, world)
+        self._w2c["programs"].clear()
+        return self
+
+    def unshard_agents(self):
+        self._w2c["shard"] = None
+        self._w2c["programs"].clear()
+        return self
+
+    def forward(self, inputs, training=True, MO_flag=False, inference="argmax"):
+        if self._w2c.get("shard") is not None:
+            return self._forward_sharded(inputs, training, MO_flag, inference)
+        n = self.agent_num
+        _check_views(inputs, n)
+        if training or inference == "softmax":
+            mode = "softmax"
+        elif inference in _MODES:
+            mode = inference
+        else:
+            raise ValueError("Incorrect inference mode")
+        if not MO_flag:
+            raise ValueError("MO_flag=False is not runnable in the reference either (agent.py:1153,1164-1165); "
+                             "pass MO_flag=True (multiple_output: True in the shipped mrms configs)")
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
+            wq, bq, temp = self._attn_weights(prog)
+            prob = prog.f32_buf(b, n, n)
+            coef = prog.f32_buf(b, n, n)
+            action = prog.f32_buf(b, n, dtype=torch.int64)
+            connect = prog.f32_buf(1, dtype=torch.int32, zero=True)
+            if self.who:
+                # decoder input = cat(fused, own features) on channels, agent.py:1382
+                cat = prog.act_buf(n * b, val.h, val.w, 2 * val.c)
+                fused = cat.slice(0, val.c)
+                prog.copy_channels(val, cat.slice(val.c, val.c))
+            else:
+                cat = fused = prog.act_buf(n * b, val.h, val.w, val.c)
+            prog.memset(connect)
+            prog.attn(keys, queries, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=n,
+                      k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], mask_self=self.who,
+                      temperature=temp, diag_bias=0.0 if self.who else 0.001)
+            return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob, "action": action,
+                    "connect": connect}
+
+        c = self._compiled(inputs, mode, build)
+        out = c.out
+        prob = self._ret(out["prob"])
+        if self.who:
+            action = torch.argmax(prob, dim=1)  # agent.py:1397,1412: always from prob_action
+        else:
+            action = self._ret(out["action"])
+        if mode == "softmax":
+            num_connect = n - 1
+        else:
+            num_connect = int(out["connect"].item()) / (n * b)
+        return self._ret(out["pred"]), prob, action, num_connect
+
+
+    def _forward_sharded(self, inputs, training, MO_flag, inference):
+        from .. import sharding
+        group, rank, world = self._w2c["shard"]
+        n = self.agent_num
+        apr = n // world
+        _check_views(inputs, apr)
+        if training or inference == "softmax":
+            mode = "softmax"
+        elif inference in _MODES:
+            mode = inference
+        else:
+            raise ValueError("Incorrect inference mode")
+        if not MO_flag:
+            raise ValueError("MO_flag=False is not runnable in the reference either; pass MO_flag=True")
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            fh, fw = h // 32, w // 32
+            lay = sharding.AgentShardLayout(n, world, rank, b, self.key_size, self.query_size, fh, fw,
+                                            FEATURE_CHANNELS, prog.planes)
+            exchange = lay.allocate(prog.device)
+            prog.keep.append(exchange)
+            k_loc, q_loc, v_loc = lay.views(exchange)
+            self._keys_queries(prog, x, b, apr, h, w, dst=(k_loc, q_loc, v_loc))
+            prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group))   # the one collective
+            k0, q0, v0 = lay.views(exchange, 0)
+            val = engine.ActMap(v0, apr * b, fh, fw, FEATURE_CHANNELS)
+            wq, bq, temp = self._attn_weights(prog)
+            prob = prog.f32_buf(b, n, n)
+            coef = prog.f32_buf(b, n, n)
+            action = prog.f32_buf(b, n, dtype=torch.int64)
+            connect = prog.f32_buf(1, dtype=torch.int32, zero=True)
+            if self.who:
+                cat = prog.act_buf(apr * b, fh, fw, 2 * FEATURE_CHANNELS)
+                fused = cat.slice(0, FEATURE_CHANNELS)
+                prog.copy_channels(engine.ActMap(v_loc, apr * b, fh, fw, FEATURE_CHANNELS),
+                                   cat.slice(FEATURE_CHANNELS, FEATURE_CHANNELS))
+            else:
+                cat = fused = prog.act_buf(apr * b, fh, fw, FEATURE_CHANNELS)
+            prog.memset(connect)
+            prog.attn(k0, q0, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=n,
+                      k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], mask_self=self.who,
+                      temperature=temp, diag_bias=0.0 if self.who else 0.001, q_first=lay.first_agent, q_count=apr,
+                      agents_per_rank=apr, keys_rank_stride=lay.keys_rank_stride,
+                      queries_rank_stride=lay.queries_rank_stride, val_rank_stride=lay.val_rank_stride)
+            return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob, "action": action,
+                    "connect": connect}
+
+        out = self._compiled(inputs, ("shard", rank, world, mode), build).out
+        prob = self._ret(out["prob"])
+        action = torch.argmax(prob, dim=1) if self.who else self._ret(out["action"])
+        num_connect = n - 1 if mode == "softmax" else int(out["connect"].item()) / (n * b)
+        return self._ret(out["pred"]), prob, action, num_connect
+
+
+class MIMOcomWho(MIMOcom):
+    who = True
+
+
+class LearnWhen2Com(_AttentionModel):
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1, attention="additive",
+                 has_query=True, sparse=False, aux_agent_num=4, shuffle_flag=False, image_size=512,
+                 shared_img_encoder=False, key_size=128, query_size=128, enc_backbone="n_segnet_encoder",
+                 dec_backbone="n_segnet_decoder"):
+        super().__init__()
+        self.aux_agent_num = aux_agent_num
+        self.shuffle_flag = shuffle_flag
+        self._init_common(n_classes, in_channels, feat_channel, feat_squeezer, attention, has_query, sparse,
+                          shared_img_encoder, image_size, key_size, query_size, enc_backbone, dec_backbone, linear,
+                          _make_attention(attention, query_size, key_size), FEATURE_CHANNELS)
+        # registered (and checkpointed) by the reference but never used by its forward, agent.py:734-735
+        self.argmax_decoder = img_decoder(n_classes=n_classes, in_channels=FEATURE_CHANNELS,
+                                          agent_num=aux_agent_num + 1, dec_backbone=dec_backbone)
+
+    def forward(self, inputs, training=True, inference="argmax"):
+        n = 5  # divide_num hard-coded, agent.py:763
+        _check_views(inputs, n)
+        if training or inference == "softmax":
+            mode = "softmax"
+        elif inference in _MODES:
+            mode = inference
+        else:
+            raise ValueError("Incorrect inference mode")
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
+            wq, bq, temp = self._attn_weights(prog)
+            prob = prog.f32_buf(b, n, 1)
+            coef = prog.f32_buf(b, n, 1)
+            action = prog.f32_buf(b, 1, dtype=torch.int64)
+            connect = prog.f32_buf(1, dtype=torch.int32, zero=True)
+            fused = prog.act_buf(b, val.h, val.w, val.c)
+            prog.memset(connect)
+            # one requester (agent 0: the first b rows of the agent-major query matrix), all five supporters
+            prog.attn(keys, queries, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=1,
+                      k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], sparse=self.sparse,
+                      temperature=temp, diag_bias=0.0)
+            return {"pred": _build_decoder(prog, self.decoder, fused), "prob": prob, "coef": coef,
+                    "action": action, "connect": connect}
+
+        out = self._compiled(inputs, mode, build).out
+        pred = self._ret(out["pred"])
+        prob = out["prob"].transpose(1, 2).clone()  # (B, 1, 5) like attn_orig.transpose(2, 1), agent.py:368
+        action = torch.argmax(prob, dim=2)
+        if training:
+            return pred, prob, action
+        if mode == "softmax":
+            return pred, prob, action, 4
+        num_connect = int(out["connect"].item()) / b
+        if mode == "activated":
+            return pred, prob, out["coef"].transpose(1, 2).clone(), num_connect  # action = thresholded weights
+        return pred, prob, action, num_connect
+
+
+class LearnWho2Com(_AttentionModel):
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1, attention="additive",
+                 has_query=True, sparse=False, aux_agent_num=4, shuffle_flag=False, image_size=512,
+                 shared_img_encoder=False, key_size=128, query_size=128, enc_backbone="n_segnet_encoder",
+                 dec_backbone="n_segnet_decoder"):
+        super().__init__()
+        self.aux_agent_num = aux_agent_num
+        self.shuffle_flag = shuffle_flag
+        self._init_common(n_classes, in_channels, feat_channel, feat_squeezer, attention, has_query, sparse,
+                          shared_img_encoder, image_size, key_size, query_size, enc_backbone, dec_backbone, linear,
+                          _make_attention(attention, query_size, key_size), FEATURE_CHANNELS * 2)
+
+    def forward(self, inputs, training=True, inference="argmax"):
+        n = 5
+        _check_views(inputs, n)
+        if training or inference == "softmax":
+            mode = "softmax"
+        elif inference == "argmax_test":
+            mode = "argmax_test"
+        else:
+            raise ValueError("Incorrect inference mode")  # 'argmax_train' needs an undefined argmax_decoder
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
+            wq, bq, temp = self._attn_weights(prog)
+            prob = prog.f32_buf(b, n - 1, 1)
+            action = prog.f32_buf(b, 1, dtype=torch.int64)
+            cat = prog.act_buf(b, val.h, val.w, 2 * val.c)  # cat(own, aux) on channels, agent.py:623
+            prog.copy_channels(val.images(0, b), cat.slice(0, val.c))
+            # supporters are agents 1..4 (agent.py:603-614): skip the first b rows / images
+            prog.attn(keys[b:], queries, wq, bq, val.images(b, (n - 1) * b), cat.slice(val.c, val.c), prob, None,
+                      action, None, b_sz=b, n_k=n - 1, n_q=1, k_dim=self.key_size, q_dim=self.query_size,
+                      mode=_MODES[mode], sparse=self.sparse, temperature=temp, diag_bias=0.0)
+            return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob}
+
+        out = self._compiled(inputs, mode, build).out
+        prob = out["prob"].transpose(1, 2).clone()
+        return self._ret(out["pred"]), prob, torch.argmax(prob, dim=2)
+
+
+class MIMO_All_agents(_W2CModel):
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, aux_agent_num=4, shuffle_flag=False,
+                 enc_backbone="n_segnet_encoder", dec_backbone="n_segnet_decoder", feat_squeezer=-1):
+        super().__init__()
+        self.agent_num = aux_agent_num
+        self.in_channels = in_channels
+        self.shuffle_flag = shuffle_flag
+        self.encoder = img_encoder(n_classes=n_classes, in_channels=in_channels, feat_channel=feat_channel,
+                                   feat_squeezer=feat_squeezer, enc_backbone=enc_backbone)
+        width = 2 if shuffle_flag in ("selection", "ComNet") else self.agent_num
+        self.decoder = img_decoder(n_classes=n_classes, in_channels=feat_channel * width,
+                                   feat_squeezer=feat_squeezer, dec_backbone=dec_backbone)
+
+    def forward(self, inputs):
+        n = self.agent_num
+        _check_views(inputs, n)
+        if self.shuffle_flag in ("selection", "ComNet"):
+            raise NotImplementedError("the random-selection / ComNet baselines (agent.py:934-961) are not on the "
+                                      "accelerated path")
+        b, _, h, w = inputs.shape
+
+        def build(prog, x):
+            feat = _build_encoder(prog, self.encoder, "encoder", x, b, n, h, w)
+            cat = prog.act_buf(n * b, feat.h, feat.w, n * feat.c)
+            for i in range(n):          # agent i decodes cat_j feat[(i + j) % n], agent.py:963-971
+                for j in range(n):
+                    src = feat.images(((i + j) % n) * b, b)
+                    prog.copy_channels(src, cat.images(i * b, b).slice(j * feat.c, feat.c))
+            return {"pred": _build_decoder(prog, self.decoder, cat)}
+
+        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+
+
+class All_agents(_W2CModel):
+    def __init__(self, n_classes=21, in_channels=3, feat_channel=512, aux_agent_num=4, shuffle_flag=False,
+                 enc_backbone="n_segnet_encoder", dec_backbone="n_segnet_decoder", feat_squeezer=-1):
+        super().__init__()
+        self.agent_num = aux_agent_num
+        self.in_channels = in_channels
+        self.shuffle_flag = shuffle_flag
+        for i in range(1, 6):
+            setattr(self, "encoder%d" % i, img_encoder(n_classes=n_classes, in_channels=in_channels,
+                                                       feat_channel=feat_channel, feat_squeezer=feat_squeezer,
+                                                       enc_backbone=enc_backbone))
+        width = 2 if shuffle_flag == "selection" else self.agent_num
+        self.decoder = img_decoder(n_classes=n_classes, in_channels=feat_channel * width,
+                                   feat_squeezer=feat_squeezer, dec_backbone=dec_backbone)
+
+    def forward(self, inputs):
+        _check_views(inputs, 5)  # divide_num hard-coded, agent.py:433
+        if self.shuffle_flag == "selection":
+            raise NotImplementedError("the random-selection baseline (agent.py:447-452) is not on the accelerated path")
+        b, _, h, w = inputs.shape
+        used = 2 if self.shuffle_flag == "fixed2" else 5
+        fc = self.encoder1.squeezer.conv.out_channels
+        if self.decoder.output_decoder.in_channels != used * fc and self.decoder.feat_squeezer not in (2, 4):
+            raise ValueError("decoder expects %d input channels but %d feature maps of %d channels are concatenated"
+                             % (self.decoder.output_decoder.in_channels, used, fc))
+
+        def build(prog, x):
+            hh, ww = h // 32, w // 32
+            if self.encoder1.feat_squeezer == 2:
+                hh, ww = hh // 2, ww // 2
+            cat = prog.act_buf(b, hh, ww, used * fc)
+            for i in range(used):       # five separate encoders write straight into their concat slice
+                _build_encoder(prog, getattr(self, "encoder%d" % (i + 1)), "encoder%d" % (i + 1), x, b, 1, h, w,
+                               c_first=3 * i, out=cat.slice(i * fc, fc))
+            return {"pred": _build_decoder(prog, self.decoder, cat)}
+
+        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])

@@ -85,17 +85,19 @@ def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind,
     return y
 
 
-def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act):
+def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, c_total=0, c_first=0):
     lib = _lib.load()
-    _lib.check(lib.w2c_stem_conv3x3_fwd(_ptr(x_nchw), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents, h,
-                                        w, cout, act, _stream()), "w2c_stem_conv3x3_fwd")
+    _lib.check(lib.w2c_stem_conv3x3_fwd(_ptr(x_nchw), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,
+                                        c_total or 3 * n_agents, c_first, h, w, cout, act, _stream()),
+               "w2c_stem_conv3x3_fwd")
     return y
 
 
-def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act):
+def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act, c_total=0, c_first=0):
     lib = _lib.load()
     _lib.check(lib.w2c_stem_conv7x7s2_fwd(_ptr(x_nchw), _ptr(w147), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,
-                                          h, w, act, _stream()), "w2c_stem_conv7x7s2_fwd")
+                                          c_total or 3 * n_agents, c_first, h, w, act, _stream()),
+               "w2c_stem_conv7x7s2_fwd")
     return y
 
 
