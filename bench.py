@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layer-table", default="", help="write a per-layer timing table (markdown) to this path")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run one eager step inside cudaProfilerStart/Stop (for ncu) and exit without a bench line")
     return ap.parse_args()
 
 
@@ -218,6 +220,19 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
+
+    if args.profile_step:
+        # one eager (no CUDA graph) step between cudaProfilerStart/Stop for `ncu --profile-from-start off`;
+        # numbers under a profiler are never bench values, so nothing is printed
+        model.set_cuda_graphs(False).set_clone_outputs(False)
+        for _ in range(2):
+            model(x_dev, **kw)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.start()
+        model(x_dev, **kw)
+        torch.cuda.synchronize(dev)
+        torch.cuda.profiler.stop()
+        return 0
 
     # ---- value: inputs resident in HBM
     model.set_clone_outputs(False)

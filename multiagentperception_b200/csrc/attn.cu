@@ -1,4 +1,4 @@
-// Key/query MLP heads and the communication-graph attention + feature fusion kernel.
+// The communication-graph attention + feature fusion kernel.
 //
 // attn_fuse_kernel is ONE launch for: query projection (W*q+b), key.query scores, softmax / sparsemax over the
 // supporting agents, the +0.001*I bias, the activated / argmax re-selection, action + connection bookkeeping,
@@ -22,52 +22,6 @@ __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
-}
-
-// out[m][j] = act( sum_k in[m][k] * W[j][k] + b[j] ),  one warp per output neuron j, MT rows of m per pass.
-// in is either fp32 [m][k] (IN_ACT = -1) or an NHWC activation map flattened per image (IN_ACT = W2C_ACT_*),
-// whose pixel layout for BF16X2 is [hi(256) | lo(256)].
-template <int MT>
-__global__ void __launch_bounds__(256) linear_rows_kernel(const void* __restrict__ in, int in_act, int in_c,
-                                                          const float* __restrict__ W, const float* __restrict__ bias,
-                                                          float* __restrict__ out, int m, int k_dim, int out_dim,
-                                                          int relu) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= out_dim) return;
-  const float* wrow = W + static_cast<size_t>(warp) * k_dim;
-  for (int m0 = 0; m0 < m; m0 += MT) {
-    float acc[MT];
-#pragma unroll
-    for (int r = 0; r < MT; ++r) acc[r] = 0.f;
-    for (int k = lane; k < k_dim; k += 32) {
-      const float wv = __ldg(wrow + k);
-#pragma unroll
-      for (int r = 0; r < MT; ++r) {
-        if (m0 + r < m) {
-          float xv;
-          if (in_act < 0) {
-            xv = static_cast<const float*>(in)[static_cast<size_t>(m0 + r) * k_dim + k];
-          } else {
-            const int planes = in_act == W2C_ACT_BF16X2 ? 2 : 1;
-            const int pixel = k / in_c, ch = k % in_c;
-            const __nv_bfloat16* pix = static_cast<const __nv_bfloat16*>(in) +
-                                       (static_cast<size_t>(m0 + r) * (k_dim / in_c) + pixel) * (in_c * planes);
-            xv = act_load(pix, ch, in_c, in_act);
-          }
-          acc[r] = fmaf(xv, wv, acc[r]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < MT; ++r) {
-      const float s = warp_sum(acc[r]);
-      if (lane == 0 && m0 + r < m) {
-        float v = s + (bias ? bias[warp] : 0.f);
-        out[static_cast<size_t>(m0 + r) * out_dim + warp] = relu ? fmaxf(v, 0.f) : v;
-      }
-    }
-  }
 }
 
 struct AttnParams {
@@ -288,24 +242,6 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
 }  // namespace w2c
 
 using namespace w2c;
-
-extern "C" int w2c_kq_mlp_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const float* w0,
-                              const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
-                              int32_t out_dim, float* out, float* ws, w2c_stream_t stream) {
-  W2C_CHECK_ARG(feat && w0 && b0 && w1 && b1 && w2 && b2 && out && ws, "kq_mlp: null pointer");
-  W2C_CHECK_ARG(m > 0 && n_feat > 0 && n_feat % 256 == 0 && out_dim > 0, "kq_mlp: bad sizes m=%d n_feat=%d out=%d", m,
-                n_feat, out_dim);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  float* h0 = ws;
-  float* h1 = ws + static_cast<size_t>(m) * 256;
-  linear_rows_kernel<8><<<ceil_div(256 * 32, 256), 256, 0, s>>>(feat, act, 256, w0, b0, h0, m, n_feat, 256, 1);
-  W2C_CHECK_LAUNCH("linear_rows_kernel(fc0)");
-  linear_rows_kernel<8><<<ceil_div(128 * 32, 256), 256, 0, s>>>(h0, -1, 0, w1, b1, h1, m, 256, 128, 1);
-  W2C_CHECK_LAUNCH("linear_rows_kernel(fc1)");
-  linear_rows_kernel<8><<<ceil_div(out_dim * 32, 256), 256, 0, s>>>(h1, -1, 0, w2, b2, out, m, 128, out_dim, 0);
-  W2C_CHECK_LAUNCH("linear_rows_kernel(fc2)");
-  return W2C_OK;
-}
 
 extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream) {
   W2C_CHECK_ARG(args, "attn: args is NULL");

@@ -15,6 +15,10 @@ namespace w2c {
 int set_error(int code, const char* fmt, ...);
 void count_launch(unsigned n = 1);
 
+// stem_tc.cu: tensor-core first layer (cout 64 / 128)
+int stem3x3_tc_forward(const float* x, const float* w, const float* scale, const float* shift, void* y, int b,
+                       int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, cudaStream_t stream);
+
 #define W2C_CHECK_ARG(cond, ...)                                   \
   do {                                                             \
     if (!(cond)) return ::w2c::set_error(W2C_ERR_INVALID, __VA_ARGS__); \

@@ -347,6 +347,13 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
   W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem3x3: channel window [%d, %d) outside %d",
                 c_first, c_first + 3 * n_agents, c_total);
   W2C_CHECK_ARG(cout % 32 == 0 && cout <= 128, "stem3x3: cout=%d must be a multiple of 32 and <= 128", cout);
+  static const bool force_simt = [] {
+    const char* e = getenv("W2C_STEM_SIMT");
+    return e && e[0] == '1';
+  }();
+  if ((cout == 64 || cout == 128) && !force_simt)
+    return stem3x3_tc_forward(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act,
+                              static_cast<cudaStream_t>(stream));
   const size_t total = static_cast<size_t>(b) * n_agents * h * w_px;
   const size_t smem = (27 * cout + 2 * cout) * sizeof(float);
   stem3x3_kernel<32><<<grid_for(total, 256, 148 * 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(

@@ -1,0 +1,117 @@
+// Key / query heads (km_generator / linear, agent.py:145-178): flatten -> Linear(n_feat,256) -> ReLU ->
+// Linear(256,128) -> ReLU -> Linear(128,out).  M = agents*scenes rows (tens), so this is weight-bandwidth work
+// (fc0 is 256 x n_feat fp32 = 4 MB at 512x512): two launches,
+//   fc0_kernel     2 output neurons per CTA, 256 threads stride K with coalesced weight and activation reads,
+//                  8 rows of M per pass, block reduction through warp shuffles + one smem hop;
+//   fc12_kernel    one CTA per row: fc1 (256 -> 128) and fc2 (128 -> out) fused, hidden vectors in shared memory,
+//                  one warp per output neuron with lanes over K and a shuffle reduction.
+#include "common.cuh"
+
+namespace w2c {
+namespace {
+
+constexpr int kRows = 8;     // rows of M per pass in fc0
+constexpr int kNeurons = 2;  // output neurons per CTA in fc0
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// feat: NHWC policy map [m][n_feat/256 pixels][planes*256]; W: [256][n_feat] (NHWC flatten order); out [m][256]
+__global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restrict__ feat, int act,
+                                                  const float* __restrict__ W, const float* __restrict__ bias,
+                                                  float* __restrict__ out, int m, int n_feat) {
+  __shared__ float red[8][kNeurons * kRows];
+  const int j0 = blockIdx.x * kNeurons;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t row_elems = static_cast<size_t>(n_feat) * planes;
+  const float* w0 = W + static_cast<size_t>(j0) * n_feat;
+  const float* w1 = w0 + n_feat;
+  for (int m0 = 0; m0 < m; m0 += kRows) {
+    float acc[kNeurons][kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) acc[0][r] = acc[1][r] = 0.f;
+    for (int k = tid; k < n_feat; k += 256) {
+      const float a = __ldg(w0 + k), b = __ldg(w1 + k);
+      const size_t off = static_cast<size_t>(k >> 8) * (256 * planes) + (k & 255);  // pixel * pixel-stride + channel
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        if (m0 + r < m) {
+          const __nv_bfloat16* p = feat + static_cast<size_t>(m0 + r) * row_elems + off;
+          float x = __bfloat162float(p[0]);
+          if (planes == 2) x += __bfloat162float(p[256]);
+          acc[0][r] = fmaf(x, a, acc[0][r]);
+          acc[1][r] = fmaf(x, b, acc[1][r]);
+        }
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < kNeurons; ++n)
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const float s = warp_sum(acc[n][r]);
+        if (lane == 0) red[warp][n * kRows + r] = s;
+      }
+    __syncthreads();
+    if (tid < kNeurons * kRows) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += red[w][tid];
+      const int n = tid / kRows, r = tid % kRows;
+      if (m0 + r < m) out[static_cast<size_t>(m0 + r) * 256 + j0 + n] = fmaxf(s + bias[j0 + n], 0.f);
+    }
+    __syncthreads();
+  }
+}
+
+// one CTA per row: h1 = relu(W1 h0 + b1) (128), out = W2 h1 + b2 (out_dim)
+__global__ void __launch_bounds__(256) fc12_kernel(const float* __restrict__ h0, const float* __restrict__ W1,
+                                                   const float* __restrict__ b1, const float* __restrict__ W2,
+                                                   const float* __restrict__ b2, float* __restrict__ out, int out_dim) {
+  __shared__ float s_h0[256];
+  __shared__ float s_h1[128];
+  const int row = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  s_h0[tid] = h0[static_cast<size_t>(row) * 256 + tid];
+  __syncthreads();
+  for (int j = warp; j < 128; j += 8) {
+    const float* wr = W1 + j * 256;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = lane; k < 256; k += 32) acc = fmaf(__ldg(wr + k), s_h0[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_h1[j] = fmaxf(acc + b1[j], 0.f);
+  }
+  __syncthreads();
+  for (int j = warp; j < out_dim; j += 8) {
+    const float* wr = W2 + static_cast<size_t>(j) * 128;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = lane; k < 128; k += 32) acc = fmaf(__ldg(wr + k), s_h1[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) out[static_cast<size_t>(row) * out_dim + j] = acc + b2[j];
+  }
+}
+
+}  // namespace
+}  // namespace w2c
+
+using namespace w2c;
+
+extern "C" int w2c_kq_mlp_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const float* w0,
+                              const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
+                              int32_t out_dim, float* out, float* ws, w2c_stream_t stream) {
+  W2C_CHECK_ARG(feat && w0 && b0 && w1 && b1 && w2 && b2 && out && ws, "kq_mlp: null pointer");
+  W2C_CHECK_ARG(m > 0 && n_feat > 0 && n_feat % 256 == 0 && out_dim > 0, "kq_mlp: bad sizes m=%d n_feat=%d out=%d", m,
+                n_feat, out_dim);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  float* h0 = ws;  // [m][256]
+  fc0_kernel<<<256 / kNeurons, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), act, w0, b0, h0, m, n_feat);
+  W2C_CHECK_LAUNCH("fc0_kernel");
+  fc12_kernel<<<m, 256, 0, s>>>(h0, w1, b1, w2, b2, out, out_dim);
+  W2C_CHECK_LAUNCH("fc12_kernel");
+  return W2C_OK;
+}

@@ -1,0 +1,230 @@
+// First encoder layer on the tensor cores: Conv2d(3 -> COUT, k3 s1 p1) + folded BN + ReLU, reading the caller's
+// fp32 NCHW views directly and writing bf16 NHWC.
+//
+// K = 27 is far too small for a TMA-fed implicit GEMM, and on the CUDA cores the layer is issue-bound (~2.7 ms for
+// 40 agent-frames against a 0.22 ms HBM floor). Here the 128 threads of a CTA each gather the 27 taps of one output
+// pixel (coalesced 4-byte reads of three channel planes), convert to bf16 and write one 64-byte K-major row of the
+// A operand straight into shared memory in the 128B-swizzle layout the UMMA descriptor expects (software im2col).
+// One thread then issues two tcgen05.mma (M=128, N=COUT, K=16) — six in the bf16x3 precision — and the same 128
+// threads read the accumulators back from TMEM, apply scale/shift/ReLU and store 128-bit vectors. A CTA loops over
+// pixel tiles with the next tile's taps prefetched into registers during the epilogue; several CTAs per SM overlap
+// gather, MMA and store phases. COUT = 128 is two encoders' first layers fused (the image is read once).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace w2c {
+namespace {
+
+constexpr int kTile = 128;     // pixels per tile = UMMA M
+constexpr int kRowBytes = 128; // one swizzle row; only the first 64 B (K = 32 bf16) are used
+
+template <int COUT>
+struct StemSmem {
+  static constexpr int kA = kTile * kRowBytes;   // 16 KB per plane
+  static constexpr int kB = COUT * kRowBytes;
+  static constexpr int kAHi = 0, kALo = kA, kBHi = 2 * kA, kBLo = 2 * kA + kB;
+  static constexpr int kBar = 2 * kA + 2 * kB;
+  static constexpr int kTmemPtr = kBar + 8;
+  static constexpr int kScale = kTmemPtr + 8;
+  static constexpr int kShift = kScale + COUT * 4;
+  static constexpr int kTotal = kShift + COUT * 4;
+  static constexpr int kDynamic = kTotal + 1024;
+};
+
+// byte offset of 16-byte chunk `c` of row `r` in a 128B-swizzled K-major tile
+__device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * kRowBytes + ((c ^ (r & 7u)) << 4); }
+
+__device__ __forceinline__ void gather_taps(const float* __restrict__ x, size_t p, size_t total, int b_sz, int c_total,
+                                            int c_first, int h, int wpx, float (&in)[27]) {
+  if (p >= total) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) in[k] = 0.f;
+    return;
+  }
+  const size_t plane = static_cast<size_t>(h) * wpx;
+  const int ow = p % wpx;
+  const int oh = (p / wpx) % h;
+  const int img = p / plane;  // agent-major: img = agent * b_sz + batch
+  const int agent = img / b_sz, bat = img % b_sz;
+  const float* xin = x + (static_cast<size_t>(bat) * c_total + c_first + 3 * agent) * plane;
+#pragma unroll
+  for (int ci = 0; ci < 3; ++ci)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ih = oh + kh - 1, iw = ow + kw - 1;
+        in[ci * 9 + kh * 3 + kw] =
+            (ih >= 0 && ih < h && iw >= 0 && iw < wpx) ? __ldg(xin + ci * plane + static_cast<size_t>(ih) * wpx + iw) : 0.f;
+      }
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           __nv_bfloat16* __restrict__ y, int b_sz, int n_agents,
+                                                           int c_total, int c_first, int h, int wpx, int act,
+                                                           int num_tiles) {
+  using L = StemSmem<COUT>;
+  constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+  float* s_scale = reinterpret_cast<float*>(smem + L::kScale);
+  float* s_shift = reinterpret_cast<float*>(smem + L::kShift);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool x3 = act == W2C_ACT_BF16X2;
+  const size_t total = static_cast<size_t>(b_sz) * n_agents * h * wpx;
+
+  // ---- one-time setup: weights -> swizzled B tiles (K padded 27 -> 32 with zeros), barrier, TMEM
+  for (int i = tid; i < COUT * 4; i += kTile) {
+    const int co = i >> 2, c = i & 3;  // 16-byte chunk c = k in [8c, 8c+8)
+    uint4 hv, lv;
+    __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
+    __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = c * 8 + e;
+      const float v = k < 27 ? w[co * 27 + k] : 0.f;
+      hb[e] = __float2bfloat16_rn(v);
+      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+    }
+    *reinterpret_cast<uint4*>(smem + L::kBHi + sw128(co, c)) = hv;
+    *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
+  }
+  for (int i = tid; i < COUT; i += kTile) s_scale[i] = scale[i], s_shift[i] = shift[i];
+  if (tid == 0) {
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t idesc = ptx::make_idesc_bf16(kTile, COUT);
+  const uint64_t a_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAHi));
+  const uint64_t a_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kALo));
+  const uint64_t b_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBHi));
+  const uint64_t b_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBLo));
+
+  float in[27];
+  int tile = blockIdx.x;
+  if (tile < num_tiles) gather_taps(x, static_cast<size_t>(tile) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
+  uint32_t phase = 0;
+  const int planes = x3 ? 2 : 1;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    // ---- software im2col: this thread's pixel -> row `tid` of the A tile(s)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint4 hv, lv;
+      __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
+      __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(&lv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int k = c * 8 + e;
+        const float v = k < 27 ? in[k < 27 ? k : 0] : 0.f;
+        hb[e] = __float2bfloat16_rn(v);
+        lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+      }
+      *reinterpret_cast<uint4*>(smem + L::kAHi + sw128(tid, c)) = hv;
+      if (x3) *reinterpret_cast<uint4*>(smem + L::kALo + sw128(tid, c)) = lv;
+    }
+    ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      ptx::tc_fence_after();
+      // K = 32 = two UMMA k-steps (32 B apart inside the swizzle row)
+      ptx::umma_bf16(tmem_base, a_hi, b_hi, idesc, 0);
+      ptx::umma_bf16(tmem_base, a_hi + 2, b_hi + 2, idesc, 1);
+      if (x3) {
+        ptx::umma_bf16(tmem_base, a_hi, b_lo, idesc, 1);
+        ptx::umma_bf16(tmem_base, a_hi + 2, b_lo + 2, idesc, 1);
+        ptx::umma_bf16(tmem_base, a_lo, b_hi, idesc, 1);
+        ptx::umma_bf16(tmem_base, a_lo + 2, b_hi + 2, idesc, 1);
+      }
+      ptx::umma_commit(bar);
+    }
+    // prefetch the next tile's taps while the MMA runs and before the store phase
+    const size_t p = static_cast<size_t>(tile) * kTile + tid;
+    const int next = tile + gridDim.x;
+    if (next < num_tiles) gather_taps(x, static_cast<size_t>(next) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
+
+    ptx::mbar_wait(bar, phase);
+    phase ^= 1;
+    ptx::tc_fence_after();
+    __nv_bfloat16* ypix = y + p * (static_cast<size_t>(COUT) * planes);
+#pragma unroll 1
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+      ptx::tmem_ld_wait();
+      if (p < total) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 hv, lv;
+          __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
+          __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int c = c0 + g * 8 + 2 * j;
+            const float a = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2 * j]), s_scale[c], s_shift[c]), 0.f);
+            const float b = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2 * j + 1]), s_scale[c + 1], s_shift[c + 1]), 0.f);
+            hb[j] = __floats2bfloat162_rn(a, b);
+            const float2 hf = __bfloat1622float2(hb[j]);
+            lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+          }
+          *reinterpret_cast<uint4*>(ypix + c0 + g * 8) = hv;
+          if (x3) *reinterpret_cast<uint4*>(ypix + COUT + c0 + g * 8) = lv;
+        }
+      }
+    }
+    // the next iteration's __syncthreads (after its smem writes) orders these TMEM reads before the next MMA
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int COUT>
+int launch_stem(const float* x, const float* w, const float* scale, const float* shift, void* y, int b, int n_agents,
+                int c_total, int c_first, int h, int wpx, int act, cudaStream_t stream) {
+  using L = StemSmem<COUT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(stem3x3_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "stem3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const size_t total = static_cast<size_t>(b) * n_agents * h * wpx;
+  const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
+  // resident CTAs per SM are bounded by TMEM (512 columns) and shared memory (~64-80 KB each)
+  const int per_sm = COUT <= 64 ? 3 : 2;
+  int grid = 148 * per_sm;
+  if (grid > num_tiles) grid = num_tiles;
+  stem3x3_tc_kernel<COUT><<<grid, kTile, L::kDynamic, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b,
+                                                                n_agents, c_total, c_first, h, wpx, act, num_tiles);
+  W2C_CHECK_LAUNCH("stem3x3_tc_kernel");
+  return W2C_OK;
+}
+
+}  // namespace
+
+int stem3x3_tc_forward(const float* x, const float* w, const float* scale, const float* shift, void* y, int b,
+                       int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, cudaStream_t stream) {
+  if (cout == 64) return launch_stem<64>(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
+  if (cout == 128) return launch_stem<128>(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
+  return set_error(W2C_ERR_UNSUPPORTED, "stem3x3_tc: cout=%d (only 64 and 128)", cout);
+}
+
+}  // namespace w2c

@@ -105,6 +105,18 @@ class WeightCache:
             self._misc[key] = st
         return st
 
+    def stem_pair(self, conv_a, bn_a, conv_b, bn_b):
+        """Two 3 -> 64 first layers concatenated on the output-channel axis (one fused 3 -> 128 stem)."""
+        key = ("stem_pair", id(conv_a), id(conv_b))
+        st = self._misc.get(key)
+        if st is None:
+            wa, sa, ha = self.stem(conv_a, bn_a)
+            wb, sb, hb = self.stem(conv_b, bn_b)
+            st = (torch.cat((wa, wb), 0).contiguous(), torch.cat((sa, sb)).contiguous(),
+                  torch.cat((ha, hb)).contiguous())
+            self._misc[key] = st
+        return st
+
     # key/query head: fc.0 permuted to NHWC flatten order
     def mlp(self, fc, spatial):
         key = ("mlp", id(fc))

@@ -101,15 +101,17 @@ def _make_attention(attention, query_size, key_size):
 
 
 # ------------------------------------------------------------------------------------------- program builders
-def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=None):
-    """img_encoder.forward (agent.py:56-60) on agents [c_first/3, ...) of the fp32 NCHW batch -> ActMap."""
+def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=None, stem=None):
+    """img_encoder.forward (agent.py:56-60) on agents [c_first/3, ...) of the fp32 NCHW batch -> ActMap.
+    stem: output of an already-issued (fused) first layer to start from instead of running conv1 here."""
     wc = prog.weights
     bb = enc.feature_backbone
     if isinstance(bb, n_segnet_encoder):
         if h % 32 or w % 32:
             raise ValueError("n_segnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
         units = bb.units()
-        a = prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h, w, c_first)
+        a = stem if stem is not None else prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h,
+                                                       w, c_first)
         for i, u in enumerate(units[1:], 2):
             a = prog.conv(a, wc.conv(u.conv, u.bn, True))
     elif isinstance(bb, resnet_encoder):
@@ -157,9 +159,21 @@ def _build_decoder(prog, dec, a):
     raise ValueError("unknown decoder backbone %r" % type(od).__name__)
 
 
-def _build_policy(prog, pol, x_nchw, b, n_agents, h, w):
+def _fused_stems(prog, enc_a, enc_b, x_nchw, b, n_agents, h, w):
+    """u_encoder and query_key_net.img_encoder convolve the same pixels with different weights (agent.py:1111,1124):
+    run both first layers as ONE 3 -> 128 stem so the image is read and im2col'd once. Returns the two 64-channel
+    slices of the shared output buffer, or (None, None) when the backbones are not both n_segnet."""
+    ba, bb = enc_a.feature_backbone, enc_b.feature_backbone
+    if not (isinstance(ba, n_segnet_encoder) and isinstance(bb, n_segnet_encoder)):
+        return None, None
+    ua, ub = ba.units()[0], bb.units()[0]
+    both = prog.stem3x3(x_nchw, prog.weights.stem_pair(ua.conv, ua.bn, ub.conv, ub.bn), b, n_agents, h, w)
+    return both.slice(0, 64), both.slice(64, 64)
+
+
+def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
     """policy_net4.forward (agent.py:134-142) -> ActMap (n_agents*b, s, s, 256)."""
-    a = _build_encoder(prog, pol.img_encoder, "img_encoder", x_nchw, b, n_agents, h, w)
+    a = _build_encoder(prog, pol.img_encoder, "img_encoder", x_nchw, b, n_agents, h, w, stem=stem)
     if a.h % 4 or a.w % 4:
         raise ValueError("policy_net4 needs the %dx%d feature map divisible by 4" % (a.h, a.w))
     for i in range(1, 6):
@@ -346,8 +360,9 @@ class _AttentionModel(_W2CModel):
         val_out = None
         if dst is not None:
             val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], FEATURE_CHANNELS)
-        val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out)
-        qk = _build_policy(prog, self.query_key_net, x, b, n, h, w)
+        stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
+        val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
+        qk = _build_policy(prog, self.query_key_net, x, b, n, h, w, stem=stem_p)
         if qk.h != qk.w:
             raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
         keys = prog.kq_mlp(qk, prog.weights.mlp(self.key_net.fc, qk.h), self.key_size,

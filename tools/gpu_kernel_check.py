@@ -142,8 +142,8 @@ def case_stem():
     torch, F, ops = _imports()
     dev = "cuda:0"
     out, ok = {}, True
-    for act in (0, 1):
-        b, na, h, w, cout = 2, 3, 20, 28, 64
+    for act, cout in ((0, 64), (1, 64), (0, 128), (1, 128), (0, 32)):
+        b, na, h, w = 2, 3, 20, 28
         x = torch.randn(b, 3 * na, h, w, device=dev)
         wt = torch.randn(cout, 3, 3, 3, device=dev) * 0.2
         scale = torch.rand(cout, device=dev) + 0.5
@@ -157,8 +157,10 @@ def case_stem():
         got = ops.act_to_nchw(y, cout, act).double()
         err = (got - ref).abs().max().item()
         tol = (6e-3 if act == 0 else 1e-4) * max(1.0, ref.abs().max().item())
-        out["stem3x3_act%d" % act] = err
+        out["stem3x3_act%d_c%d" % (act, cout)] = err
         ok &= err <= tol
+        if cout != 64:
+            continue
         # 7x7 s2 + maxpool
         h2, w2 = 32, 48
         x = torch.randn(b, 3 * na, h2, w2, device=dev)
