@@ -37,7 +37,9 @@ enum {
 
 enum { W2C_ACT_BF16 = 0, W2C_ACT_BF16X2 = 1 };
 enum { W2C_OUT_NHWC = 0, W2C_OUT_NCHW_F32 = 1 };
-enum { W2C_IMPL_TCGEN05 = 0, W2C_IMPL_SIMT = 1 };
+/* W2C_IMPL_TCGEN05 lets the library pick between its two tensor-core kernels (per-tap TMA windows, or one halo
+ * tile per channel chunk re-addressed per tap); _TC_TAPS / _TC_HALO force one; _SIMT is the CUDA-core cross-check. */
+enum { W2C_IMPL_TCGEN05 = 0, W2C_IMPL_SIMT = 1, W2C_IMPL_TC_TAPS = 2, W2C_IMPL_TC_HALO = 3, W2C_IMPL_TC_PERSIST = 4 };
 enum {
   W2C_CONV3X3_S1 = 0,   /* Conv2d k3 s1 p1                       */
   W2C_CONV3X3_S2 = 1,   /* Conv2d k3 s2 p1   (H, W even)         */
@@ -85,7 +87,7 @@ typedef struct w2c_conv_args {
   int32_t relu;     /* 0 / 1 */
   int32_t act;      /* W2C_ACT_* (storage of x, residual, and of y when out_fmt = NHWC) */
   int32_t out_fmt;  /* W2C_OUT_* */
-  int32_t impl;     /* W2C_IMPL_TCGEN05 (product) or W2C_IMPL_SIMT (on-GPU cross-check, tests only) */
+  int32_t impl;     /* W2C_IMPL_TCGEN05 (product) ... W2C_IMPL_SIMT (on-GPU cross-check, tests only) */
   int32_t block_n;  /* 0 = auto; else 16/32/64/128/256 */
 } w2c_conv_args;
 

@@ -15,7 +15,7 @@ c_vp = ctypes.c_void_p
 
 ACT_BF16, ACT_BF16X2 = 0, 1
 OUT_NHWC, OUT_NCHW_F32 = 0, 1
-IMPL_TCGEN05, IMPL_SIMT = 0, 1
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST = 0, 1, 2, 3, 4
 CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2 = 0, 1, 2, 3, 4
 FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX = 0, 1, 2
 

@@ -42,6 +42,16 @@ struct ConvPlan {
   int act, relu, out_fmt;
 };
 
+// conv_halo.cu
+bool conv_halo_supported(const ConvPlan& plan);
+bool conv_halo_preferred(const ConvPlan& plan);
+int conv_halo_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+// conv_pers.cu
+bool conv_pers_supported(const ConvPlan& plan);
+int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream);
+
 inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   W2C_CHECK_ARG(a.x && a.w && a.scale && a.shift && a.y, "conv: null pointer argument");
   W2C_CHECK_ARG(a.n > 0 && a.h_in > 0 && a.w_in > 0, "conv: bad image extent %dx%dx%d", a.n, a.h_in, a.w_in);

@@ -264,6 +264,8 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+}  // namespace
+
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, CUtensorMapL2promotion promo) {
   EncodeTiledFn enc = get_encode_tiled();
@@ -275,6 +277,8 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   if (r != CUDA_SUCCESS) return set_error(W2C_ERR_DRIVER, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
   return W2C_OK;
 }
+
+namespace {
 
 int pow2_ceil(int v) {
   int p = 1;
@@ -318,7 +322,11 @@ int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t s
   // ---- BLOCK_N
   int bn = a.block_n;
   if (bn == 0) {
-    if (plan.cout_pad % 128 == 0)
+    // N = 256 halves the A-operand shared-memory reads per FLOP (SS-mode MMAs re-read the 4 KB A slice for every
+    // instruction: at N <= 128 the kernel is smem-bandwidth bound, see profiles/r1_conv_sweep.md)
+    if (plan.cout_pad % 256 == 0 && static_cast<long long>(plan.n_img) * plan.hm * plan.wm >= 128 * 148)
+      bn = 256;
+    else if (plan.cout_pad % 128 == 0)
       bn = 128;
     else if (plan.cout_pad % 64 == 0)
       bn = 64;
@@ -437,13 +445,49 @@ int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream) {
 
 }  // namespace w2c
 
+namespace w2c {
+// Kernel choice for W2C_IMPL_TCGEN05. W2C_CONV_HALO=0 / 1 forces the per-tap / halo kernel wherever legal.
+bool conv_halo_preferred(const ConvPlan& plan) {
+  static const int mode = [] {
+    const char* e = getenv("W2C_CONV_HALO");
+    return e ? atoi(e) : -1;
+  }();
+  if (!conv_halo_supported(plan) || mode == 0) return false;
+  if (mode == 1) return true;
+  // auto: the halo kernel lost the per-layer sweep (profiles/r1_conv_sweep.md) everywhere it was tried
+  return false;
+}
+}  // namespace w2c
+
 extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream) {
   if (!args) return w2c::set_error(W2C_ERR_INVALID, "conv: args is NULL");
   w2c::ConvPlan plan;
   int rc = w2c::build_conv_plan(*args, plan);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (args->impl == W2C_IMPL_SIMT) return w2c::conv_simt_forward(plan, s);
-  if (args->impl != W2C_IMPL_TCGEN05) return w2c::set_error(W2C_ERR_INVALID, "conv: unknown impl %d", args->impl);
-  return w2c::conv_tc_forward(*args, plan, s);
+  switch (args->impl) {
+    case W2C_IMPL_SIMT:
+      return w2c::conv_simt_forward(plan, s);
+    case W2C_IMPL_TC_TAPS:
+      return w2c::conv_tc_forward(*args, plan, s);
+    case W2C_IMPL_TC_HALO:
+      if (!w2c::conv_halo_supported(plan))
+        return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the halo kernel covers 3x3 s1 conv and 3x3 s2 deconv only");
+      return w2c::conv_halo_forward(*args, plan, s);
+    case W2C_IMPL_TC_PERSIST:
+      if (!w2c::conv_pers_supported(plan))
+        return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the persistent kernel needs cout <= 512");
+      return w2c::conv_pers_forward(*args, plan, s);
+    case W2C_IMPL_TCGEN05: {
+      static const bool persist = [] {
+        const char* e = getenv("W2C_CONV_PERSIST");
+        return !(e && e[0] == '0');
+      }();
+      if (w2c::conv_halo_preferred(plan)) return w2c::conv_halo_forward(*args, plan, s);
+      if (persist && w2c::conv_pers_supported(plan)) return w2c::conv_pers_forward(*args, plan, s);
+      return w2c::conv_tc_forward(*args, plan, s);
+    }
+    default:
+      return w2c::set_error(W2C_ERR_INVALID, "conv: unknown impl %d", args->impl);
+  }
 }

@@ -135,6 +135,41 @@ CONV_CASES = {
     "tc_slices": (0, 2, 16, 16, 64, 64, 0, dict(x_cs=128, x_co=64, y_cs=192, y_co=64)),
     "tc_cinpad": (0, 2, 16, 16, 64, 64, 0, dict(cin_real=40)),
     "tc_ragged": (0, 3, 13, 21, 64, 72, 0, dict()),
+    # persistent kernel (impl=4): every kind, TMA-store and direct-store epilogues
+    "pers_s1_min": (0, 1, 8, 16, 64, 64, 0, dict(impl=4)),
+    "pers_s1_multi": (0, 3, 24, 40, 128, 128, 0, dict(impl=4)),
+    "pers_s1_bn256": (0, 2, 16, 16, 256, 256, 0, dict(impl=4, block_n=256)),
+    "pers_s1_bn256_x2": (0, 2, 16, 24, 128, 512, 1, dict(impl=4, block_n=256)),
+    "pers_s1_bn64_k512": (0, 2, 16, 16, 512, 192, 0, dict(impl=4, block_n=64)),
+    "pers_s1_x2": (0, 2, 16, 16, 128, 64, 1, dict(impl=4)),
+    "pers_s2": (1, 2, 32, 32, 64, 128, 0, dict(impl=4)),
+    "pers_s2_x2": (1, 1, 16, 48, 128, 64, 1, dict(impl=4)),
+    "pers_deconv": (2, 2, 16, 16, 128, 128, 0, dict(impl=4)),
+    "pers_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict(impl=4)),
+    "pers_deconv_big": (2, 3, 40, 24, 64, 64, 0, dict(impl=4)),
+    "pers_1x1": (3, 2, 16, 16, 128, 64, 0, dict(impl=4, relu=False)),
+    "pers_1x1s2_res": (4, 2, 16, 16, 64, 128, 0, dict(impl=4, residual=True)),
+    "pers_res_x2": (0, 2, 16, 16, 64, 128, 1, dict(impl=4, residual=True)),
+    "pers_small_8x8": (0, 5, 8, 8, 256, 256, 0, dict(impl=4)),
+    "pers_small_4x4": (1, 5, 8, 8, 256, 256, 0, dict(impl=4)),
+    "pers_nchw_c11": (0, 2, 32, 32, 64, 11, 0, dict(impl=4, nchw_out=True)),
+    "pers_nchw_c11_x2": (0, 2, 16, 32, 64, 11, 1, dict(impl=4, nchw_out=True, relu=False)),
+    "pers_slices": (0, 2, 16, 16, 64, 64, 0, dict(impl=4, x_cs=128, x_co=64, y_cs=192, y_co=64)),
+    "pers_ragged": (0, 3, 13, 21, 64, 72, 0, dict(impl=4)),
+    "pers_ragged_c64": (0, 3, 13, 21, 64, 64, 0, dict(impl=4)),
+    "pers_many_tiles": (0, 8, 64, 64, 64, 128, 0, dict(impl=4)),
+    # halo-reuse kernel (impl=3): 3x3 s1 conv and 3x3 s2 deconv
+    "halo_s1_min": (0, 1, 7, 16, 64, 64, 0, dict(impl=3)),
+    "halo_s1_multi": (0, 3, 24, 40, 128, 128, 0, dict(impl=3)),
+    "halo_s1_k512": (0, 2, 16, 16, 512, 192, 0, dict(impl=3, block_n=64)),
+    "halo_s1_x2": (0, 2, 16, 16, 128, 64, 1, dict(impl=3)),
+    "halo_deconv": (2, 2, 16, 16, 128, 128, 0, dict(impl=3)),
+    "halo_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict(impl=3)),
+    "halo_deconv_c64": (2, 2, 40, 24, 64, 64, 0, dict(impl=3)),
+    "halo_nchw_c11": (0, 2, 32, 32, 64, 11, 0, dict(impl=3, nchw_out=True)),
+    "halo_nchw_c11_x2": (0, 2, 16, 32, 64, 11, 1, dict(impl=3, nchw_out=True, relu=False)),
+    "halo_slices_res": (0, 2, 16, 16, 64, 64, 0, dict(impl=3, x_cs=128, x_co=64, y_cs=192, y_co=64, residual=True)),
+    "halo_ragged": (0, 3, 13, 21, 64, 72, 0, dict(impl=3)),
 }
 
 
