@@ -1,9 +1,7 @@
 // Persistent, warp-specialised tcgen05 implicit-GEMM convolution (the production conv kernel).
 //
-// Same math and operand layout as conv_tc.cu (per-tap TMA windows of the NHWC input, K-major packed weights, fp32
-// accumulation in TMEM, fused scale/shift(+residual)+ReLU), restructured after the first B200 profiles showed the
-// one-tile-per-CTA kernel paying ~10 us of prologue + unoverlapped epilogue per tile on the small-K layers
-// (20k-80k CTAs per launch) and issuing 16-byte scattered stores:
+// Same math and operand layout as conv_tc.cu (TMA windows of the NHWC input, K-major packed weights, fp32
+// accumulation in TMEM, fused scale/shift(+residual)+ReLU), restructured after the first B200 profiles:
 //   * one CTA per SM loops over tiles (static round-robin, n-tile fastest so concurrent CTAs share input windows);
 //     barriers, the TMEM allocation and the scale/shift tables are set up once per CTA
 //   * the accumulator is double-buffered in TMEM (2 x BLOCK_N columns): the MMA warp starts tile i+1 while the
@@ -11,6 +9,16 @@
 //   * the epilogue converts to bf16, writes a [128 pixel][64 channel] 128B-swizzled staging tile and ONE thread
 //     issues a TMA tensor store per 64 channels (full-line writes, edge tiles clipped by the TMA unit); the
 //     transposed conv writes through four parity-strided output tensor maps
+//   * ROW-HALO A operand: the filter taps that differ only in their vertical offset share ONE input box of
+//     th + (taps-1) rows; the window of the tap `j` rows further down is the same buffer advanced by j*tw*128 B,
+//     which stays 1024-byte aligned (tw >= 8), so it is just another UMMA descriptor start address at full operand
+//     bandwidth (the unaligned horizontal shifts of conv_halo.cu halve it). A 3x3 conv fetches 3 boxes of th+2
+//     rows instead of 9 of th rows per 64-channel chunk: 2.4x less L2 -> SM traffic for the activations
+//   * a pipeline stage carries up to three k-blocks ("units": the vertical taps of one row-halo box, or two merged
+//     channel chunks) behind ONE full/empty barrier pair: tcgen05.commit is expensive (measured: a second commit
+//     per k-block cost 30-90 %), so it is issued once per 8-12 MMAs instead of once per 4
+//   * when all weight tiles of the layer fit beside the ring (the 64/128-channel layers) they are loaded once per
+//     CTA and stay RESIDENT in shared memory for all its tiles
 //   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue
 #include "conv_plan.cuh"
 #include "ptx.cuh"
@@ -24,36 +32,39 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kAStageBytes = kBlockM * kBlockK * 2;
 constexpr int kNumThreads = 192;
 constexpr int kEpiThreads = 128;
 constexpr int kStagingBytes = kBlockM * 64 * 2;  // [128 px][64 ch] bf16
 constexpr int kMaxCout = 512;
+constexpr int kMaxStages = 12;
+constexpr int kMaxResident = 64;
+constexpr int kSmemBudget = 232448;  // 227 KB opt-in maximum per CTA
+
+struct TapGroup {
+  int8_t map, dw, dh0, ndh;  // input map, horizontal shift, first vertical shift, number of vertical taps
+  int8_t wtap[3];            // packed-weight tap index of each vertical tap
+  int8_t pad;
+};
 
 struct PersParams {
-  CUtensorMap a_map[4];
+  CUtensorMap a_map[4][3];  // [input map][ndh - 1]: box of th + ndh - 1 rows
   CUtensorMap b_map;
   CUtensorMap y_map[4];
   ConvPlan plan;
+  TapGroup groups[4][9];
+  int ngroups[4];
+  int tap_base[4];  // running tap index of each class's first tap (resident-B slot numbering)
+  int total_taps;
   int tw, th, tn;
   int tiles_w, tiles_h, tiles_img;
   int n_tiles, m_tiles, total_tiles;
-  int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
-};
-
-template <int BLOCK_N, int STAGES>
-struct PersSmem {
-  static constexpr int kNumStaging = BLOCK_N >= 64 ? (BLOCK_N == 256 ? 1 : 2) : 0;
-  static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kAOff = 0;
-  static constexpr int kBOff = STAGES * kAStageBytes;
-  static constexpr int kStgOff = kBOff + STAGES * kBStageBytes;
-  static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2]
-  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
-  static constexpr int kScaleOff = kTmemPtrOff + 8;
-  static constexpr int kShiftOff = kScaleOff + kMaxCout * 4;
-  static constexpr int kTotal = kShiftOff + kMaxCout * 4;
-  static constexpr int kDynamicBytes = kTotal + 1024;
+  int stages, stage_bytes, b_off;  // ring depth, bytes per stage, offset of the weight tiles inside a stage
+  int unit_a_bytes;                // distance between the A operands of consecutive units of a stage
+  int cm;                          // channel chunks merged per stage when taps are not grouped (1 or 2)
+  int res_slots, n_staging;
+  int b_resident;
+  int tma_store;
+  int ctas_per_sm;
 };
 
 struct TileCoord {
@@ -74,21 +85,24 @@ __device__ __forceinline__ TileCoord decode_tile(const PersParams& p, int t, int
   return c;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N>
 __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_constant__ PersParams p) {
-  using L = PersSmem<BLOCK_N, STAGES>;
+  constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kStageTx = kAStageBytes + L::kBStageBytes;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint8_t* smem_ring = smem;
+  uint8_t* smem_res = smem_ring + p.stages * p.stage_bytes;  // resident weight tiles
+  uint8_t* smem_stg = smem_res + p.res_slots * kBStageBytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_stg + p.n_staging * kStagingBytes);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* res_bar = empty_bar + kMaxStages;
+  uint64_t* tfull_bar = res_bar + kMaxResident;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
-  float* s_scale = reinterpret_cast<float*>(smem + L::kScaleOff);
-  float* s_shift = reinterpret_cast<float*>(smem + L::kShiftOff);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_scale = reinterpret_cast<float*>(tmem_ptr + 2);
+  float* s_shift = s_scale + kMaxCout;
 
   const ConvPlan& pl = p.plan;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -97,8 +111,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.b_map);
-    ptx::prefetch_tensormap(&p.a_map[0]);
-    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full_bar[s], 1), ptx::mbar_init(&empty_bar[s], 1);
+    ptx::prefetch_tensormap(&p.a_map[0][0]);
+    for (int s = 0; s < p.stages; ++s) ptx::mbar_init(&full_bar[s], 1), ptx::mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < p.res_slots; ++s) ptx::mbar_init(&res_bar[s], 1);
     for (int s = 0; s < 2; ++s) ptx::mbar_init(&tfull_bar[s], 1), ptx::mbar_init(&tempty_bar[s], kEpiThreads);
     ptx::fence_barrier_init();
   } else if (warp == 1) {
@@ -109,30 +124,59 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t row_px_bytes = static_cast<uint32_t>(p.tw) * p.tn * 128u;  // bytes of one box row
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
-      int stage = 0;
-      uint32_t phase = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      uint64_t loaded = 0;  // resident weight slots already requested by this CTA
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(p, t, BLOCK_N);
-        const int ntaps = pl.ntaps[tc.cls];
+        const int ng = p.ngroups[tc.cls];
         for (int pass = 0; pass < npass; ++pass) {
           const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
           const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
-          for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
-            const Tap tp = pl.taps[tc.cls][tp_i];
-            const CUtensorMap* amap = &p.a_map[tp.map];
-            for (int ch = 0; ch < chunks; ++ch) {
-              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
-              ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * kAStageBytes, a_c0 + ch * kBlockK,
-                               tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
-              ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
-                               tp.wtap * pl.cin + ch * kBlockK, b_row);
-              if (++stage == STAGES) stage = 0, phase ^= 1;
+          const int slot0 = (pass == 1) ? p.total_taps * chunks : 0;
+          // tap-group major, channel chunks inner: consecutive stages read adjacent 128-byte slices of the same
+          // pixels (the chunk-major order measured ~1.7x slower on the 512-channel layers)
+          int tap_idx = p.tap_base[tc.cls];
+          for (int g = 0; g < ng; ++g) {
+            const TapGroup grp = p.groups[tc.cls][g];
+            const int units = grp.ndh > 1 ? grp.ndh : p.cm;
+            for (int ch = 0; ch < chunks; ch += p.cm) {
+              uint8_t* stage = smem_ring + st * p.stage_bytes;
+              ptx::mbar_wait(&empty_bar[st], ph ^ 1);
+              const uint32_t a_bytes = grp.ndh > 1 ? static_cast<uint32_t>(p.th + grp.ndh - 1) * row_px_bytes
+                                                   : static_cast<uint32_t>(units) * (p.th * row_px_bytes);
+              ptx::mbar_arrive_expect_tx(&full_bar[st], a_bytes + (p.b_resident ? 0u : units * kBStageBytes));
+              if (grp.ndh > 1) {
+                ptx::tma_load_4d(&p.a_map[grp.map][grp.ndh - 1], &full_bar[st], stage, a_c0 + ch * kBlockK,
+                                 tc.w0 + grp.dw, tc.h0 + grp.dh0, tc.i0);
+              } else {
+                for (int u = 0; u < units; ++u)
+                  ptx::tma_load_4d(&p.a_map[grp.map][0], &full_bar[st], stage + u * p.unit_a_bytes,
+                                   a_c0 + (ch + u) * kBlockK, tc.w0 + grp.dw, tc.h0 + grp.dh0, tc.i0);
+              }
+              for (int u = 0; u < units; ++u) {
+                const int tap_u = grp.ndh > 1 ? u : 0;
+                const int ch_u = grp.ndh > 1 ? ch : ch + u;
+                const int bk = grp.wtap[tap_u] * pl.cin + ch_u * kBlockK;
+                if (p.b_resident) {
+                  const int slot = slot0 + (tap_idx + tap_u) * chunks + ch_u;
+                  if (!((loaded >> slot) & 1ull)) {
+                    loaded |= 1ull << slot;
+                    ptx::mbar_arrive_expect_tx(&res_bar[slot], kBStageBytes);
+                    ptx::tma_load_2d(&p.b_map, &res_bar[slot], smem_res + slot * kBStageBytes, bk, b_row);
+                  }
+                } else {
+                  ptx::tma_load_2d(&p.b_map, &full_bar[st], stage + p.b_off + u * kBStageBytes, bk, b_row);
+                }
+              }
+              if (++st == p.stages) st = 0, ph ^= 1;
             }
+            tap_idx += grp.ndh;
           }
         }
       }
@@ -141,28 +185,57 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
-      const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
-      const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
-      int stage = 0;
-      uint32_t phase = 0;
+      const uint32_t ring0 = ptx::smem_u32(smem_ring);
+      const uint32_t res0 = ptx::smem_u32(smem_res);
+      int st = 0;
+      uint32_t ph = 0;
       int it = 0;
+      uint64_t ready = 0;  // resident weight slots this thread has already seen complete
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(p, t, BLOCK_N);
-        const int num_kb = npass * pl.ntaps[tc.cls] * chunks;
+        const int ng = p.ngroups[tc.cls];
         const int acc = it & 1;
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * kAStageBytes) >> 4);
-          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * L::kBStageBytes) >> 4);
+        uint32_t accumulate = 0;
+        for (int pass = 0; pass < npass; ++pass) {
+          const int slot0 = (pass == 1) ? p.total_taps * chunks : 0;
+          int tap_idx = p.tap_base[tc.cls];
+          for (int g = 0; g < ng; ++g) {
+            const int ndh = p.groups[tc.cls][g].ndh;
+            const int units = ndh > 1 ? ndh : p.cm;
+            for (int ch = 0; ch < chunks; ch += p.cm) {
+              const uint32_t stage = ring0 + st * p.stage_bytes;
+              ptx::mbar_wait(&full_bar[st], ph);
+              ptx::tc_fence_after();
+              for (int u = 0; u < units; ++u) {
+                uint32_t b_addr;
+                if (p.b_resident) {
+                  const int slot = slot0 + (tap_idx + (ndh > 1 ? u : 0)) * chunks + (ndh > 1 ? ch : ch + u);
+                  if (!((ready >> slot) & 1ull)) {  // wait only the first time: a try_wait costs ~90 cycles
+                    ptx::mbar_wait(&res_bar[slot], 0);
+                    ptx::tc_fence_after();
+                    ready |= 1ull << slot;
+                  }
+                  b_addr = res0 + slot * kBStageBytes;
+                } else {
+                  b_addr = stage + p.b_off + u * kBStageBytes;
+                }
+                // unit u: the same row-halo box u rows further down (1024-byte aligned), or the next merged chunk
+                const uint64_t a_desc = ptx::make_sw128_kmajor_desc(stage + u * p.unit_a_bytes);
+                const uint64_t b_desc = ptx::make_sw128_kmajor_desc(b_addr);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  ptx::umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, accumulate);
+                  accumulate = 1;
+                }
+              }
+              ptx::umma_commit(&empty_bar[st]);  // ONE commit per stage (8-12 MMAs)
+              if (++st == p.stages) st = 0, ph ^= 1;
+            }
+            tap_idx += ndh;
+          }
         }
         ptx::umma_commit(&tfull_bar[acc]);
       }
@@ -196,7 +269,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
 
-      if constexpr (L::kNumStaging > 0) {
+      if constexpr (BLOCK_N >= 64) {
         if (p.tma_store) {
 #pragma unroll 1
           for (int g = 0; g < BLOCK_N / 64; ++g) {
@@ -206,6 +279,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
             ptx::tmem_ld_32x32b_x32(t_row + g * 64, r);
             ptx::tmem_ld_32x32b_x32(t_row + g * 64 + 32, r + 32);
             ptx::tmem_ld_wait();
+            if (g == BLOCK_N / 64 - 1 || cb + 64 >= pl.cout) {
+              // last read of this accumulator: hand it back to the MMA warp before the store phase
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&tempty_bar[acc]);
+            }
             float v[64];
 #pragma unroll
             for (int j = 0; j < 64; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[cb + j], s_shift[cb + j]);
@@ -228,23 +306,28 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
               for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             for (int pln = 0; pln < planes; ++pln, ++unit) {
-              uint8_t* stg = smem + L::kStgOff + (unit % L::kNumStaging) * kStagingBytes;
+              uint8_t* stg = smem_stg + (unit % p.n_staging) * kStagingBytes;
               // the TMA store that last used this staging tile must have finished reading it
-              if (et == 0) ptx::bulk_wait_group_read<L::kNumStaging - 1>();
+              if (et == 0) {
+                if (p.n_staging == 2)
+                  ptx::bulk_wait_group_read<1>();
+                else
+                  ptx::bulk_wait_group_read<0>();
+              }
               ptx::named_bar_sync(1, kEpiThreads);
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
                 uint4 pk;
-                __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+                __nv_bfloat162* pb2 = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
                   const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
                   if (pln == 0) {
-                    pb[j] = hi;
+                    pb2[j] = hi;
                   } else {
                     const float2 hf = __bfloat1622float2(hi);
-                    pb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                    pb2[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
                   }
                 }
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
@@ -257,8 +340,6 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
               }
             }
           }
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&tempty_bar[acc]);
           continue;
         }
       }
@@ -342,16 +423,14 @@ int pow2_ceil(int v) {
   return r;
 }
 
-template <int BLOCK_N, int STAGES>
-int launch_pers(const PersParams& p, cudaStream_t stream) {
-  using L = PersSmem<BLOCK_N, STAGES>;
-  static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_pers_kernel<BLOCK_N, STAGES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+template <int BLOCK_N>
+int launch_pers(const PersParams& p, size_t smem_bytes, cudaStream_t stream) {
+  static size_t attr = 0;
+  if (smem_bytes > attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_pers_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem_bytes));
     if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_pers: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
+    attr = smem_bytes;
   }
   static int num_sms = 0;
   if (num_sms == 0) {
@@ -360,10 +439,54 @@ int launch_pers(const PersParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_pers_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynamicBytes, stream>>>(p);
+  const int want = num_sms * p.ctas_per_sm;
+  const int grid = p.total_tiles < want ? p.total_tiles : want;
+  conv_pers_kernel<BLOCK_N><<<grid, kNumThreads, smem_bytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_pers_kernel");
   return W2C_OK;
+}
+
+// Group the taps of one class by (input map, horizontal shift): taps of a group differ only in dh and, when the
+// vertical shifts are consecutive, share one input box. `grouping` off = every tap its own group (per-tap boxes).
+void build_groups(const ConvPlan& plan, bool grouping, PersParams& p) {
+  p.total_taps = 0;
+  for (int cls = 0; cls < 4; ++cls) {
+    p.ngroups[cls] = 0;
+    p.tap_base[cls] = p.total_taps;
+    if (cls >= plan.num_classes) continue;
+    const int nt = plan.ntaps[cls];
+    bool used[9] = {false};
+    for (int i = 0; i < nt; ++i) {
+      if (used[i]) continue;
+      const Tap& t0 = plan.taps[cls][i];
+      // collect taps with the same (map, dw), sort by dh
+      int idx[9], n = 0;
+      for (int j = i; j < nt; ++j) {
+        const Tap& tj = plan.taps[cls][j];
+        if (!used[j] && tj.map == t0.map && tj.dw == t0.dw && (grouping || j == i)) idx[n++] = j;
+      }
+      for (int a = 1; a < n; ++a)
+        for (int b = a; b > 0 && plan.taps[cls][idx[b]].dh < plan.taps[cls][idx[b - 1]].dh; --b) {
+          const int tmp = idx[b];
+          idx[b] = idx[b - 1], idx[b - 1] = tmp;
+        }
+      // emit runs of consecutive dh (at most 3 per box)
+      int s = 0;
+      while (s < n) {
+        int e = s + 1;
+        while (e < n && e - s < 3 && plan.taps[cls][idx[e]].dh == plan.taps[cls][idx[e - 1]].dh + 1) ++e;
+        TapGroup g{};
+        g.map = plan.taps[cls][idx[s]].map;
+        g.dw = plan.taps[cls][idx[s]].dw;
+        g.dh0 = plan.taps[cls][idx[s]].dh;
+        g.ndh = static_cast<int8_t>(e - s);
+        for (int k = s; k < e; ++k) g.wtap[k - s] = plan.taps[cls][idx[k]].wtap, used[idx[k]] = true;
+        p.groups[cls][p.ngroups[cls]++] = g;
+        s = e;
+      }
+    }
+    p.total_taps += nt;
+  }
 }
 
 }  // namespace
@@ -407,28 +530,97 @@ int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t
   p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
 
+  // ---- tuning knobs: bits 8.. of args.impl (benchmark sweeps), env overrides, else the measured heuristics
+  const int flags = (a.impl >> 8) & 0xff;  // 1: no row-halo grouping, 2: no resident weights, 4: two CTAs/SM, 8: no chunk merge
+  static const int env_flags = [] {
+    const char* e = getenv("W2C_CONV_PERS_FLAGS");
+    return e ? atoi(e) : -1;
+  }();
+  const int f = (a.impl >> 8) ? flags : (env_flags >= 0 ? env_flags : 0);
+  bool grouping = !(f & 1) && tn == 1 && tw >= 8;
+  const bool allow_resident = !(f & 2);
+  p.ctas_per_sm = (f & 4) ? 2 : 1;
+  const int chunks = plan.cin / kBlockK;
+  const int b_tile = bn * kBlockK * 2;
+  const int a_tile = th * tw * tn * 128;  // one un-grouped input box (16 KB)
+  const int fixed = 1024 /*align*/ + (2 * kMaxStages + kMaxResident + 4) * 8 + 16 + 2 * kMaxCout * 4;
+  const int budget = p.ctas_per_sm == 2 ? 113 * 1024 : kSmemBudget;
+  int max_ndh = 1;
+  size_t smem_bytes = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    build_groups(plan, grouping, p);
+    max_ndh = 1;
+    for (int cls = 0; cls < plan.num_classes; ++cls)
+      for (int g = 0; g < p.ngroups[cls]; ++g) max_ndh = p.groups[cls][g].ndh > max_ndh ? p.groups[cls][g].ndh : max_ndh;
+    const bool any_group = max_ndh > 1;
+    // un-grouped taps: merge two channel chunks per stage when the stage stays small (fewer commits per MMA)
+    p.cm = (!any_group && !(f & 8) && chunks % 2 == 0 && bn <= 128) ? 2 : 1;
+    const int max_units = any_group ? max_ndh : p.cm;
+    p.unit_a_bytes = any_group ? tw * tn * 128 : a_tile;
+    const int a_region = any_group ? ((th + max_ndh - 1) * tw * tn * 128 + 1023) / 1024 * 1024 : p.cm * a_tile;
+    p.n_staging = p.tma_store ? ((bn == 256 || p.ctas_per_sm == 2) ? 1 : 2) : 0;
+    const int avail = budget - fixed - p.n_staging * kStagingBytes;
+    const int slots = (planes == 2 ? 2 : 1) * p.total_taps * chunks;
+    p.b_resident = 0;
+    p.res_slots = 0;
+    p.b_off = a_region;
+    if (allow_resident && p.n_tiles == 1 && slots <= kMaxResident && p.total_tiles > 2 * 148) {
+      int stg = p.n_staging;
+      int left = avail - slots * b_tile;
+      if (left < 3 * a_region && stg == 2) stg = 1, left += kStagingBytes;
+      if (left >= 3 * a_region) {
+        p.b_resident = 1;
+        p.res_slots = slots;
+        p.n_staging = stg;
+        p.stage_bytes = a_region;
+        p.stages = left / a_region;
+      }
+    }
+    if (!p.b_resident) {
+      p.stage_bytes = a_region + max_units * b_tile;
+      p.stages = avail / p.stage_bytes;
+    }
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    smem_bytes = static_cast<size_t>(fixed) + p.n_staging * kStagingBytes +
+                 static_cast<size_t>(p.stages) * p.stage_bytes + static_cast<size_t>(p.res_slots) * b_tile;
+    if (p.stages >= 3 || !any_group) break;
+    grouping = false;  // the grouped stages are too fat for a 3-deep ring at this BLOCK_N: per-tap boxes instead
+  }
+  W2C_CHECK_ARG(p.stages >= 2, "conv_pers: shared memory plan failed (%d stages of %d bytes)", p.stages, p.stage_bytes);
+  W2C_CHECK_ARG(smem_bytes <= static_cast<size_t>(budget), "conv_pers: shared memory plan exceeds the budget");
+
+  // ---- tensor maps
   const cuuint64_t esz = 2;
-  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
-  if (plan.in_s == 1) {
-    const cuuint64_t dims[4] = {(cuuint64_t)plan.x_pix, (cuuint64_t)plan.in_w, (cuuint64_t)plan.in_h,
-                                (cuuint64_t)plan.n_img};
-    const cuuint64_t str[3] = {plan.x_pix * esz, (cuuint64_t)plan.in_w * plan.x_pix * esz,
-                               (cuuint64_t)plan.in_h * plan.in_w * plan.x_pix * esz};
-    int rc = encode_map(&p.a_map[0], plan.x, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-    if (rc) return rc;
-    for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
-  } else {
-    for (int ph = 0; ph < 2; ++ph)
-      for (int pw = 0; pw < 2; ++pw) {
+  for (int m = 0; m < 4; ++m)
+    for (int nd = 1; nd <= 3; ++nd) {
+      CUtensorMap* dst = &p.a_map[m][nd - 1];
+      if (plan.in_s == 1 && m > 0) {
+        *dst = p.a_map[0][nd - 1];
+        continue;
+      }
+      if (nd > max_ndh) {
+        *dst = p.a_map[m][0];
+        continue;
+      }
+      const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)(th + nd - 1), (cuuint32_t)tn};
+      int rc;
+      if (plan.in_s == 1) {
+        const cuuint64_t dims[4] = {(cuuint64_t)plan.x_pix, (cuuint64_t)plan.in_w, (cuuint64_t)plan.in_h,
+                                    (cuuint64_t)plan.n_img};
+        const cuuint64_t str[3] = {plan.x_pix * esz, (cuuint64_t)plan.in_w * plan.x_pix * esz,
+                                   (cuuint64_t)plan.in_h * plan.in_w * plan.x_pix * esz};
+        rc = encode_map(dst, plan.x, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+      } else {
+        const int ph = m >> 1, pw = m & 1;
         const cuuint64_t dims[4] = {(cuuint64_t)plan.x_pix, (cuuint64_t)plan.in_w / 2, (cuuint64_t)plan.in_h / 2,
                                     (cuuint64_t)plan.n_img};
         const cuuint64_t str[3] = {2 * plan.x_pix * esz, 2 * (cuuint64_t)plan.in_w * plan.x_pix * esz,
                                    (cuuint64_t)plan.in_h * plan.in_w * plan.x_pix * esz};
         const __nv_bfloat16* base = plan.x + (static_cast<size_t>(ph) * plan.in_w + pw) * plan.x_pix;
-        int rc = encode_map(&p.a_map[ph * 2 + pw], base, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-        if (rc) return rc;
+        rc = encode_map(dst, base, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
       }
-  }
+      if (rc) return rc;
+    }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)plan.ktot, (cuuint64_t)plan.cout_pad * planes};
     const cuuint64_t str[1] = {plan.ktot * esz};
@@ -457,11 +649,11 @@ int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t
   }
 
   switch (bn) {
-    case 256: return launch_pers<256, 4>(p, stream);
-    case 128: return launch_pers<128, 5>(p, stream);
-    case 64: return launch_pers<64, 6>(p, stream);
-    case 32: return launch_pers<32, 6>(p, stream);
-    default: return launch_pers<16, 6>(p, stream);
+    case 256: return launch_pers<256>(p, smem_bytes, stream);
+    case 128: return launch_pers<128>(p, smem_bytes, stream);
+    case 64: return launch_pers<64>(p, smem_bytes, stream);
+    case 32: return launch_pers<32>(p, smem_bytes, stream);
+    default: return launch_pers<16>(p, smem_bytes, stream);
   }
 }
 

@@ -1,0 +1,468 @@
+// Persistent, warp-specialised tcgen05 implicit-GEMM convolution (the production conv kernel).
+//
+// Same math and operand layout as conv_tc.cu (per-tap TMA windows of the NHWC input, K-major packed weights, fp32
+// accumulation in TMEM, fused scale/shift(+residual)+ReLU), restructured after the first B200 profiles showed the
+// one-tile-per-CTA kernel paying ~10 us of prologue + unoverlapped epilogue per tile on the small-K layers
+// (20k-80k CTAs per launch) and issuing 16-byte scattered stores:
+//   * one CTA per SM loops over tiles (static round-robin, n-tile fastest so concurrent CTAs share input windows);
+//     barriers, the TMEM allocation and the scale/shift tables are set up once per CTA
+//   * the accumulator is double-buffered in TMEM (2 x BLOCK_N columns): the MMA warp starts tile i+1 while the
+//     epilogue warps drain tile i
+//   * the epilogue converts to bf16, writes a [128 pixel][64 channel] 128B-swizzled staging tile and ONE thread
+//     issues a TMA tensor store per 64 channels (full-line writes, edge tiles clipped by the TMA unit); the
+//     transposed conv writes through four parity-strided output tensor maps
+//   warp 0: TMA producer   warp 1: MMA issuer + TMEM owner   warps 2-5: epilogue
+#include "conv_plan.cuh"
+#include "ptx.cuh"
+
+namespace w2c {
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, CUtensorMapL2promotion promo);
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kAStageBytes = kBlockM * kBlockK * 2;
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr int kStagingBytes = kBlockM * 64 * 2;  // [128 px][64 ch] bf16
+constexpr int kMaxCout = 512;
+
+struct PersParams {
+  CUtensorMap a_map[4];
+  CUtensorMap b_map;
+  CUtensorMap y_map[4];
+  ConvPlan plan;
+  int tw, th, tn;
+  int tiles_w, tiles_h, tiles_img;
+  int n_tiles, m_tiles, total_tiles;
+  int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+};
+
+template <int BLOCK_N, int STAGES>
+struct PersSmem {
+  static constexpr int kNumStaging = BLOCK_N >= 64 ? (BLOCK_N == 256 ? 1 : 2) : 0;
+  static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kAOff = 0;
+  static constexpr int kBOff = STAGES * kAStageBytes;
+  static constexpr int kStgOff = kBOff + STAGES * kBStageBytes;
+  static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2]
+  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
+  static constexpr int kScaleOff = kTmemPtrOff + 8;
+  static constexpr int kShiftOff = kScaleOff + kMaxCout * 4;
+  static constexpr int kTotal = kShiftOff + kMaxCout * 4;
+  static constexpr int kDynamicBytes = kTotal + 1024;
+};
+
+struct TileCoord {
+  int cls, n0, w0, h0, i0;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const PersParams& p, int t, int block_n) {
+  TileCoord c;
+  const int n_tile = t % p.n_tiles;
+  t /= p.n_tiles;
+  int m = t % p.m_tiles;
+  c.cls = t / p.m_tiles;
+  c.n0 = n_tile * block_n;
+  c.w0 = (m % p.tiles_w) * p.tw;
+  m /= p.tiles_w;
+  c.h0 = (m % p.tiles_h) * p.th;
+  c.i0 = (m / p.tiles_h) * p.tn;
+  return c;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __grid_constant__ PersParams p) {
+  using L = PersSmem<BLOCK_N, STAGES>;
+  constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  constexpr uint32_t kStageTx = kAStageBytes + L::kBStageBytes;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
+  float* s_scale = reinterpret_cast<float*>(smem + L::kScaleOff);
+  float* s_shift = reinterpret_cast<float*>(smem + L::kShiftOff);
+
+  const ConvPlan& pl = p.plan;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunks = pl.cin / kBlockK;
+  const int npass = pl.act == W2C_ACT_BF16X2 ? 3 : 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&p.b_map);
+    ptx::prefetch_tensormap(&p.a_map[0]);
+    for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full_bar[s], 1), ptx::mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < 2; ++s) ptx::mbar_init(&tfull_bar[s], 1), ptx::mbar_init(&tempty_bar[s], kEpiThreads);
+    ptx::fence_barrier_init();
+  } else if (warp == 1) {
+    ptx::tmem_alloc(tmem_ptr, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(p, t, BLOCK_N);
+        const int ntaps = pl.ntaps[tc.cls];
+        for (int pass = 0; pass < npass; ++pass) {
+          const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
+          const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
+          for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
+            const Tap tp = pl.taps[tc.cls][tp_i];
+            const CUtensorMap* amap = &p.a_map[tp.map];
+            for (int ch = 0; ch < chunks; ++ch) {
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+              ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * kAStageBytes, a_c0 + ch * kBlockK,
+                               tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
+              ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
+                               tp.wtap * pl.cin + ch * kBlockK, b_row);
+              if (++stage == STAGES) stage = 0, phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
+      const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+        const TileCoord tc = decode_tile(p, t, BLOCK_N);
+        const int num_kb = npass * pl.ntaps[tc.cls] * chunks;
+        const int acc = it & 1;
+        ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * kAStageBytes) >> 4);
+          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * L::kBStageBytes) >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            ptx::umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        ptx::umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5, 128 threads) =====================
+    const int et = threadIdx.x - 64;  // 0..127
+    for (int c = et; c < kMaxCout; c += kEpiThreads) {
+      const bool ok = c < pl.cout;
+      s_scale[c] = ok ? pl.scale[c] : 0.f;
+      s_shift[c] = ok ? pl.shift[c] : 0.f;
+    }
+    ptx::named_bar_sync(1, kEpiThreads);
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % p.tw;
+    const int lh = (row / p.tw) % p.th;
+    const int li = row / (p.tw * p.th);
+    const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
+    int it = 0;
+    int unit = 0;  // staging-buffer rotation counter
+    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = decode_tile(p, t, BLOCK_N);
+      const int acc = it & 1;
+      const int mw = tc.w0 + lw, mh = tc.h0 + lh, img = tc.i0 + li;
+      const bool valid = mw < pl.wm && mh < pl.hm && img < pl.n_img;
+      const int oh = mh * pl.out_s + pl.cls_oh[tc.cls];
+      const int ow = mw * pl.out_s + pl.cls_ow[tc.cls];
+      const size_t pix = (static_cast<size_t>(img) * pl.out_h + oh) * pl.out_w + ow;
+      ptx::mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
+
+      if constexpr (L::kNumStaging > 0) {
+        if (p.tma_store) {
+#pragma unroll 1
+          for (int g = 0; g < BLOCK_N / 64; ++g) {
+            const int cb = tc.n0 + g * 64;
+            if (cb >= pl.cout) break;
+            uint32_t r[64];
+            ptx::tmem_ld_32x32b_x32(t_row + g * 64, r);
+            ptx::tmem_ld_32x32b_x32(t_row + g * 64 + 32, r + 32);
+            ptx::tmem_ld_wait();
+            float v[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) v[j] = fmaf(__uint_as_float(r[j]), s_scale[cb + j], s_shift[cb + j]);
+            if (pl.residual && valid) {
+              const __nv_bfloat16* rp = pl.residual + pix * pl.y_pix + pl.y_coffset + cb;
+              for (int pln = 0; pln < planes; ++pln)
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(rp + pln * pl.y_cstride + c8 * 8);
+                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float2 f = __bfloat1622float2(rb[j]);
+                    v[c8 * 8 + 2 * j] += f.x, v[c8 * 8 + 2 * j + 1] += f.y;
+                  }
+                }
+            }
+            if (pl.relu) {
+#pragma unroll
+              for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            for (int pln = 0; pln < planes; ++pln, ++unit) {
+              uint8_t* stg = smem + L::kStgOff + (unit % L::kNumStaging) * kStagingBytes;
+              // the TMA store that last used this staging tile must have finished reading it
+              if (et == 0) ptx::bulk_wait_group_read<L::kNumStaging - 1>();
+              ptx::named_bar_sync(1, kEpiThreads);
+#pragma unroll
+              for (int c8 = 0; c8 < 8; ++c8) {
+                uint4 pk;
+                __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
+                  const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+                  if (pln == 0) {
+                    pb[j] = hi;
+                  } else {
+                    const float2 hf = __bfloat1622float2(hi);
+                    pb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                  }
+                }
+                *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
+              }
+              ptx::fence_proxy_async();
+              ptx::named_bar_sync(1, kEpiThreads);
+              if (et == 0) {
+                ptx::tma_store_4d(&p.y_map[tc.cls], stg, pl.y_coffset + cb + pln * pl.y_cstride, tc.w0, tc.h0, tc.i0);
+                ptx::bulk_commit_group();
+              }
+            }
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          continue;
+        }
+      }
+
+      // ---- direct-store epilogue: fp32 NCHW logits, or NHWC when cout is not a multiple of 64
+      constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += kChunk) {
+        uint32_t r[kChunk];
+        if constexpr (kChunk == 32)
+          ptx::tmem_ld_32x32b_x32(t_row + c0, r);
+        else
+          ptx::tmem_ld_32x32b_x16(t_row + c0, r);
+        ptx::tmem_ld_wait();
+        const int cb = tc.n0 + c0;
+        if (cb >= pl.cout) break;
+        float v[kChunk];
+#pragma unroll
+        for (int j = 0; j < kChunk; ++j)
+          v[j] = fmaf(__uint_as_float(r[j]), s_scale[min(cb + j, kMaxCout - 1)], s_shift[min(cb + j, kMaxCout - 1)]);
+        if (pl.out_fmt == W2C_OUT_NCHW_F32) {
+          if (valid) {
+            float* y = static_cast<float*>(pl.y);
+            const size_t plane = static_cast<size_t>(pl.out_h) * pl.out_w;
+            const size_t base = static_cast<size_t>(img) * pl.cout * plane + static_cast<size_t>(oh) * pl.out_w + ow;
+#pragma unroll
+            for (int j = 0; j < kChunk; ++j)
+              if (cb + j < pl.cout) y[base + (cb + j) * plane] = pl.relu ? fmaxf(v[j], 0.f) : v[j];
+          }
+        } else if (valid) {
+          __nv_bfloat16* ypix = static_cast<__nv_bfloat16*>(pl.y) + pix * pl.y_pix + pl.y_coffset + cb;
+          const __nv_bfloat16* rpix = pl.residual ? pl.residual + pix * pl.y_pix + pl.y_coffset + cb : nullptr;
+#pragma unroll
+          for (int g = 0; g < kChunk / 8; ++g) {
+            if (cb + g * 8 >= pl.cout) break;
+            if (rpix) {
+              for (int pln = 0; pln < planes; ++pln) {
+                const uint4 rv = *reinterpret_cast<const uint4*>(rpix + pln * pl.y_cstride + g * 8);
+                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float2 f = __bfloat1622float2(rb[j]);
+                  v[g * 8 + 2 * j] += f.x, v[g * 8 + 2 * j + 1] += f.y;
+                }
+              }
+            }
+            uint4 hv, lv;
+            __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
+            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float a = v[g * 8 + 2 * j], b = v[g * 8 + 2 * j + 1];
+              if (pl.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+              hb[j] = __floats2bfloat162_rn(a, b);
+              const float2 hf = __bfloat1622float2(hb[j]);
+              lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            }
+            *reinterpret_cast<uint4*>(ypix + g * 8) = hv;
+            if (planes == 2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty_bar[acc]);
+    }
+    if (et == 0) ptx::bulk_wait_group<0>();  // all TMA stores have landed before the CTA retires
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+template <int BLOCK_N, int STAGES>
+int launch_persv1(const PersParams& p, cudaStream_t stream) {
+  using L = PersSmem<BLOCK_N, STAGES>;
+  static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_pers: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_persv1_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynamicBytes, stream>>>(p);
+  W2C_CHECK_LAUNCH("conv_persv1_kernel");
+  return W2C_OK;
+}
+
+}  // namespace
+
+bool conv_persv1_supported(const ConvPlan& plan) { return plan.cout <= kMaxCout; }
+
+int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream) {
+  PersParams p;
+  p.plan = plan;
+  const int planes = plan.act == W2C_ACT_BF16X2 ? 2 : 1;
+  W2C_CHECK_ARG(plan.cout <= kMaxCout, "conv_pers: cout=%d exceeds %d", plan.cout, kMaxCout);
+
+  int tw = plan.wm >= 16 ? 16 : pow2_ceil(plan.wm);
+  int th = pow2_ceil(plan.hm);
+  if (th > kBlockM / tw) th = kBlockM / tw;
+  const int tn = kBlockM / (tw * th);
+  p.tw = tw, p.th = th, p.tn = tn;
+  p.tiles_w = ceil_div(plan.wm, tw);
+  p.tiles_h = ceil_div(plan.hm, th);
+  p.tiles_img = ceil_div(plan.n_img, tn);
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+
+  int bn = a.block_n;
+  if (bn == 0) {
+    if (plan.cout_pad % 256 == 0)
+      bn = 256;
+    else if (plan.cout_pad % 128 == 0)
+      bn = 128;
+    else if (plan.cout_pad % 64 == 0)
+      bn = 64;
+    else if (plan.cout_pad % 32 == 0)
+      bn = 32;
+    else
+      bn = 16;
+    // not enough tiles to occupy the SMs at this width: narrower tiles
+    while (bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148) bn /= 2;
+  }
+  W2C_CHECK_ARG(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: block_n=%d not supported", bn);
+  W2C_CHECK_ARG(plan.cout_pad % bn == 0, "conv: block_n=%d does not divide cout_pad=%d", bn, plan.cout_pad);
+  p.n_tiles = plan.cout_pad / bn;
+  p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
+  p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
+
+  const cuuint64_t esz = 2;
+  const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+  if (plan.in_s == 1) {
+    const cuuint64_t dims[4] = {(cuuint64_t)plan.x_pix, (cuuint64_t)plan.in_w, (cuuint64_t)plan.in_h,
+                                (cuuint64_t)plan.n_img};
+    const cuuint64_t str[3] = {plan.x_pix * esz, (cuuint64_t)plan.in_w * plan.x_pix * esz,
+                               (cuuint64_t)plan.in_h * plan.in_w * plan.x_pix * esz};
+    int rc = encode_map(&p.a_map[0], plan.x, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (rc) return rc;
+    for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+  } else {
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const cuuint64_t dims[4] = {(cuuint64_t)plan.x_pix, (cuuint64_t)plan.in_w / 2, (cuuint64_t)plan.in_h / 2,
+                                    (cuuint64_t)plan.n_img};
+        const cuuint64_t str[3] = {2 * plan.x_pix * esz, 2 * (cuuint64_t)plan.in_w * plan.x_pix * esz,
+                                   (cuuint64_t)plan.in_h * plan.in_w * plan.x_pix * esz};
+        const __nv_bfloat16* base = plan.x + (static_cast<size_t>(ph) * plan.in_w + pw) * plan.x_pix;
+        int rc = encode_map(&p.a_map[ph * 2 + pw], base, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+        if (rc) return rc;
+      }
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)plan.ktot, (cuuint64_t)plan.cout_pad * planes};
+    const cuuint64_t str[1] = {plan.ktot * esz};
+    const cuuint32_t bbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)bn};
+    int rc = encode_map(&p.b_map, plan.w, 2, dims, str, bbox, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+    if (rc) return rc;
+  }
+  if (p.tma_store) {
+    // output maps: [128 px][64 ch] boxes of the NHWC output; a transposed conv writes one output-parity class
+    // per tile through a map that strides two pixels in H and W
+    const cuuint32_t ybox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
+    const __nv_bfloat16* y = static_cast<const __nv_bfloat16*>(plan.y);
+    for (int cls = 0; cls < plan.num_classes; ++cls) {
+      const int s = plan.out_s;
+      const cuuint64_t dims[4] = {(cuuint64_t)plan.y_pix, (cuuint64_t)plan.out_w / s, (cuuint64_t)plan.out_h / s,
+                                  (cuuint64_t)plan.n_img};
+      const cuuint64_t str[3] = {(cuuint64_t)s * plan.y_pix * esz, (cuuint64_t)s * plan.out_w * plan.y_pix * esz,
+                                 (cuuint64_t)plan.out_h * plan.out_w * plan.y_pix * esz};
+      const __nv_bfloat16* base = y + (static_cast<size_t>(plan.cls_oh[cls]) * plan.out_w + plan.cls_ow[cls]) * plan.y_pix;
+      int rc = encode_map(&p.y_map[cls], base, 4, dims, str, ybox, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+      if (rc) return rc;
+    }
+    for (int cls = plan.num_classes; cls < 4; ++cls) p.y_map[cls] = p.y_map[0];
+  } else {
+    for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
+  }
+
+  switch (bn) {
+    case 256: return launch_persv1<256, 4>(p, stream);
+    case 128: return launch_persv1<128, 5>(p, stream);
+    case 64: return launch_persv1<64, 6>(p, stream);
+    case 32: return launch_persv1<32, 6>(p, stream);
+    default: return launch_persv1<16, 6>(p, stream);
+  }
+}
+
+}  // namespace w2c

@@ -47,6 +47,8 @@ bool conv_halo_supported(const ConvPlan& plan);
 bool conv_halo_preferred(const ConvPlan& plan);
 int conv_halo_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+bool conv_persistent_preferred(const ConvPlan& plan);
 // conv_pers.cu
 bool conv_pers_supported(const ConvPlan& plan);
 int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);

@@ -459,13 +459,28 @@ bool conv_halo_preferred(const ConvPlan& plan) {
 }
 }  // namespace w2c
 
+namespace w2c {
+// Measured per-layer choice between the persistent kernel and the one-tile-per-CTA kernel
+// (profiles/r1_conv_sweep_v2_persistent.md): with narrow outputs (<= 64 channels) a stride-1 3x3 conv issues MMAs too
+// short for ONE issuing thread per SM to keep the pipe busy, and three co-resident one-tile CTAs (three issuers)
+// win; the same holds when there are too few tiles to give every persistent CTA at least two.
+bool conv_persistent_preferred(const ConvPlan& plan) {
+  const long long m_tiles = (static_cast<long long>(plan.n_img) * plan.hm * plan.wm + 127) / 128;
+  const int bn = plan.cout_pad % 256 == 0 ? 256 : plan.cout_pad % 128 == 0 ? 128 : 64;
+  const long long tiles = m_tiles * plan.num_classes * ((plan.cout_pad + bn - 1) / bn);
+  if (tiles < 2 * 148) return false;
+  if (plan.num_classes == 1 && plan.in_s == 1 && plan.cout_pad <= 64) return false;
+  return true;
+}
+}  // namespace w2c
+
 extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream) {
   if (!args) return w2c::set_error(W2C_ERR_INVALID, "conv: args is NULL");
   w2c::ConvPlan plan;
   int rc = w2c::build_conv_plan(*args, plan);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  switch (args->impl) {
+  switch (args->impl & 0xff) {
     case W2C_IMPL_SIMT:
       return w2c::conv_simt_forward(plan, s);
     case W2C_IMPL_TC_TAPS:
@@ -477,6 +492,8 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
     case W2C_IMPL_TC_PERSIST:
       if (!w2c::conv_pers_supported(plan))
         return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the persistent kernel needs cout <= 512");
+      return w2c::conv_persv1_forward(*args, plan, s);
+    case 5:  // experimental: persistent kernel with row-halo tap groups / resident weights (conv_pers.cu)
       return w2c::conv_pers_forward(*args, plan, s);
     case W2C_IMPL_TCGEN05: {
       static const bool persist = [] {
@@ -484,7 +501,8 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
         return !(e && e[0] == '0');
       }();
       if (w2c::conv_halo_preferred(plan)) return w2c::conv_halo_forward(*args, plan, s);
-      if (persist && w2c::conv_pers_supported(plan)) return w2c::conv_pers_forward(*args, plan, s);
+      if (persist && w2c::conv_pers_supported(plan) && w2c::conv_persistent_preferred(plan))
+        return w2c::conv_persv1_forward(*args, plan, s);
       return w2c::conv_tc_forward(*args, plan, s);
     }
     default:

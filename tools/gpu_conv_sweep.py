@@ -61,6 +61,13 @@ def main():
         cp = ops.cout_pad(cout)
         if cp % 256 == 0:
             variants.append(("pers bn128", ops.IMPL_TC_PERSIST, 128))
+        if os.environ.get("SWEEP_FLAGS"):
+            # persistent-kernel tuning flags (bits 8.. of impl): 1 no row-halo, 2 no resident weights, 4 two CTAs/SM,
+            # 8 no chunk merge
+            variants = [("taps", ops.IMPL_TC_TAPS, 0)]
+            for fl in [int(v) for v in os.environ["SWEEP_FLAGS"].split(",")]:
+                variants.append(("exp f%d" % fl, 5 | (fl << 8) | (1 << 16), 0))  # experimental conv_pers.cu
+            cp = 1
         if os.environ.get("SWEEP_QUICK") == "1":
             variants = variants[:3]
             cp = 1
@@ -68,7 +75,7 @@ def main():
             variants.append(("taps bn256", ops.IMPL_TC_TAPS, 256))
         if cp % 128 == 0:
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
-        if kind != 1:
+        if kind != 1 and not os.environ.get("SWEEP_FLAGS"):
             variants.append(("halo", ops.IMPL_TC_HALO, 0))
             if cp % 128 == 0 and kind == 0:
                 variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
