@@ -25,8 +25,7 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kAStageBytes = kBlockM * kBlockK * 2;
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiThreads = 128;  // one epilogue warpgroup (TMEM lane quadrants 0..3)
 constexpr int kStagingBytes = kBlockM * 64 * 2;  // [128 px][64 ch] bf16
 constexpr int kMaxCout = 512;
 
@@ -39,14 +38,27 @@ struct PersParams {
   int tiles_w, tiles_h, tiles_img;
   int n_tiles, m_tiles, total_tiles;
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+  int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
 };
 
-template <int BLOCK_N, int STAGES>
+// GROUP = k-blocks per pipeline stage. 1: one filter tap per stage (16 KB input window + one weight tile).
+// 3 ("row-halo", 3x3 stride-1 convs on 8x16 tiles): the three taps of one filter COLUMN share one input box of
+// 8+2 rows; tap kh reads it kh rows further down = +kh*2048 B, still 1024-byte aligned, so it is just another UMMA
+// descriptor start at full operand bandwidth. One barrier round trip and ONE tcgen05.commit then cover 12 MMAs
+// instead of 4, and the activations cross L2 -> SM 3.75x instead of 9x per tile.
+// EG = epilogue warpgroups. 2: warps 2-5 drain accumulator 0 (even tiles) while warps 6-9 drain accumulator 1 (odd
+// tiles), each with its own staging tile: the small-K layers are epilogue-bound with one group (ncu: 64->11 logits
+// layer 9 % tensor active, epilogue serialising ~2000 cycles per tile).
+template <int BLOCK_N, int STAGES, int GROUP, int EG>
 struct PersSmem {
-  static constexpr int kNumStaging = BLOCK_N >= 64 ? (BLOCK_N == 256 ? 1 : 2) : 0;
-  static constexpr int kBStageBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kThreads = 64 + EG * kEpiThreads;
+  static constexpr int kNumStaging = BLOCK_N >= 64 ? ((EG == 1 && (BLOCK_N == 256 || (GROUP == 3 && BLOCK_N == 128) || STAGES <= 3)) ? 1 : 2) : 0;
+  static constexpr int kABoxBytes = GROUP == 3 ? (8 + 2) * 16 * 128 : kAStageBytes;
+  static constexpr int kAStage = GROUP == 3 ? 20 * 1024 : kAStageBytes;
+  static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kBStageBytes = GROUP * kBTileBytes;
   static constexpr int kAOff = 0;
-  static constexpr int kBOff = STAGES * kAStageBytes;
+  static constexpr int kBOff = STAGES * kAStage;
   static constexpr int kStgOff = kBOff + STAGES * kBStageBytes;
   static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2]
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
@@ -74,11 +86,11 @@ __device__ __forceinline__ TileCoord decode_tile(const PersParams& p, int t, int
   return c;
 }
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __grid_constant__ PersParams p) {
-  using L = PersSmem<BLOCK_N, STAGES>;
+template <int BLOCK_N, int STAGES, int GROUP, int EG>
+__global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(const __grid_constant__ PersParams p) {
+  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG>;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
-  constexpr uint32_t kStageTx = kAStageBytes + L::kBStageBytes;
+  constexpr uint32_t kStageTx = L::kABoxBytes + L::kBStageBytes;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -121,17 +133,37 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
         for (int pass = 0; pass < npass; ++pass) {
           const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
           const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
-          for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
-            const Tap tp = pl.taps[tc.cls][tp_i];
-            const CUtensorMap* amap = &p.a_map[tp.map];
-            for (int ch = 0; ch < chunks; ++ch) {
-              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-              ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
-              ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * kAStageBytes, a_c0 + ch * kBlockK,
-                               tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
-              ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
-                               tp.wtap * pl.cin + ch * kBlockK, b_row);
-              if (++stage == STAGES) stage = 0, phase ^= 1;
+          if constexpr (GROUP == 3) {
+            // 3x3 stride-1 conv: filter column kw -> one box of th+2 rows starting one row above the tile
+            // (a_map[1]); its three weight tiles (kh = 0,1,2) land behind each other in the stage
+            for (int kw = 0; kw < 3; ++kw) {
+              int a_c = a_c0;
+              int b_k = kw * pl.cin;
+              for (int ch = 0; ch < chunks; ++ch, a_c += kBlockK, b_k += kBlockK) {
+                uint8_t* sb = smem + L::kBOff + stage * L::kBStageBytes;
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+                ptx::tma_load_4d(&p.a_map[1], &full_bar[stage], smem + L::kAOff + stage * L::kAStage, a_c,
+                                 tc.w0 + kw - 1, tc.h0 - 1, tc.i0);
+#pragma unroll
+                for (int kh = 0; kh < 3; ++kh)
+                  ptx::tma_load_2d(&p.b_map, &full_bar[stage], sb + kh * L::kBTileBytes, b_k + kh * 3 * pl.cin, b_row);
+                if (++stage == STAGES) stage = 0, phase ^= 1;
+              }
+            }
+          } else {
+            for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
+              const Tap tp = pl.taps[tc.cls][tp_i];
+              const CUtensorMap* amap = &p.a_map[tp.map];
+              for (int ch = 0; ch < chunks; ++ch) {
+                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+                ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * L::kAStage, a_c0 + ch * kBlockK,
+                                 tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
+                ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
+                                 tp.wtap * pl.cin + ch * kBlockK, b_row);
+                if (++stage == STAGES) stage = 0, phase ^= 1;
+              }
             }
           }
         }
@@ -148,7 +180,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
       int it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
         const TileCoord tc = decode_tile(p, t, BLOCK_N);
-        const int num_kb = npass * pl.ntaps[tc.cls] * chunks;
+        const int num_kb = npass * (pl.ntaps[tc.cls] / GROUP) * chunks;  // stages per tile
         const int acc = it & 1;
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
@@ -156,11 +188,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * kAStageBytes) >> 4);
+          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * L::kAStage) >> 4);
           const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * L::kBStageBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k)
-            ptx::umma_bf16(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+          for (int u = 0; u < GROUP; ++u) {
+            // unit u of a row-halo stage: the input box u rows further down (2048 B), the u-th weight tile
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              ptx::umma_bf16(d_tmem, a_desc + (u * (2048 >> 4) + 2 * k), b_desc + (u * (L::kBTileBytes >> 4) + 2 * k),
+                             idesc, (kb | u | k) != 0);
+          }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
@@ -170,23 +207,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
   } else {
     // ===================== epilogue (warps 2..5, 128 threads) =====================
     const int et = threadIdx.x - 64;  // 0..127
-    for (int c = et; c < kMaxCout; c += kEpiThreads) {
+    for (int c = et; c < kMaxCout; c += EG * kEpiThreads) {
       const bool ok = c < pl.cout;
       s_scale[c] = ok ? pl.scale[c] : 0.f;
       s_shift[c] = ok ? pl.shift[c] : 0.f;
     }
-    ptx::named_bar_sync(1, kEpiThreads);
+    ptx::named_bar_sync(3, EG * kEpiThreads);
+    const int eg = EG == 2 ? (warp - 2) >> 2 : 0;  // this thread's epilogue group
+    const int bar_id = 1 + eg;
+    const bool elected = (et & (kEpiThreads - 1)) == 0;
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int lw = row % p.tw;
     const int lh = (row / p.tw) % p.th;
     const int li = row / (p.tw * p.th);
     const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
-    int it = 0;
-    int unit = 0;  // staging-buffer rotation counter
-    for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+    int it = eg;
+    int unit = 0;  // staging-buffer rotation counter (EG == 1)
+    for (int t = blockIdx.x + eg * gridDim.x; t < p.total_tiles; t += EG * gridDim.x, it += EG) {
       const TileCoord tc = decode_tile(p, t, BLOCK_N);
-      const int acc = it & 1;
+      const int acc = it & 1;  // == eg when EG == 2
       const int mw = tc.w0 + lw, mh = tc.h0 + lh, img = tc.i0 + li;
       const bool valid = mw < pl.wm && mh < pl.hm && img < pl.n_img;
       const int oh = mh * pl.out_s + pl.cls_oh[tc.cls];
@@ -228,10 +268,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
               for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
             }
             for (int pln = 0; pln < planes; ++pln, ++unit) {
-              uint8_t* stg = smem + L::kStgOff + (unit % L::kNumStaging) * kStagingBytes;
+              uint8_t* stg = smem + L::kStgOff + (EG == 2 ? eg : unit % L::kNumStaging) * kStagingBytes;
               // the TMA store that last used this staging tile must have finished reading it
-              if (et == 0) ptx::bulk_wait_group_read<L::kNumStaging - 1>();
-              ptx::named_bar_sync(1, kEpiThreads);
+              if (elected) ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
+              ptx::named_bar_sync(bar_id, kEpiThreads);
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
                 uint4 pk;
@@ -250,8 +290,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
               }
               ptx::fence_proxy_async();
-              ptx::named_bar_sync(1, kEpiThreads);
-              if (et == 0) {
+              ptx::named_bar_sync(bar_id, kEpiThreads);
+              if (elected) {
                 ptx::tma_store_4d(&p.y_map[tc.cls], stg, pl.y_coffset + cb + pln * pl.y_cstride, tc.w0, tc.h0, tc.i0);
                 ptx::bulk_commit_group();
               }
@@ -324,7 +364,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_persv1_kernel(const __gri
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
     }
-    if (et == 0) ptx::bulk_wait_group<0>();  // all TMA stores have landed before the CTA retires
+    if (elected) ptx::bulk_wait_group<0>();  // all TMA stores have landed before the CTA retires
   }
 
   ptx::tc_fence_before();
@@ -342,13 +382,13 @@ int pow2_ceil(int v) {
   return r;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, int GROUP = 1, int EG = 1>
 int launch_persv1(const PersParams& p, cudaStream_t stream) {
-  using L = PersSmem<BLOCK_N, STAGES>;
+  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG>;
   static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES>,
+    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
     if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_pers: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -360,8 +400,9 @@ int launch_persv1(const PersParams& p, cudaStream_t stream) {
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_persv1_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynamicBytes, stream>>>(p);
+  const int want = num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
+  const int grid = p.total_tiles < want ? p.total_tiles : want;
+  conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_persv1_kernel");
   return W2C_OK;
 }
@@ -406,6 +447,13 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   p.n_tiles = plan.cout_pad / bn;
   p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
+  // row-halo stages: 3x3 stride-1 convs on full 8x16 tiles, BLOCK_N <= 128 (at 256 three weight tiles do not fit)
+  static const bool allow_row_halo = [] {
+    const char* e = getenv("W2C_CONV_ROWHALO");
+    return !(e && e[0] == '0');
+  }();
+  const bool row_halo = allow_row_halo && !((a.impl >> 8) & 1) && plan.num_classes == 1 && plan.in_s == 1 &&
+                        plan.ntaps[0] == 9 && tn == 1 && tw == 16 && th == 8 && bn <= 128;
 
   const cuuint64_t esz = 2;
   const cuuint32_t box[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
@@ -417,6 +465,11 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     int rc = encode_map(&p.a_map[0], plan.x, 4, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (rc) return rc;
     for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    if (row_halo) {  // a_map[1]: the same tensor with a box two rows taller (the three vertical taps of a column)
+      const cuuint32_t box3[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)(th + 2), 1};
+      rc = encode_map(&p.a_map[1], plan.x, 4, dims, str, box3, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+      if (rc) return rc;
+    }
   } else {
     for (int ph = 0; ph < 2; ++ph)
       for (int pw = 0; pw < 2; ++pw) {
@@ -456,12 +509,40 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
   }
 
+  // two epilogue warpgroups unless disabled (impl flag bit 1 / env) - see PersSmem
+  static const bool allow_eg2 = [] {
+    const char* e = getenv("W2C_CONV_EPI2");
+    return !(e && e[0] == '0');
+  }();
+  const bool eg2 = allow_eg2 && !((a.impl >> 8) & 2);
+  int cps = ((a.impl >> 8) & 8) ? 3 : ((a.impl >> 8) & 4) ? 2 : 1;
+  if (!(a.impl >> 8) && row_halo && bn == 16) cps = 3;  // default for the logits layer (sweep: r1_conv_sweep_v4)
+  if (!((row_halo && bn == 16) || bn == 64)) cps = 1;
+  if (bn == 64 && cps > 2) cps = 2;
+  p.ctas_per_sm = cps;
+  if (row_halo) {
+    switch (bn) {
+      case 128: return launch_persv1<128, 3, 3, 1>(p, stream);
+      case 64:
+        if (cps >= 2) return launch_persv1<64, 2, 3, 1>(p, stream);
+        return eg2 ? launch_persv1<64, 4, 3, 2>(p, stream) : launch_persv1<64, 4, 3, 1>(p, stream);
+      case 32: return eg2 ? launch_persv1<32, 5, 3, 2>(p, stream) : launch_persv1<32, 5, 3, 1>(p, stream);
+      default:
+        // 11-channel logits layer: its MMAs (N = 16) are so short that ONE issuing thread per SM is the limit
+        // (ncu: 9 % tensor active, ~1800 issue cycles per tile). Small stages -> three CTAs (three issuers) per SM.
+        if (cps == 3) return launch_persv1<16, 2, 3, 1>(p, stream);
+        if (cps == 2) return launch_persv1<16, 3, 3, 1>(p, stream);
+        return eg2 ? launch_persv1<16, 6, 3, 2>(p, stream) : launch_persv1<16, 6, 3, 1>(p, stream);
+    }
+  }
   switch (bn) {
-    case 256: return launch_persv1<256, 4>(p, stream);
-    case 128: return launch_persv1<128, 5>(p, stream);
-    case 64: return launch_persv1<64, 6>(p, stream);
-    case 32: return launch_persv1<32, 6>(p, stream);
-    default: return launch_persv1<16, 6>(p, stream);
+    case 256: return launch_persv1<256, 4, 1, 1>(p, stream);
+    case 128: return eg2 ? launch_persv1<128, 5, 1, 2>(p, stream) : launch_persv1<128, 5, 1, 1>(p, stream);
+    case 64:
+      if (cps >= 2) return launch_persv1<64, 3, 1, 1>(p, stream);
+      return eg2 ? launch_persv1<64, 6, 1, 2>(p, stream) : launch_persv1<64, 6, 1, 1>(p, stream);
+    case 32: return eg2 ? launch_persv1<32, 6, 1, 2>(p, stream) : launch_persv1<32, 6, 1, 1>(p, stream);
+    default: return eg2 ? launch_persv1<16, 6, 1, 2>(p, stream) : launch_persv1<16, 6, 1, 1>(p, stream);
   }
 }
 

@@ -57,7 +57,13 @@ def main():
             y = torch.empty(N, ho, ho, ops.planes_of(act) * cout, device=dev, dtype=torch.bfloat16)
         m = N * (ho * ho if kind != 2 else h * h)
         flop = 2.0 * m * cin * cout * 9
-        variants = [("taps", ops.IMPL_TC_TAPS, 0), ("pers", ops.IMPL_TC_PERSIST, 0)]
+        variants = [("taps", ops.IMPL_TC_TAPS, 0), ("pers", ops.IMPL_TC_PERSIST, 0),
+                    ("pers 1-epi-group", ops.IMPL_TC_PERSIST | (2 << 8), 0)]
+        if cout == 64:
+            variants += [("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
+        if cout <= 16:
+            variants += [("pers 1cta/sm", ops.IMPL_TC_PERSIST | (16 << 8), 0),
+                         ("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
         cp = ops.cout_pad(cout)
         if cp % 256 == 0:
             variants.append(("pers bn128", ops.IMPL_TC_PERSIST, 128))
