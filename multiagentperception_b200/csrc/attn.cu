@@ -88,12 +88,22 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
   }
   __syncthreads();
   if (a.wq) {
-    for (int i = threadIdx.x; i < a.n_q * a.k_dim; i += blockDim.x) {
-      const int j = i / a.k_dim, d = i % a.k_dim;
+    // one thread per key dimension d: the row W[d,:] is read once and applied to all (<= 8) queries
+    for (int d = threadIdx.x; d < a.k_dim; d += blockDim.x) {
       const float* wr = a.wq + static_cast<size_t>(d) * a.q_dim;
-      float acc = 0.f;
-      for (int e = 0; e < a.q_dim; ++e) acc = fmaf(__ldg(wr + e), s_q[j * a.q_dim + e], acc);
-      s_qt[i] = acc + (a.bq ? a.bq[d] : 0.f);
+      float acc[kMaxAgents];
+#pragma unroll
+      for (int j = 0; j < kMaxAgents; ++j) acc[j] = 0.f;
+      for (int e = 0; e < a.q_dim; ++e) {
+        const float wv = __ldg(wr + e);
+#pragma unroll
+        for (int j = 0; j < kMaxAgents; ++j)
+          if (j < a.n_q) acc[j] = fmaf(wv, s_q[j * a.q_dim + e], acc[j]);
+      }
+      const float bias = a.bq ? a.bq[d] : 0.f;
+#pragma unroll
+      for (int j = 0; j < kMaxAgents; ++j)
+        if (j < a.n_q) s_qt[j * a.k_dim + d] = acc[j] + bias;
     }
   } else {
     for (int i = threadIdx.x; i < a.n_q * a.k_dim; i += blockDim.x) s_qt[i] = s_q[i];
@@ -272,8 +282,8 @@ extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream)
   int pix = static_cast<int>((96 * 1024) / per_pix);
   if (pix < 1) pix = 1;
   if (pix > a.hw) pix = a.hw;
-  // keep enough CTAs in flight for small batches: at least ~2 waves worth when the scene allows it
-  while (pix > 4 && static_cast<long long>(a.b_sz) * ceil_div(a.hw, pix) < 296) pix = (pix + 1) / 2;
+  // every CTA recomputes its scene's score matrix, so fewer / fatter CTAs are better as long as the SMs are covered
+  while (pix > 4 && static_cast<long long>(a.b_sz) * ceil_div(a.hw, pix) < 120) pix = (pix + 1) / 2;
   p.pix_per_cta = pix;
   p.slabs = ceil_div(a.hw, pix);
   const size_t smem = head + per_pix * pix;

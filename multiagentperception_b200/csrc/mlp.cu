@@ -34,17 +34,43 @@ __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restric
     float acc[kNeurons][kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) acc[0][r] = acc[1][r] = 0.f;
-    for (int k = tid; k < n_feat; k += 256) {
-      const float a = __ldg(w0 + k), b = __ldg(w1 + k);
+    // 8 consecutive k per thread and iteration: one 16-byte activation load per row (plus one for the lo plane),
+    // two 32-byte weight loads per neuron (n_feat % 256 == 0, so a group of 8 never straddles a pixel)
+    for (int k = tid * 8; k < n_feat; k += 256 * 8) {
+      float wa[8], wb[8];
+      {
+        const float4 a0 = __ldg(reinterpret_cast<const float4*>(w0 + k)), a1 = __ldg(reinterpret_cast<const float4*>(w0 + k + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(w1 + k)), b1 = __ldg(reinterpret_cast<const float4*>(w1 + k + 4));
+        wa[0] = a0.x, wa[1] = a0.y, wa[2] = a0.z, wa[3] = a0.w, wa[4] = a1.x, wa[5] = a1.y, wa[6] = a1.z, wa[7] = a1.w;
+        wb[0] = b0.x, wb[1] = b0.y, wb[2] = b0.z, wb[3] = b0.w, wb[4] = b1.x, wb[5] = b1.y, wb[6] = b1.z, wb[7] = b1.w;
+      }
       const size_t off = static_cast<size_t>(k >> 8) * (256 * planes) + (k & 255);  // pixel * pixel-stride + channel
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         if (m0 + r < m) {
           const __nv_bfloat16* p = feat + static_cast<size_t>(m0 + r) * row_elems + off;
-          float x = __bfloat162float(p[0]);
-          if (planes == 2) x += __bfloat162float(p[256]);
-          acc[0][r] = fmaf(x, a, acc[0][r]);
-          acc[1][r] = fmaf(x, b, acc[1][r]);
+          const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p));
+          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+          float x[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = __bfloat1622float2(hb[e]);
+            x[2 * e] = f.x, x[2 * e + 1] = f.y;
+          }
+          if (planes == 2) {
+            const uint4 lv = __ldg(reinterpret_cast<const uint4*>(p + 256));
+            const __nv_bfloat162* lb = reinterpret_cast<const __nv_bfloat162*>(&lv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(lb[e]);
+              x[2 * e] += f.x, x[2 * e + 1] += f.y;
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            acc[0][r] = fmaf(x[e], wa[e], acc[0][r]);
+            acc[1][r] = fmaf(x[e], wb[e], acc[1][r]);
+          }
         }
       }
     }

@@ -6,24 +6,33 @@
 // pixel (coalesced 4-byte reads of three channel planes), convert to bf16 and write one 64-byte K-major row of the
 // A operand straight into shared memory in the 128B-swizzle layout the UMMA descriptor expects (software im2col).
 // One thread then issues two tcgen05.mma (M=128, N=COUT, K=16) — six in the bf16x3 precision — and the same 128
-// threads read the accumulators back from TMEM, apply scale/shift/ReLU and store 128-bit vectors. A CTA loops over
-// pixel tiles with the next tile's taps prefetched into registers during the epilogue; several CTAs per SM overlap
-// gather, MMA and store phases. COUT = 128 is two encoders' first layers fused (the image is read once).
+// threads read the accumulators back from TMEM, apply scale/shift/ReLU, write [128 px][64 ch] swizzled staging
+// tiles and one thread issues a TMA tensor store per tile (the direct version issued 16-byte stores at a 256-byte
+// lane stride and ran at a third of the HBM rate). A CTA loops over pixel tiles with the next tile's taps
+// prefetched into registers during the epilogue; several CTAs per SM overlap gather, MMA and store phases.
+// COUT = 128 is two encoders' first layers fused (the image is read once).
 #include "common.cuh"
 #include "ptx.cuh"
 
 namespace w2c {
+
+int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+               const cuuint32_t* box, CUtensorMapL2promotion promo);
+
 namespace {
 
-constexpr int kTile = 128;     // pixels per tile = UMMA M
-constexpr int kRowBytes = 128; // one swizzle row; only the first 64 B (K = 32 bf16) are used
+constexpr int kTile = 128;      // pixels per tile = UMMA M
+constexpr int kRowBytes = 128;  // one swizzle row; only the first 64 B (K = 32 bf16) of an operand row are used
+constexpr int kStagingBytes = kTile * 64 * 2;
+constexpr int kNumStaging = 2;
 
 template <int COUT>
 struct StemSmem {
-  static constexpr int kA = kTile * kRowBytes;   // 16 KB per plane
+  static constexpr int kA = kTile * kRowBytes;  // 16 KB per plane
   static constexpr int kB = COUT * kRowBytes;
   static constexpr int kAHi = 0, kALo = kA, kBHi = 2 * kA, kBLo = 2 * kA + kB;
-  static constexpr int kBar = 2 * kA + 2 * kB;
+  static constexpr int kStg = 2 * kA + 2 * kB;
+  static constexpr int kBar = kStg + kNumStaging * kStagingBytes;
   static constexpr int kTmemPtr = kBar + 8;
   static constexpr int kScale = kTmemPtr + 8;
   static constexpr int kShift = kScale + COUT * 4;
@@ -60,10 +69,10 @@ __device__ __forceinline__ void gather_taps(const float* __restrict__ x, size_t 
 }
 
 template <int COUT>
-__global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant__ CUtensorMap y_map,
+                                                           const float* __restrict__ x, const float* __restrict__ w,
                                                            const float* __restrict__ scale,
-                                                           const float* __restrict__ shift,
-                                                           __nv_bfloat16* __restrict__ y, int b_sz, int n_agents,
+                                                           const float* __restrict__ shift, int b_sz, int n_agents,
                                                            int c_total, int c_first, int h, int wpx, int act,
                                                            int num_tiles) {
   using L = StemSmem<COUT>;
@@ -96,6 +105,7 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const float* __restri
   }
   for (int i = tid; i < COUT; i += kTile) s_scale[i] = scale[i], s_shift[i] = shift[i];
   if (tid == 0) {
+    ptx::prefetch_tensormap(&y_map);
     ptx::mbar_init(bar, 1);
     ptx::fence_barrier_init();
   }
@@ -119,6 +129,7 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const float* __restri
   if (tile < num_tiles) gather_taps(x, static_cast<size_t>(tile) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
   uint32_t phase = 0;
   const int planes = x3 ? 2 : 1;
+  int unit = 0;  // staging-buffer rotation
   for (; tile < num_tiles; tile += gridDim.x) {
     // ---- software im2col: this thread's pixel -> row `tid` of the A tile(s)
 #pragma unroll
@@ -153,41 +164,56 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const float* __restri
       ptx::umma_commit(bar);
     }
     // prefetch the next tile's taps while the MMA runs and before the store phase
-    const size_t p = static_cast<size_t>(tile) * kTile + tid;
     const int next = tile + gridDim.x;
     if (next < num_tiles) gather_taps(x, static_cast<size_t>(next) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
 
     ptx::mbar_wait(bar, phase);
     phase ^= 1;
     ptx::tc_fence_after();
-    __nv_bfloat16* ypix = y + p * (static_cast<size_t>(COUT) * planes);
 #pragma unroll 1
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + c0, r);
+    for (int g = 0; g < COUT / 64; ++g) {
+      uint32_t r[64];
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 64, r);
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 64 + 32, r + 32);
       ptx::tmem_ld_wait();
-      if (p < total) {
+      float v[64];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 hv, lv;
-          __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
-          __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+      for (int j = 0; j < 64; ++j)
+        v[j] = fmaxf(fmaf(__uint_as_float(r[j]), s_scale[g * 64 + j], s_shift[g * 64 + j]), 0.f);
+      for (int pln = 0; pln < planes; ++pln, ++unit) {
+        uint8_t* stg = smem + L::kStg + (unit % kNumStaging) * kStagingBytes;
+        if (tid == 0) ptx::bulk_wait_group_read<kNumStaging - 1>();  // the store that last used this tile has read it
+        __syncthreads();
+#pragma unroll
+        for (int c8 = 0; c8 < 8; ++c8) {
+          uint4 pk;
+          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int c = c0 + g * 8 + 2 * j;
-            const float a = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2 * j]), s_scale[c], s_shift[c]), 0.f);
-            const float b = fmaxf(fmaf(__uint_as_float(r[g * 8 + 2 * j + 1]), s_scale[c + 1], s_shift[c + 1]), 0.f);
-            hb[j] = __floats2bfloat162_rn(a, b);
-            const float2 hf = __bfloat1622float2(hb[j]);
-            lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+            if (pln == 0) {
+              pb[j] = hi;
+            } else {
+              const float2 hf = __bfloat1622float2(hi);
+              pb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            }
           }
-          *reinterpret_cast<uint4*>(ypix + c0 + g * 8) = hv;
-          if (x3) *reinterpret_cast<uint4*>(ypix + COUT + c0 + g * 8) = lv;
+          *reinterpret_cast<uint4*>(stg + sw128(tid, c8)) = pk;
+        }
+        ptx::fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+          // rows of the output viewed as [total pixels][COUT * planes]; rows past the end are clipped by the TMA unit
+          ptx::tma_store_2d(&y_map, stg, pln * COUT + g * 64, tile * kTile);
+          ptx::bulk_commit_group();
         }
       }
     }
     // the next iteration's __syncthreads (after its smem writes) orders these TMEM reads before the next MMA
+    ptx::tc_fence_before();
   }
+  if (tid == 0) ptx::bulk_wait_group<0>();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -208,12 +234,20 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
   }
   const size_t total = static_cast<size_t>(b) * n_agents * h * wpx;
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
-  // resident CTAs per SM are bounded by TMEM (512 columns) and shared memory (~64-80 KB each)
-  const int per_sm = COUT <= 64 ? 3 : 2;
-  int grid = 148 * per_sm;
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  CUtensorMap y_map;
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)COUT * planes, (cuuint64_t)total};
+    const cuuint64_t str[1] = {(cuuint64_t)COUT * planes * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTile};
+    int rc = encode_map(&y_map, y, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+  }
+  // resident CTAs per SM are bounded by shared memory (~100 KB each) and TMEM (COUT columns each)
+  int grid = 148 * 2;
   if (grid > num_tiles) grid = num_tiles;
-  stem3x3_tc_kernel<COUT><<<grid, kTile, L::kDynamic, stream>>>(x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b,
-                                                                n_agents, c_total, c_first, h, wpx, act, num_tiles);
+  stem3x3_tc_kernel<COUT><<<grid, kTile, L::kDynamic, stream>>>(y_map, x, w, scale, shift, b, n_agents, c_total,
+                                                                c_first, h, wpx, act, num_tiles);
   W2C_CHECK_LAUNCH("stem3x3_tc_kernel");
   return W2C_OK;
 }
