@@ -30,14 +30,17 @@ template <int COUT>
 struct StemSmem {
   static constexpr int kA = kTile * kRowBytes;  // 16 KB per plane
   static constexpr int kB = COUT * kRowBytes;
-  static constexpr int kAHi = 0, kALo = kA, kBHi = 2 * kA, kBLo = 2 * kA + kB;
-  static constexpr int kStg = 2 * kA + 2 * kB;
+  // the lo-plane operand tiles (bf16x3 only) sit at the end, so the bf16 launch requests less shared memory
+  static constexpr int kAHi = 0, kBHi = kA;
+  static constexpr int kStg = kA + kB;
   static constexpr int kBar = kStg + kNumStaging * kStagingBytes;
   static constexpr int kTmemPtr = kBar + 8;
   static constexpr int kScale = kTmemPtr + 8;
   static constexpr int kShift = kScale + COUT * 4;
-  static constexpr int kTotal = kShift + COUT * 4;
-  static constexpr int kDynamic = kTotal + 1024;
+  static constexpr int kLoBase = (kShift + COUT * 4 + 1023) / 1024 * 1024;
+  static constexpr int kALo = kLoBase, kBLo = kLoBase + kA;
+  static constexpr int kDynamicBf16 = kLoBase + 1024;
+  static constexpr int kDynamic = kLoBase + kA + kB + 1024;
 };
 
 // byte offset of 16-byte chunk `c` of row `r` in a 128B-swizzled K-major tile
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant
       lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + sw128(co, c)) = hv;
-    *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
+    if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
   }
   for (int i = tid; i < COUT; i += kTile) s_scale[i] = scale[i], s_shift[i] = shift[i];
   if (tid == 0) {
@@ -243,10 +246,11 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
     int rc = encode_map(&y_map, y, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
   }
-  // resident CTAs per SM are bounded by shared memory (~100 KB each) and TMEM (COUT columns each)
-  int grid = 148 * 2;
+  // resident CTAs per SM are bounded by shared memory (bf16: ~66 KB, bf16x3: ~98 KB each) and TMEM (COUT columns)
+  const int smem_bytes = planes == 2 ? L::kDynamic : L::kDynamicBf16;
+  int grid = 148 * (planes == 2 ? 2 : 3);
   if (grid > num_tiles) grid = num_tiles;
-  stem3x3_tc_kernel<COUT><<<grid, kTile, L::kDynamic, stream>>>(y_map, x, w, scale, shift, b, n_agents, c_total,
+  stem3x3_tc_kernel<COUT><<<grid, kTile, smem_bytes, stream>>>(y_map, x, w, scale, shift, b, n_agents, c_total,
                                                                 c_first, h, wpx, act, num_tiles);
   W2C_CHECK_LAUNCH("stem3x3_tc_kernel");
   return W2C_OK;
