@@ -318,7 +318,7 @@ def run_b200(args):
                 "algorithmic_tflop_per_step_per_gpu": conv_tflop_step}
 
     if args.layer_table and rank == 0:
-        write_layer_table(args.layer_table, conv_prog, dev)
+        write_layer_table(args.layer_table, prog, dev)
 
     if rank != 0:
         if world > 1:
@@ -344,36 +344,47 @@ def run_b200(args):
     return 0
 
 
-def write_layer_table(path, conv_prog, dev):
-    """Per-launch device time of every tensor-core conv (eager, CUDA events around each launch)."""
+def write_layer_table(path, prog, dev):
+    """Per-launch device time of every call of the step program (eager, CUDA events around each call; the tensor-core
+    convs with their geometry and TFLOP/s, the other kernels by entry point)."""
     import ctypes
     import torch
+    lib_conv = prog._lib.w2c_conv_bnrelu_fwd
     rows = []
-    for fn, args in conv_prog.calls:
-        a = args[0]._obj
+    for fn, args in prog.calls:
+        if fn is None:
+            continue  # host op (collective)
         best = 1e9
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize(dev)
             e0.record()
-            fn(*args, ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            if args is None:
+                fn(stream)
+            else:
+                fn(*args, stream)
             e1.record()
             torch.cuda.synchronize(dev)
             best = min(best, e0.elapsed_time(e1))
-        taps = 1 if a.kind in (3, 4) else 9
-        if a.kind in (1, 4):
-            m = a.n * (a.h_in // 2) * (a.w_in // 2)
+        if fn is lib_conv:
+            a = args[0]._obj
+            taps = 1 if a.kind in (3, 4) else 9
+            if a.kind in (1, 4):
+                m = a.n * (a.h_in // 2) * (a.w_in // 2)
+            else:
+                m = a.n * a.h_in * a.w_in
+            flop = 2.0 * m * a.cin * a.cout * taps
+            names = {0: "conv3x3 s1", 1: "conv3x3 s2", 2: "deconv3x3 s2", 3: "conv1x1", 4: "conv1x1 s2"}
+            rows.append((names[a.kind], a.n, a.h_in, a.w_in, a.cin, a.cout, best, "%.1f" % (flop / (best * 1e-3) / 1e12)))
         else:
-            m = a.n * a.h_in * a.w_in
-        flop = 2.0 * m * a.cin * a.cout * taps
-        rows.append((a.kind, a.n, a.h_in, a.w_in, a.cin, a.cout, best, flop / (best * 1e-3) / 1e12))
+            rows.append((getattr(fn, "__name__", "host-side torch op"), "", "", "", "", "", best, ""))
     os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
     with open(path, "w") as f:
-        f.write("| # | kind | n | h_in | w_in | cin | cout | ms (best of 5, eager, CUDA events) | TFLOP/s |\n")
+        f.write("| # | launch | n | h_in | w_in | cin | cout | ms (best of 5, eager, CUDA events) | TFLOP/s |\n")
         f.write("|---|---|---|---|---|---|---|---|---|\n")
-        names = {0: "conv3x3 s1", 1: "conv3x3 s2", 2: "deconv3x3 s2", 3: "conv1x1", 4: "conv1x1 s2"}
         for i, r in enumerate(rows):
-            f.write("| %d | %s | %d | %d | %d | %d | %d | %.4f | %.1f |\n" % (i, names[r[0]], *r[1:6], r[6], r[7]))
+            f.write("| %d | %s | %s | %s | %s | %s | %s | %.4f | %s |\n" % ((i,) + r[:6] + (r[6], r[7])))
         f.write("\ntotal %.3f ms\n" % sum(r[6] for r in rows))
 
 

@@ -89,6 +89,10 @@ typedef struct w2c_conv_args {
   int32_t out_fmt;  /* W2C_OUT_* */
   int32_t impl;     /* W2C_IMPL_TCGEN05 (product) ... W2C_IMPL_SIMT (on-GPU cross-check, tests only) */
   int32_t block_n;  /* 0 = auto; else 16/32/64/128/256 */
+  /* W2C_OUT_NCHW_F32 only, cout <= 32: also write labels[n][h_out][w_out] = argmax_co y (first maximal index; the
+   * `outputs.data.max(1)[1]` of Trainer_MIMOcom.evaluate, trainer.py:804) from the same accumulators.  With labels
+   * set, y may be NULL (label map only: the eval loop never reads the logits).  NULL = no label map. */
+  uint8_t* labels;
 } w2c_conv_args;
 
 int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream);
@@ -131,6 +135,29 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
                          int32_t cout, int32_t act, w2c_stream_t stream);
 
 /*
+ * The same first layer reading the loader's RAW frames: uint8 RGB HWC [b][agents_total][h][w][3] (what
+ * airsim_loader.__getitem__ holds after cv2.cvtColor, airsim_loader.py:496), with the loader transform
+ * (airsim_loader.py:515-527: RGB->BGR, - mean, / 255, HWC->CHW) and the trainer's channel concat (trainer.py:651)
+ * fused into the im2col gather.  lut fp32 [3][256]: lut[ci][v] = float32((float64(v) - mean[ci]) / 255) for BGR channel
+ * ci, built by the caller in float64 exactly as the loader computes it, so the result equals w2c_stem_conv3x3_fwd on
+ * the transformed fp32 tensor bit for bit.  Agents [agent_first, agent_first + n_agents) are convolved.
+ */
+int w2c_stem_conv3x3_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
+                            const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
+                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                            w2c_stream_t stream);
+
+/* ---- evaluation-loop glue ----------------------------------------------------------- */
+/* labels[n][p] = argmax_c logits[n][c][p] (first maximal index), fp32 NCHW logits -> uint8; trainer.py:804. */
+int w2c_argmax_labels_fwd(const float* logits, uint8_t* labels, int32_t n, int32_t c, int64_t hw,
+                          w2c_stream_t stream);
+/* runningScore._fast_hist accumulated on the device (metrics.py:99-108): hist[n_class*gt + pred] += 1 for every
+ * pixel with 0 <= gt < n_class.  hist int64 [n_class][n_class], caller-zeroed; gt uint8 or int64 [count]. */
+enum { W2C_GT_U8 = 0, W2C_GT_I64 = 1 };
+int w2c_confusion_update(const uint8_t* pred, const void* gt, int32_t gt_dtype, int64_t count, int32_t n_class,
+                         int64_t* hist, w2c_stream_t stream);
+
+/*
  * Key / query heads: flatten -> Linear -> ReLU -> Linear -> ReLU -> Linear.  Replaces km_generator.forward and
  * linear.forward (agent.py:145-178).  feat is the NHWC policy feature map [m][s][s][256]; w0 must already be
  * permuted to NHWC flatten order (the reference flattens NCHW, agent.py:158).
@@ -139,6 +166,24 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
 int w2c_kq_mlp_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const float* w0, const float* b0,
                    const float* w1, const float* b1, const float* w2, const float* b2, int32_t out_dim,
                    float* out, float* ws, w2c_stream_t stream);
+
+/*
+ * Up to two heads over the SAME feature map in one pair of launches (key_net and query_net both read the policy
+ * map, agent.py:1132-1147).  ws: fp32 scratch of n_heads*m*256 floats.  Results are bit-identical to
+ * w2c_kq_mlp_fwd called per head.
+ */
+typedef struct w2c_mlp_head {
+  const float* w0; /* [256][n_feat], NHWC flatten order */
+  const float* b0;
+  const float* w1; /* [128][256] */
+  const float* b1;
+  const float* w2; /* [out_dim][128] */
+  const float* b2;
+  float* out;      /* [m][out_dim] */
+  int32_t out_dim;
+} w2c_mlp_head;
+int w2c_kq_mlp_heads_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const w2c_mlp_head* heads,
+                         int32_t n_heads, float* ws, w2c_stream_t stream);
 
 /*
  * Communication graph + fusion.  Replaces MIMOGeneralDotProductAttention.forward (agent.py:252-286),

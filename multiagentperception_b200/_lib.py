@@ -18,6 +18,7 @@ OUT_NHWC, OUT_NCHW_F32 = 0, 1
 IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST = 0, 1, 2, 3, 4
 CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2 = 0, 1, 2, 3, 4
 FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX = 0, 1, 2
+GT_U8, GT_I64 = 0, 1
 
 
 class ConvArgs(ctypes.Structure):
@@ -29,6 +30,7 @@ class ConvArgs(ctypes.Structure):
         ("x_cstride", c_i32), ("x_coffset", c_i32),
         ("y_cstride", c_i32), ("y_coffset", c_i32),
         ("kind", c_i32), ("relu", c_i32), ("act", c_i32), ("out_fmt", c_i32), ("impl", c_i32), ("block_n", c_i32),
+        ("labels", c_vp),
     ]
 
 
@@ -49,6 +51,12 @@ class AttnArgs(ctypes.Structure):
     ]
 
 
+class MlpHead(ctypes.Structure):
+    """struct w2c_mlp_head (include/w2c.h)."""
+    _fields_ = [("w0", c_vp), ("b0", c_vp), ("w1", c_vp), ("b1", c_vp), ("w2", c_vp), ("b2", c_vp), ("out", c_vp),
+                ("out_dim", c_i32)]
+
+
 # symbol -> (restype, argtypes); every symbol include/w2c.h declares must be listed here (tests check both ways)
 _SIGNATURES = {
     "w2c_version": (ctypes.c_int, []),
@@ -60,7 +68,11 @@ _SIGNATURES = {
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "w2c_fold_bn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp]),
     "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 8 + [c_vp]),
+    "w2c_stem_conv3x3_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 8 + [c_vp]),
+    "w2c_argmax_labels_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, c_vp]),
+    "w2c_confusion_update": (ctypes.c_int, [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp]),
     "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
+    "w2c_kq_mlp_heads_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(MlpHead), c_i32, c_vp, c_vp]),
     "w2c_attn_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs), c_vp]),
     "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 7 + [c_vp]),
     "w2c_maxpool3x3s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),

@@ -37,6 +37,8 @@ struct PersParams {
   int tw, th, tn;
   int tiles_w, tiles_h, tiles_img;
   int n_tiles, m_tiles, total_tiles;
+  int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
+  int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
   int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
 };
@@ -49,19 +51,24 @@ struct PersParams {
 // EG = epilogue warpgroups. 2: warps 2-5 drain accumulator 0 (even tiles) while warps 6-9 drain accumulator 1 (odd
 // tiles), each with its own staging tile: the small-K layers are epilogue-bound with one group (ncu: 64->11 logits
 // layer 9 % tensor active, epilogue serialising ~2000 cycles per tile).
-template <int BLOCK_N, int STAGES, int GROUP, int EG>
+// RES = weight tiles kept RESIDENT in shared memory (0: weights stream through the ring with the activations).
+// The 64-channel layers re-fetched their whole weight matrix (72-144 KB) from L2 for every 128-pixel tile - a third
+// to two thirds of their L2 -> SM bytes, on layers ncu shows bound by bytes in flight (23 % tensor, 50 % DRAM).
+// With RES = ktot/64 the producer loads every [BLOCK_N][64] weight tile once per CTA (slot = k/64) and the ring
+// carries activations only.
+template <int BLOCK_N, int STAGES, int GROUP, int EG, int RES>
 struct PersSmem {
   static constexpr int kThreads = 64 + EG * kEpiThreads;
   static constexpr int kNumStaging = BLOCK_N >= 64 ? ((EG == 1 && (BLOCK_N == 256 || (GROUP == 3 && BLOCK_N == 128) || STAGES <= 3)) ? 1 : 2) : 0;
   static constexpr int kABoxBytes = GROUP == 3 ? (8 + 2) * 16 * 128 : kAStageBytes;
   static constexpr int kAStage = GROUP == 3 ? 20 * 1024 : kAStageBytes;
   static constexpr int kBTileBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kBStageBytes = GROUP * kBTileBytes;
+  static constexpr int kBStageBytes = RES > 0 ? 0 : GROUP * kBTileBytes;
   static constexpr int kAOff = 0;
-  static constexpr int kBOff = STAGES * kAStage;
-  static constexpr int kStgOff = kBOff + STAGES * kBStageBytes;
-  static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2]
-  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 4) * 8;
+  static constexpr int kBOff = STAGES * kAStage;  // weight ring, or the resident weight tiles
+  static constexpr int kStgOff = kBOff + (RES > 0 ? RES * kBTileBytes : STAGES * kBStageBytes);
+  static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2] res
+  static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 5) * 8;
   static constexpr int kScaleOff = kTmemPtrOff + 8;
   static constexpr int kShiftOff = kScaleOff + kMaxCout * 4;
   static constexpr int kTotal = kShiftOff + kMaxCout * 4;
@@ -72,23 +79,31 @@ struct TileCoord {
   int cls, n0, w0, h0, i0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const PersParams& p, int t, int block_n) {
-  TileCoord c;
-  const int n_tile = t % p.n_tiles;
-  t /= p.n_tiles;
-  int m = t % p.m_tiles;
-  c.cls = t / p.m_tiles;
+// The it-th tile of this CTA. Groups (m-tile, n-tile; n fastest so concurrent CTAs share input windows) are dealt
+// round-robin; the output-parity classes of a transposed conv run back to back INSIDE the CTA, so the input window
+// of a group is fetched from HBM once (class-major order re-read the whole input per class: ncu 4x the bytes).
+__device__ __forceinline__ bool tile_at(const PersParams& p, int it, int block_n, TileCoord& c) {
+  const int g = blockIdx.x + (it >> p.cls_shift) * gridDim.x;
+  if (g >= p.groups) return false;
+  const int n_tile = g % p.n_tiles;
+  int m = g / p.n_tiles;
+  if (p.cls_shift) {
+    c.cls = it & 3;
+  } else {  // few tiles: classes stay separate work items (class slowest) so the CTAs share them evenly
+    c.cls = m / p.m_tiles;
+    m -= c.cls * p.m_tiles;
+  }
   c.n0 = n_tile * block_n;
   c.w0 = (m % p.tiles_w) * p.tw;
   m /= p.tiles_w;
   c.h0 = (m % p.tiles_h) * p.th;
   c.i0 = (m / p.tiles_h) * p.tn;
-  return c;
+  return true;
 }
 
-template <int BLOCK_N, int STAGES, int GROUP, int EG>
+template <int BLOCK_N, int STAGES, int GROUP, int EG, int RES>
 __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(const __grid_constant__ PersParams p) {
-  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG>;
+  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG, RES>;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   constexpr uint32_t kStageTx = L::kABoxBytes + L::kBStageBytes;
 
@@ -98,6 +113,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* res_bar = tempty_bar + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtrOff);
   float* s_scale = reinterpret_cast<float*>(smem + L::kScaleOff);
   float* s_shift = reinterpret_cast<float*>(smem + L::kShiftOff);
@@ -112,6 +128,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     ptx::prefetch_tensormap(&p.a_map[0]);
     for (int s = 0; s < STAGES; ++s) ptx::mbar_init(&full_bar[s], 1), ptx::mbar_init(&empty_bar[s], 1);
     for (int s = 0; s < 2; ++s) ptx::mbar_init(&tfull_bar[s], 1), ptx::mbar_init(&tempty_bar[s], kEpiThreads);
+    ptx::mbar_init(res_bar, 1);
     ptx::fence_barrier_init();
   } else if (warp == 1) {
     ptx::tmem_alloc(tmem_ptr, kTmemCols);
@@ -125,10 +142,15 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
+      if constexpr (RES > 0) {
+        ptx::mbar_arrive_expect_tx(res_bar, RES * L::kBTileBytes);
+        for (int s = 0; s < RES; ++s)
+          ptx::tma_load_2d(&p.b_map, res_bar, smem + L::kBOff + s * L::kBTileBytes, s * kBlockK, 0);
+      }
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(p, t, BLOCK_N);
+      TileCoord tc;
+      for (int it = 0; tile_at(p, it, BLOCK_N, tc); ++it) {
         const int ntaps = pl.ntaps[tc.cls];
         for (int pass = 0; pass < npass; ++pass) {
           const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
@@ -140,14 +162,17 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
               int a_c = a_c0;
               int b_k = kw * pl.cin;
               for (int ch = 0; ch < chunks; ++ch, a_c += kBlockK, b_k += kBlockK) {
-                uint8_t* sb = smem + L::kBOff + stage * L::kBStageBytes;
                 ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
                 ptx::tma_load_4d(&p.a_map[1], &full_bar[stage], smem + L::kAOff + stage * L::kAStage, a_c,
                                  tc.w0 + kw - 1, tc.h0 - 1, tc.i0);
+                if constexpr (RES == 0) {
+                  uint8_t* sb = smem + L::kBOff + stage * L::kBStageBytes;
 #pragma unroll
-                for (int kh = 0; kh < 3; ++kh)
-                  ptx::tma_load_2d(&p.b_map, &full_bar[stage], sb + kh * L::kBTileBytes, b_k + kh * 3 * pl.cin, b_row);
+                  for (int kh = 0; kh < 3; ++kh)
+                    ptx::tma_load_2d(&p.b_map, &full_bar[stage], sb + kh * L::kBTileBytes, b_k + kh * 3 * pl.cin,
+                                     b_row);
+                }
                 if (++stage == STAGES) stage = 0, phase ^= 1;
               }
             }
@@ -160,8 +185,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
                 ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * L::kAStage, a_c0 + ch * kBlockK,
                                  tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
-                ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
-                                 tp.wtap * pl.cin + ch * kBlockK, b_row);
+                if constexpr (RES == 0)
+                  ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
+                                   tp.wtap * pl.cin + ch * kBlockK, b_row);
                 if (++stage == STAGES) stage = 0, phase ^= 1;
               }
             }
@@ -173,33 +199,47 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     if (lane == 0) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      constexpr uint32_t kBTile16 = L::kBTileBytes >> 4;
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
       const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
       int stage = 0;
       uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
-        const TileCoord tc = decode_tile(p, t, BLOCK_N);
-        const int num_kb = npass * (pl.ntaps[tc.cls] / GROUP) * chunks;  // stages per tile
+      if constexpr (RES > 0) {
+        ptx::mbar_wait(res_bar, 0);  // the resident weight tiles have landed
+        ptx::tc_fence_after();
+      }
+      TileCoord tc;
+      for (int it = 0; tile_at(p, it, BLOCK_N, tc); ++it) {
         const int acc = it & 1;
         ptx::mbar_wait(&tempty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * L::kAStage) >> 4);
-          const uint64_t b_desc = b_desc0 + static_cast<uint64_t>((stage * L::kBStageBytes) >> 4);
+        const int nouter = npass * (GROUP == 3 ? 3 : pl.ntaps[tc.cls]);
+        uint32_t first = 0;
+        for (int o = 0; o < nouter; ++o) {
+          // resident weights: slot of (tap, chunk) = its k offset / 64
+          int slot0 = 0;
+          if constexpr (RES > 0) slot0 = (GROUP == 3 ? o : pl.taps[tc.cls][o].wtap) * chunks;
+          for (int ch = 0; ch < chunks; ++ch) {
+            ptx::mbar_wait(&full_bar[stage], phase);
+            ptx::tc_fence_after();
+            const uint64_t a_desc = a_desc0 + static_cast<uint64_t>((stage * L::kAStage) >> 4);
+            const uint64_t b_desc = RES > 0 ? b_desc0 + static_cast<uint64_t>((slot0 + ch) * kBTile16)
+                                            : b_desc0 + static_cast<uint64_t>((stage * L::kBStageBytes) >> 4);
 #pragma unroll
-          for (int u = 0; u < GROUP; ++u) {
-            // unit u of a row-halo stage: the input box u rows further down (2048 B), the u-th weight tile
+            for (int u = 0; u < GROUP; ++u) {
+              // unit u of a row-halo stage: the input box u rows further down (2048 B); its weight tile is the
+              // u-th of the stage, or (resident) tap kh = u of this filter column: 3 * chunks slots further
+              const uint32_t b_u = RES > 0 ? u * 3 * chunks * kBTile16 : u * kBTile16;
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              ptx::umma_bf16(d_tmem, a_desc + (u * (2048 >> 4) + 2 * k), b_desc + (u * (L::kBTileBytes >> 4) + 2 * k),
-                             idesc, (kb | u | k) != 0);
+              for (int k = 0; k < kBlockK / 16; ++k)
+                ptx::umma_bf16(d_tmem, a_desc + (u * (2048 >> 4) + 2 * k), b_desc + (b_u + 2 * k), idesc,
+                               first | u | k);
+            }
+            first = 1;
+            ptx::umma_commit(&empty_bar[stage]);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
           }
-          ptx::umma_commit(&empty_bar[stage]);
-          if (++stage == STAGES) stage = 0, phase ^= 1;
         }
         ptx::umma_commit(&tfull_bar[acc]);
       }
@@ -222,10 +262,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     const int lh = (row / p.tw) % p.th;
     const int li = row / (p.tw * p.th);
     const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
-    int it = eg;
     int unit = 0;  // staging-buffer rotation counter (EG == 1)
-    for (int t = blockIdx.x + eg * gridDim.x; t < p.total_tiles; t += EG * gridDim.x, it += EG) {
-      const TileCoord tc = decode_tile(p, t, BLOCK_N);
+    TileCoord tc;
+    for (int it = eg; tile_at(p, it, BLOCK_N, tc); it += EG) {
       const int acc = it & 1;  // == eg when EG == 2
       const int mw = tc.w0 + lw, mh = tc.h0 + lh, img = tc.i0 + li;
       const bool valid = mw < pl.wm && mh < pl.hm && img < pl.n_img;
@@ -263,7 +302,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                   }
                 }
             }
-            if (pl.relu) {
+            if (pl.relu && planes == 2) {  // (one plane: the ReLU rides in the bf16 conversion below)
 #pragma unroll
               for (int j = 0; j < 64; ++j) v[j] = fmaxf(v[j], 0.f);
             }
@@ -275,16 +314,27 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
                 uint4 pk;
-                __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+                uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+                if (planes == 1) {
+                  if (pl.relu) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
-                  const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
-                  if (pln == 0) {
-                    pb[j] = hi;
+                    for (int j = 0; j < 4; ++j) pw[j] = ptx::pack_relu_bf16x2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1]);
                   } else {
-                    const float2 hf = __bfloat1622float2(hi);
-                    pb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) pw[j] = ptx::pack_bf16x2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1]);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+                    if (pln == 0) {
+                      pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
+                    } else {
+                      const float2 hf = __bfloat1622float2(hi);
+                      const __nv_bfloat162 lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                      pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
+                    }
                   }
                 }
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
@@ -324,9 +374,26 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             float* y = static_cast<float*>(pl.y);
             const size_t plane = static_cast<size_t>(pl.out_h) * pl.out_w;
             const size_t base = static_cast<size_t>(img) * pl.cout * plane + static_cast<size_t>(oh) * pl.out_w + ow;
+            if (pl.relu) {
 #pragma unroll
-            for (int j = 0; j < kChunk; ++j)
-              if (cb + j < pl.cout) y[base + (cb + j) * plane] = pl.relu ? fmaxf(v[j], 0.f) : v[j];
+              for (int j = 0; j < kChunk; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (y) {
+#pragma unroll
+              for (int j = 0; j < kChunk; ++j)
+                if (cb + j < pl.cout) y[base + (cb + j) * plane] = v[j];
+            }
+            if (pl.labels && cb == 0) {
+              // every class of this pixel sits in this thread's registers (cout <= kChunk, checked on the host):
+              // first maximal index, like torch.max(1)[1]
+              float best = v[0];
+              int arg = 0;
+#pragma unroll
+              for (int j = 1; j < kChunk; ++j)
+                if (j < pl.cout && v[j] > best) best = v[j], arg = j;
+              pl.labels[static_cast<size_t>(img) * plane + static_cast<size_t>(oh) * pl.out_w + ow] =
+                  static_cast<uint8_t>(arg);
+            }
           }
         } else if (valid) {
           __nv_bfloat16* ypix = static_cast<__nv_bfloat16*>(pl.y) + pix * pl.y_pix + pl.y_coffset + cb;
@@ -382,13 +449,13 @@ int pow2_ceil(int v) {
   return r;
 }
 
-template <int BLOCK_N, int STAGES, int GROUP = 1, int EG = 1>
+template <int BLOCK_N, int STAGES, int GROUP = 1, int EG = 1, int RES = 0>
 int launch_persv1(const PersParams& p, cudaStream_t stream) {
-  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG>;
+  using L = PersSmem<BLOCK_N, STAGES, GROUP, EG, RES>;
   static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG>,
+    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
     if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_pers: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
@@ -401,8 +468,8 @@ int launch_persv1(const PersParams& p, cudaStream_t stream) {
     if (num_sms <= 0) num_sms = 148;
   }
   const int want = num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
-  const int grid = p.total_tiles < want ? p.total_tiles : want;
-  conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
+  const int grid = p.groups < want ? p.groups : want;
+  conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_persv1_kernel");
   return W2C_OK;
 }
@@ -444,8 +511,12 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   }
   W2C_CHECK_ARG(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: block_n=%d not supported", bn);
   W2C_CHECK_ARG(plan.cout_pad % bn == 0, "conv: block_n=%d does not divide cout_pad=%d", bn, plan.cout_pad);
+  W2C_CHECK_ARG(!plan.labels || plan.cout <= (bn < 32 ? 16 : 32), "conv: label map needs cout=%d within one %d-wide tile",
+                plan.cout, bn);
   p.n_tiles = plan.cout_pad / bn;
   p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
+  p.cls_shift = (plan.num_classes == 4 && p.m_tiles * p.n_tiles >= 8 * 148 && !((a.impl >> 8) & 128)) ? 2 : 0;
+  p.groups = p.cls_shift ? p.m_tiles * p.n_tiles : p.total_tiles;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
   // row-halo stages: 3x3 stride-1 convs on full 8x16 tiles, BLOCK_N <= 128 (at 256 three weight tiles do not fit)
   static const bool allow_row_halo = [] {
@@ -516,20 +587,31 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   }();
   const bool eg2 = allow_eg2 && !((a.impl >> 8) & 2);
   int cps = ((a.impl >> 8) & 8) ? 3 : ((a.impl >> 8) & 4) ? 2 : 1;
-  if (!(a.impl >> 8) && row_halo && bn == 16) cps = 3;  // default for the logits layer (sweep: r1_conv_sweep_v4)
+  if (!((a.impl >> 8) & (4 | 8 | 16)) && row_halo && bn == 16) cps = 3;  // default for the logits layer (sweep v4)
   if (!((row_halo && bn == 16) || bn == 64)) cps = 1;
   if (bn == 64 && cps > 2) cps = 2;
   p.ctas_per_sm = cps;
+  // resident weights (see PersSmem): single n-tile, one bf16 plane, every [bn][64] tile of the layer fits
+  static const bool allow_res = [] {
+    const char* e = getenv("W2C_CONV_RESIDENT");
+    return !(e && e[0] == '0');
+  }();
+  const int res_slots = plan.ktot / kBlockK;
+  const bool res_ok = allow_res && !((a.impl >> 8) & 32) && p.n_tiles == 1 && planes == 1;
   if (row_halo) {
     switch (bn) {
-      case 128: return launch_persv1<128, 3, 3, 1>(p, stream);
+      case 128:
+        if (res_ok && res_slots == 9) return launch_persv1<128, 3, 3, 1, 9>(p, stream);
+        return launch_persv1<128, 3, 3, 1>(p, stream);
       case 64:
+        if (res_ok && res_slots == 18 && ((a.impl >> 8) & 64)) return launch_persv1<64, 3, 3, 1, 18>(p, stream);
         if (cps >= 2) return launch_persv1<64, 2, 3, 1>(p, stream);
         return eg2 ? launch_persv1<64, 4, 3, 2>(p, stream) : launch_persv1<64, 4, 3, 1>(p, stream);
       case 32: return eg2 ? launch_persv1<32, 5, 3, 2>(p, stream) : launch_persv1<32, 5, 3, 1>(p, stream);
       default:
         // 11-channel logits layer: its MMAs (N = 16) are so short that ONE issuing thread per SM is the limit
         // (ncu: 9 % tensor active, ~1800 issue cycles per tile). Small stages -> three CTAs (three issuers) per SM.
+        if (cps == 3 && res_ok && res_slots == 9 && ((a.impl >> 8) & 64)) return launch_persv1<16, 2, 3, 1, 9>(p, stream);
         if (cps == 3) return launch_persv1<16, 2, 3, 1>(p, stream);
         if (cps == 2) return launch_persv1<16, 3, 3, 1>(p, stream);
         return eg2 ? launch_persv1<16, 6, 3, 2>(p, stream) : launch_persv1<16, 6, 3, 1>(p, stream);
@@ -540,6 +622,9 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     case 128: return eg2 ? launch_persv1<128, 5, 1, 2>(p, stream) : launch_persv1<128, 5, 1, 1>(p, stream);
     case 64:
       if (cps >= 2) return launch_persv1<64, 3, 1, 1>(p, stream);
+      // (resident weights measured 5-9 % SLOWER here - 64->64 s2 conv 0.469 vs 0.431 ms, deconv 0.636 vs 0.605: the
+      // per-tap slot lookup sits in the single MMA-issuing thread; opt-in only, profiles/r1_conv_sweep_v5_ab.md)
+      if (res_ok && res_slots == 9 && eg2 && ((a.impl >> 8) & 64)) return launch_persv1<64, 7, 1, 2, 9>(p, stream);
       return eg2 ? launch_persv1<64, 6, 1, 2>(p, stream) : launch_persv1<64, 6, 1, 1>(p, stream);
     case 32: return eg2 ? launch_persv1<32, 6, 1, 2>(p, stream) : launch_persv1<32, 6, 1, 1>(p, stream);
     default: return eg2 ? launch_persv1<16, 6, 1, 2>(p, stream) : launch_persv1<16, 6, 1, 1>(p, stream);

@@ -27,6 +27,7 @@ struct ConvPlan {
   const __nv_bfloat16* w;
   const __nv_bfloat16* residual;
   void* y;
+  uint8_t* labels;
   const float* scale;
   const float* shift;
   int n_img, hm, wm;     // M-space
@@ -55,7 +56,10 @@ int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t
 int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream);
 
 inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
-  W2C_CHECK_ARG(a.x && a.w && a.scale && a.shift && a.y, "conv: null pointer argument");
+  W2C_CHECK_ARG(a.x && a.w && a.scale && a.shift && (a.y || a.labels), "conv: null pointer argument");
+  W2C_CHECK_ARG(!a.labels || (a.out_fmt == W2C_OUT_NCHW_F32 && a.cout <= 32),
+                "conv: a label map needs the fp32 NCHW logits layout and cout <= 32 (got out_fmt=%d cout=%d)",
+                a.out_fmt, a.cout);
   W2C_CHECK_ARG(a.n > 0 && a.h_in > 0 && a.w_in > 0, "conv: bad image extent %dx%dx%d", a.n, a.h_in, a.w_in);
   W2C_CHECK_ARG(a.cin > 0 && a.cin % 64 == 0, "conv: cin=%d must be a positive multiple of 64", a.cin);
   W2C_CHECK_ARG(a.cout > 0, "conv: cout=%d", a.cout);
@@ -67,6 +71,7 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   p.w = static_cast<const __nv_bfloat16*>(a.w);
   p.residual = static_cast<const __nv_bfloat16*>(a.residual);
   p.y = a.y;
+  p.labels = a.labels;
   p.scale = a.scale;
   p.shift = a.shift;
   p.n_img = a.n;

@@ -483,6 +483,8 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
   int rc = w2c::build_conv_plan(*args, plan);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (plan.labels && (args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
+    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", args->impl & 0xff);
   switch (args->impl & 0xff) {
     case W2C_IMPL_SIMT:
       return w2c::conv_simt_forward(plan, s);
@@ -499,6 +501,11 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
     case 5:  // experimental: persistent kernel with row-halo tap groups / resident weights (conv_pers.cu)
       return w2c::conv_pers_forward(*args, plan, s);
     case W2C_IMPL_TCGEN05: {
+      if (plan.labels) {  // the fused label map lives in the persistent kernel's logits epilogue
+        if (!w2c::conv_pers_supported(plan))
+          return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: label map needs the persistent kernel (cout <= 512)");
+        return w2c::conv_persv1_forward(*args, plan, s);
+      }
       static const bool persist = [] {
         const char* e = getenv("W2C_CONV_PERSIST");
         return !(e && e[0] == '0');

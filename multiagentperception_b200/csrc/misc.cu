@@ -297,6 +297,48 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ eval-loop glue
+// labels[n][p] = argmax_c logits[n][c][p], first maximal index (torch.max(1)[1], trainer.py:804); one thread per
+// pixel, coalesced plane reads.
+__global__ void __launch_bounds__(256) argmax_labels_kernel(const float* __restrict__ logits,
+                                                            uint8_t* __restrict__ labels, int n, int c, size_t hw) {
+  const size_t total = static_cast<size_t>(n) * hw;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t img = i / hw, p = i % hw;
+    const float* src = logits + img * c * hw + p;
+    float best = src[0];
+    int arg = 0;
+    for (int k = 1; k < c; ++k) {
+      const float v = src[k * hw];
+      if (v > best) best = v, arg = k;
+    }
+    labels[i] = static_cast<uint8_t>(arg);
+  }
+}
+
+// runningScore._fast_hist (metrics.py:99-104): hist[n_class * gt + pred] += 1 over pixels with 0 <= gt < n_class.
+// Per-CTA shared-memory histogram, flushed with 64-bit global atomics.
+template <typename GT>
+__global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restrict__ pred, const GT* __restrict__ gt,
+                                                        size_t total, int n_class,
+                                                        unsigned long long* __restrict__ hist) {
+  extern __shared__ unsigned int s_hist[];
+  const int bins = n_class * n_class;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const long long g = static_cast<long long>(gt[i]);
+    const int pr = pred[i];
+    if (g >= 0 && g < n_class && pr < n_class) atomicAdd(&s_hist[static_cast<int>(g) * n_class + pr], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
+}
+
 }  // namespace
 }  // namespace w2c
 
@@ -359,6 +401,47 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
   stem3x3_kernel<32><<<grid_for(total, 256, 148 * 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
       x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, c_total, c_first, h, w_px, cout, act);
   W2C_CHECK_LAUNCH("stem3x3_kernel");
+  return W2C_OK;
+}
+
+int w2c_stem_conv3x3_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
+                            const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
+                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                            w2c_stream_t stream) {
+  W2C_CHECK_ARG(frames && lut && w && scale && shift && y, "stem3x3_u8: null pointer");
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3_u8: bad extent");
+  W2C_CHECK_ARG(agent_first >= 0 && agent_first + n_agents <= agents_total, "stem3x3_u8: agents [%d, %d) outside %d",
+                agent_first, agent_first + n_agents, agents_total);
+  W2C_CHECK_ARG(cout == 64 || cout == 128, "stem3x3_u8: cout=%d (64 or 128)", cout);
+  return stem3x3_tc_u8_forward(frames, lut, w, scale, shift, y, b, n_agents, agents_total, agent_first, h, w_px, cout,
+                               act, static_cast<cudaStream_t>(stream));
+}
+
+int w2c_argmax_labels_fwd(const float* logits, uint8_t* labels, int32_t n, int32_t c, int64_t hw,
+                          w2c_stream_t stream) {
+  W2C_CHECK_ARG(logits && labels && n > 0 && hw > 0, "argmax_labels: bad arguments");
+  W2C_CHECK_ARG(c > 0 && c <= 256, "argmax_labels: c=%d does not fit a uint8 label", c);
+  const size_t total = static_cast<size_t>(n) * hw;
+  argmax_labels_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(logits, labels, n, c,
+                                                                                           static_cast<size_t>(hw));
+  W2C_CHECK_LAUNCH("argmax_labels_kernel");
+  return W2C_OK;
+}
+
+int w2c_confusion_update(const uint8_t* pred, const void* gt, int32_t gt_dtype, int64_t count, int32_t n_class,
+                         int64_t* hist, w2c_stream_t stream) {
+  W2C_CHECK_ARG(pred && gt && hist && count > 0, "confusion: bad arguments");
+  W2C_CHECK_ARG(n_class > 0 && n_class <= 64, "confusion: n_class=%d (1..64)", n_class);
+  W2C_CHECK_ARG(gt_dtype == W2C_GT_U8 || gt_dtype == W2C_GT_I64, "confusion: gt_dtype=%d", gt_dtype);
+  const size_t smem = static_cast<size_t>(n_class) * n_class * sizeof(unsigned int);
+  const int grid = grid_for(static_cast<size_t>(count), 256 * 16, 148 * 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned long long* h = reinterpret_cast<unsigned long long*>(hist);
+  if (gt_dtype == W2C_GT_U8)
+    confusion_kernel<uint8_t><<<grid, 256, smem, s>>>(pred, static_cast<const uint8_t*>(gt), count, n_class, h);
+  else
+    confusion_kernel<long long><<<grid, 256, smem, s>>>(pred, static_cast<const long long*>(gt), count, n_class, h);
+  W2C_CHECK_LAUNCH("confusion_kernel");
   return W2C_OK;
 }
 

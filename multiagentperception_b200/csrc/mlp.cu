@@ -1,10 +1,12 @@
 // Key / query heads (km_generator / linear, agent.py:145-178): flatten -> Linear(n_feat,256) -> ReLU ->
 // Linear(256,128) -> ReLU -> Linear(128,out).  M = agents*scenes rows (tens), so this is weight-bandwidth work
-// (fc0 is 256 x n_feat fp32 = 4 MB at 512x512): two launches,
+// (fc0 is 256 x n_feat fp32 = 4 MB at 512x512): two launches for up to two heads reading the same feature map
+// (key_net and query_net, agent.py:1132-1147, are independent: run side by side they halve the latency-bound time),
 //   fc0_kernel     2 output neurons per CTA, 256 threads stride K with coalesced weight and activation reads,
-//                  8 rows of M per pass, block reduction through warp shuffles + one smem hop;
-//   fc12_kernel    one CTA per row: fc1 (256 -> 128) and fc2 (128 -> out) fused, hidden vectors in shared memory,
-//                  one warp per output neuron with lanes over K and a shuffle reduction.
+//                  8 rows of M per pass, block reduction through warp shuffles + one smem hop; blockIdx.y = head;
+//   fc12_kernel    one CTA per (row, slab of 128 outputs): fc1 (256 -> 128, recomputed per slab: 32 K MACs) and
+//                  fc2 (128 -> out) fused, hidden vectors in shared memory, one warp per output neuron with lanes
+//                  over K and a shuffle reduction (the single-CTA-per-row version took 78 us for the 1024-wide keys).
 #include "common.cuh"
 
 namespace w2c {
@@ -12,6 +14,12 @@ namespace {
 
 constexpr int kRows = 8;     // rows of M per pass in fc0
 constexpr int kNeurons = 2;  // output neurons per CTA in fc0
+constexpr int kSlab = 128;   // outputs of fc2 per CTA in fc12
+
+struct Heads {
+  w2c_mlp_head h[2];
+  int slabs0;  // fc12 slabs belonging to head 0
+};
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -21,9 +29,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // feat: NHWC policy map [m][n_feat/256 pixels][planes*256]; W: [256][n_feat] (NHWC flatten order); out [m][256]
 __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restrict__ feat, int act,
-                                                  const float* __restrict__ W, const float* __restrict__ bias,
-                                                  float* __restrict__ out, int m, int n_feat) {
+                                                  const __grid_constant__ Heads hd, float* __restrict__ ws, int m,
+                                                  int n_feat) {
   __shared__ float red[8][kNeurons * kRows];
+  const float* __restrict__ W = hd.h[blockIdx.y].w0;
+  const float* __restrict__ bias = hd.h[blockIdx.y].b0;
+  float* __restrict__ out = ws + static_cast<size_t>(blockIdx.y) * m * 256;
   const int j0 = blockIdx.x * kNeurons;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
@@ -94,12 +105,20 @@ __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restric
 }
 
 // one CTA per row: h1 = relu(W1 h0 + b1) (128), out = W2 h1 + b2 (out_dim)
-__global__ void __launch_bounds__(256) fc12_kernel(const float* __restrict__ h0, const float* __restrict__ W1,
-                                                   const float* __restrict__ b1, const float* __restrict__ W2,
-                                                   const float* __restrict__ b2, float* __restrict__ out, int out_dim) {
+__global__ void __launch_bounds__(256) fc12_kernel(const float* __restrict__ ws, const __grid_constant__ Heads hd,
+                                                   int m) {
   __shared__ float s_h0[256];
   __shared__ float s_h1[128];
   const int row = blockIdx.x;
+  const int head = static_cast<int>(blockIdx.y) >= hd.slabs0 ? 1 : 0;
+  const int slab = blockIdx.y - (head ? hd.slabs0 : 0);
+  const float* __restrict__ h0 = ws + static_cast<size_t>(head) * m * 256;
+  const float* __restrict__ W1 = hd.h[head].w1;
+  const float* __restrict__ b1 = hd.h[head].b1;
+  const float* __restrict__ W2 = hd.h[head].w2;
+  const float* __restrict__ b2 = hd.h[head].b2;
+  float* __restrict__ out = hd.h[head].out;
+  const int out_dim = hd.h[head].out_dim;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   s_h0[tid] = h0[static_cast<size_t>(row) * 256 + tid];
   __syncthreads();
@@ -112,7 +131,8 @@ __global__ void __launch_bounds__(256) fc12_kernel(const float* __restrict__ h0,
     if (lane == 0) s_h1[j] = fmaxf(acc + b1[j], 0.f);
   }
   __syncthreads();
-  for (int j = warp; j < out_dim; j += 8) {
+  const int j_end = min(out_dim, (slab + 1) * kSlab);
+  for (int j = slab * kSlab + warp; j < j_end; j += 8) {
     const float* wr = W2 + static_cast<size_t>(j) * 128;
     float acc = 0.f;
 #pragma unroll
@@ -127,17 +147,35 @@ __global__ void __launch_bounds__(256) fc12_kernel(const float* __restrict__ h0,
 
 using namespace w2c;
 
+extern "C" int w2c_kq_mlp_heads_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat,
+                                    const w2c_mlp_head* heads, int32_t n_heads, float* ws, w2c_stream_t stream) {
+  W2C_CHECK_ARG(feat && heads && ws, "kq_mlp: null pointer");
+  W2C_CHECK_ARG(n_heads == 1 || n_heads == 2, "kq_mlp: n_heads=%d (1 or 2)", n_heads);
+  W2C_CHECK_ARG(m > 0 && n_feat > 0 && n_feat % 256 == 0, "kq_mlp: bad sizes m=%d n_feat=%d", m, n_feat);
+  Heads hd{};
+  int slabs = 0;
+  for (int i = 0; i < n_heads; ++i) {
+    const w2c_mlp_head& h = heads[i];
+    W2C_CHECK_ARG(h.w0 && h.b0 && h.w1 && h.b1 && h.w2 && h.b2 && h.out && h.out_dim > 0,
+                  "kq_mlp: head %d has a null pointer or out_dim=%d", i, h.out_dim);
+    hd.h[i] = h;
+    if (i == 0) hd.slabs0 = ceil_div(h.out_dim, kSlab);
+    slabs += ceil_div(h.out_dim, kSlab);
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  fc0_kernel<<<dim3(256 / kNeurons, n_heads), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), act, hd, ws, m,
+                                                            n_feat);
+  W2C_CHECK_LAUNCH("fc0_kernel");
+  fc12_kernel<<<dim3(m, slabs), 256, 0, s>>>(ws, hd, m);
+  W2C_CHECK_LAUNCH("fc12_kernel");
+  return W2C_OK;
+}
+
 extern "C" int w2c_kq_mlp_fwd(const void* feat, int32_t act, int32_t m, int32_t n_feat, const float* w0,
                               const float* b0, const float* w1, const float* b1, const float* w2, const float* b2,
                               int32_t out_dim, float* out, float* ws, w2c_stream_t stream) {
   W2C_CHECK_ARG(feat && w0 && b0 && w1 && b1 && w2 && b2 && out && ws, "kq_mlp: null pointer");
-  W2C_CHECK_ARG(m > 0 && n_feat > 0 && n_feat % 256 == 0 && out_dim > 0, "kq_mlp: bad sizes m=%d n_feat=%d out=%d", m,
-                n_feat, out_dim);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  float* h0 = ws;  // [m][256]
-  fc0_kernel<<<256 / kNeurons, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(feat), act, w0, b0, h0, m, n_feat);
-  W2C_CHECK_LAUNCH("fc0_kernel");
-  fc12_kernel<<<m, 256, 0, s>>>(h0, w1, b1, w2, b2, out, out_dim);
-  W2C_CHECK_LAUNCH("fc12_kernel");
-  return W2C_OK;
+  W2C_CHECK_ARG(out_dim > 0, "kq_mlp: out_dim=%d", out_dim);
+  const w2c_mlp_head h = {w0, b0, w1, b1, w2, b2, out, out_dim};
+  return w2c_kq_mlp_heads_fwd(feat, act, m, n_feat, &h, 1, ws, stream);
 }

@@ -173,6 +173,20 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- epilogue packing
+// round-to-nearest bf16 pair, `lo` in the low half (lower address); the relu form clamps negatives to +0 in the
+// same instruction (one CVT instead of two FMNMX + CVT per channel pair)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile whose rows are 128 B (64 bf16) with the TMA
 // 128-byte swizzle: 8-row atoms of 1024 B, atoms stacked along M/N every 1024 B (SBO), one atom along K (LBO=0).

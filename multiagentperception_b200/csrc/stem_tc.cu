@@ -6,11 +6,17 @@
 // pixel (coalesced 4-byte reads of three channel planes), convert to bf16 and write one 64-byte K-major row of the
 // A operand straight into shared memory in the 128B-swizzle layout the UMMA descriptor expects (software im2col).
 // One thread then issues two tcgen05.mma (M=128, N=COUT, K=16) — six in the bf16x3 precision — and the same 128
-// threads read the accumulators back from TMEM, apply scale/shift/ReLU, write [128 px][64 ch] swizzled staging
-// tiles and one thread issues a TMA tensor store per tile (the direct version issued 16-byte stores at a 256-byte
-// lane stride and ran at a third of the HBM rate). A CTA loops over pixel tiles with the next tile's taps
-// prefetched into registers during the epilogue; several CTAs per SM overlap gather, MMA and store phases.
+// threads read the accumulators back from TMEM, write [128 px][64 ch] swizzled staging tiles and one thread issues
+// a TMA tensor store per tile (the direct version issued 16-byte stores at a 256-byte lane stride and ran at a
+// third of the HBM rate). A CTA loops over pixel tiles with the next tile's taps prefetched into registers during
+// the epilogue; four CTAs per SM overlap gather, MMA and store phases.
 // COUT = 128 is two encoders' first layers fused (the image is read once).
+//
+// The folded BatchNorm rides in the GEMM: the weight rows are pre-multiplied by scale[co] (in fp32, before the
+// bf16 split) and shift[co] is the weight of a constant-1 input in the K padding (k = 27), so the accumulator IS
+// the pre-activation and the epilogue is one cvt.rn.relu.bf16x2 per channel pair. (ncu on the first version: 411 M
+// warp instructions per step - 2 LDS + FMA + MAX + CVT per output - 1.24 ms against a 0.42 ms HBM floor, and 187
+// registers per thread, which silently capped residency at two CTAs per SM for a grid sized for three.)
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -24,9 +30,8 @@ namespace {
 constexpr int kTile = 128;      // pixels per tile = UMMA M
 constexpr int kRowBytes = 128;  // one swizzle row; only the first 64 B (K = 32 bf16) of an operand row are used
 constexpr int kStagingBytes = kTile * 64 * 2;
-constexpr int kNumStaging = 2;
 
-template <int COUT>
+template <int COUT, int kNumStaging>
 struct StemSmem {
   static constexpr int kA = kTile * kRowBytes;  // 16 KB per plane
   static constexpr int kB = COUT * kRowBytes;
@@ -35,13 +40,16 @@ struct StemSmem {
   static constexpr int kStg = kA + kB;
   static constexpr int kBar = kStg + kNumStaging * kStagingBytes;
   static constexpr int kTmemPtr = kBar + 8;
-  static constexpr int kScale = kTmemPtr + 8;
-  static constexpr int kShift = kScale + COUT * 4;
-  static constexpr int kLoBase = (kShift + COUT * 4 + 1023) / 1024 * 1024;
+  static constexpr int kLut = kTmemPtr + 8;  // [3][256] fp32 loader-transform table (uint8 input only)
+  static constexpr int kLoBase = (kLut + 3 * 256 * 4 + 1023) / 1024 * 1024;
   static constexpr int kALo = kLoBase, kBLo = kLoBase + kA;
   static constexpr int kDynamicBf16 = kLoBase + 1024;
   static constexpr int kDynamic = kLoBase + kA + kB + 1024;
 };
+
+__device__ __forceinline__ size_t total_px(int b_sz, int n_agents, int h, int wpx) {
+  return static_cast<size_t>(b_sz) * n_agents * h * wpx;
+}
 
 // byte offset of 16-byte chunk `c` of row `r` in a 128B-swizzled K-major tile
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t c) { return r * kRowBytes + ((c ^ (r & 7u)) << 4); }
@@ -71,42 +79,85 @@ __device__ __forceinline__ void gather_taps(const float* __restrict__ x, size_t 
       }
 }
 
-template <int COUT>
-__global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant__ CUtensorMap y_map,
-                                                           const float* __restrict__ x, const float* __restrict__ w,
-                                                           const float* __restrict__ scale,
-                                                           const float* __restrict__ shift, int b_sz, int n_agents,
-                                                           int c_total, int c_first, int h, int wpx, int act,
-                                                           int num_tiles) {
-  using L = StemSmem<COUT>;
+// The same taps from the loader's raw frames: uint8 RGB, HWC, [b][agents_total][h][w][3]. Conv input channel ci is
+// BGR channel ci = RGB byte 2-ci (the loader's img[:, :, ::-1], airsim_loader.py:521), mapped through the
+// (v - mean[ci]) / 255 table (airsim_loader.py:522-525; built on the host in float64 like the loader does).
+__device__ __forceinline__ void gather_taps_u8(const uint8_t* __restrict__ x, const float* __restrict__ lut, size_t p,
+                                               size_t total, int b_sz, int agents_total, int agent_first, int h,
+                                               int wpx, float (&in)[27]) {
+  if (p >= total) {
+#pragma unroll
+    for (int k = 0; k < 27; ++k) in[k] = 0.f;
+    return;
+  }
+  const size_t plane = static_cast<size_t>(h) * wpx;
+  const int ow = p % wpx;
+  const int oh = (p / wpx) % h;
+  const int img = p / plane;
+  const int agent = img / b_sz, bat = img % b_sz;
+  const uint8_t* xin = x + (static_cast<size_t>(bat) * agents_total + agent_first + agent) * plane * 3;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int ih = oh + kh - 1, iw = ow + kw - 1;
+      const bool ok = ih >= 0 && ih < h && iw >= 0 && iw < wpx;
+      const uint8_t* px = xin + (static_cast<size_t>(ih) * wpx + iw) * 3;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci) in[ci * 9 + kh * 3 + kw] = ok ? lut[ci * 256 + __ldg(px + 2 - ci)] : 0.f;
+    }
+}
+
+template <int COUT, bool U8, int NS>
+__global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_constant__ CUtensorMap y_map,
+                                                              const void* __restrict__ x_any,
+                                                              const float* __restrict__ lut_g,
+                                                              const float* __restrict__ w,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int b_sz, int n_agents,
+                                                              int c_total, int c_first, int h, int wpx, int act,
+                                                              int num_tiles) {
+  using L = StemSmem<COUT, NS>;
   constexpr int kTmemCols = COUT < 32 ? 32 : COUT;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
-  float* s_scale = reinterpret_cast<float*>(smem + L::kScale);
-  float* s_shift = reinterpret_cast<float*>(smem + L::kShift);
+  float* s_lut = reinterpret_cast<float*>(smem + L::kLut);
+  const float* x = static_cast<const float*>(x_any);
+  const uint8_t* xu8 = static_cast<const uint8_t*>(x_any);
+  const size_t total = total_px(b_sz, n_agents, h, wpx);
+  // c_total / c_first carry agents_total / agent_first for the uint8 input
+  auto gather = [&](size_t p, float (&dst)[27]) {
+    if constexpr (U8)
+      gather_taps_u8(xu8, s_lut, p, total, b_sz, c_total, c_first, h, wpx, dst);
+    else
+      gather_taps(x, p, total, b_sz, c_total, c_first, h, wpx, dst);
+  };
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool x3 = act == W2C_ACT_BF16X2;
-  const size_t total = static_cast<size_t>(b_sz) * n_agents * h * wpx;
 
-  // ---- one-time setup: weights -> swizzled B tiles (K padded 27 -> 32 with zeros), barrier, TMEM
+  // ---- one-time setup: scale * weights (k < 27) and shift (k = 27) -> swizzled B tiles, barrier, TMEM
   for (int i = tid; i < COUT * 4; i += kTile) {
     const int co = i >> 2, c = i & 3;  // 16-byte chunk c = k in [8c, 8c+8)
+    const float sc = scale[co];
     uint4 hv, lv;
     __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
     __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(&lv);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int k = c * 8 + e;
-      const float v = k < 27 ? w[co * 27 + k] : 0.f;
+      const float v = k < 27 ? w[co * 27 + k] * sc : (k == 27 ? shift[co] : 0.f);
       hb[e] = __float2bfloat16_rn(v);
       lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + sw128(co, c)) = hv;
     if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
   }
-  for (int i = tid; i < COUT; i += kTile) s_scale[i] = scale[i], s_shift[i] = shift[i];
+  if constexpr (U8) {
+    for (int i = tid; i < 3 * 256; i += kTile) s_lut[i] = lut_g[i];
+    __syncthreads();  // the first gather below reads the table
+  }
   if (tid == 0) {
     ptx::prefetch_tensormap(&y_map);
     ptx::mbar_init(bar, 1);
@@ -129,12 +180,13 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant
 
   float in[27];
   int tile = blockIdx.x;
-  if (tile < num_tiles) gather_taps(x, static_cast<size_t>(tile) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
+  if (tile < num_tiles) gather(static_cast<size_t>(tile) * kTile + tid, in);
   uint32_t phase = 0;
-  const int planes = x3 ? 2 : 1;
   int unit = 0;  // staging-buffer rotation
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
   for (; tile < num_tiles; tile += gridDim.x) {
-    // ---- software im2col: this thread's pixel -> row `tid` of the A tile(s)
+    // ---- software im2col: this thread's pixel -> row `tid` of the A tile(s); k = 27 is the constant 1 that
+    //      carries the folded shift, k = 28..31 are zero
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       uint4 hv, lv;
@@ -143,7 +195,7 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = c * 8 + e;
-        const float v = k < 27 ? in[k < 27 ? k : 0] : 0.f;
+        const float v = k < 27 ? in[k < 27 ? k : 0] : (k == 27 ? 1.f : 0.f);
         hb[e] = __float2bfloat16_rn(v);
         lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
       }
@@ -168,41 +220,50 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant
     }
     // prefetch the next tile's taps while the MMA runs and before the store phase
     const int next = tile + gridDim.x;
-    if (next < num_tiles) gather_taps(x, static_cast<size_t>(next) * kTile + tid, total, b_sz, c_total, c_first, h, wpx, in);
+    if (next < num_tiles) gather(static_cast<size_t>(next) * kTile + tid, in);
 
     ptx::mbar_wait(bar, phase);
     phase ^= 1;
     ptx::tc_fence_after();
+    const int planes = x3 ? 2 : 1;
 #pragma unroll 1
     for (int g = 0; g < COUT / 64; ++g) {
-      uint32_t r[64];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 64, r);
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + g * 64 + 32, r + 32);
-      ptx::tmem_ld_wait();
-      float v[64];
-#pragma unroll
-      for (int j = 0; j < 64; ++j)
-        v[j] = fmaxf(fmaf(__uint_as_float(r[j]), s_scale[g * 64 + j], s_shift[g * 64 + j]), 0.f);
+#pragma unroll 1
       for (int pln = 0; pln < planes; ++pln, ++unit) {
-        uint8_t* stg = smem + L::kStg + (unit % kNumStaging) * kStagingBytes;
-        if (tid == 0) ptx::bulk_wait_group_read<kNumStaging - 1>();  // the store that last used this tile has read it
+        uint8_t* stg = smem + L::kStg + (unit % NS) * kStagingBytes;
+        if (tid == 0) ptx::bulk_wait_group_read<NS - 1>();  // the store that last used this tile has read it
         __syncthreads();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {  // 32 accumulator columns at a time (register budget: 128)
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + g * 64 + half * 32, r);
+          ptx::tmem_ld_wait();
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          uint4 pk;
-          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
-            if (pln == 0) {
-              pb[j] = hi;
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 pk;
+            if (!x3) {
+              pk.x = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 0]), __uint_as_float(r[c4 * 8 + 1]));
+              pk.y = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 2]), __uint_as_float(r[c4 * 8 + 3]));
+              pk.z = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 4]), __uint_as_float(r[c4 * 8 + 5]));
+              pk.w = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 6]), __uint_as_float(r[c4 * 8 + 7]));
             } else {
-              const float2 hf = __bfloat1622float2(hi);
-              pb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+              uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float a = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j]), 0.f);
+                const float b = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j + 1]), 0.f);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
+                if (pln == 0) {
+                  pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
+                } else {
+                  const float2 hf = __bfloat1622float2(hi);
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                  pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+              }
             }
+            *reinterpret_cast<uint4*>(stg + sw128(tid, half * 4 + c4)) = pk;
           }
-          *reinterpret_cast<uint4*>(stg + sw128(tid, c8)) = pk;
         }
         ptx::fence_proxy_async();
         __syncthreads();
@@ -225,13 +286,14 @@ __global__ void __launch_bounds__(kTile) stem3x3_tc_kernel(const __grid_constant
   }
 }
 
-template <int COUT>
-int launch_stem(const float* x, const float* w, const float* scale, const float* shift, void* y, int b, int n_agents,
-                int c_total, int c_first, int h, int wpx, int act, cudaStream_t stream) {
-  using L = StemSmem<COUT>;
+template <int COUT, bool U8, int NS>
+int launch_stem_ns(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y,
+                   int b, int n_agents, int c_total, int c_first, int h, int wpx, int act, cudaStream_t stream) {
+  using L = StemSmem<COUT, NS>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(stem3x3_tc_kernel<COUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic);
+    cudaError_t e = cudaFuncSetAttribute(stem3x3_tc_kernel<COUT, U8, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kDynamic);
     if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "stem3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -246,23 +308,55 @@ int launch_stem(const float* x, const float* w, const float* scale, const float*
     int rc = encode_map(&y_map, y, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
   }
-  // resident CTAs per SM are bounded by shared memory (bf16: ~66 KB, bf16x3: ~98 KB each) and TMEM (COUT columns)
+  // resident CTAs per SM: bounded by shared memory (operand tiles + NS staging tiles; the bf16x3 precision adds
+  // the lo-plane operand tiles), by TMEM (COUT columns of 512) and by registers (<= 128 per thread: four CTAs)
   const int smem_bytes = planes == 2 ? L::kDynamic : L::kDynamicBf16;
-  int grid = 148 * (planes == 2 ? 2 : 3);
+  int per_sm = (227 * 1024) / (smem_bytes + 1024);
+  if (per_sm > 512 / (COUT < 32 ? 32 : COUT)) per_sm = 512 / (COUT < 32 ? 32 : COUT);
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
   if (grid > num_tiles) grid = num_tiles;
-  stem3x3_tc_kernel<COUT><<<grid, kTile, smem_bytes, stream>>>(y_map, x, w, scale, shift, b, n_agents, c_total,
-                                                                c_first, h, wpx, act, num_tiles);
+  stem3x3_tc_kernel<COUT, U8, NS><<<grid, kTile, smem_bytes, stream>>>(y_map, x, lut, w, scale, shift, b, n_agents,
+                                                                        c_total, c_first, h, wpx, act, num_tiles);
   W2C_CHECK_LAUNCH("stem3x3_tc_kernel");
   return W2C_OK;
+}
+
+template <int COUT, bool U8>
+int launch_stem(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y, int b,
+                int n_agents, int c_total, int c_first, int h, int wpx, int act, cudaStream_t stream) {
+  // one staging tile -> four CTAs per SM at COUT = 128 (52 KB each); W2C_STEM_STAGING=2 keeps two (three CTAs)
+  static const int ns = [] {
+    const char* e = getenv("W2C_STEM_STAGING");
+    return (e && e[0] == '2') ? 2 : 1;
+  }();
+  if (ns == 2)
+    return launch_stem_ns<COUT, U8, 2>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
+  return launch_stem_ns<COUT, U8, 1>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
 }
 
 }  // namespace
 
 int stem3x3_tc_forward(const float* x, const float* w, const float* scale, const float* shift, void* y, int b,
                        int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, cudaStream_t stream) {
-  if (cout == 64) return launch_stem<64>(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
-  if (cout == 128) return launch_stem<128>(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
+  if (cout == 64)
+    return launch_stem<64, false>(x, nullptr, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
+  if (cout == 128)
+    return launch_stem<128, false>(x, nullptr, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, stream);
   return set_error(W2C_ERR_UNSUPPORTED, "stem3x3_tc: cout=%d (only 64 and 128)", cout);
+}
+
+int stem3x3_tc_u8_forward(const uint8_t* x, const float* lut, const float* w, const float* scale, const float* shift,
+                          void* y, int b, int n_agents, int agents_total, int agent_first, int h, int wpx, int cout,
+                          int act, cudaStream_t stream) {
+  if (cout == 64)
+    return launch_stem<64, true>(x, lut, w, scale, shift, y, b, n_agents, agents_total, agent_first, h, wpx, act,
+                                 stream);
+  if (cout == 128)
+    return launch_stem<128, true>(x, lut, w, scale, shift, y, b, n_agents, agents_total, agent_first, h, wpx, act,
+                                  stream);
+  return set_error(W2C_ERR_UNSUPPORTED, "stem3x3_tc (uint8 frames): cout=%d (only 64 and 128)", cout);
 }
 
 }  // namespace w2c

@@ -154,6 +154,15 @@ class Program:
         self.graph = None
         self.n_launches = 0  # kernel launches per run (counted from the library's counter)
         self._lib = _lib.load()
+        # program-level I/O options (models/agents.py sets them before building):
+        #   input_u8   the static input is the loader's raw uint8 RGB HWC frames [b, agents, h, w, 3]; lut = the
+        #              loader-transform table (ops.loader_lut)
+        #   labels     the decoder also writes a uint8 label map; logits=False drops the fp32 logits write
+        self.input_u8 = False
+        self.lut = None
+        self.want_labels = False
+        self.want_logits = True
+        self.labels_out = None
 
     # ---- buffers
     def act_buf(self, n, h, w, c):
@@ -170,8 +179,9 @@ class Program:
     def _record(self, fn, *args):
         self.calls.append((fn, args))
 
-    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0):
-        """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given)."""
+    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None):
+        """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given). labels: uint8 [n, h, w] tensor that
+        receives the arg-max class of the fp32 NCHW logits (nchw_out may then be the string 'none': labels only)."""
         if x.c != pc.cin:
             raise ValueError("conv expects %d input channels, got %d" % (pc.cin, x.c))
         if pc.kind in (ops.CONV3X3_S2, ops.CONV1X1_S2):
@@ -180,7 +190,11 @@ class Program:
             ho, wo = x.h * 2, x.w * 2
         else:
             ho, wo = x.h, x.w
-        if nchw_out is not None:
+        if isinstance(nchw_out, str):
+            if labels is None:
+                raise ValueError("conv: logits can only be dropped when a label map is written")
+            y_ptr, out_fmt, ycs, yco, ret = None, ops.OUT_NCHW_F32, 0, 0, labels
+        elif nchw_out is not None:
             y_ptr, out_fmt, ycs, yco, ret = nchw_out.data_ptr(), ops.OUT_NCHW_F32, 0, 0, nchw_out
         else:
             if out is None:
@@ -190,7 +204,8 @@ class Program:
                           residual=residual.buf.data_ptr() if residual is not None else None, y=y_ptr, n=x.n,
                           h_in=x.h, w_in=x.w, cin=pc.cin, cout=pc.cout, x_cstride=x.cstride, x_coffset=x.coffset,
                           y_cstride=ycs, y_coffset=yco, kind=pc.kind, relu=int(pc.relu), act=self.act,
-                          out_fmt=out_fmt, impl=ops.IMPL_TCGEN05, block_n=block_n)
+                          out_fmt=out_fmt, impl=ops.IMPL_TCGEN05, block_n=block_n,
+                          labels=labels.data_ptr() if labels is not None else None)
         self.keep.append(a)
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret
@@ -199,11 +214,18 @@ class Program:
         wt, scale, shift = st
         cout = wt.shape[0]
         out = self.act_buf(b * n_agents, h, w, cout)
+        if self.input_u8:  # x_nchw is the uint8 frame buffer [b, agents_total, h, w, 3]; c_first counts channels
+            self._record(self._lib.w2c_stem_conv3x3_u8_fwd, x_nchw.data_ptr(), self.lut.data_ptr(), wt.data_ptr(),
+                         scale.data_ptr(), shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1],
+                         c_first // 3, h, w, cout, self.act)
+            return out
         self._record(self._lib.w2c_stem_conv3x3_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
                      shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act)
         return out
 
     def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0):
+        if self.input_u8:
+            raise NotImplementedError("uint8 frame input is implemented for the 3x3 (n_segnet) stem only")
         wt, scale, shift = st
         out = self.act_buf(b * n_agents, h // 2, w // 2, 64)
         self._record(self._lib.w2c_stem_conv7x7s2_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
@@ -221,6 +243,11 @@ class Program:
         self._record(self._lib.w2c_bilinear_up_fwd, x_nchw.data_ptr(), out.data_ptr(), n, c, h, w, factor)
         return out
 
+    def argmax_labels(self, logits, labels):
+        n, c, h, w = logits.shape
+        self._record(self._lib.w2c_argmax_labels_fwd, logits.data_ptr(), labels.data_ptr(), n, c, h * w)
+        return labels
+
     def kq_mlp(self, feat, mlp, out_dim, out=None):
         w0, b0, w1, b1, w2, b2 = mlp
         m = feat.n
@@ -233,6 +260,28 @@ class Program:
         self._record(self._lib.w2c_kq_mlp_fwd, feat.buf.data_ptr(), self.act, m, n_feat, w0.data_ptr(), b0.data_ptr(),
                      w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, out.data_ptr(), ws.data_ptr())
         return out
+
+    def kq_mlp_heads(self, feat, heads):
+        """heads: [(mlp weights tuple, out_dim, out tensor or None), ...] (1 or 2) over the same feature map, run as
+        ONE fc0 + ONE fc12 launch. Returns the output tensors."""
+        m = feat.n
+        n_feat = feat.h * feat.w * feat.c
+        arr = (_lib.MlpHead * len(heads))()
+        outs = []
+        for i, (mlp, out_dim, out) in enumerate(heads):
+            w0, b0, w1, b1, w2, b2 = mlp
+            if out is None:
+                out = self.f32_buf(m, out_dim)
+            elif tuple(out.shape) != (m, out_dim) or out.dtype != torch.float32 or not out.is_contiguous():
+                raise ValueError("kq_mlp: out must be a contiguous fp32 [%d, %d] tensor" % (m, out_dim))
+            arr[i] = _lib.MlpHead(w0.data_ptr(), b0.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                  b2.data_ptr(), out.data_ptr(), out_dim)
+            outs.append(out)
+        ws = self.f32_buf(len(heads) * m * 256)
+        self.keep.append(arr)
+        self._record(self._lib.w2c_kq_mlp_heads_fwd, feat.buf.data_ptr(), self.act, m, n_feat, arr, len(heads),
+                     ws.data_ptr())
+        return outs
 
     def attn(self, keys, queries, wq, bq, val, fused, prob, coef, action, connect, *, b_sz, n_k, n_q, k_dim, q_dim,
              mode, sparse=False, mask_self=False, temperature=1.0, diag_bias=0.0, thresh=0.2, q_first=0, q_count=0,

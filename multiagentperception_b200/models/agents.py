@@ -148,14 +148,27 @@ def _build_decoder(prog, dec, a):
         for u in units[:-1]:
             a = prog.conv(a, wc.conv(u.conv, u.bn, True))
         last = units[-1]
+        labels = prog.f32_buf(a.n, a.h, a.w, dtype=torch.uint8) if prog.want_labels else None
+        prog.labels_out = labels
+        if labels is not None and not prog.want_logits:
+            # label map only: the arg-max is taken on the accumulators, the fp32 logits never reach HBM
+            return prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out="none", labels=labels)
         logits = prog.f32_buf(a.n, last.conv.out_channels, a.h, a.w)
-        prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out=logits)  # logits pass BN+ReLU too, backbone.py:124
+        prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out=logits,  # logits pass BN+ReLU too, backbone.py:124
+                  labels=labels)
         return logits
     if isinstance(od, simple_decoder):
         y = prog.conv(a, wc.conv(od.pred[0], None, True))
         small = prog.f32_buf(a.n, od.pred[2].out_channels, a.h, a.w)
         prog.conv(y, wc.conv(od.pred[2], None, False), nchw_out=small)
-        return prog.bilinear(small, 32)
+        up = prog.bilinear(small, 32)
+        prog.labels_out = None
+        if prog.want_labels:
+            prog.labels_out = prog.argmax_labels(up, prog.f32_buf(up.shape[0], up.shape[2], up.shape[3],
+                                                                   dtype=torch.uint8))
+            if not prog.want_logits:
+                return prog.labels_out
+        return up
     raise ValueError("unknown decoder backbone %r" % type(od).__name__)
 
 
@@ -192,7 +205,8 @@ class _W2CModel(nn.Module):
     def __init__(self):
         super().__init__()
         self._w2c = {"precision": engine.default_precision(), "graphs": engine.use_graphs_default(),
-                     "programs": {}, "weights": {}, "clone_outputs": True}
+                     "programs": {}, "weights": {}, "clone_outputs": True, "last": None,
+                     "io": {"u8": False, "mean": ops.LOADER_MEAN_BGR, "norm": True, "labels": False, "logits": True}}
 
     # ---- configuration
     def set_precision(self, name):
@@ -211,6 +225,31 @@ class _W2CModel(nn.Module):
         """False returns views of the engine's static output buffers (valid until the next forward)."""
         self._w2c["clone_outputs"] = bool(enabled)
         return self
+
+    def set_input_format(self, fmt="f32_nchw", mean_bgr=ops.LOADER_MEAN_BGR, img_norm=True):
+        """'f32_nchw' (the reference's forward() input: views already transformed and concatenated on the channel
+        axis, (B, 3N, H, W) float32) or 'u8_hwc': the loader's RAW frames, (B, N, H, W, 3) uint8 RGB; the loader
+        transform (airsim_loader.py:515-527) and the trainer's cat (trainer.py:651) are then fused into the first
+        conv's gather, bit-identical to transforming on the host. n_segnet encoders only."""
+        if fmt not in ("f32_nchw", "u8_hwc"):
+            raise ValueError("input format must be 'f32_nchw' or 'u8_hwc'")
+        self._w2c["io"].update(u8=fmt == "u8_hwc", mean=tuple(float(m) for m in mean_bgr), norm=bool(img_norm))
+        self._w2c["programs"].clear()
+        return self
+
+    def set_label_output(self, enabled=True, logits=True):
+        """Also produce the uint8 arg-max label map (`outputs.data.max(1)[1]`, trainer.py:804) on the device, read with
+        last_labels(). logits=False drops the fp32 logits altogether: forward() then returns the (N*B, H, W) uint8
+        label map in place of `pred` (what an evaluation loop consumes)."""
+        self._w2c["io"].update(labels=bool(enabled), logits=bool(logits) or not enabled)
+        self._w2c["programs"].clear()
+        return self
+
+    def last_labels(self):
+        c = self._w2c["last"]
+        if c is None or c.prog.labels_out is None:
+            raise RuntimeError("no label map: call set_label_output(True) before forward()")
+        return self._ret(c.prog.labels_out)
 
     def invalidate(self):
         """Drop packed weights and compiled programs (call after mutating parameters in place)."""
@@ -241,11 +280,16 @@ class _W2CModel(nn.Module):
                 % type(self).__name__)
         if not (torch.is_tensor(inputs) and inputs.is_cuda):
             raise RuntimeError("%s.forward needs a CUDA tensor: there is no CPU fallback" % type(self).__name__)
-        if inputs.dim() != 4:
+        io = self._w2c["io"]
+        if io["u8"]:
+            if inputs.dim() != 5 or inputs.dtype != torch.uint8 or inputs.shape[-1] != 3:
+                raise ValueError("expected (B, N, H, W, 3) uint8 frames (input format 'u8_hwc'), got %s %s"
+                                 % (inputs.dtype, tuple(inputs.shape)))
+        elif inputs.dim() != 4:
             raise ValueError("expected (B, 3*N, H, W) input, got shape %s" % (tuple(inputs.shape),))
         dev = inputs.device
         act = engine.PRECISIONS[self._w2c["precision"]]
-        key = (dev, act, tuple(inputs.shape), tag)
+        key = (dev, act, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"])
         c = self._w2c["programs"].get(key)
         if c is None:
             wkey = (dev, act)
@@ -255,21 +299,35 @@ class _W2CModel(nn.Module):
                 self._w2c["weights"][wkey] = wc
             with torch.cuda.device(dev), torch.no_grad():
                 prog = engine.Program(wc, dev, act)
+                prog.want_labels, prog.want_logits = io["labels"], io["logits"]
+                if io["u8"]:
+                    prog.input_u8 = True
+                    prog.lut = ops.loader_lut(io["mean"], io["norm"], dev)
                 c = _Compiled()
                 c.prog = prog
-                c.x = prog.f32_buf(*inputs.shape)
+                c.x = prog.f32_buf(*inputs.shape, dtype=torch.uint8 if io["u8"] else torch.float32)
                 c.out = builder(prog, c.x)
             self._w2c["programs"][key] = c
         with torch.cuda.device(dev), torch.no_grad():
             c.x.copy_(inputs)
             c.prog.run(self._w2c["graphs"])
+        self._w2c["last"] = c
         return c
 
     def _ret(self, t):
         return t.clone() if self._w2c["clone_outputs"] else t
 
 
+def _bhw(inputs):
+    """(B, H, W) of a (B, 3N, H, W) float batch or of (B, N, H, W, 3) uint8 frames."""
+    return inputs.shape[0], inputs.shape[2], inputs.shape[3]  # H, W sit at dims 2, 3 in both layouts
+
+
 def _check_views(inputs, n_agents):
+    if inputs.dim() == 5:
+        if inputs.shape[1] != n_agents:
+            raise ValueError("expected frames of %d agents, got %d" % (n_agents, inputs.shape[1]))
+        return
     if inputs.shape[1] != 3 * n_agents:
         raise ValueError("expected %d channels (3 per agent x %d agents), got %d" % (3 * n_agents, n_agents,
                                                                                       inputs.shape[1]))
@@ -288,7 +346,7 @@ class Single_agent(_W2CModel):
 
     def forward(self, inputs):
         _check_views(inputs, 1)
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             feat = _build_encoder(prog, self.encoder, "encoder", x, b, 1, h, w)
@@ -365,12 +423,13 @@ class _AttentionModel(_W2CModel):
         qk = _build_policy(prog, self.query_key_net, x, b, n, h, w, stem=stem_p)
         if qk.h != qk.w:
             raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
-        keys = prog.kq_mlp(qk, prog.weights.mlp(self.key_net.fc, qk.h), self.key_size,
-                           out=None if dst is None else dst[0])
+        heads = [(prog.weights.mlp(self.key_net.fc, qk.h), self.key_size, None if dst is None else dst[0])]
         if self.has_query:
-            queries = prog.kq_mlp(qk, prog.weights.mlp(self.query_net.fc, qk.h), self.query_size,
-                                  out=None if dst is None else dst[1])
+            heads.append((prog.weights.mlp(self.query_net.fc, qk.h), self.query_size,
+                          None if dst is None else dst[1]))
+            keys, queries = prog.kq_mlp_heads(qk, heads)  # both heads in one pair of launches
         else:
+            keys, = prog.kq_mlp_heads(qk, heads)
             queries = prog.f32_buf(n * b, self.query_size) if dst is None else dst[1]
             queries.fill_(1.0)  # torch.ones(batch, 1, query_size), agent.py:1144
         return val, keys, queries
@@ -432,7 +491,7 @@ class MIMOcom(_AttentionModel):
         if not MO_flag:
             raise ValueError("MO_flag=False is not runnable in the reference either (agent.py:1153,1164-1165); "
                              "pass MO_flag=True (multiple_output: True in the shipped mrms configs)")
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
@@ -483,7 +542,7 @@ class MIMOcom(_AttentionModel):
             raise ValueError("Incorrect inference mode")
         if not MO_flag:
             raise ValueError("MO_flag=False is not runnable in the reference either; pass MO_flag=True")
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             fh, fw = h // 32, w // 32
@@ -552,7 +611,7 @@ class LearnWhen2Com(_AttentionModel):
             mode = inference
         else:
             raise ValueError("Incorrect inference mode")
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
@@ -605,7 +664,7 @@ class LearnWho2Com(_AttentionModel):
             mode = "argmax_test"
         else:
             raise ValueError("Incorrect inference mode")  # 'argmax_train' needs an undefined argmax_decoder
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
@@ -644,7 +703,7 @@ class MIMO_All_agents(_W2CModel):
         if self.shuffle_flag in ("selection", "ComNet"):
             raise NotImplementedError("the random-selection / ComNet baselines (agent.py:934-961) are not on the "
                                       "accelerated path")
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
 
         def build(prog, x):
             feat = _build_encoder(prog, self.encoder, "encoder", x, b, n, h, w)
@@ -677,7 +736,7 @@ class All_agents(_W2CModel):
         _check_views(inputs, 5)  # divide_num hard-coded, agent.py:433
         if self.shuffle_flag == "selection":
             raise NotImplementedError("the random-selection baseline (agent.py:447-452) is not on the accelerated path")
-        b, _, h, w = inputs.shape
+        b, h, w = _bhw(inputs)
         used = 2 if self.shuffle_flag == "fixed2" else 5
         fc = self.encoder1.squeezer.conv.out_channels
         if self.decoder.output_decoder.in_channels != used * fc and self.decoder.feat_squeezer not in (2, 4):

@@ -11,7 +11,10 @@ import torch
 
 from . import _lib
 from ._lib import (ACT_BF16, ACT_BF16X2, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
-                   DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX)
+                   DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX, GT_U8, GT_I64)
+
+# airsim_loader.py:191 (mean_rgb['airsim'], indexed by BGR channel after the loader's flip)
+LOADER_MEAN_BGR = (103.939, 116.779, 123.68)
 
 
 def _stream():
@@ -75,10 +78,13 @@ def pack_conv_weight(w, cin_pad, transposed, act):
 
 # ------------------------------------------------------------------------------------------------ hot-path ops
 def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind, relu, act, out_fmt=OUT_NHWC,
-                residual=None, x_cstride=0, x_coffset=0, y_cstride=0, y_coffset=0, impl=IMPL_TCGEN05, block_n=0):
+                residual=None, x_cstride=0, x_coffset=0, y_cstride=0, y_coffset=0, impl=IMPL_TCGEN05, block_n=0,
+                labels=None):
+    """labels: optional uint8 [n, h_out, w_out] tensor receiving argmax_co y (NCHW fp32 logits layout only); with
+    labels given, y may be None (label map only)."""
     lib = _lib.load()
     a = _lib.ConvArgs(x=_ptr(x), w=_ptr(w_packed), scale=_ptr(scale), shift=_ptr(shift), residual=_ptr(residual),
-                      y=_ptr(y), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout, x_cstride=x_cstride,
+                      y=_ptr(y), labels=_ptr(labels), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout, x_cstride=x_cstride,
                       x_coffset=x_coffset, y_cstride=y_cstride, y_coffset=y_coffset, kind=kind, relu=int(relu),
                       act=act, out_fmt=out_fmt, impl=impl, block_n=block_n)
     _lib.check(lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), _stream()), "w2c_conv_bnrelu_fwd")
@@ -91,6 +97,54 @@ def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, 
                                         c_total or 3 * n_agents, c_first, h, w, cout, act, _stream()),
                "w2c_stem_conv3x3_fwd")
     return y
+
+
+def loader_lut(mean_bgr=LOADER_MEAN_BGR, img_norm=True, device=None):
+    """fp32 [3, 256] table of the loader transform per BGR channel: float32((float64(v) - mean[c]) / 255.0)
+    (airsim_loader.py:522-525 computes in float64, then torch.from_numpy(img).float(), :535)."""
+    import numpy as np
+    v = np.arange(256, dtype=np.float64)[None, :] - np.asarray(mean_bgr, dtype=np.float64)[:, None]
+    if img_norm:
+        v = v.astype(float) / 255.0
+    t = torch.from_numpy(v).float().contiguous()
+    return t.to(device) if device is not None else t
+
+
+def stem_conv3x3_u8(frames, lut, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, agents_total=0, agent_first=0):
+    """frames: uint8 RGB HWC [b, agents_total, h, w, 3] (raw loader frames); lut from loader_lut()."""
+    lib = _lib.load()
+    if frames.dtype != torch.uint8:
+        raise ValueError("stem_conv3x3_u8 needs uint8 frames")
+    _lib.check(lib.w2c_stem_conv3x3_u8_fwd(_ptr(frames), _ptr(lut), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b,
+                                           n_agents, agents_total or n_agents, agent_first, h, w, cout, act,
+                                           _stream()), "w2c_stem_conv3x3_u8_fwd")
+    return y
+
+
+def argmax_labels(logits, labels=None):
+    """uint8 [n, h, w] = logits.max(1)[1] (first maximal index) of fp32 NCHW logits."""
+    lib = _lib.load()
+    n, c, h, w = logits.shape
+    if labels is None:
+        labels = torch.empty((n, h, w), dtype=torch.uint8, device=logits.device)
+    _lib.check(lib.w2c_argmax_labels_fwd(_ptr(logits), _ptr(labels), n, c, h * w, _stream()), "w2c_argmax_labels_fwd")
+    return labels
+
+
+def confusion_update(pred_labels, gt, n_classes, hist):
+    """hist[n_classes*gt + pred] += 1 over pixels with 0 <= gt < n_classes (runningScore._fast_hist,
+    metrics.py:99-104). pred_labels uint8, gt uint8 or int64 (same number of elements), hist int64 [n, n] on device."""
+    lib = _lib.load()
+    if pred_labels.dtype != torch.uint8 or pred_labels.numel() != gt.numel():
+        raise ValueError("confusion_update: pred must be uint8 with as many elements as gt")
+    if hist.dtype != torch.int64 or hist.numel() != n_classes * n_classes:
+        raise ValueError("confusion_update: hist must be int64 [%d, %d]" % (n_classes, n_classes))
+    dt = {torch.uint8: GT_U8, torch.int64: GT_I64}.get(gt.dtype)
+    if dt is None:
+        raise ValueError("confusion_update: gt must be uint8 or int64 (got %s)" % gt.dtype)
+    _lib.check(lib.w2c_confusion_update(_ptr(pred_labels), _ptr(gt), dt, gt.numel(), n_classes, _ptr(hist), _stream()),
+               "w2c_confusion_update")
+    return hist
 
 
 def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act, c_total=0, c_first=0):

@@ -357,6 +357,36 @@ def forward(sd, cfg, x, **kw):
     raise ValueError("Model {} not available".format(arch))
 
 
+# --------------------------------------------------------------------------------------------- loader / eval glue
+LOADER_MEAN = (103.939, 116.779, 123.68)  # airsim_loader.py:191, applied per channel AFTER the BGR flip
+
+
+def loader_transform(img_rgb_u8, mean=LOADER_MEAN, img_norm=True):
+    """airsimLoader.transform, airsim_loader.py:515-535, image half: one (H, W, 3) uint8 RGB frame ->
+    (3, H, W) float32 (BGR, mean-subtracted in float64, /255)."""
+    img = np.asarray(img_rgb_u8)[:, :, ::-1]      # :521
+    img = img.astype(np.float64)                  # :522
+    img = img - np.asarray(mean, dtype=np.float64)  # :523
+    if img_norm:
+        img = img.astype(float) / 255.0           # :524-525
+    img = img.transpose(2, 0, 1)                  # :527
+    return torch.from_numpy(np.ascontiguousarray(img)).float()  # :535
+
+
+def views_from_frames(frames_u8, mean=LOADER_MEAN, img_norm=True):
+    """(B, N, H, W, 3) uint8 RGB frames -> the (B, 3N, H, W) float32 batch forward() takes: the loader transform per
+    frame, then the trainer's channel concat `torch.cat(tuple(images_list), dim=1)` (trainer.py:651,785)."""
+    frames = np.asarray(frames_u8)
+    b, n = frames.shape[:2]
+    return torch.stack([torch.cat([loader_transform(frames[i, a], mean, img_norm) for a in range(n)], 0)
+                        for i in range(b)], 0)
+
+
+def labels_from_logits(logits):
+    """`outputs.data.max(1)[1]`, trainer.py:804 (first maximal index on ties)."""
+    return torch.as_tensor(logits).max(1)[1]
+
+
 # --------------------------------------------------------------------------------------------- metrics
 def confusion_matrix(label_true, label_pred, n_class):
     """runningScore._fast_hist, metrics.py:99-105."""

@@ -55,6 +55,7 @@ def test_struct_layouts_match_header():
 
     assert fields("w2c_conv_args") == [f[0] for f in _lib.ConvArgs._fields_]
     assert fields("w2c_attn_args") == [f[0] for f in _lib.AttnArgs._fields_]
+    assert fields("w2c_mlp_head") == [f[0] for f in _lib.MlpHead._fields_]
 
 
 def test_tensor_core_and_tma_instructions_present():

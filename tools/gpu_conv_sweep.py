@@ -59,12 +59,23 @@ def main():
         flop = 2.0 * m * cin * cout * 9
         variants = [("taps", ops.IMPL_TC_TAPS, 0), ("pers", ops.IMPL_TC_PERSIST, 0),
                     ("pers 1-epi-group", ops.IMPL_TC_PERSIST | (2 << 8), 0)]
-        if cout == 64:
+        ab = os.environ.get("SWEEP_AB") == "1"
+        if ab:
+            # A/B of the round-1 late changes: resident weights (flag 32 = off, 64 = opt-in variants) and the
+            # class-inner tile order of transposed convs (flag 128 = old class-major order)
+            if cin * cout * 9 * 2 > 147456 and kind != 2:
+                continue
+            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-resident", ops.IMPL_TC_PERSIST | (32 << 8), 0)]
+            if (kind == 0 and cin == 128 and cout == 64) or cout <= 16:
+                variants.append(("pers resident opt-in", ops.IMPL_TC_PERSIST | (64 << 8), 0))
+            if kind == 2:
+                variants.append(("pers class-major", ops.IMPL_TC_PERSIST | (128 << 8), 0))
+        if cout == 64 and not ab:
             variants += [("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
-        if cout <= 16:
+        if cout <= 16 and not ab:
             variants += [("pers 1cta/sm", ops.IMPL_TC_PERSIST | (16 << 8), 0),
                          ("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
-        cp = ops.cout_pad(cout)
+        cp = 1 if ab else ops.cout_pad(cout)
         if cp % 256 == 0:
             variants.append(("pers bn128", ops.IMPL_TC_PERSIST, 128))
         if os.environ.get("SWEEP_FLAGS"):
@@ -81,7 +92,7 @@ def main():
             variants.append(("taps bn256", ops.IMPL_TC_TAPS, 256))
         if cp % 128 == 0:
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
-        if kind != 1 and not os.environ.get("SWEEP_FLAGS"):
+        if kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1":
             variants.append(("halo", ops.IMPL_TC_HALO, 0))
             if cp % 128 == 0 and kind == 0:
                 variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
