@@ -42,6 +42,8 @@ def parse():
     ap.add_argument("--inference", default="softmax", choices=["softmax", "activated", "argmax_test"])
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-e2e", action="store_true")
+    ap.add_argument("--no-parity-value", action="store_true")
     ap.add_argument("--layer-table", default="", help="write a per-layer timing table (markdown) to this path")
     ap.add_argument("--profile-step", action="store_true",
                     help="run one eager step inside cudaProfilerStart/Stop (for ncu) and exit without a bench line")
@@ -56,6 +58,20 @@ def measured_peaks():
         return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
                 "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def traffic_per_launch(n_conv):
+    """dram__bytes_read.sum + dram__bytes_write.sum per conv launch (bytes), from the committed ncu pass of this
+    command (profiles/r1_traffic.json, written by tools/summarize_ncu_launches.py); None if absent or stale."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        if t.get("conv_launches") == n_conv:
+            return t["conv_dram_bytes_per_step"] / n_conv
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 class ClockSampler:
@@ -297,10 +313,68 @@ def run_b200(args):
            "d2h_bytes_per_step": int(labels_host[0].numel() * 8 * world), "ms_per_step": ms_e2e,
            "pipeline": "double-buffered H2D / D2H on side streams, every step's copies inside the timed region"}
 
+    # ---- e2e through the fused evaluation path of the public API: the loader's RAW uint8 frames in
+    # (transform + cat fused into the first conv), the uint8 label map out (arg-max fused into the logits layer, the
+    # fp32 logits never written); same double-buffered pipeline. Bit-identical labels to the drop-in path above.
+    e2e_fused = None
+    if not args.no_fused_e2e and args.backbones == "n_segnet":
+        fmodel = get_model(cfg, configs.N_CLASSES)
+        fmodel.load_state_dict(model.state_dict())
+        fmodel = fmodel.to(dev).eval().set_clone_outputs(False)
+        if world > 1:
+            fmodel.shard_agents()
+        fmodel.set_input_format("u8_hwc").set_label_output(True, logits=False)
+        frames_host = synth.synthetic_frames(scenes, local_agents, IMG, IMG, seed=1337 + rank).pin_memory()
+        f_buf = [torch.empty(frames_host.shape, dtype=torch.uint8, device=dev) for _ in range(2)]
+        l_dev = [torch.empty((local_agents * scenes, IMG, IMG), dtype=torch.uint8, device=dev) for _ in range(2)]
+        l_host = [torch.empty((local_agents * scenes, IMG, IMG), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        fstate = {"i": 0}
+
+        def step_fused():
+            b = fstate["i"] & 1
+            fstate["i"] += 1
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_used[b])
+                f_buf[b].copy_(frames_host, non_blocking=True)
+                ev_in[b].record(s_in)
+            main.wait_event(ev_in[b])
+            labels = fmodel(f_buf[b], **kw)[0]
+            ev_used[b].record(main)
+            main.wait_event(ev_out[b])
+            l_dev[b].copy_(labels)
+            ev_lab[b].record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_lab[b])
+                l_host[b].copy_(l_dev[b], non_blocking=True)
+                ev_out[b].record(s_out)
+
+        for _ in range(4):
+            step_fused()
+        drain()
+        ms_f = timed(step_fused, args.steps, drain) / args.steps
+        e2e_fused = {"value": frames_total / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f,
+                     "h2d_bytes_per_step": int(frames_host.numel() * world),
+                     "d2h_bytes_per_step": int(l_host[0].numel() * world),
+                     "api": "model.set_input_format('u8_hwc').set_label_output(True, logits=False); raw uint8 RGB "
+                            "frames in, uint8 label map out (what Trainer_MIMOcom.evaluate consumes)"}
+        del fmodel, f_buf, l_dev
+
+    # ---- the same step in the parity precision (bf16x3: hi/lo split operands, <= 1e-3 of the logit range vs fp32)
+    parity_precision = None
+    if not args.no_parity_value and args.precision == "bf16":
+        model.set_precision("bf16x3")
+        for _ in range(3):
+            step_dev()
+        ms_x3 = timed(step_dev, max(3, args.steps // 2)) / max(3, args.steps // 2)
+        parity_precision = {"precision": "bf16x3", "value": frames_total / (ms_x3 * 1e-3), "unit": UNIT,
+                            "ms_per_step": ms_x3, "logit_tolerance": "1e-3 of max|logit| vs the fp32 oracle "
+                            "(tests/test_parity_gpu.py)"}
+        model.set_precision("bf16")
+
     # ---- roofline of the dominant kernel (conv_tc_kernel): replay ONLY its launches, same buffers, CUDA events
     prog = max(model._w2c["programs"].values(), key=lambda c: c.prog.n_launches).prog
     conv_prog = prog.conv_only_program()
-    n_conv = len(conv_prog.calls)
+    n_conv = sum(1 for c in conv_prog.calls if c[1] is not None)
     for _ in range(3):
         conv_prog.run(True)
     ms_conv = timed(lambda: conv_prog.run(True), args.steps) / args.steps
@@ -312,7 +386,7 @@ def run_b200(args):
     achieved = conv_tflop_step / (ms_conv * 1e-3)
     roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/deconv, all instantiations)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic_per_launch(n_conv),
                 "launches_per_step": n_conv, "avg_launch_ms": ms_conv / n_conv, "share_of_step": ms_conv / ms_step,
                 "peak_source": "%s (sustained cuBLAS bf16, kernel timed inside a long step)" % peaks["source"],
                 "algorithmic_tflop_per_step_per_gpu": conv_tflop_step}
@@ -334,7 +408,7 @@ def run_b200(args):
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (hi/lo split, fp32-grade)",
             "data": "synthetic", "config": workload_config(args, world, n_agents, scenes),
-            "e2e": e2e, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
+            "e2e": e2e, "e2e_fused": e2e_fused, "parity_precision": parity_precision, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "frames_per_step": frames_total,
             "model_tflops": GFLOP_PER_FRAME * value / 1e3 if args.backbones == "n_segnet" else None}
@@ -351,9 +425,9 @@ def write_layer_table(path, prog, dev):
     import torch
     lib_conv = prog._lib.w2c_conv_bnrelu_fwd
     rows = []
-    for fn, args in prog.calls:
-        if fn is None:
-            continue  # host op (collective)
+    for fn, args, _sid in prog.calls:
+        if fn is None or isinstance(fn, str):
+            continue  # host op (collective) / fork-join marker
         best = 1e9
         for _ in range(5):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

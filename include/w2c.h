@@ -128,11 +128,12 @@ int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, c
  *         channels [c_first + 3a, c_first + 3a + 3)
  *   w     fp32 [cout][27]  (k = ci*9 + kh*3 + kw, i.e. Conv2d.weight flattened), scale/shift fp32 [cout]
  *   y     NHWC [(n_agents*b)][h][w][cout], image index = agent*b + batch ("agent-major", agent.py:1103-1108)
- * cout must be a multiple of 32 and <= 128.
+ * cout must be a multiple of 32 and <= 128.  n_split = 2 (cout = 128: two encoders' first layers fused, the image is
+ * read once): y receives TWO dense NHWC maps of 64 channels, one after the other, instead of one of 128.
  */
 int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
                          int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
-                         int32_t cout, int32_t act, w2c_stream_t stream);
+                         int32_t cout, int32_t act, int32_t n_split, w2c_stream_t stream);
 
 /*
  * The same first layer reading the loader's RAW frames: uint8 RGB HWC [b][agents_total][h][w][3] (what
@@ -144,7 +145,7 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
  */
 int w2c_stem_conv3x3_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
                             const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
-                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act, int32_t n_split,
                             w2c_stream_t stream);
 
 /* ---- evaluation-loop glue ----------------------------------------------------------- */

@@ -67,8 +67,8 @@ _SIGNATURES = {
     "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "w2c_fold_bn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp]),
-    "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 8 + [c_vp]),
-    "w2c_stem_conv3x3_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 8 + [c_vp]),
+    "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "w2c_stem_conv3x3_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_argmax_labels_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, c_vp]),
     "w2c_confusion_update": (ctypes.c_int, [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp]),
     "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),

@@ -17,11 +17,12 @@ void count_launch(unsigned n = 1);
 
 // stem_tc.cu: tensor-core first layer (cout 64 / 128)
 int stem3x3_tc_forward(const float* x, const float* w, const float* scale, const float* shift, void* y, int b,
-                       int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, cudaStream_t stream);
+                       int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, int n_split,
+                       cudaStream_t stream);
 
 int stem3x3_tc_u8_forward(const uint8_t* x, const float* lut, const float* w, const float* scale, const float* shift,
                           void* y, int b, int n_agents, int agents_total, int agent_first, int h, int wpx, int cout,
-                          int act, cudaStream_t stream);
+                          int act, int n_split, cudaStream_t stream);
 
 #define W2C_CHECK_ARG(cond, ...)                                   \
   do {                                                             \

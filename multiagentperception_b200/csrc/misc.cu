@@ -383,7 +383,8 @@ int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, c
 
 int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
                          int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout,
-                         int32_t act, w2c_stream_t stream) {
+                         int32_t act, int32_t n_split, w2c_stream_t stream) {
+  W2C_CHECK_ARG(n_split == 1 || (n_split == 2 && cout == 128), "stem3x3: n_split=%d needs cout=128", n_split);
   W2C_CHECK_ARG(x && w && scale && shift && y, "stem3x3: null pointer");
   W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3: bad extent");
   W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem3x3: channel window [%d, %d) outside %d",
@@ -394,7 +395,7 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
     return e && e[0] == '1';
   }();
   if ((cout == 64 || cout == 128) && !force_simt)
-    return stem3x3_tc_forward(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act,
+    return stem3x3_tc_forward(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act, n_split,
                               static_cast<cudaStream_t>(stream));
   const size_t total = static_cast<size_t>(b) * n_agents * h * w_px;
   const size_t smem = (27 * cout + 2 * cout) * sizeof(float);
@@ -406,15 +407,16 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
 
 int w2c_stem_conv3x3_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
                             const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
-                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                            int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act, int32_t n_split,
                             w2c_stream_t stream) {
+  W2C_CHECK_ARG(n_split == 1 || (n_split == 2 && cout == 128), "stem3x3_u8: n_split=%d needs cout=128", n_split);
   W2C_CHECK_ARG(frames && lut && w && scale && shift && y, "stem3x3_u8: null pointer");
   W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3_u8: bad extent");
   W2C_CHECK_ARG(agent_first >= 0 && agent_first + n_agents <= agents_total, "stem3x3_u8: agents [%d, %d) outside %d",
                 agent_first, agent_first + n_agents, agents_total);
   W2C_CHECK_ARG(cout == 64 || cout == 128, "stem3x3_u8: cout=%d (64 or 128)", cout);
   return stem3x3_tc_u8_forward(frames, lut, w, scale, shift, y, b, n_agents, agents_total, agent_first, h, w_px, cout,
-                               act, static_cast<cudaStream_t>(stream));
+                               act, n_split, static_cast<cudaStream_t>(stream));
 }
 
 int w2c_argmax_labels_fwd(const float* logits, uint8_t* labels, int32_t n, int32_t c, int64_t hw,

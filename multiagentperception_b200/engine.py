@@ -25,6 +25,10 @@ def default_precision():
     return p
 
 
+# W2C_TWO_STREAMS=0 records every model as one serial chain (A/B switch for Program.side_stream)
+TWO_STREAMS = os.environ.get("W2C_TWO_STREAMS", "1") != "0"
+
+
 def use_graphs_default():
     return os.environ.get("W2C_CUDA_GRAPH", "1") != "0"
 
@@ -149,7 +153,9 @@ class Program:
         self.device = device
         self.act = act
         self.planes = ops.planes_of(act)
-        self.calls = []      # (fn, args tuple) with the stream appended at run time
+        self.calls = []      # (fn, args tuple, stream id) with the stream appended at run time; see side_stream()
+        self._sid = 0        # stream id new calls are recorded on (0 = the caller's stream, 1 = the side stream)
+        self._side = None    # torch.cuda.Stream of the side chain, created on first use
         self.keep = []       # keeps ctypes structs / tensors alive
         self.graph = None
         self.n_launches = 0  # kernel launches per run (counted from the library's counter)
@@ -177,7 +183,35 @@ class Program:
 
     # ---- recorded launches
     def _record(self, fn, *args):
-        self.calls.append((fn, args))
+        self.calls.append((fn, args, self._sid))
+
+    # ---- two concurrent chains
+    # u_encoder and query_key_net are independent kernel chains between the stem and the attention (agent.py:1111 and
+    # 1124 read the same views). Recorded on two streams they become parallel branches of the CUDA graph, so one
+    # chain's CTAs fill the other's tails: persistent kernels with 4.3 waves of tiles, ~5 us ramp-up per launch and
+    # the sub-wave layers at 16x16 otherwise leave SMs idle at every kernel boundary.
+    _FORK, _JOIN = "fork", "join"
+
+    def side_stream(self):
+        """Context manager: calls recorded inside run on the side stream, which first waits for everything recorded
+        so far. join() makes the main chain wait for them."""
+        prog = self
+
+        class _Ctx:
+            def __enter__(self):
+                if TWO_STREAMS:
+                    prog.calls.append((Program._FORK, None, 0))
+                    prog._sid = 1
+
+            def __exit__(self, *exc):
+                prog._sid = 0
+                return False
+
+        return _Ctx()
+
+    def join(self):
+        if TWO_STREAMS:
+            self.calls.append((Program._JOIN, None, 0))
 
     def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None):
         """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given). labels: uint8 [n, h, w] tensor that
@@ -210,17 +244,28 @@ class Program:
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret
 
-    def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0):
+    def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False):
+        """split=True (a fused pair of 64-channel first layers): returns TWO dense 64-channel maps."""
         wt, scale, shift = st
         cout = wt.shape[0]
-        out = self.act_buf(b * n_agents, h, w, cout)
+        n_split = 2 if split else 1
+        if split:
+            if cout != 128:
+                raise ValueError("a split stem needs 128 output channels")
+            buf = torch.empty((2, b * n_agents, h, w, self.planes * 64), dtype=torch.bfloat16, device=self.device)
+            self.keep.append(buf)
+            out = tuple(ActMap(buf[i], b * n_agents, h, w, 64) for i in range(2))
+            y_ptr = buf.data_ptr()
+        else:
+            out = self.act_buf(b * n_agents, h, w, cout)
+            y_ptr = out.buf.data_ptr()
         if self.input_u8:  # x_nchw is the uint8 frame buffer [b, agents_total, h, w, 3]; c_first counts channels
             self._record(self._lib.w2c_stem_conv3x3_u8_fwd, x_nchw.data_ptr(), self.lut.data_ptr(), wt.data_ptr(),
-                         scale.data_ptr(), shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1],
-                         c_first // 3, h, w, cout, self.act)
+                         scale.data_ptr(), shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first // 3, h, w,
+                         cout, self.act, n_split)
             return out
         self._record(self._lib.w2c_stem_conv3x3_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
-                     shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act)
+                     shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act, n_split)
         return out
 
     def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0):
@@ -304,7 +349,9 @@ class Program:
     def host_op(self, fn):
         """A step that must run outside CUDA-graph capture (a torch.distributed collective): splits the program
         into separately captured segments around it. fn() is called on the current stream at run time."""
-        self.calls.append((None, fn))
+        if self._sid:
+            raise RuntimeError("host ops cannot be recorded on the side stream")
+        self.calls.append((None, fn, 0))
 
     def copy_channels(self, src, dst):
         """dst[..., slice] = src (device-to-device strided copy through torch; used for concat inputs only)."""
@@ -314,33 +361,59 @@ class Program:
                 s = src.buf[..., pl * src.cstride + src.coffset: pl * src.cstride + src.coffset + src.c]
                 d.copy_(s)
             return 0
-        self.calls.append((run, None))
+        self.calls.append((run, None, self._sid))
 
     def memset(self, t):
         def run(_stream):
             t.zero_()
             return 0
-        self.calls.append((run, None))
+        self.calls.append((run, None, self._sid))
 
     # ---- execution
     def _segments(self):
         """Split the call list at host ops: [(calls, host_fn_or_None), ...]."""
         segs, cur = [], []
-        for fn, args in self.calls:
+        for fn, args, sid in self.calls:
             if fn is None:
                 segs.append((cur, args))
                 cur = []
             else:
-                cur.append((fn, args))
+                cur.append((fn, args, sid))
         segs.append((cur, None))
         return segs
 
     def _run_calls(self, calls):
-        stream = ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        for fn, args in calls:
-            rc = fn(stream) if args is None else fn(*args, stream)
+        main = torch.cuda.current_stream(self.device)
+        streams = [main, None]
+        ptrs = [ctypes.c_void_p(main.cuda_stream), None]
+        forked = False
+        for fn, args, sid in calls:
+            if fn is Program._FORK:
+                if self._side is None:
+                    self._side = torch.cuda.Stream(self.device)
+                streams[1], ptrs[1] = self._side, ctypes.c_void_p(self._side.cuda_stream)
+                self._side.wait_stream(main)
+                forked = True
+                continue
+            if fn is Program._JOIN:
+                if forked:
+                    main.wait_stream(self._side)
+                    forked = False
+                continue
+            if sid and not forked:
+                sid = 0  # (a sub-program that dropped the fork marker)
+            if args is None:  # torch-side op (strided copy / memset): runs on the stream that is current
+                if sid:
+                    with torch.cuda.stream(streams[1]):
+                        rc = fn(ptrs[1])
+                else:
+                    rc = fn(ptrs[0])
+            else:
+                rc = fn(*args, ptrs[sid])
             if rc != 0:
                 _lib.check(rc, getattr(fn, "__name__", "launch"))
+        if forked:
+            main.wait_stream(self._side)
 
     def _run_eager(self):
         for calls, host in self._segments():
@@ -384,5 +457,6 @@ class Program:
         time the dominant kernel in isolation from the stems / attention / layout kernels."""
         sub = Program(self.weights, self.device, self.act)
         sub.keep = self.keep
-        sub.calls = [(fn, args) for fn, args in self.calls if fn is self._lib.w2c_conv_bnrelu_fwd]
+        sub.calls = [c for c in self.calls if c[0] is self._lib.w2c_conv_bnrelu_fwd or c[0] in (Program._FORK,
+                                                                                                  Program._JOIN)]
         return sub

@@ -180,8 +180,9 @@ def _fused_stems(prog, enc_a, enc_b, x_nchw, b, n_agents, h, w):
     if not (isinstance(ba, n_segnet_encoder) and isinstance(bb, n_segnet_encoder)):
         return None, None
     ua, ub = ba.units()[0], bb.units()[0]
-    both = prog.stem3x3(x_nchw, prog.weights.stem_pair(ua.conv, ua.bn, ub.conv, ub.bn), b, n_agents, h, w)
-    return both.slice(0, 64), both.slice(64, 64)
+    # two dense 64-channel maps (not one interleaved 128-channel map: each encoder's stride-2 conv would read half of
+    # every 256-byte pixel)
+    return prog.stem3x3(x_nchw, prog.weights.stem_pair(ua.conv, ua.bn, ub.conv, ub.bn), b, n_agents, h, w, split=True)
 
 
 def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
@@ -419,7 +420,8 @@ class _AttentionModel(_W2CModel):
         if dst is not None:
             val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], FEATURE_CHANNELS)
         stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
-        val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
+        with prog.side_stream():  # the feature encoder runs beside the policy net + heads (independent chains)
+            val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
         qk = _build_policy(prog, self.query_key_net, x, b, n, h, w, stem=stem_p)
         if qk.h != qk.w:
             raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
@@ -432,6 +434,7 @@ class _AttentionModel(_W2CModel):
             keys, = prog.kq_mlp_heads(qk, heads)
             queries = prog.f32_buf(n * b, self.query_size) if dst is None else dst[1]
             queries.fill_(1.0)  # torch.ones(batch, 1, query_size), agent.py:1144
+        prog.join()
         return val, keys, queries
 
 

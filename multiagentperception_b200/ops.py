@@ -91,10 +91,11 @@ def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind,
     return y
 
 
-def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, c_total=0, c_first=0):
+def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, c_total=0, c_first=0, n_split=1):
+    """n_split=2 (cout=128): y holds two dense 64-channel NHWC maps, [2, n, h, w, planes*64]."""
     lib = _lib.load()
     _lib.check(lib.w2c_stem_conv3x3_fwd(_ptr(x_nchw), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,
-                                        c_total or 3 * n_agents, c_first, h, w, cout, act, _stream()),
+                                        c_total or 3 * n_agents, c_first, h, w, cout, act, n_split, _stream()),
                "w2c_stem_conv3x3_fwd")
     return y
 
@@ -110,13 +111,14 @@ def loader_lut(mean_bgr=LOADER_MEAN_BGR, img_norm=True, device=None):
     return t.to(device) if device is not None else t
 
 
-def stem_conv3x3_u8(frames, lut, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, agents_total=0, agent_first=0):
+def stem_conv3x3_u8(frames, lut, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, agents_total=0, agent_first=0,
+                    n_split=1):
     """frames: uint8 RGB HWC [b, agents_total, h, w, 3] (raw loader frames); lut from loader_lut()."""
     lib = _lib.load()
     if frames.dtype != torch.uint8:
         raise ValueError("stem_conv3x3_u8 needs uint8 frames")
     _lib.check(lib.w2c_stem_conv3x3_u8_fwd(_ptr(frames), _ptr(lut), _ptr(w27), _ptr(scale), _ptr(shift), _ptr(y), b,
-                                           n_agents, agents_total or n_agents, agent_first, h, w, cout, act,
+                                           n_agents, agents_total or n_agents, agent_first, h, w, cout, act, n_split,
                                            _stream()), "w2c_stem_conv3x3_u8_fwd")
     return y
 

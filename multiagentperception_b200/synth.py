@@ -23,6 +23,13 @@ def synthetic_views(batch, n_agents, height, width, seed=1337, device="cpu"):
     return x.to(device)
 
 
+def synthetic_frames(batch, n_agents, height, width, seed=1337):
+    """(batch, n_agents, H, W, 3) uint8 RGB: raw camera frames as airsimLoader.__getitem__ holds them before
+    transform() (airsim_loader.py:493-496)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return torch.randint(0, 256, (batch, n_agents, height, width, 3), generator=g, dtype=torch.uint8)
+
+
 def randomize_(module, seed=1337):
     """Re-initialise every parameter and buffer of `module` in place. Each tensor is drawn from its own generator
     seeded by (seed, crc32(state_dict key)), so the values do not depend on registration order."""

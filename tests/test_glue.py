@@ -85,6 +85,30 @@ def test_stem_on_raw_frames_equals_stem_on_transformed_views(cout, act, cuda_dev
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("act", [ops.ACT_BF16, ops.ACT_BF16X2])
+def test_fused_stem_pair_written_as_two_dense_maps(act, cuda_device):
+    """The two encoders' fused 3 -> 128 first layer stored as two dense 64-channel maps equals the one 128-channel
+    map, half by half (same accumulators, different tensor maps)."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(8)
+    b, n, h, w = 2, 2, 24, 40
+    x = torch.randn(b, 3 * n, h, w, generator=g).to(dev)
+    wt = (torch.randn(128, 27, generator=g) * 0.2).to(dev)
+    scale = (torch.rand(128, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(128, generator=g) * 0.1).to(dev)
+    pl = ops.planes_of(act)
+    one = ops.new_act(b * n, h, w, 128, act, dev)
+    ops.stem_conv3x3(x, wt, scale, shift, one, b=b, n_agents=n, h=h, w=w, cout=128, act=act)
+    two = torch.empty((2, b * n, h, w, pl * 64), dtype=torch.bfloat16, device=dev)
+    ops.stem_conv3x3(x, wt, scale, shift, two, b=b, n_agents=n, h=h, w=w, cout=128, act=act, n_split=2)
+    torch.cuda.synchronize()
+    for half in range(2):
+        for p in range(pl):
+            assert torch.equal(two[half][..., p * 64:(p + 1) * 64],
+                               one[..., p * 128 + half * 64:p * 128 + (half + 1) * 64])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("hw", [(16, 16), (24, 40), (128, 128)])
 def test_fused_label_map_equals_argmax_of_the_logits(hw, cuda_device):
     dev = cuda_device

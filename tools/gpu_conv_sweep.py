@@ -66,7 +66,7 @@ def main():
             if cin * cout * 9 * 2 > 147456 and kind != 2:
                 continue
             variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-resident", ops.IMPL_TC_PERSIST | (32 << 8), 0)]
-            if (kind == 0 and cin == 128 and cout == 64) or cout <= 16:
+            if (kind == 0 and cin == 128 and cout == 64) or cout <= 16 or (cin == 64 and cout == 64):
                 variants.append(("pers resident opt-in", ops.IMPL_TC_PERSIST | (64 << 8), 0))
             if kind == 2:
                 variants.append(("pers class-major", ops.IMPL_TC_PERSIST | (128 << 8), 0))
