@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== TMA producer =====================
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_halo_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(128, BLOCK_N);
       int sa = 0, sb = 0;

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
   const uint32_t row_px_bytes = static_cast<uint32_t>(p.tw) * p.tn * 128u;  // bytes of one box row
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== TMA producer =====================
       int st = 0;
       uint32_t ph = 0;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_pers_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
       const uint32_t ring0 = ptx::smem_u32(smem_ring);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {
       // ===================== TMA producer =====================
       if constexpr (RES > 0) {
         ptx::mbar_arrive_expect_tx(res_bar, RES * L::kBTileBytes);
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
       constexpr uint32_t kBTile16 = L::kBTileBytes >> 4;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     ptx::named_bar_sync(3, EG * kEpiThreads);
     const int eg = EG == 2 ? (warp - 2) >> 2 : 0;  // this thread's epilogue group
     const int bar_id = 1 + eg;
-    const bool elected = (et & (kEpiThreads - 1)) == 0;
+    const bool lead_warp = ((warp - 2) & 3) == 0;  // its elected lane issues this group's TMA stores
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int lw = row % p.tw;
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             for (int pln = 0; pln < planes; ++pln, ++unit) {
               uint8_t* stg = smem + L::kStgOff + (EG == 2 ? eg : unit % L::kNumStaging) * kStagingBytes;
               // the TMA store that last used this staging tile must have finished reading it
-              if (elected) ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
+              if (lead_warp && ptx::elect_one_sync()) ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
               ptx::named_bar_sync(bar_id, kEpiThreads);
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
               }
               ptx::fence_proxy_async();
               ptx::named_bar_sync(bar_id, kEpiThreads);
-              if (elected) {
+              if (lead_warp && ptx::elect_one_sync()) {
                 ptx::tma_store_4d(&p.y_map[tc.cls], stg, pl.y_coffset + cb + pln * pl.y_cstride, tc.w0, tc.h0, tc.i0);
                 ptx::bulk_commit_group();
               }
@@ -444,7 +444,8 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
     }
-    if (elected) ptx::bulk_wait_group<0>();  // all TMA stores have landed before the CTA retires
+    __syncwarp();
+    if (lead_warp && ptx::elect_one_sync()) ptx::bulk_wait_group<0>();  // all TMA stores landed before the CTA retires
   }
 
   ptx::tc_fence_before();

@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== MMA issuer =====================
       constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));

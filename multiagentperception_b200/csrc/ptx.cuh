@@ -19,6 +19,22 @@ __device__ __forceinline__ uint32_t lane_id() {
   return l;
 }
 
+// One lane of a fully converged warp (elect.sync). Unlike `lane == 0`, ptxas knows the guarded region runs on a
+// single thread, so tcgen05 / TMA instructions with uniform-register operands are issued directly instead of inside
+// a per-instruction ELECT "waterfall" loop (measured on the persistent conv kernel: ~75 SASS instructions and ~600
+// cycles per k-block in the MMA-issuing thread, 5x the time of the four N = 64 MMAs it issues).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
     ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
     ptx::tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && ptx::elect_one_sync()) {
       ptx::tc_fence_after();
       // K = 32 = two UMMA k-steps (32 B apart inside the swizzle row)
       ptx::umma_bf16(tmem_base, a_hi, b_hi, idesc, 0);
@@ -239,7 +239,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
 #pragma unroll 1
       for (int pln = 0; pln < planes; ++pln, ++unit) {
         uint8_t* stg = smem + L::kStg + (unit % NS) * kStagingBytes;
-        if (tid == 0) ptx::bulk_wait_group_read<NS - 1>();  // the store that last used this tile has read it
+        if (warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group_read<NS - 1>();  // last store has read the tile
         __syncthreads();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {  // 32 accumulator columns at a time (register budget: 128)
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
         }
         ptx::fence_proxy_async();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && ptx::elect_one_sync()) {
           // rows of the output viewed as [total pixels][COUT * planes]; rows past the end are clipped by the TMA unit
           const int split = (g * 64) / y_maps.cs;
           ptx::tma_store_2d(&y_maps.m[split], stg, pln * y_maps.cs + g * 64 - split * y_maps.cs, tile * kTile);
@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
     // the next iteration's __syncthreads (after its smem writes) orders these TMEM reads before the next MMA
     ptx::tc_fence_before();
   }
-  if (tid == 0) ptx::bulk_wait_group<0>();
+  __syncwarp();
+  if (warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group<0>();
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 0) {

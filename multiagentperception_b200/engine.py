@@ -25,8 +25,10 @@ def default_precision():
     return p
 
 
-# W2C_TWO_STREAMS=0 records every model as one serial chain (A/B switch for Program.side_stream)
-TWO_STREAMS = os.environ.get("W2C_TWO_STREAMS", "1") != "0"
+# W2C_TWO_STREAMS=1 records the two encoder chains as parallel graph branches (Program.side_stream). Measured on
+# B200: no gain (3399 / 3386 vs 3419 agent-frames/s serial) - the step runs at the 1 kW power cap, where overlapping
+# kernels cannot add throughput - so the default is one serial chain.
+TWO_STREAMS = os.environ.get("W2C_TWO_STREAMS", "0") == "1"
 
 
 def use_graphs_default():

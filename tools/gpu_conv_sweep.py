@@ -44,7 +44,11 @@ def main():
     dev = torch.device("cuda:0")
     act = ops.ACT_BF16X2 if os.environ.get("SWEEP_X3") == "1" else ops.ACT_BF16
     lines = ["| kind | hw | cin | cout | variant | ms | TFLOP/s |", "|---|---|---|---|---|---|---|"]
+    only = os.environ.get("SWEEP_ONLY")  # "kind,h,cin,cout[;kind,h,cin,cout...]": restrict to these layers (ncu captures)
+    only = [tuple(int(v) for v in o.split(",")) for o in only.split(";")] if only else None
     for kind, h, cin, cout, nchw in LAYERS:
+        if only is not None and (kind, h, cin, cout) not in only:
+            continue
         x = torch.randn(N, h, h, ops.planes_of(act) * cin, device=dev).to(torch.bfloat16)
         wt = torch.randn((cin, cout, 3, 3) if kind == 2 else (cout, cin, 3, 3), device=dev) * 0.05
         wp = ops.pack_conv_weight(wt, cin, kind == 2, act)
@@ -87,6 +91,9 @@ def main():
             cp = 1
         if os.environ.get("SWEEP_QUICK") == "1":
             variants = variants[:3]
+            cp = 1
+        if os.environ.get("SWEEP_PROD") == "1":  # only the production dispatch (for ncu captures)
+            variants = [("production dispatch", ops.IMPL_TCGEN05, 0)]
             cp = 1
         if cp % 256 == 0:
             variants.append(("taps bn256", ops.IMPL_TC_TAPS, 256))
