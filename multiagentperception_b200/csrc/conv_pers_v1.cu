@@ -20,6 +20,9 @@ namespace w2c {
 int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                const cuuint32_t* box, CUtensorMapL2promotion promo);
 
+int encode_map_f32(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box);
+
 namespace {
 
 constexpr int kBlockM = 128;
@@ -40,6 +43,7 @@ struct PersParams {
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+  int nchw_tma;   // 1: fp32 NCHW logits through a [cout][8][16] staging box + TMA store (y_map[0] is that fp32 map)
   int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
 };
 
@@ -67,7 +71,10 @@ struct PersSmem {
   static constexpr int kAOff = 0;
   static constexpr int kBOff = STAGES * kAStage;  // weight ring, or the resident weight tiles
   static constexpr int kStgOff = kBOff + (RES > 0 ? RES * kBTileBytes : STAGES * kBStageBytes);
-  static constexpr int kBarOff = kStgOff + kNumStaging * kStagingBytes;  // full[S] empty[S] tfull[2] tempty[2] res
+  // fp32 [16 ch][128 px] staging box per epilogue group for the NCHW logits layer (BLOCK_N = 16 only)
+  static constexpr int kNchwOff = kStgOff + kNumStaging * kStagingBytes;
+  static constexpr int kNchwBytes = BLOCK_N == 16 ? 16 * kBlockM * 4 : 0;
+  static constexpr int kBarOff = kNchwOff + EG * kNchwBytes;  // full[S] empty[S] tfull[2] tempty[2] res
   static constexpr int kTmemPtrOff = kBarOff + (2 * STAGES + 5) * 8;
   static constexpr int kScaleOff = kTmemPtrOff + 8;
   static constexpr int kShiftOff = kScaleOff + kMaxCout * 4;
@@ -366,6 +373,41 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
         }
       }
 
+      // ---- fp32 NCHW logits of a full 8x16 tile: [class][8][16] staging box, one TMA store (the per-thread stores
+      //      of this layout are 64-byte segments, 11 per thread: ncu had the LSU/L1 pipe at 77 % on this layer)
+      if constexpr (BLOCK_N == 16) {
+        if (p.nchw_tma) {
+          float* stg = reinterpret_cast<float*>(smem + L::kNchwOff + eg * L::kNchwBytes);
+          uint32_t r[16];
+          ptx::tmem_ld_32x32b_x16(t_row, r);
+          ptx::tmem_ld_wait();
+          if (lead_warp && ptx::elect_one_sync()) ptx::bulk_wait_group_read<0>();  // previous store has read the box
+          ptx::named_bar_sync(bar_id, kEpiThreads);
+          float best = -1.f;
+          int arg = 0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = fmaf(__uint_as_float(r[j]), s_scale[j], s_shift[j]);
+            if (pl.relu) v = fmaxf(v, 0.f);
+            if (j < pl.cout) {
+              stg[j * kBlockM + row] = v;
+              if (j == 0 || v > best) best = v, arg = j;
+            }
+          }
+          if (pl.labels && valid)
+            pl.labels[(static_cast<size_t>(img) * pl.out_h + oh) * pl.out_w + ow] = static_cast<uint8_t>(arg);
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(bar_id, kEpiThreads);
+          if (lead_warp && ptx::elect_one_sync()) {
+            ptx::tma_store_4d(&p.y_map[0], stg, tc.w0, tc.h0, 0, tc.i0);
+            ptx::bulk_commit_group();
+          }
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty_bar[acc]);
+          continue;
+        }
+      }
+
       // ---- direct-store epilogue: fp32 NCHW logits, or NHWC when cout is not a multiple of 64
       constexpr int kChunk = BLOCK_N < 32 ? 16 : 32;
 #pragma unroll 1
@@ -593,6 +635,22 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   } else {
     for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
   }
+  static const bool allow_nchw_tma = [] {
+    const char* e = getenv("W2C_CONV_NCHW_TMA");
+    return !(e && e[0] == '0');
+  }();
+  p.nchw_tma = 0;
+  if (allow_nchw_tma && !((a.impl >> 8) & 256) && plan.out_fmt == W2C_OUT_NCHW_F32 && plan.y && bn == 16 && p.n_tiles == 1 && tn == 1 &&
+      tw == 16 && th == 8 && plan.num_classes == 1 && plan.out_w % 4 == 0) {
+    const cuuint64_t dims[4] = {(cuuint64_t)plan.out_w, (cuuint64_t)plan.out_h, (cuuint64_t)plan.cout,
+                                (cuuint64_t)plan.n_img};
+    const cuuint64_t str[3] = {(cuuint64_t)plan.out_w * 4, (cuuint64_t)plan.out_h * plan.out_w * 4,
+                               (cuuint64_t)plan.cout * plan.out_h * plan.out_w * 4};
+    const cuuint32_t ybox[4] = {(cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)plan.cout, 1};
+    int rc = encode_map_f32(&p.y_map[0], plan.y, 4, dims, str, ybox);
+    if (rc) return rc;
+    p.nchw_tma = 1;
+  }
 
   // two epilogue warpgroups unless disabled (impl flag bit 1 / env) - see PersSmem
   static const bool allow_eg2 = [] {
@@ -601,7 +659,9 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   }();
   const bool eg2 = allow_eg2 && !((a.impl >> 8) & 2);
   int cps = ((a.impl >> 8) & 8) ? 3 : ((a.impl >> 8) & 4) ? 2 : 1;
-  if (!((a.impl >> 8) & (4 | 8 | 16)) && row_halo && bn == 16) cps = 3;  // default for the logits layer (sweep v4)
+  // default for the logits layer: two CTAs per SM (with the lean elect.sync issue loops 0.50 ms, against 0.53 with
+  // three and 0.72 with one; before that change three were best - profiles/r1_conv_sweep_v6_elect.md)
+  if (!((a.impl >> 8) & (4 | 8 | 16)) && row_halo && bn == 16) cps = 2;
   if (!((row_halo && bn == 16) || bn == 64)) cps = 1;
   if (bn == 64 && cps > 2) cps = 2;
   p.ctas_per_sm = cps;

@@ -278,6 +278,19 @@ int encode_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* d
   return W2C_OK;
 }
 
+// fp32 tensor, no swizzle (the NCHW logits written through TMA)
+int encode_map_f32(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                   const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return set_error(W2C_ERR_DRIVER, "cuTensorMapEncodeTiled driver entry point not available");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(W2C_ERR_DRIVER, "cuTensorMapEncodeTiled (f32) failed with CUresult %d", (int)r);
+  return W2C_OK;
+}
+
 namespace {
 
 int pow2_ceil(int v) {

@@ -78,7 +78,9 @@ def main():
             variants += [("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
         if cout <= 16 and not ab:
             variants += [("pers 1cta/sm", ops.IMPL_TC_PERSIST | (16 << 8), 0),
-                         ("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
+                         ("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0),
+                         ("pers direct stores", ops.IMPL_TC_PERSIST | (256 << 8), 0),
+                         ("pers 1cta/sm 1-epi-group", ops.IMPL_TC_PERSIST | ((16 | 2) << 8), 0)]
         cp = 1 if ab else ops.cout_pad(cout)
         if cp % 256 == 0:
             variants.append(("pers bn128", ops.IMPL_TC_PERSIST, 128))
