@@ -99,8 +99,8 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        path = _build.LIB_PATH
-        if not os.path.exists(path) or os.environ.get("W2C_REBUILD") == "1":
+        path = os.environ.get("W2C_LIB") or _build.LIB_PATH   # W2C_LIB: an alternative build, for A/B runs
+        if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("W2C_REBUILD") == "1"):
             path = _build.build()
         lib = ctypes.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():

@@ -43,6 +43,7 @@ struct PersParams {
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+  int prefetch;   // tiles of L2 prefetch distance for the input windows (0 = off)
   int nchw_tma;   // 1: fp32 NCHW logits through a [cout][8][16] staging box + TMA store (y_map[0] is that fp32 map)
   int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
 };
@@ -159,6 +160,20 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       TileCoord tc;
       for (int it = 0; tile_at(p, it, BLOCK_N, tc); ++it) {
         const int ntaps = pl.ntaps[tc.cls];
+        // Experiment (off by default, W2C_CONV_PREFETCH=n): L2-prefetch the input windows of the tile n iterations ahead.
+        // Hypothesis was that the ring of the narrow layers is bound by HBM-miss latency (6 stages x 24 KB / ~1.4 us =
+        // the ~540 cycles per k-block measured); measured on B200 it made the stride-2 convs 9-22 % SLOWER and
+        // nothing faster (profiles/r1_conv_sweep_v8_prefetch.md), so first-touch latency is not what binds them.
+        if (p.prefetch && (tc.cls == 0)) {
+          TileCoord nx;
+          if (tile_at(p, it + (p.prefetch << p.cls_shift), BLOCK_N, nx) && nx.n0 == 0) {
+            const int nmaps = pl.in_s == 2 ? 4 : 1;
+            for (int ch = 0; ch < chunks; ++ch)
+              for (int mi = 0; mi < nmaps; ++mi)
+                ptx::tma_prefetch_4d(&p.a_map[GROUP == 3 ? 1 : mi], pl.x_coffset + ch * kBlockK, nx.w0,
+                                     nx.h0 - (GROUP == 3 ? 1 : 0), nx.i0);
+          }
+        }
         for (int pass = 0; pass < npass; ++pass) {
           const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
           const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
@@ -562,6 +577,9 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
       bn = 32;
     else
       bn = 16;
+    // fewer than two waves of 256-wide tiles (the 16x16 maps: 160 tiles on 148 SMs): 128-wide tiles balance better
+    // (0.058 vs 0.067 ms; one-tile kernel 0.073 - profiles/r1_conv_sweep_v7_full.md)
+    if (bn == 256 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 2 * 148) bn = 128;
     // not enough tiles to occupy the SMs at this width: narrower tiles
     while (bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148) bn /= 2;
   }
@@ -635,6 +653,12 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   } else {
     for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
   }
+  // L2 prefetch distance in tiles (experiment, default off; impl flag 512 forces it off)
+  static const int prefetch_dist = [] {
+    const char* e = getenv("W2C_CONV_PREFETCH");
+    return e ? atoi(e) : 0;
+  }();
+  p.prefetch = ((a.impl >> 8) & 512) ? 0 : prefetch_dist;
   static const bool allow_nchw_tma = [] {
     const char* e = getenv("W2C_CONV_NCHW_TMA");
     return !(e && e[0] == '0');

@@ -479,9 +479,11 @@ namespace w2c {
 // win; the same holds when there are too few tiles to give every persistent CTA at least two.
 bool conv_persistent_preferred(const ConvPlan& plan) {
   const long long m_tiles = (static_cast<long long>(plan.n_img) * plan.hm * plan.wm + 127) / 128;
-  const int bn = plan.cout_pad % 256 == 0 ? 256 : plan.cout_pad % 128 == 0 ? 128 : 64;
+  // at least one 128-wide tile per SM (with the lean elect.sync issue loops the persistent kernel wins from there on;
+  // the 8x8 / 4x4 policy-tail layers stay on the one-tile kernel)
+  const int bn = plan.cout_pad % 128 == 0 ? 128 : 64;
   const long long tiles = m_tiles * plan.num_classes * ((plan.cout_pad + bn - 1) / bn);
-  if (tiles < 2 * 148) return false;
+  if (tiles < 148) return false;
   // narrow stride-1 convs: only with row-halo stages (12 MMAs per barrier round trip) does one issuer keep up;
   // the 11-channel logits layer additionally runs three persistent CTAs (issuers) per SM: 0.53 vs 0.98 ms
   const bool row_halo = plan.num_classes == 1 && plan.in_s == 1 && plan.ntaps[0] == 9 && plan.wm >= 16 && plan.hm >= 8;

@@ -97,6 +97,13 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* m, uint64_t* bar,
       "r"(c3)
       : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared memory, no barrier): turns the later ring load of the same box from an
+// HBM-latency load into an L2-latency one.
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
 // 1-D bulk copy global -> shared (no tensor map), completes on an mbarrier.
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile(

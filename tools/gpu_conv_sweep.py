@@ -97,11 +97,15 @@ def main():
         if os.environ.get("SWEEP_PROD") == "1":  # only the production dispatch (for ncu captures)
             variants = [("production dispatch", ops.IMPL_TCGEN05, 0)]
             cp = 1
+        if os.environ.get("SWEEP_PF") == "1":  # A/B of the L2 prefetch (impl flag 512 = off)
+            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-prefetch", ops.IMPL_TC_PERSIST | (512 << 8), 0)]
+            cp = 1
         if cp % 256 == 0:
             variants.append(("taps bn256", ops.IMPL_TC_TAPS, 256))
         if cp % 128 == 0:
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
-        if kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1":
+        if (kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1"
+                and os.environ.get("SWEEP_PROD") != "1" and os.environ.get("SWEEP_PF") != "1"):
             variants.append(("halo", ops.IMPL_TC_HALO, 0))
             if cp % 128 == 0 and kind == 0:
                 variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
