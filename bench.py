@@ -140,9 +140,9 @@ def cpu_reference_rate(backbones, inference, steps, warmup, n_agents=5):
         orc.forward(sd, cfg, x, **kw)
     t0 = time.perf_counter()
     for _ in range(steps):
-        orc.forward(sd, cfg, x, **kw)
+        out = orc.forward(sd, cfg, x, **kw)
     dt = time.perf_counter() - t0
-    return {"value": n_agents * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+    return {"oracle_out": out, "oracle_in": x, "value": n_agents * steps / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
             "sample": "%d step(s) x 1 scene x %d agents @%dx%d, fp32 torch-CPU restatement of the reference forward "
                       "(oracle/when2com_oracle.py), %.1f s" % (steps, n_agents, IMG, IMG, dt),
             "ms_per_step": dt / steps * 1e3}
@@ -400,16 +400,28 @@ def run_b200(args):
         return 0
 
     cpu_baseline = None
+    parity = None
     if world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_rate(args.backbones, args.inference, steps=2, warmup=1)
         cpu_baseline = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        # the metric's second half, "mIoU vs reference": the oracle's fp32 output of that one scene is the checker for
+        # the CUDA path on the same views, in both precisions (arg-max labels of the oracle as ground truth)
+        from oracle import when2com_oracle as orc
+        ref_pred = r["oracle_out"][0]
+        parity = {"sample": "1 scene x 5 agents @%dx%d, same weights and views as cpu_baseline" % (IMG, IMG)}
+        for prec in ("bf16", "bf16x3"):
+            model.set_precision(prec)
+            pred = model(r["oracle_in"].to(dev), **kw)[0].float().cpu()
+            parity[prec] = {"max_logit_err_over_max_logit": float((pred - ref_pred).abs().max() / ref_pred.abs().max()),
+                            "miou_vs_reference_argmax": orc.miou_between(ref_pred, pred)}
+        model.set_precision(args.precision)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (hi/lo split, fp32-grade)",
             "data": "synthetic", "config": workload_config(args, world, n_agents, scenes),
             "e2e": e2e, "e2e_fused": e2e_fused, "parity_precision": parity_precision, "gpu_launches": int(launches_per_step * args.steps), "launches_per_step": int(launches_per_step),
-            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "frames_per_step": frames_total,
             "model_tflops": GFLOP_PER_FRAME * value / 1e3 if args.backbones == "n_segnet" else None}
     print(json.dumps(line), flush=True)

@@ -199,20 +199,22 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
               }
             }
           } else {
-            for (int tp_i = 0; tp_i < ntaps; ++tp_i) {
-              const Tap tp = pl.taps[tc.cls][tp_i];
-              const CUtensorMap* amap = &p.a_map[tp.map];
-              for (int ch = 0; ch < chunks; ++ch) {
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
-                ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * L::kAStage, a_c0 + ch * kBlockK,
-                                 tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
-                if constexpr (RES == 0)
-                  ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
-                                   tp.wtap * pl.cin + ch * kBlockK, b_row);
-                if (++stage == STAGES) stage = 0, phase ^= 1;
-              }
-            }
+            // canonical K order (ConvPlan::kw_major): (kw, chunk, kh) for 3x3 s1 convs - what the row-halo stages
+            // above run - and (tap, chunk) otherwise
+            const int n_outer = pl.kw_major ? 3 : ntaps, n_inner = pl.kw_major ? 3 : 1;
+            for (int o = 0; o < n_outer; ++o)
+              for (int ch = 0; ch < chunks; ++ch)
+                for (int i = 0; i < n_inner; ++i) {
+                  const Tap tp = pl.taps[tc.cls][pl.kw_major ? i * 3 + o : o];
+                  ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                  ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+                  ptx::tma_load_4d(&p.a_map[tp.map], &full_bar[stage], smem + L::kAOff + stage * L::kAStage,
+                                   a_c0 + ch * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh, tc.i0);
+                  if constexpr (RES == 0)
+                    ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
+                                     tp.wtap * pl.cin + ch * kBlockK, b_row);
+                  if (++stage == STAGES) stage = 0, phase ^= 1;
+                }
           }
         }
       }
@@ -722,7 +724,8 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
       if (cps >= 2) return launch_persv1<64, 3, 1, 1>(p, stream);
       // (resident weights measured 5-9 % SLOWER here - 64->64 s2 conv 0.469 vs 0.431 ms, deconv 0.636 vs 0.605: the
       // per-tap slot lookup sits in the single MMA-issuing thread; opt-in only, profiles/r1_conv_sweep_v5_ab.md)
-      if (res_ok && res_slots == 9 && eg2 && ((a.impl >> 8) & 64)) return launch_persv1<64, 7, 1, 2, 9>(p, stream);
+      if (res_ok && res_slots == 9 && eg2 && !plan.kw_major && ((a.impl >> 8) & 64))
+        return launch_persv1<64, 7, 1, 2, 9>(p, stream);
       return eg2 ? launch_persv1<64, 6, 1, 2>(p, stream) : launch_persv1<64, 6, 1, 1>(p, stream);
     case 32: return eg2 ? launch_persv1<32, 6, 1, 2>(p, stream) : launch_persv1<32, 6, 1, 1>(p, stream);
     default: return eg2 ? launch_persv1<16, 6, 1, 2>(p, stream) : launch_persv1<16, 6, 1, 1>(p, stream);

@@ -41,6 +41,11 @@ struct ConvPlan {
   int x_pix, x_cstride, x_coffset;  // x_pix = elements per input pixel (all planes)
   int y_pix, y_cstride, y_coffset;
   int act, relu, out_fmt;
+  // K order of the accumulation. 3x3 stride-1 convs run (filter column kw, 64-channel chunk, filter row kh) in EVERY
+  // tensor-core kernel - the order the row-halo stages of the persistent kernel impose - so that the result does not
+  // depend on which kernel / tile width the dispatch picks for a given batch (sharded == unsharded, scene i alone
+  // == scene i inside a batch, bit for bit). Everything else runs (tap, chunk).
+  int kw_major;
 };
 
 // conv_halo.cu
@@ -113,6 +118,7 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
       p.hm = a.h_in, p.wm = a.w_in;
       p.ktot = 9 * a.cin;
       p.ntaps[0] = 9;
+      p.kw_major = 1;
       for (int kh = 0; kh < 3; ++kh)
         for (int kw = 0; kw < 3; ++kw) p.taps[0][kh * 3 + kw] = tap(kw - 1, kh - 1, 0, kh * 3 + kw, kw - 1, kh - 1);
       break;

@@ -112,19 +112,20 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       for (int pass = 0; pass < npass; ++pass) {
         const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
         const int b_row = n0 + (pass == 1 ? pl.cout_pad : 0);
-        for (int t = 0; t < ntaps; ++t) {
-          const Tap tp = pl.taps[cls][t];
-          const CUtensorMap* amap = &p.a_map[tp.map];
-          for (int ch = 0; ch < chunks; ++ch) {
-            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-            ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
-            ptx::tma_load_4d(amap, &full_bar[stage], smem + L::kAOff + stage * kAStageBytes, a_c0 + ch * kBlockK,
-                             w0 + tp.dw, h0 + tp.dh, i0);
-            ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
-                             tp.wtap * pl.cin + ch * kBlockK, b_row);
-            if (++stage == STAGES) stage = 0, phase ^= 1;
-          }
-        }
+        // canonical K order (ConvPlan::kw_major): (kw, chunk, kh) for 3x3 s1 convs, (tap, chunk) otherwise
+        const int n_outer = pl.kw_major ? 3 : ntaps, n_inner = pl.kw_major ? 3 : 1;
+        for (int o = 0; o < n_outer; ++o)
+          for (int ch = 0; ch < chunks; ++ch)
+            for (int i = 0; i < n_inner; ++i) {
+              const Tap tp = pl.taps[cls][pl.kw_major ? i * 3 + o : o];
+              ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageTx);
+              ptx::tma_load_4d(&p.a_map[tp.map], &full_bar[stage], smem + L::kAOff + stage * kAStageBytes,
+                               a_c0 + ch * kBlockK, w0 + tp.dw, h0 + tp.dh, i0);
+              ptx::tma_load_2d(&p.b_map, &full_bar[stage], smem + L::kBOff + stage * L::kBStageBytes,
+                               tp.wtap * pl.cin + ch * kBlockK, b_row);
+              if (++stage == STAGES) stage = 0, phase ^= 1;
+            }
       }
     }
   } else if (warp == 1) {
