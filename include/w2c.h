@@ -255,6 +255,15 @@ int w2c_maxpool3x3s2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w
 int w2c_bilinear_up_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
                         w2c_stream_t stream);
 
+/* Indexed copy of image groups between NHWC maps: dst image (g*b + i), channels [dst_coffset, dst_coffset + c)  <-
+ * src image (sel[g]*b + i), channels [src_coffset, src_coffset + c), for g < n_groups, i < b.  sel is a DEVICE int32
+ * array (NULL = identity): the random-selection baselines (All_agents / MIMO_All_agents with shuffle_features =
+ * 'selection', agent.py:447-452,934-947) redraw it per forward without rebuilding the captured program; it is also
+ * the concat of `torch.cat(feature maps, 1)` (agent.py:460,970).  Channel counts / strides / offsets % 8 == 0. */
+int w2c_gather_images_fwd(const void* src, void* dst, const int32_t* sel, int32_t n_groups, int32_t b, int32_t h,
+                          int32_t w_px, int32_t c, int32_t src_cstride, int32_t src_coffset, int32_t dst_cstride,
+                          int32_t dst_coffset, int32_t act, w2c_stream_t stream);
+
 /* ---- layout helpers --------------------------------------------------------------------------------- */
 /* NHWC activation (act storage) -> fp32 NCHW, and back.  Used at module boundaries and by the tests. */
 int w2c_nhwc_to_nchw_f32(const void* x, float* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,

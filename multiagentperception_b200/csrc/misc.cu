@@ -298,6 +298,31 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* 
 }
 
 
+// ------------------------------------------------------------------------------------------ indexed image copy
+// dst image (g*b + i), channels [dst_coffset, +c)  <-  src image (sel[g]*b + i), channels [src_coffset, +c), NHWC in
+// units of 8 channels (16 bytes). sel lives on the DEVICE, so a captured program stays static while the host redraws
+// the selection per forward (the random-selection baselines, agent.py:447-452,934-947). sel == NULL: identity.
+__global__ void __launch_bounds__(256) gather_images_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst,
+                                                            const int* __restrict__ sel, int n_groups, int b,
+                                                            size_t px, int c8, int planes, int scs8, int sco8,
+                                                            int dcs8, int dco8) {
+  const size_t per_img = px * planes * c8;
+  const size_t total = static_cast<size_t>(n_groups) * b * per_img;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int cc = idx % c8;
+    size_t t = idx / c8;
+    const int pl = t % planes;
+    t /= planes;
+    const size_t pix = t % px;
+    const size_t img = t / px;  // destination image
+    const int g = img / b, i = img % b;
+    const size_t simg = static_cast<size_t>(sel ? sel[g] : g) * b + i;
+    dst[(img * px + pix) * planes * dcs8 + pl * dcs8 + dco8 + cc] =
+        src[(simg * px + pix) * planes * scs8 + pl * scs8 + sco8 + cc];
+  }
+}
+
 // ------------------------------------------------------------------------------------------ eval-loop glue
 // labels[n][p] = argmax_c logits[n][c][p], first maximal index (torch.max(1)[1], trainer.py:804); one thread per
 // pixel, coalesced plane reads.
@@ -444,6 +469,23 @@ int w2c_confusion_update(const uint8_t* pred, const void* gt, int32_t gt_dtype, 
   else
     confusion_kernel<long long><<<grid, 256, smem, s>>>(pred, static_cast<const long long*>(gt), count, n_class, h);
   W2C_CHECK_LAUNCH("confusion_kernel");
+  return W2C_OK;
+}
+
+int w2c_gather_images_fwd(const void* src, void* dst, const int32_t* sel, int32_t n_groups, int32_t b, int32_t h,
+                          int32_t w_px, int32_t c, int32_t src_cstride, int32_t src_coffset, int32_t dst_cstride,
+                          int32_t dst_coffset, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(src && dst && n_groups > 0 && b > 0 && h > 0 && w_px > 0 && c > 0, "gather_images: bad arguments");
+  W2C_CHECK_ARG(c % 8 == 0 && src_cstride % 8 == 0 && src_coffset % 8 == 0 && dst_cstride % 8 == 0 && dst_coffset % 8 == 0,
+                "gather_images: channel counts, strides and offsets must be multiples of 8");
+  W2C_CHECK_ARG(src_coffset + c <= src_cstride && dst_coffset + c <= dst_cstride, "gather_images: slice out of range");
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t px = static_cast<size_t>(h) * w_px;
+  const size_t total = static_cast<size_t>(n_groups) * b * px * planes * (c / 8);
+  gather_images_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(src), static_cast<uint4*>(dst), sel, n_groups, b, px, c / 8, planes, src_cstride / 8,
+      src_coffset / 8, dst_cstride / 8, dst_coffset / 8);
+  W2C_CHECK_LAUNCH("gather_images_kernel");
   return W2C_OK;
 }
 

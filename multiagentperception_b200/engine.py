@@ -355,6 +355,15 @@ class Program:
             raise RuntimeError("host ops cannot be recorded on the side stream")
         self.calls.append((None, fn, 0))
 
+    def gather_images(self, src, dst, b, n_groups, sel=None):
+        """dst image group g (b images), channel slice of `dst`  <-  src image group sel[g] (device int32 tensor; None =
+        identity), channel slice of `src`."""
+        if src.c != dst.c or (src.h, src.w) != (dst.h, dst.w):
+            raise ValueError("gather_images: source and destination maps differ in shape")
+        self._record(self._lib.w2c_gather_images_fwd, src.buf.data_ptr(), dst.buf.data_ptr(),
+                     sel.data_ptr() if sel is not None else None, n_groups, b, src.h, src.w, src.c, src.cstride,
+                     src.coffset, dst.cstride, dst.coffset, self.act)
+
     def copy_channels(self, src, dst):
         """dst[..., slice] = src (device-to-device strided copy through torch; used for concat inputs only)."""
         def run(_stream):

@@ -9,6 +9,8 @@ kernel launches through engine.Program and runs it; there is no eager PyTorch pa
   MIMO_All_agents   agent.py:892-981        MIMOcom           agent.py:983-1204
   MIMOcomWho        agent.py:1207-1423
 """
+import random
+
 import torch
 import torch.nn as nn
 
@@ -91,12 +93,27 @@ class _ScaledAttention(_Container):
         self.temperature = temperature
 
 
+class _AdditiveAttention(_Container):
+    """AdditiveAttentin, agent.py:215-240: score_i = linear_out(linear_feat(k_i) + linear_context(q)). The query term
+    is the same for every supporter i, and softmax / sparsemax over i are shift-invariant, so the attention weights
+    are those of a dot product of the keys with ONE fixed vector u = linear_feat.weight^T linear_out.weight^T: the
+    attention kernel runs it as a projection-free dot attention whose "query" rows all hold u."""
+
+    def __init__(self):
+        super().__init__()
+        self.linear_feat = nn.Linear(128, 128)
+        self.linear_context = nn.Linear(128, 128)
+        self.linear_out = nn.Linear(128, 1)
+
+
 def _make_attention(attention, query_size, key_size):
     if attention == "general":
         return _DotAttention(query_size, key_size)
     if attention == "additive":
-        raise NotImplementedError("AdditiveAttentin (agent.py:215-240) has no accelerated kernel; no shipped "
-                                  "config selects it")
+        if key_size != 128:
+            raise ValueError("AdditiveAttentin has fixed 128-wide projections (agent.py:221-223); key_size=%d"
+                             % key_size)
+        return _AdditiveAttention()
     return _ScaledAttention(128 ** 0.5)
 
 
@@ -273,7 +290,7 @@ class _W2CModel(nn.Module):
         return {k: c.prog.n_launches for k, c in self._w2c["programs"].items()}
 
     # ---- compile / run
-    def _compiled(self, inputs, tag, builder):
+    def _compiled(self, inputs, tag, builder, pre_run=None):
         if self.training:
             raise RuntimeError(
                 "%s: the B200 path implements the eval-mode forward only (BatchNorm folded from running statistics, "
@@ -311,6 +328,8 @@ class _W2CModel(nn.Module):
             self._w2c["programs"][key] = c
         with torch.cuda.device(dev), torch.no_grad():
             c.x.copy_(inputs)
+            if pre_run is not None:
+                pre_run(c)  # per-call device state of a static program (e.g. the drawn selection indices)
             c.prog.run(self._w2c["graphs"])
         self._w2c["last"] = c
         return c
@@ -371,12 +390,18 @@ class _AttentionModel(_W2CModel):
         self.sparse = sparse
         self.attention = attention
         self.image_size = image_size
-        if shared_img_encoder != "unified":
-            raise NotImplementedError(
-                "only shared_img_encoder='unified' (every shipped config) is on the accelerated path; got %r"
-                % (shared_img_encoder,))
-        self.u_encoder = img_encoder(n_classes=n_classes, in_channels=in_channels, feat_channel=feat_channel,
-                                     feat_squeezer=feat_squeezer, enc_backbone=enc_backbone)
+        mk = lambda: img_encoder(n_classes=n_classes, in_channels=in_channels, feat_channel=feat_channel,
+                                 feat_squeezer=feat_squeezer, enc_backbone=enc_backbone)
+        if shared_img_encoder == "unified" or isinstance(self, MIMOcom):
+            if shared_img_encoder != "unified" and self.who:
+                raise ValueError("Incorrect shared_img_encoder flag")  # agent.py:1229-1230
+            self.u_encoder = mk()                   # (MIMOcom builds it unconditionally, agent.py:1001)
+        elif shared_img_encoder == "only_normal_agents":   # agent.py:494-498,697-701 (srms_who2com.yml)
+            self.degarded_encoder = mk()
+            self.normal_encoder = mk()
+        else:                                       # one encoder per agent, agent.py:500-510,703-713
+            for i in range(1, 6):
+                setattr(self, "encoder%d" % i, mk())
         self.key_net = head_cls(out_size=key_size, input_feat_sz=image_size / 32)
         self.attention_net = attention_module
         self.query_key_net = policy_net4(n_classes=n_classes, in_channels=in_channels, enc_backbone=enc_backbone)
@@ -390,10 +415,21 @@ class _AttentionModel(_W2CModel):
     def attention_paras(self):
         return list(self.attention_net.parameters())
 
+    def _value_encoders(self):
+        """[(encoder module, first agent, number of agents)] producing the feature maps, in agent order."""
+        if hasattr(self, "u_encoder"):
+            return None
+        if hasattr(self, "degarded_encoder"):
+            return [(self.degarded_encoder, 0, 1), (self.normal_encoder, 1, 4)]
+        return [(getattr(self, "encoder%d" % (i + 1)), i, 1) for i in range(5)]
+
     @property
     def img_net_paras(self):
         extra = list(self.argmax_decoder.parameters()) if hasattr(self, "argmax_decoder") else []
-        return list(self.u_encoder.parameters()) + list(self.decoder.parameters()) + extra
+        encs = self._value_encoders()
+        enc_p = (list(self.u_encoder.parameters()) if encs is None
+                 else [p for e, _, _ in encs for p in e.parameters()])
+        return enc_p + list(self.decoder.parameters()) + extra
 
     @property
     def policy_net_paras(self):
@@ -411,7 +447,22 @@ class _AttentionModel(_W2CModel):
             wq = prog.weights.tensor(self.attention_net.linear.weight, ("attn_w", id(self.attention_net)))
             bq = prog.weights.tensor(self.attention_net.linear.bias, ("attn_b", id(self.attention_net)))
             return wq, bq, 1.0
+        if isinstance(self.attention_net, _AdditiveAttention):
+            return None, None, 1.0
         return None, None, float(self.attention_net.temperature)
+
+    def _additive_queries(self, prog, rows):
+        """[rows, 128] fp32 buffer whose every row is u = linear_feat.weight^T linear_out.weight^T (see
+        _AdditiveAttention): the stand-in query matrix of the additive attention."""
+        a = self.attention_net
+        key = ("additive_u", id(a), rows)
+        u = prog.weights._misc.get(key)
+        if u is None:
+            w = a.linear_out.weight.detach().to(prog.device, torch.float32) @ \
+                a.linear_feat.weight.detach().to(prog.device, torch.float32)          # [1, 128]
+            u = w.expand(rows, 128).contiguous()
+            prog.weights._misc[key] = u
+        return u
 
     def _keys_queries(self, prog, x, b, n, h, w, dst=None):
         """u_encoder features, key and query vectors for the n agents in x (agent.py:1111-1148). dst = (keys,
@@ -419,9 +470,20 @@ class _AttentionModel(_W2CModel):
         val_out = None
         if dst is not None:
             val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], FEATURE_CHANNELS)
-        stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
-        with prog.side_stream():  # the feature encoder runs beside the policy net + heads (independent chains)
-            val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
+        encs = self._value_encoders()
+        if encs is None:
+            stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
+            with prog.side_stream():  # the feature encoder runs beside the policy net + heads (independent chains)
+                val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
+        else:
+            # separate encoders per agent group (agent.py:579-594,823-838), each writing its agents' images of the
+            # agent-major feature buffer
+            stem_p = None
+            sq = 2 if encs[0][0].feat_squeezer == 2 else 1
+            val = prog.act_buf(n * b, h // 32 // sq, w // 32 // sq, encs[0][0].squeezer.conv.out_channels)
+            for enc, first, count in encs:
+                _build_encoder(prog, enc, "enc%d" % first, x, b, count, h, w, c_first=3 * first,
+                               out=val.images(first * b, count * b))
         qk = _build_policy(prog, self.query_key_net, x, b, n, h, w, stem=stem_p)
         if qk.h != qk.w:
             raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
@@ -625,9 +687,12 @@ class LearnWhen2Com(_AttentionModel):
             connect = prog.f32_buf(1, dtype=torch.int32, zero=True)
             fused = prog.act_buf(b, val.h, val.w, val.c)
             prog.memset(connect)
+            q_dim = self.query_size
+            if isinstance(self.attention_net, _AdditiveAttention):
+                queries, q_dim = self._additive_queries(prog, queries.shape[0]), 128
             # one requester (agent 0: the first b rows of the agent-major query matrix), all five supporters
             prog.attn(keys, queries, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=1,
-                      k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], sparse=self.sparse,
+                      k_dim=self.key_size, q_dim=q_dim, mode=_MODES[mode], sparse=self.sparse,
                       temperature=temp, diag_bias=0.0)
             return {"pred": _build_decoder(prog, self.decoder, fused), "prob": prob, "coef": coef,
                     "action": action, "connect": connect}
@@ -677,8 +742,11 @@ class LearnWho2Com(_AttentionModel):
             cat = prog.act_buf(b, val.h, val.w, 2 * val.c)  # cat(own, aux) on channels, agent.py:623
             prog.copy_channels(val.images(0, b), cat.slice(0, val.c))
             # supporters are agents 1..4 (agent.py:603-614): skip the first b rows / images
+            q_dim = self.query_size
+            if isinstance(self.attention_net, _AdditiveAttention):
+                queries, q_dim = self._additive_queries(prog, queries.shape[0]), 128
             prog.attn(keys[b:], queries, wq, bq, val.images(b, (n - 1) * b), cat.slice(val.c, val.c), prob, None,
-                      action, None, b_sz=b, n_k=n - 1, n_q=1, k_dim=self.key_size, q_dim=self.query_size,
+                      action, None, b_sz=b, n_k=n - 1, n_q=1, k_dim=self.key_size, q_dim=q_dim,
                       mode=_MODES[mode], sparse=self.sparse, temperature=temp, diag_bias=0.0)
             return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob}
 
@@ -703,13 +771,23 @@ class MIMO_All_agents(_W2CModel):
     def forward(self, inputs):
         n = self.agent_num
         _check_views(inputs, n)
-        if self.shuffle_flag in ("selection", "ComNet"):
-            raise NotImplementedError("the random-selection / ComNet baselines (agent.py:934-961) are not on the "
-                                      "accelerated path")
         b, h, w = _bhw(inputs)
+        if self.shuffle_flag == "selection":
+            return self._forward_selection(inputs, n, b, h, w)
 
         def build(prog, x):
             feat = _build_encoder(prog, self.encoder, "encoder", x, b, n, h, w)
+            if self.shuffle_flag == "ComNet":
+                # cat(own, mean of the other agents' maps), agent.py:948-961: the attention kernel with all-equal
+                # scores and the diagonal masked gives exactly the 1/(n-1) weights
+                cat = prog.act_buf(n * b, feat.h, feat.w, 2 * feat.c)
+                prog.gather_images(feat, cat.slice(0, feat.c), b, n)
+                zeros = prog.f32_buf(n * b, 8, zero=True)
+                prob = prog.f32_buf(b, n, n)
+                action = prog.f32_buf(b, n, dtype=torch.int64)
+                prog.attn(zeros, zeros, None, None, feat, cat.slice(feat.c, feat.c), prob, None, action, None, b_sz=b,
+                          n_k=n, n_q=n, k_dim=8, q_dim=8, mode=ops.FUSE_SOFTMAX, mask_self=True)
+                return {"pred": _build_decoder(prog, self.decoder, cat)}
             cat = prog.act_buf(n * b, feat.h, feat.w, n * feat.c)
             for i in range(n):          # agent i decodes cat_j feat[(i + j) % n], agent.py:963-971
                 for j in range(n):
@@ -718,6 +796,27 @@ class MIMO_All_agents(_W2CModel):
             return {"pred": _build_decoder(prog, self.decoder, cat)}
 
         return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+
+    def _forward_selection(self, inputs, n, b, h, w):
+        """Random-selection baseline, agent.py:934-947: agent i decodes cat(own map, map of a randomly drawn agent).
+        The draws come from Python's `random` exactly like the reference (same call order, so the same seed gives the
+        same selection); they are copied into a device index array that the captured program reads."""
+        picks = [random.randint(0, n - 1) for _ in range(n)]
+
+        def build(prog, x):
+            feat = _build_encoder(prog, self.encoder, "encoder", x, b, n, h, w)
+            cat = prog.act_buf(n * b, feat.h, feat.w, 2 * feat.c)
+            sel = prog.f32_buf(n, dtype=torch.int32)
+            prog.gather_images(feat, cat.slice(0, feat.c), b, n)
+            prog.gather_images(feat, cat.slice(feat.c, feat.c), b, n, sel=sel)
+            return {"pred": _build_decoder(prog, self.decoder, cat), "sel": sel}
+
+        def pre_run(c):
+            c.out["sel"].copy_(torch.tensor(picks, dtype=torch.int32))
+
+        out = self._compiled(inputs, "selection", build, pre_run).out
+        action = torch.tensor(picks, dtype=torch.long, device=inputs.device).view(1, n).expand(b, n).contiguous()
+        return self._ret(out["pred"]), action
 
 
 class All_agents(_W2CModel):
@@ -737,11 +836,11 @@ class All_agents(_W2CModel):
 
     def forward(self, inputs):
         _check_views(inputs, 5)  # divide_num hard-coded, agent.py:433
-        if self.shuffle_flag == "selection":
-            raise NotImplementedError("the random-selection baseline (agent.py:447-452) is not on the accelerated path")
         b, h, w = _bhw(inputs)
-        used = 2 if self.shuffle_flag == "fixed2" else 5
         fc = self.encoder1.squeezer.conv.out_channels
+        if self.shuffle_flag == "selection":
+            return self._forward_selection(inputs, b, h, w, fc)
+        used = 2 if self.shuffle_flag == "fixed2" else 5
         if self.decoder.output_decoder.in_channels != used * fc and self.decoder.feat_squeezer not in (2, 4):
             raise ValueError("decoder expects %d input channels but %d feature maps of %d channels are concatenated"
                              % (self.decoder.output_decoder.in_channels, used, fc))
@@ -757,3 +856,29 @@ class All_agents(_W2CModel):
             return {"pred": _build_decoder(prog, self.decoder, cat)}
 
         return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+
+    def _forward_selection(self, inputs, b, h, w, fc):
+        """Random-selection baseline, agent.py:447-452,466-467: the requester decodes cat(own map, map of ONE randomly
+        drawn agent - possibly itself); one `random.randint(0, 4)` per forward like the reference."""
+        aux_id = random.randint(0, 4)
+
+        def build(prog, x):
+            hh, ww = h // 32, w // 32
+            if self.encoder1.feat_squeezer == 2:
+                hh, ww = hh // 2, ww // 2
+            feats = prog.act_buf(5 * b, hh, ww, fc)          # agent-major: all five encoders run, like the reference
+            for i in range(5):
+                _build_encoder(prog, getattr(self, "encoder%d" % (i + 1)), "encoder%d" % (i + 1), x, b, 1, h, w,
+                               c_first=3 * i, out=feats.images(i * b, b))
+            cat = prog.act_buf(b, hh, ww, 2 * fc)
+            sel = prog.f32_buf(1, dtype=torch.int32)
+            prog.gather_images(feats, cat.slice(0, fc), b, 1)
+            prog.gather_images(feats, cat.slice(fc, fc), b, 1, sel=sel)
+            return {"pred": _build_decoder(prog, self.decoder, cat), "sel": sel}
+
+        def pre_run(c):
+            c.out["sel"].fill_(aux_id)
+
+        out = self._compiled(inputs, "selection", build, pre_run).out
+        action = torch.full((b,), aux_id, dtype=torch.long, device=inputs.device)
+        return self._ret(out["pred"]), action

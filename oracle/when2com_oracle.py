@@ -12,6 +12,7 @@ tests or golden vectors of its own, so that is the only pi
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
 """
 import math
+import random
 
 import numpy as np
 import torch
@@ -173,7 +174,10 @@ def single_request_attention(q, k, v, sd, p, attention, sparse):
         qt = F.linear(q, sd[p + ".linear.weight"], sd[p + ".linear.bias"])
         s = torch.bmm(k, qt.transpose(2, 1))
     elif attention == "additive":
-        raise NotImplementedError("AdditiveAttentin (agent.py:215-240) is not on the accelerated path")
+        # AdditiveAttentin.forward, agent.py:225-240: linear_out(linear_feat(k) + linear_context(q))
+        t1 = F.linear(k, sd[p + ".linear_feat.weight"], sd[p + ".linear_feat.bias"])
+        t2 = F.linear(q, sd[p + ".linear_context.weight"], sd[p + ".linear_context.bias"])
+        s = F.linear(t1 + t2, sd[p + ".linear_out.weight"], sd[p + ".linear_out.bias"])  # (B, n_key, 1)
     else:
         s = torch.bmm(k, q.transpose(2, 1)) / (128 ** 0.5)
     a = sparsemax_dim1(s) if sparse else torch.softmax(s, dim=1)  # (B, n_key, 1)
@@ -251,16 +255,28 @@ def mimocom_forward(sd, cfg, x, training=True, MO_flag=True, inference="argmax",
     raise ValueError("Incorrect inference mode")
 
 
+def _value_maps(x, sd, m, enc, n, b):
+    """Feature maps of the n agents, (B, N, C, h, w), by encoder-sharing mode (agent.py:569-594,814-838)."""
+    mode = m["shared_img_encoder"]
+    if mode == "unified":
+        feat = img_encoder(_split_agents(x, n), sd, "u_encoder", enc, m["feat_squeezer"])
+        return feat.view(n, b, *feat.shape[1:]).transpose(0, 1)
+    if mode == "only_normal_agents":
+        f0 = img_encoder(x[:, 0:3], sd, "degarded_encoder", enc, m["feat_squeezer"])
+        rest = img_encoder(torch.cat([x[:, 3 * i:3 * i + 3] for i in range(1, n)], 0), sd, "normal_encoder", enc,
+                           m["feat_squeezer"])
+        return torch.cat((f0.unsqueeze(1), rest.view(n - 1, b, *rest.shape[1:]).transpose(0, 1)), 1)
+    feats = [img_encoder(x[:, 3 * i:3 * i + 3], sd, "encoder%d" % (i + 1), enc, m["feat_squeezer"]) for i in range(n)]
+    return torch.stack(feats, 1)
+
+
 def learn_when2com_forward(sd, cfg, x, training=True, inference="argmax"):
     """LearnWhen2Com.forward, agent.py:811-889 (5 agents hard-coded, agent.py:763)."""
     m, enc, dec = _cfg(cfg)
     n = 5
-    if m["shared_img_encoder"] != "unified":
-        raise NotImplementedError("only shared_img_encoder='unified' is on the accelerated path")
     b = x.shape[0]
     imgs = _split_agents(x, n)
-    feat = img_encoder(imgs, sd, "u_encoder", enc)
-    val = feat.view(n, b, *feat.shape[1:]).transpose(0, 1)
+    val = _value_maps(x, sd, m, enc, n, b)
     qk = policy_net4(imgs, sd, "query_key_net", enc)
     keys = km_generator(qk, sd, "key_net").view(n, b, -1).transpose(0, 1)
     if m["query"]:
@@ -288,12 +304,9 @@ def learn_who2com_forward(sd, cfg, x, training=True, inference="argmax"):
     cat(own, aux)."""
     m, enc, dec = _cfg(cfg)
     n = 5
-    if m["shared_img_encoder"] != "unified":
-        raise NotImplementedError("only shared_img_encoder='unified' is on the accelerated path")
     b = x.shape[0]
     imgs = _split_agents(x, n)
-    feat = img_encoder(imgs, sd, "u_encoder", enc)
-    val = feat.view(n, b, *feat.shape[1:]).transpose(0, 1)
+    val = _value_maps(x, sd, m, enc, n, b)
     qk = policy_net4(imgs, sd, "query_key_net", enc)
     keys = km_generator(qk, sd, "key_net").view(n, b, -1).transpose(0, 1)[:, 1:]
     if m["query"]:
@@ -314,11 +327,25 @@ def mimo_all_agents_forward(sd, cfg, x):
     """MIMO_All_agents.forward catall branch, agent.py:924-981: each agent decodes the rotation-concatenated maps."""
     m, enc, dec = _cfg(cfg)
     n = m["agent_num"]
-    if m["shuffle_features"] in ("selection", "ComNet"):
-        raise NotImplementedError("random-selection / ComNet baselines are not deterministic parity targets")
     b = x.shape[0]
     feat = img_encoder(_split_agents(x, n), sd, "encoder", enc, m["feat_squeezer"])
     fm = feat.view(n, b, *feat.shape[1:])
+    if m["shuffle_features"] == "selection":
+        # agent.py:934-947: one random.randint(0, n-1) per agent, in agent order (Python's global `random`)
+        picks = [random.randint(0, n - 1) for _ in range(n)]
+        rows = [torch.cat((fm[i], fm[picks[i]]), 1) for i in range(n)]
+        action = torch.tensor(picks, dtype=torch.long).view(1, n).expand(b, n).contiguous()
+        return img_decoder(torch.cat(rows, 0), sd, "decoder", dec, m["feat_squeezer"]), action
+    if m["shuffle_features"] == "ComNet":
+        # agent.py:948-961: cat(own, mean of the other agents' maps)
+        rows = []
+        for i in range(n):
+            other = torch.zeros_like(fm[0])
+            for j in range(n):
+                if j != i:
+                    other = other + fm[j]
+            rows.append(torch.cat((fm[i], other / (n - 1)), 1))
+        return img_decoder(torch.cat(rows, 0), sd, "decoder", dec, m["feat_squeezer"])
     rows = [torch.cat([fm[(i + j) % n] for j in range(n)], 1) for i in range(n)]
     return img_decoder(torch.cat(rows, 0), sd, "decoder", dec, m["feat_squeezer"])
 
@@ -326,9 +353,12 @@ def mimo_all_agents_forward(sd, cfg, x):
 def all_agents_forward(sd, cfg, x):
     """All_agents.forward catall / fixed2 branches, agent.py:437-469 (five separate encoders)."""
     m, enc, dec = _cfg(cfg)
-    if m["shuffle_features"] == "selection":
-        raise NotImplementedError("random-selection baseline is not a deterministic parity target")
     feats = [img_encoder(x[:, 3 * i:3 * i + 3], sd, "encoder%d" % (i + 1), enc, m["feat_squeezer"]) for i in range(5)]
+    if m["shuffle_features"] == "selection":
+        # agent.py:447-452,466-467: one random.randint(0, 4); the requester decodes cat(own, drawn agent's map)
+        aux_id = random.randint(0, 4)
+        pred = img_decoder(torch.cat((feats[0], feats[aux_id]), 1), sd, "decoder", dec, m["feat_squeezer"])
+        return pred, torch.ones(feats[0].shape[0], dtype=torch.long) * aux_id
     if m["shuffle_features"] == "fixed2":
         feats = feats[:2]
     return img_decoder(torch.cat(feats, 1), sd, "decoder", dec, m["feat_squeezer"])

@@ -7,6 +7,7 @@ from multiagentperception_b200 import configs
 
 WEIGHT_SEED = 1337
 INPUT_SEED = 7
+RANDOM_SEED = 20   # random.seed() before every forward: the random-selection baselines draw from Python's `random`
 IMG = 128     # smallest size every arch accepts: policy_net4 needs (H/32) % 4 == 0
 BATCH = 2
 
@@ -35,6 +36,16 @@ CASES = {
     "who2com_resnet_argmax": ("LearnWho2Com", "resnet", dict(query_size=8),
                               dict(training=False, inference="argmax_test"), 5),
     "mimo_all_resnet": ("MIMO_All_agents", "resnet", dict(agent_num=3), {}, 3),
+    # shipped-YAML variants added in the second session (srms_who2com.yml, *_randcom.yml) and the additive attention
+    "who2com_resnet_normal_agents": ("LearnWho2Com", "resnet", dict(query_size=8, shared_img_encoder="only_normal_agents"),
+                                     dict(training=False, inference="argmax_test"), 5),
+    "when2com_segnet_separate_additive": ("LearnWhen2Com", "n_segnet",
+                                          dict(query_size=128, key_size=128, attention="additive",
+                                               shared_img_encoder=False),
+                                          dict(training=False, inference="softmax"), 5),
+    "mimo_all_resnet_selection": ("MIMO_All_agents", "resnet", dict(agent_num=4, shuffle_features="selection"), {}, 4),
+    "mimo_all_segnet_comnet": ("MIMO_All_agents", "n_segnet", dict(agent_num=3, shuffle_features="ComNet"), {}, 3),
+    "all_agents_resnet_selection": ("All_agents", "resnet", dict(agent_num=5, shuffle_features="selection"), {}, 5),
     "all_agents_resnet": ("All_agents", "resnet", dict(agent_num=5), {}, 5),
 }
 

@@ -1,6 +1,7 @@
 """CPU: the oracle restatement against the golden vectors produced by the unmodified reference
 (tests/golden/make_golden.py), and — where /root/reference is mounted — against the live reference."""
 import os
+import random
 
 import numpy as np
 import pytest
@@ -21,6 +22,7 @@ def _oracle_outputs(name):
     model = get_model(cfg, 11)
     synth.randomize_(model, cases.WEIGHT_SEED)
     x = synth.synthetic_views(cases.BATCH, n, cases.IMG, cases.IMG, seed=cases.INPUT_SEED)
+    random.seed(cases.RANDOM_SEED)   # the random-selection baselines draw from Python's `random`, like the reference
     return cases.as_tuple(orc.forward(model.state_dict(), cfg, x, **kw)), model, cfg, x, kw
 
 
@@ -51,12 +53,15 @@ def test_oracle_matches_reference_golden(name):
 
 
 @pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
-@pytest.mark.parametrize("name", ["mimocom_segnet_activated", "when2com_resnet_sparse", "who2com_resnet_argmax"])
+@pytest.mark.parametrize("name", ["mimocom_segnet_activated", "when2com_resnet_sparse", "who2com_resnet_argmax",
+                                  "who2com_resnet_normal_agents", "mimo_all_resnet_selection",
+                                  "all_agents_resnet_selection"])
 def test_oracle_matches_live_reference(name):
     outs, model, cfg, x, kw = _oracle_outputs(name)
     ref = ref_harness.build_reference_model(cfg)
     missing = ref.load_state_dict(model.state_dict(), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
+    random.seed(cases.RANDOM_SEED)
     routs = cases.as_tuple(ref_harness.reference_forward(ref, x, **kw))
     assert len(routs) == len(outs)
     for a, b in zip(routs, outs):
