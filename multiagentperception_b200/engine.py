@@ -53,7 +53,16 @@ class ActMap:
 
 
 class PackedConv:
-    __slots__ = ("w", "scale", "shift", "cin", "cout", "kind", "relu")
+    __slots__ = ("w", "scale", "shift", "cin", "cout", "kind", "relu", "subsample")
+
+
+def _stride2_view(pc):
+    """The same packed conv with the stride-4 post-subsampling switched off (Program.conv runs it first)."""
+    v = PackedConv()
+    for k in PackedConv.__slots__:
+        setattr(v, k, getattr(pc, k))
+    v.subsample = 1
+    return v
 
 
 class WeightCache:
@@ -80,7 +89,9 @@ class WeightCache:
         if transposed:
             kind = ops.DECONV3X3_S2
         elif (kh, kw) == (3, 3):
-            kind = {1: ops.CONV3X3_S1, 2: ops.CONV3X3_S2}.get(stride)
+            # stride 4 (img_encoder.squeezer with feat_squeezer=4, agent.py:51-52): out4[m] = sum_k x[4m + k - 1] is the
+            # stride-2 conv at the even output positions, out2[2m]: run the stride-2 kernel, keep every other pixel
+            kind = {1: ops.CONV3X3_S1, 2: ops.CONV3X3_S2, 4: ops.CONV3X3_S2}.get(stride)
         elif (kh, kw) == (1, 1):
             kind = {1: ops.CONV1X1_S1, 2: ops.CONV1X1_S2}.get(stride)
         else:
@@ -90,6 +101,7 @@ class WeightCache:
         pc = PackedConv()
         pc.w = ops.pack_conv_weight(w, cin, transposed, self.act)
         pc.cin, pc.cout, pc.kind, pc.relu = cin, conv.out_channels, kind, bool(relu)
+        pc.subsample = 2 if (not transposed and stride == 4) else 1
         pc.scale, pc.shift = self._fold(conv, bn)
         self._convs[key] = pc
         return pc
@@ -220,6 +232,22 @@ class Program:
         receives the arg-max class of the fp32 NCHW logits (nchw_out may then be the string 'none': labels only)."""
         if x.c != pc.cin:
             raise ValueError("conv expects %d input channels, got %d" % (pc.cin, x.c))
+        if pc.subsample == 2:
+            if nchw_out is not None or residual is not None or x.h % 4 or x.w % 4:
+                raise ValueError("stride-4 conv: NHWC output, no residual, H and W divisible by 4")
+            full = self.conv(x, _stride2_view(pc))                      # (h/2, w/2) map
+            if out is None:
+                out = self.act_buf(x.n, x.h // 4, x.w // 4, pc.cout)
+            planes = self.planes
+
+            def run(_stream, full=full, out=out):
+                for pl in range(planes):
+                    d = out.buf[..., pl * out.cstride + out.coffset: pl * out.cstride + out.coffset + out.c]
+                    sv = full.buf[:, ::2, ::2, pl * full.cstride + full.coffset: pl * full.cstride + full.coffset + full.c]
+                    d.copy_(sv)
+                return 0
+            self.calls.append((run, None, self._sid))
+            return out
         if pc.kind in (ops.CONV3X3_S2, ops.CONV1X1_S2):
             ho, wo = x.h // 2, x.w // 2
         elif pc.kind == ops.DECONV3X3_S2:

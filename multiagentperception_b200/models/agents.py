@@ -146,8 +146,6 @@ def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=Non
                 a = prog.conv(y, wc.conv(blk.conv2, blk.bn2, True), residual=idt)
     else:
         raise ValueError("unknown encoder backbone %r" % type(bb).__name__)
-    if enc.feat_squeezer == 4:
-        raise NotImplementedError("feat_squeezer=4 (stride-4 squeezer, agent.py:51-52) has no accelerated kernel")
     return prog.conv(a, wc.conv(enc.squeezer.conv, enc.squeezer.bn, True), out=out)
 
 
@@ -479,7 +477,7 @@ class _AttentionModel(_W2CModel):
             # separate encoders per agent group (agent.py:579-594,823-838), each writing its agents' images of the
             # agent-major feature buffer
             stem_p = None
-            sq = 2 if encs[0][0].feat_squeezer == 2 else 1
+            sq = {2: 2, 4: 4}.get(encs[0][0].feat_squeezer, 1)
             val = prog.act_buf(n * b, h // 32 // sq, w // 32 // sq, encs[0][0].squeezer.conv.out_channels)
             for enc, first, count in encs:
                 _build_encoder(prog, enc, "enc%d" % first, x, b, count, h, w, c_first=3 * first,
@@ -847,8 +845,8 @@ class All_agents(_W2CModel):
 
         def build(prog, x):
             hh, ww = h // 32, w // 32
-            if self.encoder1.feat_squeezer == 2:
-                hh, ww = hh // 2, ww // 2
+            sq = {2: 2, 4: 4}.get(self.encoder1.feat_squeezer, 1)
+            hh, ww = hh // sq, ww // sq
             cat = prog.act_buf(b, hh, ww, used * fc)
             for i in range(used):       # five separate encoders write straight into their concat slice
                 _build_encoder(prog, getattr(self, "encoder%d" % (i + 1)), "encoder%d" % (i + 1), x, b, 1, h, w,
@@ -864,8 +862,8 @@ class All_agents(_W2CModel):
 
         def build(prog, x):
             hh, ww = h // 32, w // 32
-            if self.encoder1.feat_squeezer == 2:
-                hh, ww = hh // 2, ww // 2
+            sq = {2: 2, 4: 4}.get(self.encoder1.feat_squeezer, 1)
+            hh, ww = hh // sq, ww // sq
             feats = prog.act_buf(5 * b, hh, ww, fc)          # agent-major: all five encoders run, like the reference
             for i in range(5):
                 _build_encoder(prog, getattr(self, "encoder%d" % (i + 1)), "encoder%d" % (i + 1), x, b, 1, h, w,

@@ -45,6 +45,8 @@ CASES = {
                                           dict(training=False, inference="softmax"), 5),
     "mimo_all_resnet_selection": ("MIMO_All_agents", "resnet", dict(agent_num=4, shuffle_features="selection"), {}, 4),
     "mimo_all_segnet_comnet": ("MIMO_All_agents", "n_segnet", dict(agent_num=3, shuffle_features="ComNet"), {}, 3),
+    "single_segnet_squeeze4": ("Single_agent", "n_segnet", dict(feat_squeezer=4), {}, 1),
+    "mimo_all_resnet_squeeze2": ("MIMO_All_agents", "resnet", dict(agent_num=2, feat_squeezer=2), {}, 2),
     "all_agents_resnet_selection": ("All_agents", "resnet", dict(agent_num=5, shuffle_features="selection"), {}, 5),
     "all_agents_resnet": ("All_agents", "resnet", dict(agent_num=5), {}, 5),
 }
