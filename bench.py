@@ -455,13 +455,14 @@ def write_layer_table(path, prog, dev):
             best = min(best, e0.elapsed_time(e1))
         if fn is lib_conv:
             a = args[0]._obj
-            taps = 1 if a.kind in (3, 4) else 9
+            taps = 1 if a.kind in (3, 4) else 9   # (kind 5, the dense transposed conv: useful MACs = the 9-tap count)
             if a.kind in (1, 4):
                 m = a.n * (a.h_in // 2) * (a.w_in // 2)
             else:
                 m = a.n * a.h_in * a.w_in
             flop = 2.0 * m * a.cin * a.cout * taps
-            names = {0: "conv3x3 s1", 1: "conv3x3 s2", 2: "deconv3x3 s2", 3: "conv1x1", 4: "conv1x1 s2"}
+            names = {0: "conv3x3 s1", 1: "conv3x3 s2", 2: "deconv3x3 s2", 3: "conv1x1", 4: "conv1x1 s2",
+                     5: "deconv3x3 s2 (dense)"}
             rows.append((names[a.kind], a.n, a.h_in, a.w_in, a.cin, a.cout, best, "%.1f" % (flop / (best * 1e-3) / 1e12)))
         else:
             rows.append((getattr(fn, "__name__", "host-side torch op"), "", "", "", "", "", best, ""))

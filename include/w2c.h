@@ -45,7 +45,13 @@ enum {
   W2C_CONV3X3_S2 = 1,   /* Conv2d k3 s2 p1   (H, W even)         */
   W2C_DECONV3X3_S2 = 2, /* ConvTranspose2d k3 s2 p1 output_padding 1 */
   W2C_CONV1X1_S1 = 3,   /* Conv2d k1 s1 p0                       */
-  W2C_CONV1X1_S2 = 4    /* Conv2d k1 s2 p0   (resnet downsample) */
+  W2C_CONV1X1_S2 = 4,   /* Conv2d k1 s2 p0   (resnet downsample) */
+  /* The same ConvTranspose2d k3 s2 p1 op1 evaluated as ONE dense GEMM per input tile: N = 4 output-parity classes x
+   * cout, K = the 2x2 input neighbourhood x cin (weights packed by w2c_pack_deconv_dense_weight, zero where a class
+   * does not use a neighbour: 16/9 of the useful MACs).  For cout = 64 the four 64-wide classes fill one 256-wide
+   * tcgen05 tile, the input tile is fetched 4x instead of 9x and the 128 KB of weights stay resident in shared
+   * memory - the 64-channel 256->512 layer of the decoder is bound by L2->SM traffic, not by MACs.  cout must be 64. */
+  W2C_DECONV3X3_S2_DENSE = 5
 };
 
 /* Library / build identification. */
@@ -111,6 +117,13 @@ size_t w2c_packed_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t
  */
 int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
                          int32_t transposed, int32_t act, void* packed, w2c_stream_t stream);
+
+/* Dense packing for W2C_DECONV3X3_S2_DENSE: bf16 [planes][4*cout][4*cin], row = class*cout + co with class =
+ * (oh & 1)*2 + (ow & 1), k = (dh*2 + dw)*cin + ci for the input pixel (oh/2 + dh, ow/2 + dw); w is
+ * ConvTranspose2d.weight [cin_real][cout][3][3]. */
+size_t w2c_packed_deconv_dense_bytes(int32_t cout, int32_t cin, int32_t act);
+int w2c_pack_deconv_dense_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t act,
+                                 void* packed, w2c_stream_t stream);
 
 /*
  * Fold eval-mode BatchNorm2d (+ the conv bias) into the per-channel affine the conv epilogue applies

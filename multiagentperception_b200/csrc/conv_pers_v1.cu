@@ -43,6 +43,7 @@ struct PersParams {
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+  int direct_store;  // 1: coalesced 16-byte stores from the staging tile instead of a TMA store (8x16 tiles only)
   int prefetch;   // tiles of L2 prefetch distance for the input windows (0 = off)
   int nchw_tma;   // 1: fp32 NCHW logits through a [cout][8][16] staging box + TMA store (y_map[0] is that fp32 map)
   int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
@@ -285,9 +286,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     // ===================== epilogue (warps 2..5, 128 threads) =====================
     const int et = threadIdx.x - 64;  // 0..127
     for (int c = et; c < kMaxCout; c += EG * kEpiThreads) {
-      const bool ok = c < pl.cout;
-      s_scale[c] = ok ? pl.scale[c] : 0.f;
-      s_shift[c] = ok ? pl.shift[c] : 0.f;
+      const bool ok = c < pl.n_cols;  // (dense transposed conv: the four class column groups share scale / shift)
+      s_scale[c] = ok ? pl.scale[c % pl.cout] : 0.f;
+      s_shift[c] = ok ? pl.shift[c % pl.cout] : 0.f;
     }
     ptx::named_bar_sync(3, EG * kEpiThreads);
     const int eg = EG == 2 ? (warp - 2) >> 2 : 0;  // this thread's epilogue group
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
 #pragma unroll 1
           for (int g = 0; g < BLOCK_N / 64; ++g) {
             const int cb = tc.n0 + g * 64;
-            if (cb >= pl.cout) break;
+            if (cb >= pl.n_cols) break;
             uint32_t r[64];
             ptx::tmem_ld_32x32b_x32(t_row + g * 64, r);
             ptx::tmem_ld_32x32b_x32(t_row + g * 64 + 32, r + 32);
@@ -346,7 +347,8 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             for (int pln = 0; pln < planes; ++pln, ++unit) {
               uint8_t* stg = smem + L::kStgOff + (EG == 2 ? eg : unit % L::kNumStaging) * kStagingBytes;
               // the TMA store that last used this staging tile must have finished reading it
-              if (lead_warp && ptx::elect_one_sync()) ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
+              if (!p.direct_store && lead_warp && ptx::elect_one_sync())
+                ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
               ptx::named_bar_sync(bar_id, kEpiThreads);
 #pragma unroll
               for (int c8 = 0; c8 < 8; ++c8) {
@@ -376,11 +378,37 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                 }
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
               }
-              ptx::fence_proxy_async();
-              ptx::named_bar_sync(bar_id, kEpiThreads);
-              if (lead_warp && ptx::elect_one_sync()) {
-                ptx::tma_store_4d(&p.y_map[tc.cls], stg, pl.y_coffset + cb + pln * pl.y_cstride, tc.w0, tc.h0, tc.i0);
-                ptx::bulk_commit_group();
+              // dense transposed conv: column group g IS output-parity class g (cout = 64), channels from 0
+              const int ocls = pl.dense ? cb / pl.cout : tc.cls;
+              const int och = pl.y_coffset + (pl.dense ? cb % pl.cout : cb) + pln * pl.y_cstride;
+              if (p.direct_store) {
+                // Coalesced 16-byte stores from the staging tile (8 rows x 16 pixels x 128 B): thread t writes chunk
+                // t & 7 of pixel column t >> 3 in each of the 8 rows, so 8 consecutive threads complete one 128-byte
+                // line. The TMA store engine takes ~8-15 cycles per 128-byte row of a box (ncu: epilogue warps parked
+                // in cp.async.bulk.wait_group.read on the 64-channel 512x512 outputs), below the HBM write rate.
+                ptx::named_bar_sync(bar_id, kEpiThreads);
+                const int te = et & (kEpiThreads - 1);
+                const int plw = te >> 3, c8 = te & 7;
+                const int pmw = tc.w0 + plw;
+                if (pmw < pl.wm) {
+                  const size_t pixb = static_cast<size_t>(pl.y_pix) * 2;
+                  uint8_t* gp = static_cast<uint8_t*>(pl.y) +
+                                ((static_cast<size_t>(tc.i0) * pl.out_h + tc.h0 * pl.out_s + pl.cls_oh[ocls]) * pl.out_w +
+                                 pmw * pl.out_s + pl.cls_ow[ocls]) * pixb + static_cast<size_t>(och) * 2 + c8 * 16;
+                  const size_t rowb = static_cast<size_t>(pl.out_s) * pl.out_w * pixb;
+                  const uint8_t* sp = stg + plw * 128 + ((c8 ^ (plw & 7)) << 4);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    if (tc.h0 + i < pl.hm)
+                      *reinterpret_cast<uint4*>(gp + i * rowb) = *reinterpret_cast<const uint4*>(sp + i * 16 * 128);
+                }
+              } else {
+                ptx::fence_proxy_async();
+                ptx::named_bar_sync(bar_id, kEpiThreads);
+                if (lead_warp && ptx::elect_one_sync()) {
+                  ptx::tma_store_4d(&p.y_map[ocls], stg, och, tc.w0, tc.h0, tc.i0);
+                  ptx::bulk_commit_group();
+                }
               }
             }
           }
@@ -581,9 +609,12 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
       bn = 16;
     // fewer than two waves of 256-wide tiles (the 16x16 maps: 160 tiles on 148 SMs): 128-wide tiles balance better
     // (0.058 vs 0.067 ms; one-tile kernel 0.073 - profiles/r1_conv_sweep_v7_full.md)
-    if (bn == 256 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 2 * 148) bn = 128;
-    // not enough tiles to occupy the SMs at this width: narrower tiles
-    while (bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148) bn /= 2;
+    if (!plan.dense && bn == 256 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 2 * 148)
+      bn = 128;
+    // not enough tiles to occupy the SMs at this width: narrower tiles (the dense transposed conv keeps its one
+    // 256-wide tile: its column groups are the output-parity classes)
+    while (!plan.dense && bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148)
+      bn /= 2;
   }
   W2C_CHECK_ARG(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: block_n=%d not supported", bn);
   W2C_CHECK_ARG(plan.cout_pad % bn == 0, "conv: block_n=%d does not divide cout_pad=%d", bn, plan.cout_pad);
@@ -594,6 +625,8 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   p.cls_shift = (plan.num_classes == 4 && p.m_tiles * p.n_tiles >= 8 * 148 && !((a.impl >> 8) & 128)) ? 2 : 0;
   p.groups = p.cls_shift ? p.m_tiles * p.n_tiles : p.total_tiles;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
+  W2C_CHECK_ARG(!plan.dense || (p.tma_store && bn == 256 && p.n_tiles == 1),
+                "dense deconv needs one 256-wide tile and the TMA-store epilogue (bn=%d)", bn);
   // row-halo stages: 3x3 stride-1 convs on full 8x16 tiles, BLOCK_N <= 128 (at 256 three weight tiles do not fit)
   static const bool allow_row_halo = [] {
     const char* e = getenv("W2C_CONV_ROWHALO");
@@ -641,7 +674,8 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     // per tile through a map that strides two pixels in H and W
     const cuuint32_t ybox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
     const __nv_bfloat16* y = static_cast<const __nv_bfloat16*>(plan.y);
-    for (int cls = 0; cls < plan.num_classes; ++cls) {
+    const int n_out_maps = plan.dense ? 4 : plan.num_classes;
+    for (int cls = 0; cls < n_out_maps; ++cls) {
       const int s = plan.out_s;
       const cuuint64_t dims[4] = {(cuuint64_t)plan.y_pix, (cuuint64_t)plan.out_w / s, (cuuint64_t)plan.out_h / s,
                                   (cuuint64_t)plan.n_img};
@@ -651,7 +685,7 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
       int rc = encode_map(&p.y_map[cls], base, 4, dims, str, ybox, CU_TENSOR_MAP_L2_PROMOTION_NONE);
       if (rc) return rc;
     }
-    for (int cls = plan.num_classes; cls < 4; ++cls) p.y_map[cls] = p.y_map[0];
+    for (int cls = n_out_maps; cls < 4; ++cls) p.y_map[cls] = p.y_map[0];
   } else {
     for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
   }
@@ -661,6 +695,21 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     return e ? atoi(e) : 0;
   }();
   p.prefetch = ((a.impl >> 8) & 512) ? 0 : prefetch_dist;
+  // Experiment (off by default): coalesced 16-byte stores from the staging tile instead of TMA stores. W2C_CONV_DIRECT =
+  // 1 turns them on where the tile is 8x16, 2 for outputs of <= 128 channels; impl flag 1024 forces them on, 2048 off.
+  // Hypothesis was that the TMA store engine binds the 64-channel 512x512 outputs (epilogue warps parked in
+  // cp.async.bulk.wait_group.read); measured, direct stores are slower everywhere (transposed convs 0.576 -> 0.649 ms,
+  // 64->128 0.315 -> 0.379, profiles/r1_conv_sweep_v9_direct_store.md), so the TMA path stays.
+  static const int direct_mode = [] {
+    const char* e = getenv("W2C_CONV_DIRECT");
+    return e ? atoi(e) : 0;
+  }();
+  p.direct_store = 0;
+  if (p.tma_store && tw == 16 && th == 8 && tn == 1) {
+    if (direct_mode == 1 || (direct_mode == 2 && plan.cout <= 128)) p.direct_store = 1;
+    if ((a.impl >> 8) & 1024) p.direct_store = 1;
+    if ((a.impl >> 8) & 2048) p.direct_store = 0;
+  }
   static const bool allow_nchw_tma = [] {
     const char* e = getenv("W2C_CONV_NCHW_TMA");
     return !(e && e[0] == '0');
@@ -718,7 +767,10 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     }
   }
   switch (bn) {
-    case 256: return launch_persv1<256, 4, 1, 1>(p, stream);
+    case 256:
+      // dense transposed conv, 64 -> 4 x 64: its four [256][64] weight tiles (128 KB) stay resident
+      if (plan.dense && res_ok && res_slots == 4) return launch_persv1<256, 4, 1, 1, 4>(p, stream);
+      return launch_persv1<256, 4, 1, 1>(p, stream);
     case 128: return eg2 ? launch_persv1<128, 5, 1, 2>(p, stream) : launch_persv1<128, 5, 1, 1>(p, stream);
     case 64:
       if (cps >= 2) return launch_persv1<64, 3, 1, 1>(p, stream);

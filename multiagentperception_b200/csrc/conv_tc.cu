@@ -501,6 +501,11 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan.labels && (args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
     return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", args->impl & 0xff);
+  if (plan.dense) {  // the dense transposed conv exists in the persistent kernel only
+    if ((args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
+      return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no dense transposed conv", args->impl & 0xff);
+    return w2c::conv_persv1_forward(*args, plan, s);
+  }
   switch (args->impl & 0xff) {
     case W2C_IMPL_SIMT:
       return w2c::conv_simt_forward(plan, s);

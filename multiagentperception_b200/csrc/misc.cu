@@ -50,6 +50,28 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
+// dense transposed-conv packing (W2C_DECONV3X3_S2_DENSE): row = cls*cout + co, k = (dh*2+dw)*cin + ci.
+// oh = 2*ih - 1 + kh: even oh reads kh = 1 at dh = 0 only; odd oh reads kh = 0 at dh = 1 and kh = 2 at dh = 0.
+__global__ void pack_deconv_dense_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int planes,
+                                         __nv_bfloat16* __restrict__ out) {
+  const size_t ktot = 4 * static_cast<size_t>(cin);
+  const size_t total = 4 * static_cast<size_t>(cout) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int row = idx / ktot, k = idx % ktot;
+    const int cls = row / cout, co = row % cout;
+    const int t = k / cin, ci = k % cin;
+    const int ph = cls >> 1, pw = cls & 1, dh = t >> 1, dw = t & 1;
+    const int kh = ph == 0 ? (dh == 0 ? 1 : -1) : (dh == 1 ? 0 : 2);
+    const int kw = pw == 0 ? (dw == 0 ? 1 : -1) : (dw == 1 ? 0 : 2);
+    float v = 0.f;
+    if (kh >= 0 && kw >= 0 && ci < cin_real) v = w[(static_cast<size_t>(ci) * cout + co) * 9 + kh * 3 + kw];
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    out[idx] = hi;
+    if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  }
+}
+
 __global__ void fold_bn_kernel(const float* bias, const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int cout, float* scale, float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -392,6 +414,25 @@ int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin_real, cin, ntaps, transposed, planes, cout_pad, static_cast<__nv_bfloat16*>(packed));
   W2C_CHECK_LAUNCH("pack_weight_kernel");
+  return W2C_OK;
+}
+
+size_t w2c_packed_deconv_dense_bytes(int32_t cout, int32_t cin, int32_t act) {
+  const size_t planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  return planes * 4 * static_cast<size_t>(cout) * 4 * static_cast<size_t>(cin) * sizeof(__nv_bfloat16);
+}
+
+int w2c_pack_deconv_dense_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t act, void* packed,
+                                 w2c_stream_t stream) {
+  W2C_CHECK_ARG(w && packed, "pack_deconv_dense: null pointer");
+  W2C_CHECK_ARG(cout == 64, "pack_deconv_dense: cout=%d (the dense transposed conv covers cout = 64)", cout);
+  W2C_CHECK_ARG(cin > 0 && cin % 64 == 0 && cin_real > 0 && cin_real <= cin, "pack_deconv_dense: cin=%d cin_real=%d",
+                cin, cin_real);
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const size_t total = 16 * static_cast<size_t>(cout) * cin;
+  pack_deconv_dense_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin_real, cin, planes, static_cast<__nv_bfloat16*>(packed));
+  W2C_CHECK_LAUNCH("pack_deconv_dense_kernel");
   return W2C_OK;
 }
 

@@ -114,6 +114,11 @@ __device__ __forceinline__ void gather_taps_u8(const uint8_t* __restrict__ x, co
 struct StemMaps {
   CUtensorMap m[2];
   int cs;  // channels per split
+  // direct (non-TMA) store path: base of each split's map, bytes per pixel row, pixels in total
+  uint8_t* base[2];
+  int pitch;
+  int direct;
+  size_t total;
 };
 
 template <int COUT, bool U8, int NS>
@@ -239,7 +244,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
 #pragma unroll 1
       for (int pln = 0; pln < planes; ++pln, ++unit) {
         uint8_t* stg = smem + L::kStg + (unit % NS) * kStagingBytes;
-        if (warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group_read<NS - 1>();  // last store has read the tile
+        // the store that last used this staging tile has read it (TMA: bulk group; direct: every thread's loads)
+        if (!y_maps.direct && warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group_read<NS - 1>();
         __syncthreads();
 #pragma unroll 1
         for (int half = 0; half < 2; ++half) {  // 32 accumulator columns at a time (register budget: 128)
@@ -273,13 +279,29 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
             *reinterpret_cast<uint4*>(stg + sw128(tid, half * 4 + c4)) = pk;
           }
         }
-        ptx::fence_proxy_async();
-        __syncthreads();
-        if (warp == 0 && ptx::elect_one_sync()) {
-          // rows of the output viewed as [total pixels][COUT * planes]; rows past the end are clipped by the TMA unit
-          const int split = (g * 64) / y_maps.cs;
-          ptx::tma_store_2d(&y_maps.m[split], stg, pln * y_maps.cs + g * 64 - split * y_maps.cs, tile * kTile);
-          ptx::bulk_commit_group();
+        const int split = (g * 64) / y_maps.cs;
+        const int col = pln * y_maps.cs + g * 64 - split * y_maps.cs;  // first channel of this group in its map
+        if (y_maps.direct) {
+          // Experiment: coalesced 16-byte stores straight from the staging tile (eight consecutive threads write one
+          // pixel's 128 bytes) in place of the TMA store, to test whether the TMA store engine binds this kernel. It
+          // does not: measured 1 % slower (3451 vs 3496 agent-frames/s in one run).
+          __syncthreads();
+          uint8_t* gdst = y_maps.base[split] + static_cast<size_t>(tile) * kTile * y_maps.pitch + col * 2;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int q = i * kTile + tid, row = q >> 3, c8 = q & 7;
+            if (static_cast<size_t>(tile) * kTile + row < y_maps.total)
+              *reinterpret_cast<uint4*>(gdst + static_cast<size_t>(row) * y_maps.pitch + c8 * 16) =
+                  *reinterpret_cast<const uint4*>(stg + sw128(row, c8));
+          }
+        } else {
+          ptx::fence_proxy_async();
+          __syncthreads();
+          if (warp == 0 && ptx::elect_one_sync()) {
+            // rows of the output viewed as [total pixels][COUT * planes]; rows past the end are clipped by the TMA unit
+            ptx::tma_store_2d(&y_maps.m[split], stg, col, tile * kTile);
+            ptx::bulk_commit_group();
+          }
         }
       }
     }
@@ -313,6 +335,14 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
   const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
+  // (experiment, off by default: W2C_STEM_DIRECT=1 - measured 1 % slower than the TMA stores)
+  static const bool direct = [] {
+    const char* e = getenv("W2C_STEM_DIRECT");
+    return e && e[0] == '1';
+  }();
+  y_maps.direct = direct ? 1 : 0;
+  y_maps.pitch = y_maps.cs * planes * 2;
+  y_maps.total = total;
   for (int sp = 0; sp < 2; ++sp) {
     const cuuint64_t dims[2] = {(cuuint64_t)y_maps.cs * planes, (cuuint64_t)total};
     const cuuint64_t str[1] = {(cuuint64_t)y_maps.cs * planes * 2};
@@ -320,6 +350,7 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y) + (sp < n_split ? sp : 0) * total * y_maps.cs * planes;
     int rc = encode_map(&y_maps.m[sp], base, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
     if (rc) return rc;
+    y_maps.base[sp] = reinterpret_cast<uint8_t*>(const_cast<__nv_bfloat16*>(base));
   }
   // resident CTAs per SM: bounded by shared memory (operand tiles + NS staging tiles; the bf16x3 precision adds
   // the lo-plane operand tiles), by TMEM (COUT columns of 512) and by registers (<= 128 per thread: four CTAs)

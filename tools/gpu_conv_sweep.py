@@ -97,6 +97,14 @@ def main():
         if os.environ.get("SWEEP_PROD") == "1":  # only the production dispatch (for ncu captures)
             variants = [("production dispatch", ops.IMPL_TCGEN05, 0)]
             cp = 1
+        if os.environ.get("SWEEP_DIRECT") == "1":  # A/B of direct coalesced stores (flag 1024 on / 2048 off)
+            variants = [("pers tma-store", ops.IMPL_TC_PERSIST | (2048 << 8), 0),
+                        ("pers direct-store", ops.IMPL_TC_PERSIST | (1024 << 8), 0)]
+            if kind == 2 and cin == 64 and cout == 64:
+                variants += [("dense tma-store", ops.IMPL_TCGEN05 | (2048 << 8), 0),
+                             ("dense direct-store", ops.IMPL_TCGEN05 | (1024 << 8), 0)]
+                wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
+            cp = 1
         if os.environ.get("SWEEP_PF") == "1":  # A/B of the L2 prefetch (impl flag 512 = off)
             variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-prefetch", ops.IMPL_TC_PERSIST | (512 << 8), 0)]
             cp = 1
@@ -105,15 +113,21 @@ def main():
         if cp % 128 == 0:
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
         if (kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1"
-                and os.environ.get("SWEEP_PROD") != "1" and os.environ.get("SWEEP_PF") != "1"):
+                and os.environ.get("SWEEP_PROD") != "1" and os.environ.get("SWEEP_PF") != "1"
+                and os.environ.get("SWEEP_DIRECT") != "1"):
             variants.append(("halo", ops.IMPL_TC_HALO, 0))
             if cp % 128 == 0 and kind == 0:
                 variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
             if cp % 128 == 0 and kind == 2:
                 variants.append(("halo bn128", ops.IMPL_TC_HALO, 128))
+        if kind == 2 and cin == 64 and cout == 64 and os.environ.get("SWEEP_DIRECT") != "1":
+            variants.append(("dense deconv", ops.IMPL_TCGEN05, 0))
+            wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
         for name, impl, bn in variants:
-            def run():
-                ops.conv_bnrelu(x, wp, scale, shift, y, n=N, h_in=h, w_in=h, cin=cin, cout=cout, kind=kind, relu=True,
+            k2, w2 = (5, wp_dense) if name.startswith("dense") else (kind, wp)
+
+            def run(k2=k2, w2=w2, impl=impl, bn=bn):
+                ops.conv_bnrelu(x, w2, scale, shift, y, n=N, h_in=h, w_in=h, cin=cin, cout=cout, kind=k2, relu=True,
                                 act=act, out_fmt=ops.OUT_NCHW_F32 if nchw else ops.OUT_NHWC, impl=impl, block_n=bn)
             try:
                 ms = time_ms(run)

@@ -47,7 +47,7 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     cin_real = cin_real or cin
     ksz = 1 if kind in (ops.CONV1X1_S1, ops.CONV1X1_S2) else 3
     x = torch.randn(n, cin_real, h, w, generator=g)
-    transposed = kind == ops.DECONV3X3_S2
+    transposed = kind in (ops.DECONV3X3_S2, ops.DECONV3X3_S2_DENSE)
     wshape = (cin_real, cout, ksz, ksz) if transposed else (cout, cin_real, ksz, ksz)
     wt = torch.randn(*wshape, generator=g) / (cin_real * ksz * ksz) ** 0.5
     scale = torch.rand(cout, generator=g) + 0.5
@@ -58,13 +58,14 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     xa = ops.nchw_to_act(x, act, cstride=x_cs_eff, coffset=x_co)      # zero-filled outside the slice
     if cin_real < cin or x_cs:
         pass  # padded channels are zero in xa by construction (nchw_to_act zero-initialises)
-    wp = ops.pack_conv_weight(wt, cin, transposed, act)
+    wp = (ops.pack_deconv_dense_weight(wt, cin, act) if kind == ops.DECONV3X3_S2_DENSE
+          else ops.pack_conv_weight(wt, cin, transposed, act))
     xq, wq = _quant(x, act), _quant(wt, act)
     if kind == ops.CONV3X3_S1:
         ref = F.conv2d(xq, wq, padding=1)
     elif kind == ops.CONV3X3_S2:
         ref = F.conv2d(xq, wq, padding=1, stride=2)
-    elif kind == ops.DECONV3X3_S2:
+    elif kind in (ops.DECONV3X3_S2, ops.DECONV3X3_S2_DENSE):
         ref = F.conv_transpose2d(xq, wq, stride=2, padding=1, output_padding=1)
     elif kind == ops.CONV1X1_S1:
         ref = F.conv2d(xq, wq)
@@ -148,6 +149,13 @@ CONV_CASES = {
     "pers_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict(impl=4)),
     "pers_deconv_big": (2, 3, 40, 24, 64, 64, 0, dict(impl=4)),
     "pers_1x1": (3, 2, 16, 16, 128, 64, 0, dict(impl=4, relu=False)),
+    # dense transposed conv (kind 5): resident weights (bf16), streamed (bf16x3), ragged edges, cin 128, slices
+    "dense_deconv": (5, 2, 16, 32, 64, 64, 0, dict()),
+    "dense_deconv_x2": (5, 2, 8, 16, 64, 64, 1, dict()),
+    "dense_deconv_ragged": (5, 3, 13, 21, 64, 64, 0, dict(relu=False)),
+    "dense_deconv_cin128": (5, 2, 16, 16, 128, 64, 0, dict()),
+    "dense_deconv_slices": (5, 2, 16, 16, 64, 64, 0, dict(x_cs=128, x_co=64, y_cs=192, y_co=64)),
+    "dense_deconv_many": (5, 6, 64, 64, 64, 64, 0, dict()),
     "pers_1x1s2_res": (4, 2, 16, 16, 64, 128, 0, dict(impl=4, residual=True)),
     "pers_res_x2": (0, 2, 16, 16, 64, 128, 1, dict(impl=4, residual=True)),
     "pers_small_8x8": (0, 5, 8, 8, 256, 256, 0, dict(impl=4)),
