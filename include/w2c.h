@@ -257,10 +257,17 @@ int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream);
 
 /* ---- resnet18 trunk / simple_decoder specifics (backbone.py:58-96,143-164) ------------------------- */
 
-/* Conv2d(3 -> 64, k7 s2 p3, no bias) + BN + ReLU on the fp32 NCHW batch; same input convention as the stem. */
+/* Conv2d(3 -> 64, k7 s2 p3, no bias) + BN + ReLU on the fp32 NCHW batch; same input convention as the stem.  Runs on
+ * the tensor cores (software im2col, K = 147 + the shift column padded to 160).  cout = 64, or 128 for two encoders'
+ * first layers fused (w [128][147]); n_split = 2 then writes two dense 64-channel maps like w2c_stem_conv3x3_fwd. */
 int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
                            int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
-                           int32_t act, w2c_stream_t stream);
+                           int32_t cout, int32_t act, int32_t n_split, w2c_stream_t stream);
+/* The same on the loader's raw uint8 RGB HWC frames (see w2c_stem_conv3x3_u8_fwd). */
+int w2c_stem_conv7x7s2_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
+                              const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
+                              int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act,
+                              int32_t n_split, w2c_stream_t stream);
 /* MaxPool2d(k3 s2 p1) on NHWC. */
 int w2c_maxpool3x3s2_fwd(const void* x, void* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t act,
                          w2c_stream_t stream);

@@ -76,7 +76,8 @@ _SIGNATURES = {
     "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "w2c_kq_mlp_heads_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(MlpHead), c_i32, c_vp, c_vp]),
     "w2c_attn_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs), c_vp]),
-    "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 7 + [c_vp]),
+    "w2c_stem_conv7x7s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "w2c_stem_conv7x7s2_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_maxpool3x3s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_bilinear_up_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_gather_images_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp] + [c_i32] * 10 + [c_vp]),

@@ -24,6 +24,11 @@ int stem3x3_tc_u8_forward(const uint8_t* x, const float* lut, const float* w, co
                           void* y, int b, int n_agents, int agents_total, int agent_first, int h, int wpx, int cout,
                           int act, int n_split, cudaStream_t stream);
 
+// 7x7 stride-2 first layer of the resnet18 trunk on the tensor cores (x: fp32 NCHW views, or uint8 frames with u8 = 1)
+int stem7x7_tc_forward(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y,
+                       int b, int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, int n_split,
+                       int u8, cudaStream_t stream);
+
 #define W2C_CHECK_ARG(cond, ...)                                   \
   do {                                                             \
     if (!(cond)) return ::w2c::set_error(W2C_ERR_INVALID, __VA_ARGS__); \

@@ -382,6 +382,267 @@ int launch_stem(const void* x, const float* lut, const float* w, const float* sc
                                      stream);
 }
 
+
+// ================================================================================================ 7x7 stride-2 stem
+// resnet18's first layer (Conv2d(3 -> 64, k7 s2 p3, no bias) + BN + ReLU, backbone.py:63-75) on the tensor cores with
+// the same software im2col: K = 147 taps + the constant-1 shift column = 148, padded to 160 = ten K16 steps, laid
+// out as three 64-wide K chunks (three 128B-swizzled [128 px][64] A tiles, three [COUT][64] B tiles). A thread
+// gathers its output pixel's taps chunk by chunk (64 fp32 in registers at a time). The CUDA-core version took 2.94 ms
+// per 40 frames (17 TFLOP/s) - 63 % of the whole resnet-backbone step; COUT = 128 fuses two encoders' first layers.
+template <int COUT>
+struct Stem7Smem {
+  static constexpr int kA = 3 * kTile * kRowBytes;  // 48 KB per plane
+  static constexpr int kB = 3 * COUT * kRowBytes;
+  static constexpr int kAHi = 0, kBHi = kA;
+  static constexpr int kStg = kA + kB;
+  static constexpr int kBar = kStg + kStagingBytes;
+  static constexpr int kTmemPtr = kBar + 8;
+  static constexpr int kLut = kTmemPtr + 8;
+  static constexpr int kLoBase = (kLut + 3 * 256 * 4 + 1023) / 1024 * 1024;
+  static constexpr int kALo = kLoBase, kBLo = kLoBase + kA;
+  static constexpr int kDynamicBf16 = kLoBase + 1024;
+  static constexpr int kDynamic = kLoBase + kA + kB + 1024;
+};
+
+template <int COUT, bool U8>
+__global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_constant__ StemMaps y_maps,
+                                                              const void* __restrict__ x_any,
+                                                              const float* __restrict__ lut_g,
+                                                              const float* __restrict__ w,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int b_sz, int n_agents,
+                                                              int c_total, int c_first, int h, int wpx, int act,
+                                                              int num_tiles) {
+  using L = Stem7Smem<COUT>;
+  constexpr int KT = 147;  // taps; k = 147 carries the folded shift
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L::kBar);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
+  float* s_lut = reinterpret_cast<float*>(smem + L::kLut);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const bool x3 = act == W2C_ACT_BF16X2;
+  const int ho = h / 2, wo = wpx / 2;
+  const size_t total = static_cast<size_t>(b_sz) * n_agents * ho * wo;
+  const size_t plane = static_cast<size_t>(h) * wpx;
+
+  // ---- one-time setup: scale * weights and shift -> the three swizzled B chunk tiles, barrier, TMEM
+  for (int i = tid; i < COUT * 24; i += kTile) {
+    const int co = i / 24, piece = i % 24;  // 16-byte piece = k in [8*piece, 8*piece + 8)
+    const int ck = piece >> 3, c = piece & 7;
+    const float sc = scale[co];
+    uint4 hv, lv;
+    __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
+    __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = piece * 8 + e;
+      const float v = k < KT ? w[co * KT + k] * sc : (k == KT ? shift[co] : 0.f);
+      hb[e] = __float2bfloat16_rn(v);
+      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+    }
+    *reinterpret_cast<uint4*>(smem + L::kBHi + ck * COUT * kRowBytes + sw128(co, c)) = hv;
+    if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + ck * COUT * kRowBytes + sw128(co, c)) = lv;
+  }
+  if constexpr (U8)
+    for (int i = tid; i < 3 * 256; i += kTile) s_lut[i] = lut_g[i];
+  if (tid == 0) {
+    ptx::prefetch_tensormap(&y_maps.m[0]);
+    ptx::mbar_init(bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 0) {
+    ptx::tmem_alloc(tmem_ptr, COUT);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t idesc = ptx::make_idesc_bf16(kTile, COUT);
+  const uint64_t a_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAHi));
+  const uint64_t a_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kALo));
+  const uint64_t b_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBHi));
+  const uint64_t b_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBLo));
+  constexpr uint32_t kAChunk16 = (kTile * kRowBytes) >> 4, kBChunk16 = (COUT * kRowBytes) >> 4;
+
+  uint32_t phase = 0;
+  const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
+  const int planes = x3 ? 2 : 1;
+  for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    // ---- this thread's output pixel and the validity of its 7 input rows / columns
+    const size_t p = static_cast<size_t>(tile) * kTile + tid;
+    const bool live = p < total;
+    const int ow = live ? static_cast<int>(p % wo) : 0;
+    const int oh = live ? static_cast<int>((p / wo) % ho) : 0;
+    const int img = live ? static_cast<int>(p / (static_cast<size_t>(ho) * wo)) : 0;
+    const int agent = img / b_sz, bat = img % b_sz;
+    const int ih0 = 2 * oh - 3, iw0 = 2 * ow - 3;
+    uint32_t rmask = 0, cmask = 0;
+#pragma unroll
+    for (int t = 0; t < 7; ++t) {
+      rmask |= (live && ih0 + t >= 0 && ih0 + t < h) ? (1u << t) : 0u;
+      cmask |= (iw0 + t >= 0 && iw0 + t < wpx) ? (1u << t) : 0u;
+    }
+    const float* xf = nullptr;
+    const uint8_t* xb = nullptr;
+    if constexpr (U8)  // c_total / c_first carry agents_total / agent_first
+      xb = static_cast<const uint8_t*>(x_any) + (static_cast<size_t>(bat) * c_total + c_first + agent) * plane * 3;
+    else
+      xf = static_cast<const float*>(x_any) + (static_cast<size_t>(bat) * c_total + c_first + 3 * agent) * plane;
+    const ptrdiff_t pix0 = static_cast<ptrdiff_t>(ih0) * wpx + iw0;
+
+    // ---- software im2col, one 64-wide K chunk at a time
+#pragma unroll
+    for (int ck = 0; ck < 3; ++ck) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 hv, lv;
+        __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
+        __nv_bfloat16* lb = reinterpret_cast<__nv_bfloat16*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          constexpr int dummy = 0;
+          (void)dummy;
+          const int k = ck * 64 + c * 8 + e;  // compile-time after unrolling
+          float v = 0.f;
+          if (k < KT) {
+            const int ci = k / 49, r = k % 49, kh = r / 7, kw = r % 7;
+            if ((rmask >> kh) & (cmask >> kw) & 1u) {
+              if constexpr (U8)
+                v = s_lut[ci * 256 + __ldg(xb + (pix0 + kh * wpx + kw) * 3 + (2 - ci))];
+              else
+                v = __ldg(xf + ci * plane + pix0 + kh * wpx + kw);
+            }
+          } else if (k == KT) {
+            v = 1.f;
+          }
+          hb[e] = __float2bfloat16_rn(v);
+          lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+        }
+        if (ck * 64 + c * 8 < 160) {  // K is padded to 160: the last 32 columns of chunk 2 are never read
+          *reinterpret_cast<uint4*>(smem + L::kAHi + ck * kTile * kRowBytes + sw128(tid, c)) = hv;
+          if (x3) *reinterpret_cast<uint4*>(smem + L::kALo + ck * kTile * kRowBytes + sw128(tid, c)) = lv;
+        }
+      }
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && ptx::elect_one_sync()) {
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int s = 0; s < 10; ++s) {  // ten K16 steps: chunk s / 4, 32 B per step inside the swizzle row
+        const uint32_t ao = (s >> 2) * kAChunk16 + 2 * (s & 3), bo = (s >> 2) * kBChunk16 + 2 * (s & 3);
+        ptx::umma_bf16(tmem_base, a_hi + ao, b_hi + bo, idesc, s);
+        if (x3) {
+          ptx::umma_bf16(tmem_base, a_hi + ao, b_lo + bo, idesc, 1);
+          ptx::umma_bf16(tmem_base, a_lo + ao, b_hi + bo, idesc, 1);
+        }
+      }
+      ptx::umma_commit(bar);
+    }
+    ptx::mbar_wait(bar, phase);
+    phase ^= 1;
+    ptx::tc_fence_after();
+    uint8_t* stg = smem + L::kStg;
+#pragma unroll 1
+    for (int g = 0; g < COUT / 64; ++g) {
+#pragma unroll 1
+      for (int pln = 0; pln < planes; ++pln) {
+        if (warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group_read<0>();  // last store has read the tile
+        __syncthreads();
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(t_row + g * 64 + half * 32, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            uint4 pk;
+            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = __uint_as_float(r[c4 * 8 + 2 * j]), b = __uint_as_float(r[c4 * 8 + 2 * j + 1]);
+              if (!x3) {
+                pw[j] = ptx::pack_relu_bf16x2(a, b);
+              } else {
+                const float ar = fmaxf(a, 0.f), br = fmaxf(b, 0.f);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(ar, br);
+                if (pln == 0) {
+                  pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
+                } else {
+                  const float2 hf = __bfloat1622float2(hi);
+                  const __nv_bfloat162 lo = __floats2bfloat162_rn(ar - hf.x, br - hf.y);
+                  pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
+                }
+              }
+            }
+            *reinterpret_cast<uint4*>(stg + sw128(tid, half * 4 + c4)) = pk;
+          }
+        }
+        ptx::fence_proxy_async();
+        __syncthreads();
+        if (warp == 0 && ptx::elect_one_sync()) {
+          const int split = (g * 64) / y_maps.cs;
+          ptx::tma_store_2d(&y_maps.m[split], stg, pln * y_maps.cs + g * 64 - split * y_maps.cs, tile * kTile);
+          ptx::bulk_commit_group();
+        }
+      }
+    }
+    ptx::tc_fence_before();  // (the next tile's __syncthreads orders these TMEM reads before its MMAs)
+  }
+  __syncwarp();
+  if (warp == 0 && ptx::elect_one_sync()) ptx::bulk_wait_group<0>();
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, COUT);
+  }
+}
+
+template <int COUT, bool U8>
+int launch_stem7(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y, int b,
+                 int n_agents, int c_total, int c_first, int h, int wpx, int act, int n_split, cudaStream_t stream) {
+  using L = Stem7Smem<COUT>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(stem7x7_tc_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kDynamic);
+    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "stem7x7_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (wpx / 2);
+  const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
+  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  StemMaps y_maps;
+  y_maps.cs = COUT / n_split;
+  y_maps.direct = 0;
+  y_maps.pitch = y_maps.cs * planes * 2;
+  y_maps.total = total;
+  for (int sp = 0; sp < 2; ++sp) {
+    const cuuint64_t dims[2] = {(cuuint64_t)y_maps.cs * planes, (cuuint64_t)total};
+    const cuuint64_t str[1] = {(cuuint64_t)y_maps.cs * planes * 2};
+    const cuuint32_t box[2] = {64, (cuuint32_t)kTile};
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(y) + (sp < n_split ? sp : 0) * total * y_maps.cs * planes;
+    int rc = encode_map(&y_maps.m[sp], base, 2, dims, str, box, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+    if (rc) return rc;
+    y_maps.base[sp] = reinterpret_cast<uint8_t*>(const_cast<__nv_bfloat16*>(base));
+  }
+  const int smem_bytes = planes == 2 ? L::kDynamic : L::kDynamicBf16;
+  int per_sm = (227 * 1024) / (smem_bytes + 1024);
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int grid = 148 * per_sm;
+  if (grid > num_tiles) grid = num_tiles;
+  stem7x7_tc_kernel<COUT, U8><<<grid, kTile, smem_bytes, stream>>>(y_maps, x, lut, w, scale, shift, b, n_agents, c_total,
+                                                                  c_first, h, wpx, act, num_tiles);
+  W2C_CHECK_LAUNCH("stem7x7_tc_kernel");
+  return W2C_OK;
+}
+
 }  // namespace
 
 int stem3x3_tc_forward(const float* x, const float* w, const float* scale, const float* shift, void* y, int b,
@@ -405,6 +666,20 @@ int stem3x3_tc_u8_forward(const uint8_t* x, const float* lut, const float* w, co
     return launch_stem<128, true>(x, lut, w, scale, shift, y, b, n_agents, agents_total, agent_first, h, wpx, act,
                                   n_split, stream);
   return set_error(W2C_ERR_UNSUPPORTED, "stem3x3_tc (uint8 frames): cout=%d n_split=%d", cout, n_split);
+}
+
+int stem7x7_tc_forward(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y,
+                       int b, int n_agents, int c_total, int c_first, int h, int wpx, int cout, int act, int n_split,
+                       int u8, cudaStream_t stream) {
+  if (!((cout == 64 && n_split == 1) || (cout == 128 && (n_split == 1 || n_split == 2))))
+    return set_error(W2C_ERR_UNSUPPORTED, "stem7x7_tc: cout=%d n_split=%d (64, or 128 as one or two maps)", cout, n_split);
+  if (cout == 64)
+    return u8 ? launch_stem7<64, true>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, 1, stream)
+              : launch_stem7<64, false>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, 1, stream);
+  return u8 ? launch_stem7<128, true>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, n_split,
+                                      stream)
+            : launch_stem7<128, false>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, n_split,
+                                       stream);
 }
 
 }  // namespace w2c

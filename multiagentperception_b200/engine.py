@@ -309,13 +309,29 @@ class Program:
                      shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act, n_split)
         return out
 
-    def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0):
-        if self.input_u8:
-            raise NotImplementedError("uint8 frame input is implemented for the 3x3 (n_segnet) stem only")
+    def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False):
+        """resnet18 first layer (7x7 s2). split=True (a fused pair of 64-channel first layers): two dense maps."""
         wt, scale, shift = st
-        out = self.act_buf(b * n_agents, h // 2, w // 2, 64)
+        cout = wt.shape[0]
+        n_split = 2 if split else 1
+        if split:
+            if cout != 128:
+                raise ValueError("a split stem needs 128 output channels")
+            buf = torch.empty((2, b * n_agents, h // 2, w // 2, self.planes * 64), dtype=torch.bfloat16,
+                              device=self.device)
+            self.keep.append(buf)
+            out = tuple(ActMap(buf[i], b * n_agents, h // 2, w // 2, 64) for i in range(2))
+            y_ptr = buf.data_ptr()
+        else:
+            out = self.act_buf(b * n_agents, h // 2, w // 2, cout)
+            y_ptr = out.buf.data_ptr()
+        if self.input_u8:
+            self._record(self._lib.w2c_stem_conv7x7s2_u8_fwd, x_nchw.data_ptr(), self.lut.data_ptr(), wt.data_ptr(),
+                         scale.data_ptr(), shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first // 3, h, w,
+                         cout, self.act, n_split)
+            return out
         self._record(self._lib.w2c_stem_conv7x7s2_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
-                     shift.data_ptr(), out.buf.data_ptr(), b, n_agents, x_nchw.shape[1], c_first, h, w, self.act)
+                     shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act, n_split)
         return out
 
     def maxpool(self, x):

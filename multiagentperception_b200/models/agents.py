@@ -135,7 +135,7 @@ def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=Non
         if h % 32 or w % 32:
             raise ValueError("resnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
         fb = bb.feature_backbone
-        a = prog.stem7x7(x_nchw, wc.stem(fb.conv1, fb.bn1), b, n_agents, h, w, c_first)
+        a = stem if stem is not None else prog.stem7x7(x_nchw, wc.stem(fb.conv1, fb.bn1), b, n_agents, h, w, c_first)
         a = prog.maxpool(a)
         for li in range(1, 5):
             for blk in getattr(fb, "layer%d" % li):
@@ -192,6 +192,10 @@ def _fused_stems(prog, enc_a, enc_b, x_nchw, b, n_agents, h, w):
     run both first layers as ONE 3 -> 128 stem so the image is read and im2col'd once. Returns the two 64-channel
     slices of the shared output buffer, or (None, None) when the backbones are not both n_segnet."""
     ba, bb = enc_a.feature_backbone, enc_b.feature_backbone
+    if isinstance(ba, resnet_encoder) and isinstance(bb, resnet_encoder):
+        fa, fb = ba.feature_backbone, bb.feature_backbone
+        return prog.stem7x7(x_nchw, prog.weights.stem_pair(fa.conv1, fa.bn1, fb.conv1, fb.bn1), b, n_agents, h, w,
+                            split=True)
     if not (isinstance(ba, n_segnet_encoder) and isinstance(bb, n_segnet_encoder)):
         return None, None
     ua, ub = ba.units()[0], bb.units()[0]

@@ -161,11 +161,22 @@ def confusion_update(pred_labels, gt, n_classes, hist):
     return hist
 
 
-def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act, c_total=0, c_first=0):
+def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act, c_total=0, c_first=0, cout=64, n_split=1):
     lib = _lib.load()
     _lib.check(lib.w2c_stem_conv7x7s2_fwd(_ptr(x_nchw), _ptr(w147), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,
-                                          c_total or 3 * n_agents, c_first, h, w, act, _stream()),
+                                          c_total or 3 * n_agents, c_first, h, w, cout, act, n_split, _stream()),
                "w2c_stem_conv7x7s2_fwd")
+    return y
+
+
+def stem_conv7x7s2_u8(frames, lut, w147, scale, shift, y, *, b, n_agents, h, w, act, agents_total=0, agent_first=0,
+                      cout=64, n_split=1):
+    lib = _lib.load()
+    if frames.dtype != torch.uint8:
+        raise ValueError("stem_conv7x7s2_u8 needs uint8 frames")
+    _lib.check(lib.w2c_stem_conv7x7s2_u8_fwd(_ptr(frames), _ptr(lut), _ptr(w147), _ptr(scale), _ptr(shift), _ptr(y), b,
+                                             n_agents, agents_total or n_agents, agent_first, h, w, cout, act,
+                                             n_split, _stream()), "w2c_stem_conv7x7s2_u8_fwd")
     return y
 
 

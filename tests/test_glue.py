@@ -86,6 +86,27 @@ def test_stem_on_raw_frames_equals_stem_on_transformed_views(cout, act, cuda_dev
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("act", [ops.ACT_BF16, ops.ACT_BF16X2])
+def test_7x7_stem_on_raw_frames_equals_stem_on_transformed_views(act, cuda_device):
+    """resnet18's first layer (7x7 s2) on the loader's uint8 frames == on the host-transformed float views, bit for bit."""
+    dev = cuda_device
+    g = torch.Generator().manual_seed(6)
+    b, n, h, w = 2, 2, 40, 56
+    frames = torch.randint(0, 256, (b, n, h, w, 3), dtype=torch.uint8, generator=g)
+    views = orc.views_from_frames(frames.numpy())
+    wt = (torch.randn(64, 147, generator=g) * 0.08).to(dev)
+    scale = (torch.rand(64, generator=g) + 0.5).to(dev)
+    shift = (torch.randn(64, generator=g) * 0.1).to(dev)
+    y_ref = ops.new_act(b * n, h // 2, w // 2, 64, act, dev)
+    ops.stem_conv7x7s2(views.to(dev), wt, scale, shift, y_ref, b=b, n_agents=n, h=h, w=w, act=act)
+    y_u8 = ops.new_act(b * n, h // 2, w // 2, 64, act, dev)
+    ops.stem_conv7x7s2_u8(frames.to(dev), ops.loader_lut(device=dev), wt, scale, shift, y_u8, b=b, n_agents=n, h=h, w=w,
+                          act=act)
+    torch.cuda.synchronize()
+    assert torch.equal(y_u8, y_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("act", [ops.ACT_BF16, ops.ACT_BF16X2])
 def test_fused_stem_pair_written_as_two_dense_maps(act, cuda_device):
     """The two encoders' fused 3 -> 128 first layer stored as two dense 64-channel maps equals the one 128-channel
     map, half by half (same accumulators, different tensor maps)."""
@@ -192,11 +213,6 @@ def test_model_on_raw_frames_with_label_output(arch, bb, cuda_device):
     want = orc.labels_from_logits(pred.cpu())
     assert torch.equal(model.last_labels().cpu().long(), want)
 
-    if bb == "resnet":
-        model.set_input_format("u8_hwc")
-        with pytest.raises(NotImplementedError):
-            model(frames.to(dev), **kw)
-        return
     model.set_input_format("u8_hwc").set_label_output(True, logits=False)
     for _ in range(2):                                   # second call replays the CUDA graph
         out = model(frames.to(dev), **kw)

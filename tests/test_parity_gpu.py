@@ -155,6 +155,24 @@ def test_full_size_one_scene_against_oracle(cuda_device):
     assert torch.equal(action.cpu(), ref_act[2]) and nconn == pytest.approx(ref_act[3], abs=1e-9)
 
 
+@pytest.mark.parametrize("hw", [(96, 160), (32, 32), (224, 64)])
+def test_single_agent_ragged_sizes_against_oracle(hw, cuda_device):
+    """Non-square and minimum sizes (any multiple of 32 is legal for Single_agent): partial 8x16 tiles at every
+    scale, 1x1 feature maps at 32x32; odd batch."""
+    dev = cuda_device
+    h, w = hw
+    cfg = configs.make_config("Single_agent", img_size=max(h, w))
+    model = get_model(cfg, 11)
+    synth.randomize_(model, 1337)
+    x = synth.synthetic_views(3, 1, h, w, seed=9)
+    ref = orc.forward(model.state_dict(), cfg, x)
+    model = model.to(dev).eval()
+    for prec, tol in (("bf16x3", X3_LOGIT_TOL), ("bf16", BF16_LOGIT_TOL)):
+        pred = model.set_precision(prec)(x.to(dev))
+        assert pred.shape == (3, 11, h, w)
+        assert _rel(pred, ref) <= tol
+
+
 def test_single_agent_1024_against_oracle(cuda_device):
     """BASELINE config 4 shape (Single_agent, n_segnet pair, 1024x1024; one view - the oracle takes ~10 s for it)."""
     dev = cuda_device

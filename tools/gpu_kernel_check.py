@@ -217,6 +217,15 @@ def case_stem():
         err7 = (got7 - ref7).abs().max().item()
         out["stem7x7_act%d" % act] = err7
         ok &= err7 <= (6e-3 if act == 0 else 1e-4) * max(1.0, ref7.abs().max().item())
+        # two first layers fused (cout 128) written as two dense 64-channel maps: map 0 == the single-layer result
+        w14 = torch.cat((wt7, torch.randn(64, 3, 7, 7, device=dev) * 0.08), 0).reshape(128, 147).contiguous()
+        two = torch.empty((2, b * na, h2 // 2, w2 // 2, ops.planes_of(act) * 64), dtype=torch.bfloat16, device=dev)
+        ops.stem_conv7x7s2(x, w14, torch.cat((scale, scale)), torch.cat((shift, shift)), two, b=b, n_agents=na, h=h2,
+                           w=w2, act=act, cout=128, n_split=2)
+        torch.cuda.synchronize()
+        same = bool(torch.equal(two[0], y7))
+        out["stem7x7_pair_act%d" % act] = 0.0 if same else 1.0
+        ok &= same
         yp = ops.new_act(b * na, h2 // 4, w2 // 4, 64, act, dev)
         ops.maxpool3x3s2(y7, yp, n=b * na, h=h2 // 2, w=w2 // 2, c=64, act=act)
         refp = F.max_pool2d(got7, 3, 2, 1)
