@@ -317,7 +317,7 @@ def run_b200(args):
     # (transform + cat fused into the first conv), the uint8 label map out (arg-max fused into the logits layer, the
     # fp32 logits never written); same double-buffered pipeline. Bit-identical labels to the drop-in path above.
     e2e_fused = None
-    if not args.no_fused_e2e and args.backbones == "n_segnet":
+    if not args.no_fused_e2e:
         fmodel = get_model(cfg, configs.N_CLASSES)
         fmodel.load_state_dict(model.state_dict())
         fmodel = fmodel.to(dev).eval().set_clone_outputs(False)

@@ -284,6 +284,11 @@ int w2c_gather_images_fwd(const void* src, void* dst, const int32_t* sel, int32_
                           int32_t w_px, int32_t c, int32_t src_cstride, int32_t src_coffset, int32_t dst_cstride,
                           int32_t dst_coffset, int32_t act, w2c_stream_t stream);
 
+/* The same up-sampling fused with the arg-max over the c channels: labels uint8 [n][h*factor][w*factor] only (the
+ * label-map output of a simple_decoder model; equals w2c_bilinear_up_fwd + w2c_argmax_labels_fwd bit for bit). */
+int w2c_bilinear_argmax_fwd(const float* x, uint8_t* labels, int32_t n, int32_t c, int32_t h, int32_t w_px,
+                            int32_t factor, w2c_stream_t stream);
+
 /* ---- layout helpers --------------------------------------------------------------------------------- */
 /* NHWC activation (act storage) -> fp32 NCHW, and back.  Used at module boundaries and by the tests. */
 int w2c_nhwc_to_nchw_f32(const void* x, float* y, int32_t n, int32_t h, int32_t w_px, int32_t c, int32_t cstride,

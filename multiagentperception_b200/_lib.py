@@ -81,6 +81,7 @@ _SIGNATURES = {
     "w2c_maxpool3x3s2_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_bilinear_up_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_gather_images_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp] + [c_i32] * 10 + [c_vp]),
+    "w2c_bilinear_argmax_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_nhwc_to_nchw_f32": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_nchw_f32_to_nhwc": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }

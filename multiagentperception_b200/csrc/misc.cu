@@ -326,6 +326,39 @@ __global__ void __launch_bounds__(256) bilinear_up_kernel(const float* __restric
   }
 }
 
+// The same up-sampling with the arg-max over the channels taken per output pixel (first maximal index) and ONLY the
+// uint8 label written: the evaluation loop of a simple_decoder model needs neither the small logits up-sampled in HBM
+// (461 MB per 40 frames at 512x512) nor a second pass over them.
+__global__ void __launch_bounds__(256) bilinear_argmax_kernel(const float* __restrict__ x, uint8_t* __restrict__ labels,
+                                                             int n, int c, int h, int wpx, int factor) {
+  const int ho = h * factor, wo = wpx * factor;
+  const float rs = 1.f / static_cast<float>(factor);
+  const size_t total = static_cast<size_t>(n) * ho * wo;
+  const size_t plane = static_cast<size_t>(h) * wpx;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ow = idx % wo;
+    const int oh = (idx / wo) % ho;
+    const size_t img = idx / (static_cast<size_t>(ho) * wo);
+    float sh = (oh + 0.5f) * rs - 0.5f, sw = (ow + 0.5f) * rs - 0.5f;
+    sh = sh < 0.f ? 0.f : sh;
+    sw = sw < 0.f ? 0.f : sw;
+    const int h0 = static_cast<int>(sh), w0 = static_cast<int>(sw);
+    const int h1 = h0 + (h0 < h - 1 ? 1 : 0), w1 = w0 + (w0 < wpx - 1 ? 1 : 0);
+    const float lh = sh - h0, lw = sw - w0;
+    const float* xp = x + img * c * plane;
+    float best = 0.f;
+    int arg = 0;
+    for (int k = 0; k < c; ++k, xp += plane) {
+      const float v00 = __ldg(xp + h0 * wpx + w0), v01 = __ldg(xp + h0 * wpx + w1);
+      const float v10 = __ldg(xp + h1 * wpx + w0), v11 = __ldg(xp + h1 * wpx + w1);
+      const float v = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);  // as above
+      if (k == 0 || v > best) best = v, arg = k;
+    }
+    labels[idx] = static_cast<uint8_t>(arg);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ layout helpers
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int h, int wpx,
                                     int c, int cstride, int coffset, int act) {
@@ -631,6 +664,16 @@ int w2c_bilinear_up_fwd(const float* x, float* y, int32_t n, int32_t c, int32_t 
   const size_t total = static_cast<size_t>(n) * c * h * factor * (w_px * factor / 4);
   bilinear_up_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n * c, h, w_px, factor);
   W2C_CHECK_LAUNCH("bilinear_up_kernel");
+  return W2C_OK;
+}
+
+int w2c_bilinear_argmax_fwd(const float* x, uint8_t* labels, int32_t n, int32_t c, int32_t h, int32_t w_px,
+                            int32_t factor, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && labels && n > 0 && c > 0 && c <= 256 && h > 0 && w_px > 0 && factor >= 1, "bilinear_argmax: bad arguments");
+  const size_t total = static_cast<size_t>(n) * h * factor * w_px * factor;
+  bilinear_argmax_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, labels, n, c, h, w_px,
+                                                                                             factor);
+  W2C_CHECK_LAUNCH("bilinear_argmax_kernel");
   return W2C_OK;
 }
 

@@ -25,10 +25,13 @@ def default_precision():
     return p
 
 
-# W2C_TWO_STREAMS=1 records the two encoder chains as parallel graph branches (Program.side_stream). Measured on
-# B200: no gain (3399 / 3386 vs 3419 agent-frames/s serial) - the step runs at the 1 kW power cap, where overlapping
-# kernels cannot add throughput - so the default is one serial chain.
-TWO_STREAMS = os.environ.get("W2C_TWO_STREAMS", "0") == "1"
+# Program.side_stream records the two encoder chains as parallel CUDA-graph branches. W2C_TWO_STREAMS = 1 always,
+# 0 never, unset: only where the builder asks for it (auto=True). Measured on B200: no gain for the n_segnet pair
+# (3399 / 3386 vs 3419 agent-frames/s serial - that step runs at the 1 kW power cap, where overlapping kernels cannot
+# add throughput) but +7 % for the resnet18 pair, whose 55 launches of 20-90 us each leave SMs idle (12310 -> 13208
+# agent-frames/s, two runs each): the models switch it on for resnet backbones.
+_TS = os.environ.get("W2C_TWO_STREAMS")
+TWO_STREAMS = None if _TS is None else _TS == "1"
 
 
 # W2C_DECONV_DENSE=1 runs the 64-channel transposed conv as one dense 256-wide GEMM per input tile (kind 5). Measured:
@@ -217,14 +220,16 @@ class Program:
     # the sub-wave layers at 16x16 otherwise leave SMs idle at every kernel boundary.
     _FORK, _JOIN = "fork", "join"
 
-    def side_stream(self):
+    def side_stream(self, auto=False):
         """Context manager: calls recorded inside run on the side stream, which first waits for everything recorded
-        so far. join() makes the main chain wait for them."""
+        so far. join() makes the main chain wait for them. auto: the builder's own preference, used when
+        W2C_TWO_STREAMS is unset."""
         prog = self
+        enabled = auto if TWO_STREAMS is None else TWO_STREAMS
 
         class _Ctx:
             def __enter__(self):
-                if TWO_STREAMS:
+                if enabled:
                     prog.calls.append((Program._FORK, None, 0))
                     prog._sid = 1
 
@@ -235,8 +240,8 @@ class Program:
         return _Ctx()
 
     def join(self):
-        if TWO_STREAMS:
-            self.calls.append((Program._JOIN, None, 0))
+        # (a join without a preceding fork is a no-op at run time)
+        self.calls.append((Program._JOIN, None, 0))
 
     def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None):
         """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given). labels: uint8 [n, h, w] tensor that
@@ -344,6 +349,11 @@ class Program:
         out = self.f32_buf(n, c, h * factor, w * factor)
         self._record(self._lib.w2c_bilinear_up_fwd, x_nchw.data_ptr(), out.data_ptr(), n, c, h, w, factor)
         return out
+
+    def bilinear_argmax(self, x_nchw, factor, labels):
+        n, c, h, w = x_nchw.shape
+        self._record(self._lib.w2c_bilinear_argmax_fwd, x_nchw.data_ptr(), labels.data_ptr(), n, c, h, w, factor)
+        return labels
 
     def argmax_labels(self, logits, labels):
         n, c, h, w = logits.shape

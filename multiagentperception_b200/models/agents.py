@@ -176,13 +176,15 @@ def _build_decoder(prog, dec, a):
         y = prog.conv(a, wc.conv(od.pred[0], None, True))
         small = prog.f32_buf(a.n, od.pred[2].out_channels, a.h, a.w)
         prog.conv(y, wc.conv(od.pred[2], None, False), nchw_out=small)
-        up = prog.bilinear(small, 32)
         prog.labels_out = None
+        if prog.want_labels and not prog.want_logits:
+            # label map only: up-sample and take the arg-max per output pixel in one kernel, nothing else is written
+            prog.labels_out = prog.bilinear_argmax(small, 32, prog.f32_buf(a.n, a.h * 32, a.w * 32, dtype=torch.uint8))
+            return prog.labels_out
+        up = prog.bilinear(small, 32)
         if prog.want_labels:
             prog.labels_out = prog.argmax_labels(up, prog.f32_buf(up.shape[0], up.shape[2], up.shape[3],
                                                                    dtype=torch.uint8))
-            if not prog.want_logits:
-                return prog.labels_out
         return up
     raise ValueError("unknown decoder backbone %r" % type(od).__name__)
 
@@ -475,7 +477,10 @@ class _AttentionModel(_W2CModel):
         encs = self._value_encoders()
         if encs is None:
             stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
-            with prog.side_stream():  # the feature encoder runs beside the policy net + heads (independent chains)
+            # the feature encoder runs beside the policy net + heads (independent chains); worth it for the resnet
+            # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
+            small_kernels = isinstance(self.u_encoder.feature_backbone, resnet_encoder)
+            with prog.side_stream(auto=small_kernels):
                 val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
         else:
             # separate encoders per agent group (agent.py:579-594,823-838), each writing its agents' images of the
