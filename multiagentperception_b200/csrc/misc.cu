@@ -311,14 +311,31 @@ __global__ void __launch_bounds__(256) bilinear_up_kernel(const float* __restric
     const float* r0 = x + pl * static_cast<size_t>(h) * wpx + static_cast<size_t>(h0) * wpx;
     const float* r1 = x + pl * static_cast<size_t>(h) * wpx + static_cast<size_t>(h1) * wpx;
     float o[4];
+    // the four columns usually fall into one source cell (always for factors that are multiples of 8: the cell
+    // boundaries sit at ow = factor/2 mod factor): one set of four corner loads then serves all of them
+    float swj[4];
+    int w0j[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float sw = (ow0 + j + 0.5f) * rs - 0.5f;
-      sw = sw < 0.f ? 0.f : sw;
-      const int w0 = static_cast<int>(sw);
-      const int w1 = w0 + (w0 < wpx - 1 ? 1 : 0);
-      const float lw = sw - w0;
-      const float v00 = __ldg(r0 + w0), v01 = __ldg(r0 + w1), v10 = __ldg(r1 + w0), v11 = __ldg(r1 + w1);
+      swj[j] = sw < 0.f ? 0.f : sw;
+      w0j[j] = static_cast<int>(swj[j]);
+    }
+    const bool one_cell = w0j[0] == w0j[3];
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
+    if (one_cell) {
+      const int w0 = w0j[0], w1 = w0 + (w0 < wpx - 1 ? 1 : 0);
+      c00 = __ldg(r0 + w0), c01 = __ldg(r0 + w1), c10 = __ldg(r1 + w0), c11 = __ldg(r1 + w1);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w0 = w0j[j];
+      const float lw = swj[j] - w0;
+      float v00 = c00, v01 = c01, v10 = c10, v11 = c11;
+      if (!one_cell) {
+        const int w1 = w0 + (w0 < wpx - 1 ? 1 : 0);
+        v00 = __ldg(r0 + w0), v01 = __ldg(r0 + w1), v10 = __ldg(r1 + w0), v11 = __ldg(r1 + w1);
+      }
       // same evaluation order as ATen's upsample_bilinear2d: h0lambda*(w0lambda*v00 + w1lambda*v01) + h1lambda*(...)
       o[j] = (1.f - lh) * ((1.f - lw) * v00 + lw * v01) + lh * ((1.f - lw) * v10 + lw * v11);
     }
