@@ -160,7 +160,7 @@ def run_reference(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -424,7 +424,7 @@ def run_b200(args):
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "frames_per_step": frames_total,
             "model_tflops": GFLOP_PER_FRAME * value / 1e3 if args.backbones == "n_segnet" else None}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -475,11 +475,49 @@ def write_layer_table(path, prog, dev):
         f.write("\ntotal %.3f ms\n" % sum(r[6] for r in rows))
 
 
+class _QuietStdout:
+    """Everything libraries print to fd 1 while the bench runs (e.g. NCCL's version banner) goes to stderr, so that
+    stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.saved, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+OUT = None
+
+
+def emit_line(obj):
+    text = json.dumps(obj)
+    if OUT is not None:
+        OUT.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global OUT
     args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_b200(args)
+    with _QuietStdout() as q:
+        OUT = q
+        try:
+            if args.impl == "reference":
+                return run_reference(args)
+            return run_b200(args)
+        finally:
+            OUT = None
 
 
 if __name__ == "__main__":
