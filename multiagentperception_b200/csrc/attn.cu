@@ -201,10 +201,10 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
       if (i < a.n_k) {
         const __nv_bfloat16* src = s_V + (static_cast<size_t>(i) * p.pix_per_cta + px) * vpix + g * 8;
         const uint4 hv = *reinterpret_cast<const uint4*>(src);
-        const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+        const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = __bfloat1622float2(hb[e]);
+          const float2 f = unpack_act2(hb[e], a.act == W2C_ACT_FP16);
           v[i][2 * e] = f.x, v[i][2 * e + 1] = f.y;
         }
         if (planes == 2) {
@@ -236,9 +236,15 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
       __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        hb[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-        const float2 hf = __bfloat1622float2(hb[e]);
-        lb[e] = __floats2bfloat162_rn(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
+        if (a.act == W2C_ACT_FP16) {
+          const uint32_t pk16 = ptx::pack_f16x2(o[2 * e], o[2 * e + 1]);
+          hb[e] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
+          lb[e] = hb[e];
+        } else {
+          hb[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+          const float2 hf = __bfloat1622float2(hb[e]);
+          lb[e] = __floats2bfloat162_rn(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
+        }
       }
       __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(a.fused) +
                            (static_cast<size_t>((j - a.q_first) * a.b_sz + scene) * a.hw + pix0 + px) * fpix + a.fused_coffset + g * 8;

@@ -6,6 +6,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include "../../include/w2c.h"
@@ -42,13 +43,35 @@ int stem7x7_tc_forward(const void* x, const float* lut, const float* w, const fl
     ::w2c::count_launch();                                                                      \
   } while (0)
 
+// 16-bit storage element <-> float in either storage type (the buffers are typed __nv_bfloat16 for addressing only)
+__device__ __forceinline__ float elem_to_float(__nv_bfloat16 v, bool f16) {
+  return f16 ? __half2float(*reinterpret_cast<const __half*>(&v)) : __bfloat162float(v);
+}
+__device__ __forceinline__ __nv_bfloat16 float_to_elem(float v, bool f16) {
+  if (f16) {
+    const __half h = __float2half_rn(v);
+    return *reinterpret_cast<const __nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16_rn(v);
+}
+// a packed pair of storage elements -> two floats
+__device__ __forceinline__ float2 unpack_act2(uint32_t bits, bool f16) {
+  return f16 ? __half22float2(*reinterpret_cast<const __half2*>(&bits))
+             : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bits));
+}
+
 // value = hi (+ lo).  Pixel layout for BF16X2: [hi: cstride channels][lo: cstride channels].
 __device__ __forceinline__ float act_load(const __nv_bfloat16* pix, int c, int cstride, int act) {
+  if (act == W2C_ACT_FP16) return elem_to_float(pix[c], true);
   float v = __bfloat162float(pix[c]);
   if (act == W2C_ACT_BF16X2) v += __bfloat162float(pix[cstride + c]);
   return v;
 }
 __device__ __forceinline__ void act_store(__nv_bfloat16* pix, int c, int cstride, int act, float v) {
+  if (act == W2C_ACT_FP16) {
+    pix[c] = float_to_elem(v, true);
+    return;
+  }
   __nv_bfloat16 hi = __float2bfloat16_rn(v);
   pix[c] = hi;
   if (act == W2C_ACT_BF16X2) pix[cstride + c] = __float2bfloat16_rn(v - __bfloat162float(hi));

@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   } else if (warp == 1) {
     if (ptx::elect_one_sync()) {
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, pl.act == W2C_ACT_FP16);
       constexpr uint32_t kBTile16 = L::kBTileBytes >> 4;
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
       const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
@@ -300,6 +300,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     const int lh = (row / p.tw) % p.th;
     const int li = row / (p.tw * p.th);
     const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
+    const bool f16 = pl.act == W2C_ACT_FP16;
     int unit = 0;  // staging-buffer rotation counter (EG == 1)
     TileCoord tc;
     for (int it = eg; tile_at(p, it, BLOCK_N, tc); it += EG) {
@@ -332,10 +333,10 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
 #pragma unroll
                 for (int c8 = 0; c8 < 8; ++c8) {
                   const uint4 rv = *reinterpret_cast<const uint4*>(rp + pln * pl.y_cstride + c8 * 8);
-                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                  const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const float2 f = __bfloat1622float2(rb[j]);
+                    const float2 f = unpack_act2(rb[j], f16);
                     v[c8 * 8 + 2 * j] += f.x, v[c8 * 8 + 2 * j + 1] += f.y;
                   }
                 }
@@ -355,13 +356,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                 uint4 pk;
                 uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
                 if (planes == 1) {
-                  if (pl.relu) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) pw[j] = ptx::pack_relu_bf16x2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1]);
-                  } else {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) pw[j] = ptx::pack_bf16x2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1]);
-                  }
+                  for (int j = 0; j < 4; ++j)
+                    pw[j] = ptx::pack_act2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1], pl.relu != 0, f16);
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -504,10 +501,10 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             if (rpix) {
               for (int pln = 0; pln < planes; ++pln) {
                 const uint4 rv = *reinterpret_cast<const uint4*>(rpix + pln * pl.y_cstride + g * 8);
-                const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                  const float2 f = __bfloat1622float2(rb[j]);
+                  const float2 f = unpack_act2(rb[j], f16);
                   v[g * 8 + 2 * j] += f.x, v[g * 8 + 2 * j + 1] += f.y;
                 }
               }
@@ -519,9 +516,15 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             for (int j = 0; j < 4; ++j) {
               float a = v[g * 8 + 2 * j], b = v[g * 8 + 2 * j + 1];
               if (pl.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-              hb[j] = __floats2bfloat162_rn(a, b);
-              const float2 hf = __bfloat1622float2(hb[j]);
-              lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+              if (f16) {
+                const uint32_t pk16 = ptx::pack_f16x2(a, b);
+                hb[j] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
+                lb[j] = hb[j];
+              } else {
+                hb[j] = __floats2bfloat162_rn(a, b);
+                const float2 hf = __bfloat1622float2(hb[j]);
+                lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+              }
             }
             *reinterpret_cast<uint4*>(ypix + g * 8) = hv;
             if (planes == 2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;

@@ -71,7 +71,7 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   W2C_CHECK_ARG(a.n > 0 && a.h_in > 0 && a.w_in > 0, "conv: bad image extent %dx%dx%d", a.n, a.h_in, a.w_in);
   W2C_CHECK_ARG(a.cin > 0 && a.cin % 64 == 0, "conv: cin=%d must be a positive multiple of 64", a.cin);
   W2C_CHECK_ARG(a.cout > 0, "conv: cout=%d", a.cout);
-  W2C_CHECK_ARG(a.act == W2C_ACT_BF16 || a.act == W2C_ACT_BF16X2, "conv: bad act %d", a.act);
+  W2C_CHECK_ARG(a.act == W2C_ACT_BF16 || a.act == W2C_ACT_BF16X2 || a.act == W2C_ACT_FP16, "conv: bad act %d", a.act);
   W2C_CHECK_ARG(a.out_fmt == W2C_OUT_NHWC || a.out_fmt == W2C_OUT_NCHW_F32, "conv: bad out_fmt %d", a.out_fmt);
   const int planes = a.act == W2C_ACT_BF16X2 ? 2 : 1;
   p = ConvPlan{};

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   } else if (warp == 1) {
     if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== MMA issuer =====================
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(kBlockM, BLOCK_N);
+      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, pl.act == W2C_ACT_FP16);
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
       const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
       int stage = 0;
@@ -204,10 +204,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           if (n0 + c0 + g * 8 >= pl.cout) break;
           if (rpix) {
             const uint4 rv = *reinterpret_cast<const uint4*>(rpix + g * 8);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+            const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(rb[j]);
+              const float2 f = unpack_act2(rb[j], pl.act == W2C_ACT_FP16);
               v[g * 8 + 2 * j] += f.x, v[g * 8 + 2 * j + 1] += f.y;
             }
             if (pl.act == W2C_ACT_BF16X2) {
@@ -227,9 +227,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
           for (int j = 0; j < 4; ++j) {
             float a = v[g * 8 + 2 * j], b = v[g * 8 + 2 * j + 1];
             if (pl.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-            hb[j] = __floats2bfloat162_rn(a, b);
-            const float2 hf = __bfloat1622float2(hb[j]);
-            lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            if (pl.act == W2C_ACT_FP16) {
+              const uint32_t pk16 = ptx::pack_f16x2(a, b);
+              hb[j] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
+              lb[j] = hb[j];
+            } else {
+              hb[j] = __floats2bfloat162_rn(a, b);
+              const float2 hf = __bfloat1622float2(hb[j]);
+              lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+            }
           }
           *reinterpret_cast<uint4*>(ypix + g * 8) = hv;
           if (pl.act == W2C_ACT_BF16X2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;
@@ -422,8 +428,9 @@ __global__ void conv_simt_kernel(const ConvPlan pl) {
       const __nv_bfloat16* wp = pl.w + static_cast<size_t>(co) * pl.ktot + tap.wtap * pl.cin;
       const __nv_bfloat16* wl = wp + static_cast<size_t>(pl.cout_pad) * pl.ktot;
       for (int ci = 0; ci < pl.cin; ++ci) {
-        const float xh = __bfloat162float(xp[ci]);
-        const float wh = __bfloat162float(wp[ci]);
+        const bool f16 = pl.act == W2C_ACT_FP16;
+        const float xh = elem_to_float(xp[ci], f16);
+        const float wh = elem_to_float(wp[ci], f16);
         acc = fmaf(xh, wh, acc);
         if (planes == 2) {
           acc = fmaf(xh, __bfloat162float(wl[ci]), acc);
@@ -501,6 +508,8 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (plan.labels && (args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
     return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", args->impl & 0xff);
+  if (plan.act == W2C_ACT_FP16 && ((args->impl & 0xff) == W2C_IMPL_TC_HALO || (args->impl & 0xff) == 5))
+    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the experimental kernels (impl %d) are bf16-only", args->impl & 0xff);
   if (plan.dense) {  // the dense transposed conv exists in the persistent kernel only
     if ((args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
       return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no dense transposed conv", args->impl & 0xff);

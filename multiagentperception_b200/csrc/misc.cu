@@ -30,7 +30,7 @@ inline int grid_for(size_t total, int threads, int max_blocks = 148 * 32) {
 
 // ------------------------------------------------------------------------------------------ weight packing
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int ntaps,
-                                   int transposed, int planes, int cout_pad, __nv_bfloat16* __restrict__ out) {
+                                   int transposed, int planes, int cout_pad, __nv_bfloat16* __restrict__ out, bool f16) {
   const size_t ktot = static_cast<size_t>(ntaps) * cin;
   const size_t total = static_cast<size_t>(cout_pad) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -44,7 +44,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
       v = transposed ? w[(static_cast<size_t>(ci) * cout + co) * ntaps + tap]
                      : w[(static_cast<size_t>(co) * cin_real + ci) * ntaps + tap];
     }
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = float_to_elem(v, f16);
     out[idx] = hi;
     if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
@@ -53,7 +53,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 // dense transposed-conv packing (W2C_DECONV3X3_S2_DENSE): row = cls*cout + co, k = (dh*2+dw)*cin + ci.
 // oh = 2*ih - 1 + kh: even oh reads kh = 1 at dh = 0 only; odd oh reads kh = 0 at dh = 1 and kh = 2 at dh = 0.
 __global__ void pack_deconv_dense_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int planes,
-                                         __nv_bfloat16* __restrict__ out) {
+                                         __nv_bfloat16* __restrict__ out, bool f16) {
   const size_t ktot = 4 * static_cast<size_t>(cin);
   const size_t total = 4 * static_cast<size_t>(cout) * ktot;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -66,7 +66,7 @@ __global__ void pack_deconv_dense_kernel(const float* __restrict__ w, int cout, 
     const int kw = pw == 0 ? (dw == 0 ? 1 : -1) : (dw == 1 ? 0 : 2);
     float v = 0.f;
     if (kh >= 0 && kw >= 0 && ci < cin_real) v = w[(static_cast<size_t>(ci) * cout + co) * 9 + kh * 3 + kw];
-    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 hi = float_to_elem(v, f16);
     out[idx] = hi;
     if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
   }
@@ -263,7 +263,12 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
         const __nv_bfloat16* pix = x + ((static_cast<size_t>(img) * h + ih) * wpx + iw) * pixs + cg * 8;
         const uint4 hv = __ldg(reinterpret_cast<const uint4*>(pix));
         const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
-        if (planes == 1) {
+        if (planes == 1 && act == W2C_ACT_FP16) {
+          const __half2* hh = reinterpret_cast<const __half2*>(&hv);
+          __half2* bh = reinterpret_cast<__half2*>(best);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) bh[e] = first ? hh[e] : __hmax2(bh[e], hh[e]);
+        } else if (planes == 1) {
 #pragma unroll
           for (int e = 0; e < 4; ++e) best[e] = first ? hb[e] : __hmax2(best[e], hb[e]);
         } else {
@@ -504,7 +509,8 @@ int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t
   const int cout_pad = w2c_cout_pad(cout);
   const size_t total = static_cast<size_t>(cout_pad) * ntaps * cin;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin_real, cin, ntaps, transposed, planes, cout_pad, static_cast<__nv_bfloat16*>(packed));
+      w, cout, cin_real, cin, ntaps, transposed, planes, cout_pad, static_cast<__nv_bfloat16*>(packed),
+      act == W2C_ACT_FP16);
   W2C_CHECK_LAUNCH("pack_weight_kernel");
   return W2C_OK;
 }
@@ -523,7 +529,7 @@ int w2c_pack_deconv_dense_weight(const float* w, int32_t cout, int32_t cin_real,
   const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
   const size_t total = 16 * static_cast<size_t>(cout) * cin;
   pack_deconv_dense_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin_real, cin, planes, static_cast<__nv_bfloat16*>(packed));
+      w, cout, cin_real, cin, planes, static_cast<__nv_bfloat16*>(packed), act == W2C_ACT_FP16);
   W2C_CHECK_LAUNCH("pack_deconv_dense_kernel");
   return W2C_OK;
 }

@@ -61,11 +61,11 @@ __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restric
         if (m0 + r < m) {
           const __nv_bfloat16* p = feat + static_cast<size_t>(m0 + r) * row_elems + off;
           const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p));
-          const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
+          const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
           float x[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(hb[e]);
+            const float2 f = unpack_act2(hb[e], act == W2C_ACT_FP16);
             x[2 * e] = f.x, x[2 * e + 1] = f.y;
           }
           if (planes == 2) {

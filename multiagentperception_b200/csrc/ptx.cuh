@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace w2c {
 namespace ptx {
@@ -210,6 +211,21 @@ __device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
   return d;
 }
 
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_relu_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+// 16-bit activation pairs in either storage type (f16 = true: IEEE half, else bf16)
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi, bool relu, bool f16) {
+  return f16 ? (relu ? pack_relu_f16x2(lo, hi) : pack_f16x2(lo, hi)) : (relu ? pack_relu_bf16x2(lo, hi) : pack_bf16x2(lo, hi));
+}
+
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile whose rows are 128 B (64 bf16) with the TMA
 // 128-byte swizzle: 8-row atoms of 1024 B, atoms stacked along M/N every 1024 B (SBO), one atom along K (LBO=0).
@@ -228,6 +244,10 @@ __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
 // [17,23) N>>3, [24,29) M>>4.
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// the same with fp16 A/B operands (a_format = b_format = 0) when f16 is set
+__host__ __device__ constexpr uint32_t make_idesc_16(uint32_t m, uint32_t n, bool f16) {
+  return f16 ? (make_idesc_bf16(m, n) & ~((1u << 7) | (1u << 10))) : make_idesc_bf16(m, n);
 }
 
 }  // namespace ptx

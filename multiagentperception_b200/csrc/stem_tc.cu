@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
   };
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool x3 = act == W2C_ACT_BF16X2;
+  const bool f16 = act == W2C_ACT_FP16;
 
   // ---- one-time setup: scale * weights (k < 27) and shift (k = 27) -> swizzled B tiles, barrier, TMEM
   for (int i = tid; i < COUT * 4; i += kTile) {
@@ -161,8 +162,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
     for (int e = 0; e < 8; ++e) {
       const int k = c * 8 + e;
       const float v = k < 27 ? w[co * 27 + k] * sc : (k == 27 ? shift[co] : 0.f);
-      hb[e] = __float2bfloat16_rn(v);
-      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+      hb[e] = float_to_elem(v, f16);
+      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + sw128(co, c)) = hv;
     if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t idesc = ptx::make_idesc_bf16(kTile, COUT);
+  const uint32_t idesc = ptx::make_idesc_16(kTile, COUT, f16);
   const uint64_t a_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAHi));
   const uint64_t a_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kALo));
   const uint64_t b_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBHi));
@@ -209,8 +210,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
       for (int e = 0; e < 8; ++e) {
         const int k = c * 8 + e;
         const float v = k < 27 ? in[k < 27 ? k : 0] : (k == 27 ? 1.f : 0.f);
-        hb[e] = __float2bfloat16_rn(v);
-        lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+        hb[e] = float_to_elem(v, f16);
+        lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
       }
       *reinterpret_cast<uint4*>(smem + L::kAHi + sw128(tid, c)) = hv;
       if (x3) *reinterpret_cast<uint4*>(smem + L::kALo + sw128(tid, c)) = lv;
@@ -256,10 +257,10 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4 pk;
             if (!x3) {
-              pk.x = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 0]), __uint_as_float(r[c4 * 8 + 1]));
-              pk.y = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 2]), __uint_as_float(r[c4 * 8 + 3]));
-              pk.z = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 4]), __uint_as_float(r[c4 * 8 + 5]));
-              pk.w = ptx::pack_relu_bf16x2(__uint_as_float(r[c4 * 8 + 6]), __uint_as_float(r[c4 * 8 + 7]));
+              pk.x = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 0]), __uint_as_float(r[c4 * 8 + 1]), true, f16);
+              pk.y = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 2]), __uint_as_float(r[c4 * 8 + 3]), true, f16);
+              pk.z = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 4]), __uint_as_float(r[c4 * 8 + 5]), true, f16);
+              pk.w = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 6]), __uint_as_float(r[c4 * 8 + 7]), true, f16);
             } else {
               uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
@@ -422,6 +423,7 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
   float* s_lut = reinterpret_cast<float*>(smem + L::kLut);
   const int tid = threadIdx.x, warp = tid >> 5;
   const bool x3 = act == W2C_ACT_BF16X2;
+  const bool f16 = act == W2C_ACT_FP16;
   const int ho = h / 2, wo = wpx / 2;
   const size_t total = static_cast<size_t>(b_sz) * n_agents * ho * wo;
   const size_t plane = static_cast<size_t>(h) * wpx;
@@ -438,8 +440,8 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
     for (int e = 0; e < 8; ++e) {
       const int k = piece * 8 + e;
       const float v = k < KT ? w[co * KT + k] * sc : (k == KT ? shift[co] : 0.f);
-      hb[e] = __float2bfloat16_rn(v);
-      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+      hb[e] = float_to_elem(v, f16);
+      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + ck * COUT * kRowBytes + sw128(co, c)) = hv;
     if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + ck * COUT * kRowBytes + sw128(co, c)) = lv;
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t idesc = ptx::make_idesc_bf16(kTile, COUT);
+  const uint32_t idesc = ptx::make_idesc_16(kTile, COUT, f16);
   const uint64_t a_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAHi));
   const uint64_t a_lo = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kALo));
   const uint64_t b_hi = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBHi));
@@ -518,8 +520,8 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
           } else if (k == KT) {
             v = 1.f;
           }
-          hb[e] = __float2bfloat16_rn(v);
-          lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));
+          hb[e] = float_to_elem(v, f16);
+          lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
         }
         if (ck * 64 + c * 8 < 160) {  // K is padded to 160: the last 32 columns of chunk 2 are never read
           *reinterpret_cast<uint4*>(smem + L::kAHi + ck * kTile * kRowBytes + sw128(tid, c)) = hv;
@@ -566,7 +568,7 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
             for (int j = 0; j < 4; ++j) {
               const float a = __uint_as_float(r[c4 * 8 + 2 * j]), b = __uint_as_float(r[c4 * 8 + 2 * j + 1]);
               if (!x3) {
-                pw[j] = ptx::pack_relu_bf16x2(a, b);
+                pw[j] = ptx::pack_act2(a, b, true, f16);
               } else {
                 const float ar = fmaxf(a, 0.f), br = fmaxf(b, 0.f);
                 const __nv_bfloat162 hi = __floats2bfloat162_rn(ar, br);

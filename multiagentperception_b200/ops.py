@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_BF16, ACT_BF16X2, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
+from ._lib import (ACT_BF16, ACT_BF16X2, ACT_FP16, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
                    DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, DECONV3X3_S2_DENSE, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX, GT_U8, GT_I64)
 
 # airsim_loader.py:191 (mean_rgb['airsim'], indexed by BGR channel after the loader's flip)

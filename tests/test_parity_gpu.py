@@ -25,6 +25,8 @@ GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 X3_LOGIT_TOL, X3_PROB_TOL, X3_MIOU = 1e-3, 1e-3, 0.995
 BF16_LOGIT_TOL, BF16_MIOU = 5e-2, 0.93
+# fp16 ("fast" speed, IEEE-half storage): eight times finer rounding than bf16 through the same 27 layers
+FP16_LOGIT_TOL, FP16_MIOU = 8e-3, 0.985
 
 
 def _run_case(name, dev, precision, graphs=True):
@@ -78,6 +80,14 @@ def test_parity_bf16_fast_precision(name, cuda_device):
     ref, outs = _run_case(name, cuda_device, "bf16")
     assert _rel(outs[0], ref[0]) <= BF16_LOGIT_TOL
     assert orc.miou_between(ref[0], outs[0].cpu()) >= BF16_MIOU
+
+
+@pytest.mark.parametrize("name", ["single_segnet", "mimocom_segnet_softmax", "mimocom_resnet_activated",
+                                  "when2com_resnet_sparse", "mimocomwho_segnet_argmax", "single_segnet_squeeze4"])
+def test_parity_fp16_precision(name, cuda_device):
+    ref, outs = _run_case(name, cuda_device, "fp16")
+    assert _rel(outs[0], ref[0]) <= FP16_LOGIT_TOL
+    assert orc.miou_between(ref[0], outs[0].cpu()) >= FP16_MIOU
 
 
 def test_graph_replay_equals_eager(cuda_device):
@@ -143,7 +153,8 @@ def test_full_size_one_scene_against_oracle(cuda_device):
     ref_act = orc.forward(sd, cfg, x, **act)
     model = model.to(dev).eval()
     # logits in both precisions on the continuous (softmax-fusion) path
-    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU)):
+    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU),
+                            ("fp16", FP16_LOGIT_TOL, FP16_MIOU)):
         pred, prob, action, nconn = model.set_precision(prec)(x.to(dev), **soft)
         assert _rel(pred, ref_soft[0]) <= tol
         assert orc.miou_between(ref_soft[0], pred.cpu()) >= miou

@@ -32,6 +32,8 @@ def _bf16_round(t):
 def _quant(t, act):
     """What the kernels see of an fp32 tensor in the given activation storage (as float64)."""
     import torch
+    if act == 2:
+        return t.to(torch.float16).to(torch.float64)
     hi = t.to(torch.bfloat16)
     if act == 0:
         return hi.to(torch.float64)
@@ -92,8 +94,8 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     got = y.double() if nchw_out else ops.act_to_nchw(y, cout, act, cstride=y_cs_eff, coffset=y_co).double()
     err = (got - ref).abs().max().item()
     mag = ref.abs().max().item()
-    # bf16 output rounding: 2^-9 relative per element; bf16x2 / fp32 outputs: ~1e-5
-    tol = (6e-3 if (act == 0 and not nchw_out) else 2e-4) * max(mag, 1.0)
+    # bf16 output rounding: 2^-9 relative per element (fp16: 2^-12); bf16x2 / fp32 outputs: ~1e-5
+    tol = (6e-3 if (act == 0 and not nchw_out) else 8e-4 if (act == 2 and not nchw_out) else 2e-4) * max(mag, 1.0)
     return {"max_err": err, "ref_max": mag, "tol": tol, "ok": bool(err <= tol) and bool(torch.isfinite(got).all())}
 
 
@@ -101,7 +103,7 @@ def case_layout():
     torch, F, ops = _imports()
     out = {}
     ok = True
-    for act in (0, 1):
+    for act in (0, 1, 2):
         x = torch.randn(2, 24, 5, 7, device="cuda:0")
         a = ops.nchw_to_act(x, act, cstride=32, coffset=8)
         back = ops.act_to_nchw(a, 24, act, cstride=32, coffset=8)
@@ -149,6 +151,18 @@ CONV_CASES = {
     "pers_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict(impl=4)),
     "pers_deconv_big": (2, 3, 40, 24, 64, 64, 0, dict(impl=4)),
     "pers_1x1": (3, 2, 16, 16, 128, 64, 0, dict(impl=4, relu=False)),
+    # IEEE-half storage (act 2) through every kernel family
+    "f16_tc_s1": (0, 2, 16, 16, 128, 64, 2, dict(impl=2)),
+    "f16_tc_res": (0, 2, 16, 16, 64, 128, 2, dict(impl=2, residual=True)),
+    "f16_simt_s2": (1, 2, 8, 12, 64, 32, 2, dict(impl=1)),
+    "f16_pers_rowhalo": (0, 3, 24, 40, 128, 128, 2, dict(impl=4)),
+    "f16_pers_s2": (1, 2, 32, 32, 64, 128, 2, dict(impl=4)),
+    "f16_pers_deconv": (2, 2, 16, 16, 128, 128, 2, dict(impl=4)),
+    "f16_pers_res": (0, 2, 16, 16, 64, 128, 2, dict(impl=4, residual=True)),
+    "f16_pers_bn256": (0, 2, 32, 32, 256, 256, 2, dict(impl=4)),
+    "f16_pers_nchw_c11": (0, 2, 32, 32, 64, 11, 2, dict(impl=4, nchw_out=True)),
+    "f16_pers_ragged": (0, 3, 13, 21, 64, 72, 2, dict(impl=4)),
+    "f16_dense_deconv": (5, 2, 16, 32, 64, 64, 2, dict()),
     # dense transposed conv (kind 5): resident weights (bf16), streamed (bf16x3), ragged edges, cin 128, slices
     "dense_deconv": (5, 2, 16, 32, 64, 64, 0, dict()),
     "dense_deconv_x2": (5, 2, 8, 16, 64, 64, 1, dict()),
@@ -185,7 +199,7 @@ def case_stem():
     torch, F, ops = _imports()
     dev = "cuda:0"
     out, ok = {}, True
-    for act, cout in ((0, 64), (1, 64), (0, 128), (1, 128), (0, 32)):
+    for act, cout in ((0, 64), (1, 64), (2, 64), (0, 128), (1, 128), (2, 128), (0, 32)):
         b, na, h, w = 2, 3, 20, 28
         x = torch.randn(b, 3 * na, h, w, device=dev)
         wt = torch.randn(cout, 3, 3, 3, device=dev) * 0.2
@@ -199,7 +213,7 @@ def case_stem():
         ref = ref.clamp_min(0)
         got = ops.act_to_nchw(y, cout, act).double()
         err = (got - ref).abs().max().item()
-        tol = (6e-3 if act == 0 else 1e-4) * max(1.0, ref.abs().max().item())
+        tol = (6e-3 if act == 0 else 8e-4 if act == 2 else 1e-4) * max(1.0, ref.abs().max().item())
         out["stem3x3_act%d_c%d" % (act, cout)] = err
         ok &= err <= tol
         if cout != 64:
@@ -216,7 +230,7 @@ def case_stem():
         got7 = ops.act_to_nchw(y7, 64, act).double()
         err7 = (got7 - ref7).abs().max().item()
         out["stem7x7_act%d" % act] = err7
-        ok &= err7 <= (6e-3 if act == 0 else 1e-4) * max(1.0, ref7.abs().max().item())
+        ok &= err7 <= (6e-3 if act == 0 else 8e-4 if act == 2 else 1e-4) * max(1.0, ref7.abs().max().item())
         # two first layers fused (cout 128) written as two dense 64-channel maps: map 0 == the single-layer result
         w14 = torch.cat((wt7, torch.randn(64, 3, 7, 7, device=dev) * 0.08), 0).reshape(128, 147).contiguous()
         two = torch.empty((2, b * na, h2 // 2, w2 // 2, ops.planes_of(act) * 64), dtype=torch.bfloat16, device=dev)
@@ -292,6 +306,7 @@ def case_attn():
         dict(b_sz=2, n_k=5, n_q=1, kd=128, qd=128, mode=1, act=0, diag=0.0, sparse=True, wq=False, temp=128 ** 0.5),
         dict(b_sz=2, n_k=5, n_q=1, kd=1024, qd=32, mode=2, act=1, diag=0.0),
         dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=0, act=0, diag=0.0, mask_self=True),
+        dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=1, act=2, diag=0.001),
     ]
     for ci, cf in enumerate(cfgs):
         b_sz, n_k, n_q, kd, qd = cf["b_sz"], cf["n_k"], cf["n_q"], cf["kd"], cf["qd"]
@@ -322,7 +337,7 @@ def case_attn():
         e_f = (ops.act_to_nchw(fused, C, act).double() - fref).abs().max().item()
         a_ok = bool((action == aref).all().item())
         c_ok = (int(connect.item()) == nconn) if cf["mode"] != 0 else True
-        tol_f = (6e-3 if act == 0 else 1e-4) * max(1.0, fref.abs().max().item())
+        tol_f = (6e-3 if act == 0 else 8e-4 if act == 2 else 1e-4) * max(1.0, fref.abs().max().item())
         good = e_p < 1e-5 and e_c < 1e-5 and e_f <= tol_f and a_ok and c_ok
         out["cfg%d" % ci] = dict(e_prob=e_p, e_coef=e_c, e_fused=e_f, action_ok=a_ok, connect_ok=c_ok, ok=good)
         ok &= good
@@ -334,7 +349,7 @@ def case_mlp():
     torch, F, ops = _imports()
     dev = "cuda:0"
     out, ok = {}, True
-    for act in (0, 1):
+    for act in (0, 1, 2):
         for (m, s, od) in ((5, 4, 1024), (10, 1, 32), (13, 2, 128)):
             n_feat = 256 * s * s
             feat = torch.randn(m, 256, s, s, device=dev)
