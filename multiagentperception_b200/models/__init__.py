@@ -2,7 +2,7 @@
 
 Mirrors ptsemseg/models/__init__.py:8-101 — the whole YAML dict goes in, the arch name selects the class and the
 keyword plumbing. Optional extra key (ignored by the reference, absent from its YAMLs):
-  model.precision: 'bf16' | 'bf16x3'   (default: env W2C_PRECISION, else 'bf16')
+  model.precision: 'bf16' | 'fp16' | 'bf16x3'   (default: env W2C_PRECISION, else 'bf16')
 """
 from .agents import (All_agents, LearnWhen2Com, LearnWho2Com, MIMO_All_agents, MIMOcom, MIMOcomWho, Single_agent)
 
