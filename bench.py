@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "agent-frames/sec (512x512, 5 agents) at 1/2/4/8 B200; mIoU vs reference"
 UNIT = "agent-frames/s"
-IMG = 512
+IMG = int(os.environ.get("W2C_BENCH_IMG", "512"))  # (the contract tests shrink it; the benchmark is 512x512)
 FRAMES_PER_GPU = 40
 # algorithmic work per agent-frame, n_segnet MIMOcom softmax/train path (SURVEY.md 8d / BASELINE.md section 2)
 GFLOP_PER_FRAME = 283.74

@@ -57,11 +57,13 @@ def main():
     gt, pred = labels()
     rs = runningScore(N_CLASSES)
     rs.update(gt, pred)
-    score, _ = rs.get_scores()
+    score, cls_iu = rs.get_scores()
     here = os.path.dirname(os.path.abspath(__file__))
     np.savez_compressed(os.path.join(here, "glue_loader_metrics.npz"), transformed=out,
                         confusion=rs.confusion_matrix.astype(np.int64),
-                        mean_iou=np.float64([v for k, v in score.items() if "Mean IoU" in k][0]))
+                        mean_iou=np.float64([v for k, v in score.items() if "Mean IoU" in k][0]),
+                        score_keys=np.array(sorted(score)), score_values=np.float64([score[k] for k in sorted(score)]),
+                        class_iou=np.float64([cls_iu[i] for i in range(N_CLASSES)]))
     print("transformed", out.shape, float(out.min()), float(out.max()), "confusion sum", int(rs.confusion_matrix.sum()))
 
 

@@ -40,6 +40,18 @@ def test_oracle_confusion_matches_reference_vectors():
     assert orc.mean_iou(hist) == pytest.approx(float(g["mean_iou"]), abs=1e-12)
 
 
+def test_scores_from_confusion_match_reference_get_scores():
+    """multiagentperception_b200.eval_loop.scores_from_confusion against runningScore.get_scores of the unmodified
+    reference (same key strings, same values, per-class IoU)."""
+    from multiagentperception_b200 import eval_loop
+    g = np.load(GOLDEN)
+    scores, cls_iu = eval_loop.scores_from_confusion(g["confusion"])
+    assert sorted(scores) == [str(k) for k in g["score_keys"]]
+    for k, v in zip(g["score_keys"], g["score_values"]):
+        assert scores[str(k)] == pytest.approx(float(v), abs=1e-12)
+    assert np.allclose([cls_iu[i] for i in range(gg.N_CLASSES)], g["class_iou"], atol=1e-12, equal_nan=True)
+
+
 def test_loader_table_equals_the_transform_for_every_byte():
     lut = ops.loader_lut()
     assert tuple(lut.shape) == (3, 256) and lut.dtype == torch.float32
@@ -160,6 +172,41 @@ def test_fused_label_map_equals_argmax_of_the_logits(hw, cuda_device):
     assert torch.equal(labels.cpu().long(), want)
     assert torch.equal(only, labels)
     assert torch.equal(alone, labels)
+
+
+@pytest.mark.gpu
+def test_evaluate_loop_equals_reference_style_evaluation(cuda_device):
+    """eval_loop.evaluate (raw frames in, device label maps + device confusion matrix) against the reference-style loop:
+    host transform -> forward -> max(1)[1] -> runningScore._fast_hist on the host."""
+    from multiagentperception_b200 import eval_loop
+    dev = cuda_device
+    n = 3
+    cfg = configs.make_config("MIMOcom", agent_num=n, img_size=128)
+    model = get_model(cfg, 11)
+    synth.randomize_(model, 1337)
+    model = model.to(dev).eval()
+    g = torch.Generator().manual_seed(4)
+    batches = []
+    for _ in range(3):
+        frames = torch.randint(0, 256, (2, n, 128, 128, 3), dtype=torch.uint8, generator=g)
+        labels = torch.randint(0, 12, (n * 2, 128, 128), dtype=torch.uint8, generator=g)
+        labels[labels == 11] = 250           # ignore regions
+        batches.append((frames, labels))
+    kw = dict(training=False, MO_flag=True, inference="activated")
+    hist = np.zeros((11, 11), dtype=np.int64)
+    bw = []
+    for frames, labels in batches:            # the reference-style loop on the same model (float views, host metrics)
+        out = model(orc.views_from_frames(frames.numpy()).to(dev), **kw)
+        pred = out[0].max(1)[1].cpu().numpy()
+        hist += sum(orc.confusion_matrix(t, p, 11) for t, p in zip(labels.numpy(), pred))
+        bw.append(out[3])
+    want_scores, want_iou = eval_loop.scores_from_confusion(hist)
+    scores, cls_iou, avg_bw = eval_loop.evaluate(model, batches, 11, kw)
+    for k in want_scores:
+        assert scores[k] == pytest.approx(want_scores[k], abs=1e-12)
+    assert np.allclose([cls_iou[i] for i in range(11)], [want_iou[i] for i in range(11)], equal_nan=True)
+    assert avg_bw == pytest.approx(sum(bw) / len(bw), abs=1e-12)
+    assert model._w2c["io"]["u8"] is False    # the model's I/O format is restored
 
 
 @pytest.mark.gpu
