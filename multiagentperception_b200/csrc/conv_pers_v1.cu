@@ -43,6 +43,7 @@ struct PersParams {
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
+  int pdl;           // launched with programmatic stream serialization: wait for the previous grid after the prologue
   int direct_store;  // 1: coalesced 16-byte stores from the staging tile instead of a TMA store (8x16 tiles only)
   int prefetch;   // tiles of L2 prefetch distance for the input windows (0 = off)
   int nchw_tma;   // 1: fp32 NCHW logits through a [cout][8][16] staging box + TMA store (y_map[0] is that fp32 map)
@@ -147,6 +148,14 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (p.pdl) {
+    // Programmatic dependent launch: this CTA may have started while the previous kernel of the stream was still
+    // draining its last tiles; barrier init, the TMEM allocation and the tensor-map prefetch above overlapped with
+    // that tail. Nothing the previous kernel wrote (our input, the residual) is touched before this point, and the
+    // next kernel may start its own prologue as soon as our CTAs free their SMs.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
 
   if (warp == 0) {
     if (ptx::elect_one_sync()) {
@@ -573,6 +582,22 @@ int launch_persv1(const PersParams& p, cudaStream_t stream) {
   }
   const int want = num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
   const int grid = p.groups < want ? p.groups : want;
+  if (p.pdl) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(L::kThreads);
+    cfg.dynamicSmemBytes = L::kDynamicBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>, p);
+    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_persv1_kernel (PDL launch): %s", cudaGetErrorString(e));
+    count_launch();
+    return W2C_OK;
+  }
   conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_persv1_kernel");
   return W2C_OK;
@@ -713,6 +738,14 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     if ((a.impl >> 8) & 1024) p.direct_store = 1;
     if ((a.impl >> 8) & 2048) p.direct_store = 0;
   }
+  // programmatic dependent launch (W2C_PDL=1; experiment, off): overlap this kernel's prologue with the previous kernel's
+  // tail. Correct (110 GPU tests pass with it) but no gain: 3476 / 3447 vs 3471 / 3463 agent-frames/s in one run - the
+  // kernel boundaries of the CUDA-graph step are not where the time goes.
+  static const bool use_pdl = [] {
+    const char* e = getenv("W2C_PDL");
+    return e && e[0] == '1';
+  }();
+  p.pdl = use_pdl ? 1 : 0;
   static const bool allow_nchw_tma = [] {
     const char* e = getenv("W2C_CONV_NCHW_TMA");
     return !(e && e[0] == '0');
