@@ -42,6 +42,7 @@ struct PersParams {
   int n_tiles, m_tiles, total_tiles;
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
+  int cls_rotate; // 1: CTA b starts with class b & 3 (experiment, impl flag 4096)
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
   int pdl;           // launched with programmatic stream serialization: wait for the previous grid after the prologue
   int direct_store;  // 1: coalesced 16-byte stores from the staging tile instead of a TMA store (8x16 tiles only)
@@ -98,7 +99,9 @@ __device__ __forceinline__ bool tile_at(const PersParams& p, int it, int block_n
   const int n_tile = g % p.n_tiles;
   int m = g / p.n_tiles;
   if (p.cls_shift) {
-    c.cls = it & 3;
+    // rotate the class order per CTA: the four output-parity classes write alternate 128-byte lines (256-byte pitch),
+    // and CTAs running in lockstep would all hit the even lines, then all the odd ones
+    c.cls = (it + (p.cls_rotate ? blockIdx.x : 0)) & 3;
   } else {  // few tiles: classes stay separate work items (class slowest) so the CTAs share them evenly
     c.cls = m / p.m_tiles;
     m -= c.cls * p.m_tiles;
@@ -652,6 +655,7 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
   p.cls_shift = (plan.num_classes == 4 && p.m_tiles * p.n_tiles >= 8 * 148 && !((a.impl >> 8) & 128)) ? 2 : 0;
   p.groups = p.cls_shift ? p.m_tiles * p.n_tiles : p.total_tiles;
+  p.cls_rotate = ((a.impl >> 8) & 4096) ? 1 : 0;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
   W2C_CHECK_ARG(!plan.dense || (p.tma_store && bn == 256 && p.n_tiles == 1),
                 "dense deconv needs one 256-wide tile and the TMA-store epilogue (bn=%d)", bn);

@@ -105,6 +105,12 @@ def main():
                              ("dense direct-store", ops.IMPL_TCGEN05 | (1024 << 8), 0)]
                 wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
             cp = 1
+        if os.environ.get("SWEEP_ROT") == "1":  # A/B of the per-CTA class rotation of transposed convs (flag 4096)
+            if kind != 2:
+                continue
+            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers class-rotate", ops.IMPL_TC_PERSIST | (4096 << 8), 0),
+                        ("pers", ops.IMPL_TC_PERSIST, 0), ("pers class-rotate", ops.IMPL_TC_PERSIST | (4096 << 8), 0)]
+            cp = 1
         if os.environ.get("SWEEP_PF") == "1":  # A/B of the L2 prefetch (impl flag 512 = off)
             variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-prefetch", ops.IMPL_TC_PERSIST | (512 << 8), 0)]
             cp = 1
@@ -114,13 +120,14 @@ def main():
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
         if (kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1"
                 and os.environ.get("SWEEP_PROD") != "1" and os.environ.get("SWEEP_PF") != "1"
-                and os.environ.get("SWEEP_DIRECT") != "1"):
+                and os.environ.get("SWEEP_DIRECT") != "1" and os.environ.get("SWEEP_ROT") != "1"):
             variants.append(("halo", ops.IMPL_TC_HALO, 0))
             if cp % 128 == 0 and kind == 0:
                 variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
             if cp % 128 == 0 and kind == 2:
                 variants.append(("halo bn128", ops.IMPL_TC_HALO, 128))
-        if kind == 2 and cin == 64 and cout == 64 and os.environ.get("SWEEP_DIRECT") != "1":
+        if (kind == 2 and cin == 64 and cout == 64 and os.environ.get("SWEEP_DIRECT") != "1"
+                and os.environ.get("SWEEP_ROT") != "1"):
             variants.append(("dense deconv", ops.IMPL_TCGEN05, 0))
             wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
         for name, impl, bn in variants:
