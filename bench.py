@@ -379,7 +379,7 @@ def run_b200(args):
                 fp16_precision = rec
         model.set_precision("bf16")
 
-    # ---- roofline of the dominant kernel (conv_tc_kernel): replay ONLY its launches, same buffers, CUDA events
+    # ---- roofline of the dominant kernel (the tcgen05 conv): replay ONLY its launches, same buffers, CUDA events
     prog = max(model._w2c["programs"].values(), key=lambda c: c.prog.n_launches).prog
     conv_prog = prog.conv_only_program()
     n_conv = sum(1 for c in conv_prog.calls if c[1] is not None)
@@ -392,7 +392,9 @@ def run_b200(args):
     gflop_frame = GFLOP_PER_FRAME if args.backbones == "n_segnet" else 42.92
     conv_tflop_step = (gflop_frame - stem_gflop - 0.005) * local_agents * scenes / 1e3
     achieved = conv_tflop_step / (ms_conv * 1e-3)
-    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (tcgen05 implicit-GEMM conv/deconv, all instantiations)",
+    roofline = {"bound": "tensor",
+                "kernel": "conv_persv1_kernel / conv_tc_kernel (tcgen05 implicit-GEMM conv + transposed conv, every "
+                          "instantiation of the step: 43 launches for the n_segnet pair)",
                 "achieved": achieved, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": traffic_per_launch(n_conv),
                 "launches_per_step": n_conv, "avg_launch_ms": ms_conv / n_conv, "share_of_step": ms_conv / ms_step,
