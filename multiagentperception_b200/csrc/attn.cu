@@ -94,11 +94,27 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
       float acc[kMaxAgents];
 #pragma unroll
       for (int j = 0; j < kMaxAgents; ++j) acc[j] = 0.f;
-      for (int e = 0; e < a.q_dim; ++e) {
-        const float wv = __ldg(wr + e);
+      if ((a.q_dim & 3) == 0) {
+        // 16-byte weight loads (the row W[d,:] is contiguous and 16-byte aligned when q_dim % 4 == 0)
+        for (int e = 0; e < a.q_dim; e += 4) {
+          const float4 wv = __ldg(reinterpret_cast<const float4*>(wr + e));
 #pragma unroll
-        for (int j = 0; j < kMaxAgents; ++j)
-          if (j < a.n_q) acc[j] = fmaf(wv, s_q[j * a.q_dim + e], acc[j]);
+          for (int j = 0; j < kMaxAgents; ++j)
+            if (j < a.n_q) {
+              const float* qj = s_q + j * a.q_dim + e;
+              acc[j] = fmaf(wv.x, qj[0], acc[j]);
+              acc[j] = fmaf(wv.y, qj[1], acc[j]);
+              acc[j] = fmaf(wv.z, qj[2], acc[j]);
+              acc[j] = fmaf(wv.w, qj[3], acc[j]);
+            }
+        }
+      } else {
+        for (int e = 0; e < a.q_dim; ++e) {
+          const float wv = __ldg(wr + e);
+#pragma unroll
+          for (int j = 0; j < kMaxAgents; ++j)
+            if (j < a.n_q) acc[j] = fmaf(wv, s_q[j * a.q_dim + e], acc[j]);
+        }
       }
       const float bias = a.bq ? a.bq[d] : 0.f;
 #pragma unroll
