@@ -10,7 +10,12 @@
  *  - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in _host;
  *  - the caller owns every buffer (no allocation inside, no hidden global state);
  *  - every call enqueues work on the given CUDA stream and returns without synchronising (graph-capturable);
- *  - return value: 0 = W2C_OK, negative = error; w2c_last_error() gives a thread-local message.
+ *  - return value: 0 = W2C_OK, negative = error; w2c_last_error() returns a pointer to a thread-local message
+ *    buffer owned by the library (valid until the next failing call on the same thread) - the reference has no FFI
+ *    error convention to mirror; SURVEY 8(b) sketched a (char*, size_t) copy-out form, the pointer form was kept
+ *    because ctypes reads it without a scratch buffer;
+ *  - re-entrant across devices and streams: the only library-side state is per-device, immutable after first use
+ *    (kernel attribute opt-ins and the SM count, keyed by the device current at the call - see csrc/common.cuh);
  *  - activations are NHWC.  "act" selects the storage:  W2C_ACT_BF16 = one bf16 plane per pixel;
  *    W2C_ACT_BF16X2 = two bf16 planes per pixel [hi(C) | lo(C)] with value = hi + lo (the "bf16x3" parity
  *    precision: every product is evaluated as hi*hi + hi*lo + lo*hi on the tensor cores, fp32 accumulate).
@@ -40,21 +45,17 @@ enum {
  * below 65504 (BatchNorm-ed feature maps do). */
 enum { W2C_ACT_BF16 = 0, W2C_ACT_BF16X2 = 1, W2C_ACT_FP16 = 2 };
 enum { W2C_OUT_NHWC = 0, W2C_OUT_NCHW_F32 = 1 };
-/* W2C_IMPL_TCGEN05 lets the library pick between its two tensor-core kernels (per-tap TMA windows, or one halo
- * tile per channel chunk re-addressed per tap); _TC_TAPS / _TC_HALO force one; _SIMT is the CUDA-core cross-check. */
-enum { W2C_IMPL_TCGEN05 = 0, W2C_IMPL_SIMT = 1, W2C_IMPL_TC_TAPS = 2, W2C_IMPL_TC_HALO = 3, W2C_IMPL_TC_PERSIST = 4 };
+/* W2C_IMPL_TCGEN05 (the product setting) lets the library pick between its two tensor-core kernels: the persistent
+ * warp-specialised kernel wherever a layer has at least one tile per SM, the one-tile-per-CTA kernel for the
+ * sub-wave layers; _TC_PERSIST / _TC_TAPS force one (tests); _SIMT is the CUDA-core cross-check (tests only).
+ * Value 3 is retired (the halo-tile experiment lives in experiments/csrc, outside the product build). */
+enum { W2C_IMPL_TCGEN05 = 0, W2C_IMPL_SIMT = 1, W2C_IMPL_TC_TAPS = 2, W2C_IMPL_TC_PERSIST = 4 };
 enum {
   W2C_CONV3X3_S1 = 0,   /* Conv2d k3 s1 p1                       */
   W2C_CONV3X3_S2 = 1,   /* Conv2d k3 s2 p1   (H, W even)         */
   W2C_DECONV3X3_S2 = 2, /* ConvTranspose2d k3 s2 p1 output_padding 1 */
   W2C_CONV1X1_S1 = 3,   /* Conv2d k1 s1 p0                       */
-  W2C_CONV1X1_S2 = 4,   /* Conv2d k1 s2 p0   (resnet downsample) */
-  /* The same ConvTranspose2d k3 s2 p1 op1 evaluated as ONE dense GEMM per input tile: N = 4 output-parity classes x
-   * cout, K = the 2x2 input neighbourhood x cin (weights packed by w2c_pack_deconv_dense_weight, zero where a class
-   * does not use a neighbour: 16/9 of the useful MACs).  For cout = 64 the four 64-wide classes fill one 256-wide
-   * tcgen05 tile, the input tile is fetched 4x instead of 9x and the 128 KB of weights stay resident in shared
-   * memory - the 64-channel 256->512 layer of the decoder is bound by L2->SM traffic, not by MACs.  cout must be 64. */
-  W2C_DECONV3X3_S2_DENSE = 5
+  W2C_CONV1X1_S2 = 4    /* Conv2d k1 s2 p0   (resnet downsample) */
 };
 
 /* Library / build identification. */
@@ -120,13 +121,6 @@ size_t w2c_packed_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t
  */
 int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
                          int32_t transposed, int32_t act, void* packed, w2c_stream_t stream);
-
-/* Dense packing for W2C_DECONV3X3_S2_DENSE: bf16 [planes][4*cout][4*cin], row = class*cout + co with class =
- * (oh & 1)*2 + (ow & 1), k = (dh*2 + dw)*cin + ci for the input pixel (oh/2 + dh, ow/2 + dw); w is
- * ConvTranspose2d.weight [cin_real][cout][3][3]. */
-size_t w2c_packed_deconv_dense_bytes(int32_t cout, int32_t cin, int32_t act);
-int w2c_pack_deconv_dense_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t act,
-                                 void* packed, w2c_stream_t stream);
 
 /*
  * Fold eval-mode BatchNorm2d (+ the conv bias) into the per-channel affine the conv epilogue applies

@@ -15,8 +15,8 @@ c_vp = ctypes.c_void_p
 
 ACT_BF16, ACT_BF16X2, ACT_FP16 = 0, 1, 2
 OUT_NHWC, OUT_NCHW_F32 = 0, 1
-IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST = 0, 1, 2, 3, 4
-CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, DECONV3X3_S2_DENSE = 0, 1, 2, 3, 4, 5
+IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_PERSIST = 0, 1, 2, 4
+CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2 = 0, 1, 2, 3, 4
 FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX = 0, 1, 2
 GT_U8, GT_I64 = 0, 1
 
@@ -66,8 +66,6 @@ _SIGNATURES = {
     "w2c_cout_pad": (c_i32, [c_i32]),
     "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
-    "w2c_packed_deconv_dense_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32]),
-    "w2c_pack_deconv_dense_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "w2c_fold_bn": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_f32, c_i32, c_vp, c_vp, c_vp]),
     "w2c_stem_conv3x3_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_stem_conv3x3_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),

@@ -310,12 +310,11 @@ extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream)
   p.slabs = ceil_div(a.hw, pix);
   const size_t smem = head + per_pix * pix;
   W2C_CHECK_ARG(smem <= 200 * 1024, "attn: shared memory request %zu too large", smem);
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "attn: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = smem;
-  }
+  static DeviceOnce attr;  // per device, not per process; opted in to the largest request the check above allows
+  if (int rc = attr.ensure([] {
+        return cudaFuncSetAttribute(attn_fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      }, "attn_fuse_kernel"))
+    return rc;
   attn_fuse_kernel<<<a.b_sz * p.slabs, 256, smem, static_cast<cudaStream_t>(stream)>>>(p);
   W2C_CHECK_LAUNCH("attn_fuse_kernel");
   return W2C_OK;

@@ -79,4 +79,45 @@ __device__ __forceinline__ void act_store(__nv_bfloat16* pix, int c, int cstride
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// ---- per-device launch state. cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to a DEVICE,
+// and one process may drive several (nn.DataParallel replicas, a model moved with .to('cuda:1'), train.py:177): every
+// launcher keeps its one-time setup per device ordinal, never per process.
+constexpr int kMaxDevices = 64;
+
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= kMaxDevices ? 0 : dev;
+}
+
+struct DeviceOnce {
+  std::atomic<int> done[kMaxDevices];
+  DeviceOnce() {
+    for (auto& d : done) d.store(0, std::memory_order_relaxed);
+  }
+  // Runs fn() (returning cudaError_t) once per device; racing threads may both run it, which is harmless for an
+  // idempotent attribute write.
+  template <typename Fn>
+  int ensure(Fn fn, const char* what) {
+    const int dev = current_device();
+    if (done[dev].load(std::memory_order_acquire)) return W2C_OK;
+    const cudaError_t e = fn();
+    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
+    done[dev].store(1, std::memory_order_release);
+    return W2C_OK;
+  }
+};
+
+// SM count of the current device (cached per device)
+inline int device_sm_count() {
+  static std::atomic<int> sms[kMaxDevices];
+  const int dev = current_device();
+  int n = sms[dev].load(std::memory_order_relaxed);
+  if (n <= 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    sms[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
+
 }  // namespace w2c

@@ -42,11 +42,7 @@ struct PersParams {
   int n_tiles, m_tiles, total_tiles;
   int groups;     // work items dealt to the CTAs: total_tiles, or m_tiles * n_tiles when cls_shift = 2
   int cls_shift;  // 2: a CTA runs the four output-parity classes of a transposed-conv tile back to back
-  int cls_rotate; // 1: CTA b starts with class b & 3 (experiment, impl flag 4096)
   int tma_store;  // 1: NHWC output through the staging tile + TMA store; 0: direct stores
-  int pdl;           // launched with programmatic stream serialization: wait for the previous grid after the prologue
-  int direct_store;  // 1: coalesced 16-byte stores from the staging tile instead of a TMA store (8x16 tiles only)
-  int prefetch;   // tiles of L2 prefetch distance for the input windows (0 = off)
   int nchw_tma;   // 1: fp32 NCHW logits through a [cout][8][16] staging box + TMA store (y_map[0] is that fp32 map)
   int ctas_per_sm;  // persistent CTAs per SM (small-footprint instantiations: several MMA issuers per SM)
 };
@@ -99,9 +95,7 @@ __device__ __forceinline__ bool tile_at(const PersParams& p, int it, int block_n
   const int n_tile = g % p.n_tiles;
   int m = g / p.n_tiles;
   if (p.cls_shift) {
-    // rotate the class order per CTA: the four output-parity classes write alternate 128-byte lines (256-byte pitch),
-    // and CTAs running in lockstep would all hit the even lines, then all the odd ones
-    c.cls = (it + (p.cls_rotate ? blockIdx.x : 0)) & 3;
+    c.cls = it & 3;
   } else {  // few tiles: classes stay separate work items (class slowest) so the CTAs share them evenly
     c.cls = m / p.m_tiles;
     m -= c.cls * p.m_tiles;
@@ -151,14 +145,6 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  if (p.pdl) {
-    // Programmatic dependent launch: this CTA may have started while the previous kernel of the stream was still
-    // draining its last tiles; barrier init, the TMEM allocation and the tensor-map prefetch above overlapped with
-    // that tail. Nothing the previous kernel wrote (our input, the residual) is touched before this point, and the
-    // next kernel may start its own prologue as soon as our CTAs free their SMs.
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
 
   if (warp == 0) {
     if (ptx::elect_one_sync()) {
@@ -173,20 +159,6 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       TileCoord tc;
       for (int it = 0; tile_at(p, it, BLOCK_N, tc); ++it) {
         const int ntaps = pl.ntaps[tc.cls];
-        // Experiment (off by default, W2C_CONV_PREFETCH=n): L2-prefetch the input windows of the tile n iterations ahead.
-        // Hypothesis was that the ring of the narrow layers is bound by HBM-miss latency (6 stages x 24 KB / ~1.4 us =
-        // the ~540 cycles per k-block measured); measured on B200 it made the stride-2 convs 9-22 % SLOWER and
-        // nothing faster (profiles/r1_conv_sweep_v8_prefetch.md), so first-touch latency is not what binds them.
-        if (p.prefetch && (tc.cls == 0)) {
-          TileCoord nx;
-          if (tile_at(p, it + (p.prefetch << p.cls_shift), BLOCK_N, nx) && nx.n0 == 0) {
-            const int nmaps = pl.in_s == 2 ? 4 : 1;
-            for (int ch = 0; ch < chunks; ++ch)
-              for (int mi = 0; mi < nmaps; ++mi)
-                ptx::tma_prefetch_4d(&p.a_map[GROUP == 3 ? 1 : mi], pl.x_coffset + ch * kBlockK, nx.w0,
-                                     nx.h0 - (GROUP == 3 ? 1 : 0), nx.i0);
-          }
-        }
         for (int pass = 0; pass < npass; ++pass) {
           const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
           const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
@@ -298,9 +270,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     // ===================== epilogue (warps 2..5, 128 threads) =====================
     const int et = threadIdx.x - 64;  // 0..127
     for (int c = et; c < kMaxCout; c += EG * kEpiThreads) {
-      const bool ok = c < pl.n_cols;  // (dense transposed conv: the four class column groups share scale / shift)
-      s_scale[c] = ok ? pl.scale[c % pl.cout] : 0.f;
-      s_shift[c] = ok ? pl.shift[c % pl.cout] : 0.f;
+      const bool ok = c < pl.cout;
+      s_scale[c] = ok ? pl.scale[c] : 0.f;
+      s_shift[c] = ok ? pl.shift[c] : 0.f;
     }
     ptx::named_bar_sync(3, EG * kEpiThreads);
     const int eg = EG == 2 ? (warp - 2) >> 2 : 0;  // this thread's epilogue group
@@ -331,7 +303,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
 #pragma unroll 1
           for (int g = 0; g < BLOCK_N / 64; ++g) {
             const int cb = tc.n0 + g * 64;
-            if (cb >= pl.n_cols) break;
+            if (cb >= pl.cout) break;
             uint32_t r[64];
             ptx::tmem_ld_32x32b_x32(t_row + g * 64, r);
             ptx::tmem_ld_32x32b_x32(t_row + g * 64 + 32, r + 32);
@@ -360,7 +332,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
             for (int pln = 0; pln < planes; ++pln, ++unit) {
               uint8_t* stg = smem + L::kStgOff + (EG == 2 ? eg : unit % L::kNumStaging) * kStagingBytes;
               // the TMA store that last used this staging tile must have finished reading it
-              if (!p.direct_store && lead_warp && ptx::elect_one_sync())
+              if (lead_warp && ptx::elect_one_sync())
                 ptx::bulk_wait_group_read<EG == 2 ? 0 : L::kNumStaging - 1>();
               ptx::named_bar_sync(bar_id, kEpiThreads);
 #pragma unroll
@@ -387,31 +359,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                 }
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
               }
-              // dense transposed conv: column group g IS output-parity class g (cout = 64), channels from 0
-              const int ocls = pl.dense ? cb / pl.cout : tc.cls;
-              const int och = pl.y_coffset + (pl.dense ? cb % pl.cout : cb) + pln * pl.y_cstride;
-              if (p.direct_store) {
-                // Coalesced 16-byte stores from the staging tile (8 rows x 16 pixels x 128 B): thread t writes chunk
-                // t & 7 of pixel column t >> 3 in each of the 8 rows, so 8 consecutive threads complete one 128-byte
-                // line. The TMA store engine takes ~8-15 cycles per 128-byte row of a box (ncu: epilogue warps parked
-                // in cp.async.bulk.wait_group.read on the 64-channel 512x512 outputs), below the HBM write rate.
-                ptx::named_bar_sync(bar_id, kEpiThreads);
-                const int te = et & (kEpiThreads - 1);
-                const int plw = te >> 3, c8 = te & 7;
-                const int pmw = tc.w0 + plw;
-                if (pmw < pl.wm) {
-                  const size_t pixb = static_cast<size_t>(pl.y_pix) * 2;
-                  uint8_t* gp = static_cast<uint8_t*>(pl.y) +
-                                ((static_cast<size_t>(tc.i0) * pl.out_h + tc.h0 * pl.out_s + pl.cls_oh[ocls]) * pl.out_w +
-                                 pmw * pl.out_s + pl.cls_ow[ocls]) * pixb + static_cast<size_t>(och) * 2 + c8 * 16;
-                  const size_t rowb = static_cast<size_t>(pl.out_s) * pl.out_w * pixb;
-                  const uint8_t* sp = stg + plw * 128 + ((c8 ^ (plw & 7)) << 4);
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    if (tc.h0 + i < pl.hm)
-                      *reinterpret_cast<uint4*>(gp + i * rowb) = *reinterpret_cast<const uint4*>(sp + i * 16 * 128);
-                }
-              } else {
+              const int ocls = tc.cls;
+              const int och = pl.y_coffset + cb + pln * pl.y_cstride;
+              {
                 ptx::fence_proxy_async();
                 ptx::named_bar_sync(bar_id, kEpiThreads);
                 if (lead_warp && ptx::elect_one_sync()) {
@@ -569,38 +519,16 @@ template <int BLOCK_N, int STAGES, int GROUP = 1, int EG = 1, int RES = 0>
 int launch_persv1(const PersParams& p, cudaStream_t stream) {
   using L = PersSmem<BLOCK_N, STAGES, GROUP, EG, RES>;
   static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_pers: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
+  // the opt-in is per DEVICE: one process may drive several (nn.DataParallel replicas, model.to('cuda:1'))
+  static DeviceOnce attr_set;
+  int rc = attr_set.ensure([] {
+    return cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+  }, "conv_persv1_kernel");
+  if (rc) return rc;
+  const int num_sms = device_sm_count();
   const int want = num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
   const int grid = p.groups < want ? p.groups : want;
-  if (p.pdl) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(L::kThreads);
-    cfg.dynamicSmemBytes = L::kDynamicBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>, p);
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_persv1_kernel (PDL launch): %s", cudaGetErrorString(e));
-    count_launch();
-    return W2C_OK;
-  }
   conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_persv1_kernel");
   return W2C_OK;
@@ -640,11 +568,10 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
       bn = 16;
     // fewer than two waves of 256-wide tiles (the 16x16 maps: 160 tiles on 148 SMs): 128-wide tiles balance better
     // (0.058 vs 0.067 ms; one-tile kernel 0.073 - profiles/r1_conv_sweep_v7_full.md)
-    if (!plan.dense && bn == 256 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 2 * 148)
+    if (bn == 256 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 2 * 148)
       bn = 128;
-    // not enough tiles to occupy the SMs at this width: narrower tiles (the dense transposed conv keeps its one
-    // 256-wide tile: its column groups are the output-parity classes)
-    while (!plan.dense && bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148)
+    // not enough tiles to occupy the SMs at this width: narrower tiles
+    while (bn > 64 && static_cast<long long>(p.m_tiles) * plan.num_classes * (plan.cout_pad / bn) < 148)
       bn /= 2;
   }
   W2C_CHECK_ARG(bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "conv: block_n=%d not supported", bn);
@@ -655,16 +582,9 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   p.total_tiles = p.m_tiles * p.n_tiles * plan.num_classes;
   p.cls_shift = (plan.num_classes == 4 && p.m_tiles * p.n_tiles >= 8 * 148 && !((a.impl >> 8) & 128)) ? 2 : 0;
   p.groups = p.cls_shift ? p.m_tiles * p.n_tiles : p.total_tiles;
-  p.cls_rotate = ((a.impl >> 8) & 4096) ? 1 : 0;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
-  W2C_CHECK_ARG(!plan.dense || (p.tma_store && bn == 256 && p.n_tiles == 1),
-                "dense deconv needs one 256-wide tile and the TMA-store epilogue (bn=%d)", bn);
   // row-halo stages: 3x3 stride-1 convs on full 8x16 tiles, BLOCK_N <= 128 (at 256 three weight tiles do not fit)
-  static const bool allow_row_halo = [] {
-    const char* e = getenv("W2C_CONV_ROWHALO");
-    return !(e && e[0] == '0');
-  }();
-  const bool row_halo = allow_row_halo && !((a.impl >> 8) & 1) && plan.num_classes == 1 && plan.in_s == 1 &&
+  const bool row_halo = !((a.impl >> 8) & 1) && plan.num_classes == 1 && plan.in_s == 1 &&
                         plan.ntaps[0] == 9 && tn == 1 && tw == 16 && th == 8 && bn <= 128;
 
   const cuuint64_t esz = 2;
@@ -706,7 +626,7 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
     // per tile through a map that strides two pixels in H and W
     const cuuint32_t ybox[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tn};
     const __nv_bfloat16* y = static_cast<const __nv_bfloat16*>(plan.y);
-    const int n_out_maps = plan.dense ? 4 : plan.num_classes;
+    const int n_out_maps = plan.num_classes;
     for (int cls = 0; cls < n_out_maps; ++cls) {
       const int s = plan.out_s;
       const cuuint64_t dims[4] = {(cuuint64_t)plan.y_pix, (cuuint64_t)plan.out_w / s, (cuuint64_t)plan.out_h / s,
@@ -721,41 +641,8 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   } else {
     for (int cls = 0; cls < 4; ++cls) p.y_map[cls] = p.b_map;  // unused, but keep the bytes defined
   }
-  // L2 prefetch distance in tiles (experiment, default off; impl flag 512 forces it off)
-  static const int prefetch_dist = [] {
-    const char* e = getenv("W2C_CONV_PREFETCH");
-    return e ? atoi(e) : 0;
-  }();
-  p.prefetch = ((a.impl >> 8) & 512) ? 0 : prefetch_dist;
-  // Experiment (off by default): coalesced 16-byte stores from the staging tile instead of TMA stores. W2C_CONV_DIRECT =
-  // 1 turns them on where the tile is 8x16, 2 for outputs of <= 128 channels; impl flag 1024 forces them on, 2048 off.
-  // Hypothesis was that the TMA store engine binds the 64-channel 512x512 outputs (epilogue warps parked in
-  // cp.async.bulk.wait_group.read); measured, direct stores are slower everywhere (transposed convs 0.576 -> 0.649 ms,
-  // 64->128 0.315 -> 0.379, profiles/r1_conv_sweep_v9_direct_store.md), so the TMA path stays.
-  static const int direct_mode = [] {
-    const char* e = getenv("W2C_CONV_DIRECT");
-    return e ? atoi(e) : 0;
-  }();
-  p.direct_store = 0;
-  if (p.tma_store && tw == 16 && th == 8 && tn == 1) {
-    if (direct_mode == 1 || (direct_mode == 2 && plan.cout <= 128)) p.direct_store = 1;
-    if ((a.impl >> 8) & 1024) p.direct_store = 1;
-    if ((a.impl >> 8) & 2048) p.direct_store = 0;
-  }
-  // programmatic dependent launch (W2C_PDL=1; experiment, off): overlap this kernel's prologue with the previous kernel's
-  // tail. Correct (110 GPU tests pass with it) but no gain: 3476 / 3447 vs 3471 / 3463 agent-frames/s in one run - the
-  // kernel boundaries of the CUDA-graph step are not where the time goes.
-  static const bool use_pdl = [] {
-    const char* e = getenv("W2C_PDL");
-    return e && e[0] == '1';
-  }();
-  p.pdl = use_pdl ? 1 : 0;
-  static const bool allow_nchw_tma = [] {
-    const char* e = getenv("W2C_CONV_NCHW_TMA");
-    return !(e && e[0] == '0');
-  }();
   p.nchw_tma = 0;
-  if (allow_nchw_tma && !((a.impl >> 8) & 256) && plan.out_fmt == W2C_OUT_NCHW_F32 && plan.y && bn == 16 && p.n_tiles == 1 && tn == 1 &&
+  if (!((a.impl >> 8) & 256) && plan.out_fmt == W2C_OUT_NCHW_F32 && plan.y && bn == 16 && p.n_tiles == 1 && tn == 1 &&
       tw == 16 && th == 8 && plan.num_classes == 1 && plan.out_w % 4 == 0) {
     const cuuint64_t dims[4] = {(cuuint64_t)plan.out_w, (cuuint64_t)plan.out_h, (cuuint64_t)plan.cout,
                                 (cuuint64_t)plan.n_img};
@@ -768,11 +655,7 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   }
 
   // two epilogue warpgroups unless disabled (impl flag bit 1 / env) - see PersSmem
-  static const bool allow_eg2 = [] {
-    const char* e = getenv("W2C_CONV_EPI2");
-    return !(e && e[0] == '0');
-  }();
-  const bool eg2 = allow_eg2 && !((a.impl >> 8) & 2);
+  const bool eg2 = !((a.impl >> 8) & 2);
   int cps = ((a.impl >> 8) & 8) ? 3 : ((a.impl >> 8) & 4) ? 2 : 1;
   // default for the logits layer: two CTAs per SM (with the lean elect.sync issue loops 0.50 ms, against 0.53 with
   // three and 0.72 with one; before that change three were best - profiles/r1_conv_sweep_v6_elect.md)
@@ -781,12 +664,8 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   if (bn == 64 && cps > 2) cps = 2;
   p.ctas_per_sm = cps;
   // resident weights (see PersSmem): single n-tile, one bf16 plane, every [bn][64] tile of the layer fits
-  static const bool allow_res = [] {
-    const char* e = getenv("W2C_CONV_RESIDENT");
-    return !(e && e[0] == '0');
-  }();
   const int res_slots = plan.ktot / kBlockK;
-  const bool res_ok = allow_res && !((a.impl >> 8) & 32) && p.n_tiles == 1 && planes == 1;
+  const bool res_ok = !((a.impl >> 8) & 32) && p.n_tiles == 1 && planes == 1;
   if (row_halo) {
     switch (bn) {
       case 128:
@@ -808,8 +687,6 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   }
   switch (bn) {
     case 256:
-      // dense transposed conv, 64 -> 4 x 64: its four [256][64] weight tiles (128 KB) stay resident
-      if (plan.dense && res_ok && res_slots == 4) return launch_persv1<256, 4, 1, 1, 4>(p, stream);
       return launch_persv1<256, 4, 1, 1>(p, stream);
     case 128: return eg2 ? launch_persv1<128, 5, 1, 2>(p, stream) : launch_persv1<128, 5, 1, 1>(p, stream);
     case 64:

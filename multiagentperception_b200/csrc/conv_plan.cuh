@@ -46,21 +46,12 @@ struct ConvPlan {
   // depend on which kernel / tile width the dispatch picks for a given batch (sharded == unsharded, scene i alone
   // == scene i inside a batch, bit for bit). Everything else runs (tap, chunk).
   int kw_major;
-  // W2C_DECONV3X3_S2_DENSE: one GEMM of n_cols = 4 * cout columns (output-parity class = column / cout) per input
-  // tile; otherwise n_cols = cout
-  int dense, n_cols;
 };
 
-// conv_halo.cu
-bool conv_halo_supported(const ConvPlan& plan);
-bool conv_halo_preferred(const ConvPlan& plan);
-int conv_halo_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 bool conv_persistent_preferred(const ConvPlan& plan);
-// conv_pers.cu
-bool conv_pers_supported(const ConvPlan& plan);
-int conv_pers_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
+bool conv_persv1_supported(const ConvPlan& plan);
 int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream);
 
 inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
@@ -174,24 +165,9 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
         }
       break;
     }
-    case W2C_DECONV3X3_S2_DENSE: {
-      W2C_CHECK_ARG(a.cout == 64, "dense deconv: cout=%d (covers cout = 64)", a.cout);
-      W2C_CHECK_ARG(a.out_fmt == W2C_OUT_NHWC && a.residual == nullptr, "dense deconv: NHWC output, no residual");
-      p.hm = a.h_in, p.wm = a.w_in;
-      p.out_s = 2;
-      p.ktot = 4 * a.cin;
-      p.dense = 1;
-      p.cout_pad = 4 * a.cout;  // rows of the packed weight = GEMM N
-      p.ntaps[0] = 4;
-      for (int dh = 0; dh < 2; ++dh)
-        for (int dw = 0; dw < 2; ++dw) p.taps[0][dh * 2 + dw] = tap(dw, dh, 0, dh * 2 + dw, dw, dh);
-      for (int cls = 0; cls < 4; ++cls) p.cls_oh[cls] = cls >> 1, p.cls_ow[cls] = cls & 1;
-      break;
-    }
     default:
       return set_error(W2C_ERR_INVALID, "conv: unknown kind %d", a.kind);
   }
-  p.n_cols = p.dense ? 4 * p.cout : p.cout;
   p.out_h = p.hm * p.out_s;
   p.out_w = p.wm * p.out_s;
   return W2C_OK;

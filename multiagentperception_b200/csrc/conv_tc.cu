@@ -309,13 +309,12 @@ int pow2_ceil(int v) {
 template <int BLOCK_N, int STAGES>
 int launch(const ConvTcParams& p, cudaStream_t stream) {
   using L = SmemLayout<BLOCK_N, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kDynamicBytes);
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "conv_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr_set = true;
-  }
+  static DeviceOnce attr_set;  // per device, not per process (common.cuh)
+  if (int rc = attr_set.ensure([] {
+        return cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kDynamicBytes);
+      }, "conv_tc_kernel"))
+    return rc;
   dim3 grid(p.tiles_w * p.tiles_h * p.tiles_img * p.n_tiles, p.plan.num_classes, 1);
   conv_tc_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_tc_kernel");
@@ -467,20 +466,6 @@ int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream) {
 }  // namespace w2c
 
 namespace w2c {
-// Kernel choice for W2C_IMPL_TCGEN05. W2C_CONV_HALO=0 / 1 forces the per-tap / halo kernel wherever legal.
-bool conv_halo_preferred(const ConvPlan& plan) {
-  static const int mode = [] {
-    const char* e = getenv("W2C_CONV_HALO");
-    return e ? atoi(e) : -1;
-  }();
-  if (!conv_halo_supported(plan) || mode == 0) return false;
-  if (mode == 1) return true;
-  // auto: the halo kernel lost the per-layer sweep (profiles/r1_conv_sweep.md) everywhere it was tried
-  return false;
-}
-}  // namespace w2c
-
-namespace w2c {
 // Measured per-layer choice between the persistent kernel and the one-tile-per-CTA kernel
 // (profiles/r1_conv_sweep_v2_persistent.md): with narrow outputs (<= 64 channels) a stride-1 3x3 conv issues MMAs too
 // short for ONE issuing thread per SM to keep the pipe busy, and three co-resident one-tile CTAs (three issuers)
@@ -506,46 +491,31 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
   int rc = w2c::build_conv_plan(*args, plan);
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (plan.labels && (args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
-    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", args->impl & 0xff);
-  if (plan.act == W2C_ACT_FP16 && ((args->impl & 0xff) == W2C_IMPL_TC_HALO || (args->impl & 0xff) == 5))
-    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the experimental kernels (impl %d) are bf16-only", args->impl & 0xff);
-  if (plan.dense) {  // the dense transposed conv exists in the persistent kernel only
-    if ((args->impl & 0xff) != W2C_IMPL_TCGEN05 && (args->impl & 0xff) != W2C_IMPL_TC_PERSIST)
-      return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no dense transposed conv", args->impl & 0xff);
-    return w2c::conv_persv1_forward(*args, plan, s);
-  }
-  switch (args->impl & 0xff) {
-    case W2C_IMPL_SIMT:
+  const int impl = args->impl & 0xff;
+  if (plan.labels && impl != W2C_IMPL_TCGEN05 && impl != W2C_IMPL_TC_PERSIST)
+    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", impl);
+  switch (impl) {
+    case W2C_IMPL_SIMT:  // CUDA-core cross-check of the tensor-core kernels (tests only)
       return w2c::conv_simt_forward(plan, s);
     case W2C_IMPL_TC_TAPS:
       return w2c::conv_tc_forward(*args, plan, s);
-    case W2C_IMPL_TC_HALO:
-      if (!w2c::conv_halo_supported(plan))
-        return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the halo kernel covers 3x3 s1 conv and 3x3 s2 deconv only");
-      return w2c::conv_halo_forward(*args, plan, s);
     case W2C_IMPL_TC_PERSIST:
-      if (!w2c::conv_pers_supported(plan))
+      if (!w2c::conv_persv1_supported(plan))
         return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: the persistent kernel needs cout <= 512");
       return w2c::conv_persv1_forward(*args, plan, s);
-    case 5:  // experimental: persistent kernel with row-halo tap groups / resident weights (conv_pers.cu)
-      return w2c::conv_pers_forward(*args, plan, s);
     case W2C_IMPL_TCGEN05: {
-      if (plan.labels) {  // the fused label map lives in the persistent kernel's logits epilogue
-        if (!w2c::conv_pers_supported(plan))
+      // production dispatch: the persistent kernel wherever a layer has a tile per SM (and for the fused label map,
+      // which lives in its logits epilogue), the one-tile-per-CTA kernel for the sub-wave layers
+      if (plan.labels) {
+        if (!w2c::conv_persv1_supported(plan))
           return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: label map needs the persistent kernel (cout <= 512)");
         return w2c::conv_persv1_forward(*args, plan, s);
       }
-      static const bool persist = [] {
-        const char* e = getenv("W2C_CONV_PERSIST");
-        return !(e && e[0] == '0');
-      }();
-      if (w2c::conv_halo_preferred(plan)) return w2c::conv_halo_forward(*args, plan, s);
-      if (persist && w2c::conv_pers_supported(plan) && w2c::conv_persistent_preferred(plan))
+      if (w2c::conv_persv1_supported(plan) && w2c::conv_persistent_preferred(plan))
         return w2c::conv_persv1_forward(*args, plan, s);
       return w2c::conv_tc_forward(*args, plan, s);
     }
     default:
-      return w2c::set_error(W2C_ERR_INVALID, "conv: unknown impl %d", args->impl);
+      return w2c::set_error(W2C_ERR_INVALID, "conv: unknown impl %d (the halo / row-halo experiments live in experiments/csrc)", args->impl);
   }
 }

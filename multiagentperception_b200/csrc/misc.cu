@@ -50,28 +50,6 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
   }
 }
 
-// dense transposed-conv packing (W2C_DECONV3X3_S2_DENSE): row = cls*cout + co, k = (dh*2+dw)*cin + ci.
-// oh = 2*ih - 1 + kh: even oh reads kh = 1 at dh = 0 only; odd oh reads kh = 0 at dh = 1 and kh = 2 at dh = 0.
-__global__ void pack_deconv_dense_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int planes,
-                                         __nv_bfloat16* __restrict__ out, bool f16) {
-  const size_t ktot = 4 * static_cast<size_t>(cin);
-  const size_t total = 4 * static_cast<size_t>(cout) * ktot;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int row = idx / ktot, k = idx % ktot;
-    const int cls = row / cout, co = row % cout;
-    const int t = k / cin, ci = k % cin;
-    const int ph = cls >> 1, pw = cls & 1, dh = t >> 1, dw = t & 1;
-    const int kh = ph == 0 ? (dh == 0 ? 1 : -1) : (dh == 1 ? 0 : 2);
-    const int kw = pw == 0 ? (dw == 0 ? 1 : -1) : (dw == 1 ? 0 : 2);
-    float v = 0.f;
-    if (kh >= 0 && kw >= 0 && ci < cin_real) v = w[(static_cast<size_t>(ci) * cout + co) * 9 + kh * 3 + kw];
-    const __nv_bfloat16 hi = float_to_elem(v, f16);
-    out[idx] = hi;
-    if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
-  }
-}
-
 __global__ void fold_bn_kernel(const float* bias, const float* gamma, const float* beta, const float* mean,
                                const float* var, float eps, int cout, float* scale, float* shift) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -162,68 +140,6 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ 
         }
         *reinterpret_cast<uint4*>(ypix + g + j8 * 8) = hv;
         if (planes == 2) *reinterpret_cast<uint4*>(ypix + cout + g + j8 * 8) = lv;
-      }
-    }
-  }
-}
-
-// Conv2d(3->64, k7 s2 p3) + affine + ReLU (resnet18 conv1/bn1/relu). One thread per output pixel, 32 output
-// channels per pass; weights in shared memory as [147][64].
-__global__ void __launch_bounds__(128) stem7x7_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                      const float* __restrict__ scale,
-                                                      const float* __restrict__ shift, __nv_bfloat16* __restrict__ y,
-                                                      int b_sz, int n_agents, int c_total, int c_first, int h,
-                                                      int wpx, int act) {
-  constexpr int COUT = 64, K = 147;
-  extern __shared__ float sm[];
-  float* s_w = sm;  // [147][64]
-  float* s_scale = sm + K * COUT;
-  float* s_shift = s_scale + COUT;
-  for (int i = threadIdx.x; i < K * COUT; i += blockDim.x) {
-    const int k = i / COUT, co = i % COUT;
-    s_w[i] = w[co * K + k];
-  }
-  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_scale[i] = scale[i], s_shift[i] = shift[i];
-  __syncthreads();
-  const int ho = h / 2, wo = wpx / 2;
-  const size_t plane = static_cast<size_t>(h) * wpx;
-  const size_t total = static_cast<size_t>(b_sz) * n_agents * ho * wo;
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int ow = idx % wo;
-    const int oh = (idx / wo) % ho;
-    const int img = idx / (static_cast<size_t>(ho) * wo);
-    const int agent = img / b_sz, bat = img % b_sz;
-    const float* xin = x + (static_cast<size_t>(bat) * c_total + c_first + 3 * agent) * plane;
-    __nv_bfloat16* ypix = y + idx * (static_cast<size_t>(COUT) * planes);
-    for (int g = 0; g < COUT; g += 32) {
-      float acc[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-      for (int ci = 0; ci < 3; ++ci)
-        for (int kh = 0; kh < 7; ++kh) {
-          const int ih = oh * 2 + kh - 3;
-          if (ih < 0 || ih >= h) continue;
-#pragma unroll
-          for (int kw = 0; kw < 7; ++kw) {
-            const int iw = ow * 2 + kw - 3;
-            const float v = (iw >= 0 && iw < wpx) ? __ldg(xin + ci * plane + static_cast<size_t>(ih) * wpx + iw) : 0.f;
-            const float4* wr = reinterpret_cast<const float4*>(s_w + (ci * 49 + kh * 7 + kw) * COUT + g);
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const float4 wv = wr[j4];
-              acc[4 * j4 + 0] = fmaf(v, wv.x, acc[4 * j4 + 0]);
-              acc[4 * j4 + 1] = fmaf(v, wv.y, acc[4 * j4 + 1]);
-              acc[4 * j4 + 2] = fmaf(v, wv.z, acc[4 * j4 + 2]);
-              acc[4 * j4 + 3] = fmaf(v, wv.w, acc[4 * j4 + 3]);
-            }
-          }
-        }
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float v = fmaxf(fmaf(acc[j], s_scale[g + j], s_shift[g + j]), 0.f);
-        act_store(ypix, g + j, COUT, act, v);
       }
     }
   }
@@ -515,24 +431,6 @@ int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t
   return W2C_OK;
 }
 
-size_t w2c_packed_deconv_dense_bytes(int32_t cout, int32_t cin, int32_t act) {
-  const size_t planes = act == W2C_ACT_BF16X2 ? 2 : 1;
-  return planes * 4 * static_cast<size_t>(cout) * 4 * static_cast<size_t>(cin) * sizeof(__nv_bfloat16);
-}
-
-int w2c_pack_deconv_dense_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t act, void* packed,
-                                 w2c_stream_t stream) {
-  W2C_CHECK_ARG(w && packed, "pack_deconv_dense: null pointer");
-  W2C_CHECK_ARG(cout == 64, "pack_deconv_dense: cout=%d (the dense transposed conv covers cout = 64)", cout);
-  W2C_CHECK_ARG(cin > 0 && cin % 64 == 0 && cin_real > 0 && cin_real <= cin, "pack_deconv_dense: cin=%d cin_real=%d",
-                cin, cin_real);
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
-  const size_t total = 16 * static_cast<size_t>(cout) * cin;
-  pack_deconv_dense_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      w, cout, cin_real, cin, planes, static_cast<__nv_bfloat16*>(packed), act == W2C_ACT_FP16);
-  W2C_CHECK_LAUNCH("pack_deconv_dense_kernel");
-  return W2C_OK;
-}
 
 int w2c_fold_bn(const float* conv_bias, const float* gamma, const float* beta, const float* mean, const float* var,
                 float eps, int32_t cout, float* scale, float* shift, w2c_stream_t stream) {
@@ -554,11 +452,7 @@ int w2c_stem_conv3x3_fwd(const float* x, const float* w, const float* scale, con
   W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem3x3: channel window [%d, %d) outside %d",
                 c_first, c_first + 3 * n_agents, c_total);
   W2C_CHECK_ARG(cout % 32 == 0 && cout <= 128, "stem3x3: cout=%d must be a multiple of 32 and <= 128", cout);
-  static const bool force_simt = [] {
-    const char* e = getenv("W2C_STEM_SIMT");
-    return e && e[0] == '1';
-  }();
-  if ((cout == 64 || cout == 128) && !force_simt)
+  if (cout == 64 || cout == 128)
     return stem3x3_tc_forward(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act, n_split,
                               static_cast<cudaStream_t>(stream));
   const size_t total = static_cast<size_t>(b) * n_agents * h * w_px;
@@ -636,24 +530,8 @@ int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, c
   W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0, "stem7x7: bad extent");
   W2C_CHECK_ARG((cout == 64 && n_split == 1) || (cout == 128 && (n_split == 1 || n_split == 2)),
                 "stem7x7: cout=%d n_split=%d (64, or 128 as one or two maps)", cout, n_split);
-  static const bool force_simt = [] {
-    const char* e = getenv("W2C_STEM_SIMT");
-    return e && e[0] == '1';
-  }();
-  if (!(force_simt && cout == 64))
-    return stem7x7_tc_forward(x, nullptr, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act, n_split,
-                              0, static_cast<cudaStream_t>(stream));
-  const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (w_px / 2);
-  const size_t smem = (147 * 64 + 128) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(stem7x7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    attr = true;
-  }
-  stem7x7_kernel<<<grid_for(total, 128, 148 * 4), 128, smem, static_cast<cudaStream_t>(stream)>>>(
-      x, w, scale, shift, static_cast<__nv_bfloat16*>(y), b, n_agents, c_total, c_first, h, w_px, act);
-  W2C_CHECK_LAUNCH("stem7x7_kernel");
-  return W2C_OK;
+  return stem7x7_tc_forward(x, nullptr, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act, n_split,
+                            0, static_cast<cudaStream_t>(stream));
 }
 
 int w2c_stem_conv7x7s2_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,

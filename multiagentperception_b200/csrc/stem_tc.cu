@@ -324,24 +324,18 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
                    int b, int n_agents, int c_total, int c_first, int h, int wpx, int act, int n_split,
                    cudaStream_t stream) {
   using L = StemSmem<COUT, NS>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(stem3x3_tc_kernel<COUT, U8, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kDynamic);
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "stem3x3_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
-  }
+  static DeviceOnce attr;  // per device, not per process (common.cuh)
+  if (int rc = attr.ensure([] {
+        return cudaFuncSetAttribute(stem3x3_tc_kernel<COUT, U8, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kDynamic);
+      }, "stem3x3_tc_kernel"))
+    return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * h * wpx;
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
   const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
-  // (experiment, off by default: W2C_STEM_DIRECT=1 - measured 1 % slower than the TMA stores)
-  static const bool direct = [] {
-    const char* e = getenv("W2C_STEM_DIRECT");
-    return e && e[0] == '1';
-  }();
-  y_maps.direct = direct ? 1 : 0;
+  y_maps.direct = 0;
   y_maps.pitch = y_maps.cs * planes * 2;
   y_maps.total = total;
   for (int sp = 0; sp < 2; ++sp) {
@@ -360,7 +354,7 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
   if (per_sm > 512 / (COUT < 32 ? 32 : COUT)) per_sm = 512 / (COUT < 32 ? 32 : COUT);
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
-  int grid = 148 * per_sm;
+  int grid = device_sm_count() * per_sm;
   if (grid > num_tiles) grid = num_tiles;
   stem3x3_tc_kernel<COUT, U8, NS><<<grid, kTile, smem_bytes, stream>>>(y_maps, x, lut, w, scale, shift, b, n_agents,
                                                                         c_total, c_first, h, wpx, act, num_tiles);
@@ -371,14 +365,7 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
 template <int COUT, bool U8>
 int launch_stem(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y, int b,
                 int n_agents, int c_total, int c_first, int h, int wpx, int act, int n_split, cudaStream_t stream) {
-  // one staging tile -> four CTAs per SM at COUT = 128 (52 KB each); W2C_STEM_STAGING=2 keeps two (three CTAs)
-  static const int ns = [] {
-    const char* e = getenv("W2C_STEM_STAGING");
-    return (e && e[0] == '2') ? 2 : 1;
-  }();
-  if (ns == 2)
-    return launch_stem_ns<COUT, U8, 2>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, n_split,
-                                       stream);
+  // one staging tile -> four CTAs per SM at COUT = 128 (52 KB each; two tiles / three CTAs measured slower)
   return launch_stem_ns<COUT, U8, 1>(x, lut, w, scale, shift, y, b, n_agents, c_total, c_first, h, wpx, act, n_split,
                                      stream);
 }
@@ -609,13 +596,12 @@ template <int COUT, bool U8>
 int launch_stem7(const void* x, const float* lut, const float* w, const float* scale, const float* shift, void* y, int b,
                  int n_agents, int c_total, int c_first, int h, int wpx, int act, int n_split, cudaStream_t stream) {
   using L = Stem7Smem<COUT>;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(stem7x7_tc_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         L::kDynamic);
-    if (e != cudaSuccess) return set_error(W2C_ERR_CUDA, "stem7x7_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    attr = true;
-  }
+  static DeviceOnce attr;
+  if (int rc = attr.ensure([] {
+        return cudaFuncSetAttribute(stem7x7_tc_kernel<COUT, U8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    L::kDynamic);
+      }, "stem7x7_tc_kernel"))
+    return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (wpx / 2);
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
   const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
@@ -637,7 +623,7 @@ int launch_stem7(const void* x, const float* lut, const float* w, const float* s
   int per_sm = (227 * 1024) / (smem_bytes + 1024);
   if (per_sm > 2) per_sm = 2;
   if (per_sm < 1) per_sm = 1;
-  int grid = 148 * per_sm;
+  int grid = device_sm_count() * per_sm;
   if (grid > num_tiles) grid = num_tiles;
   stem7x7_tc_kernel<COUT, U8><<<grid, kTile, smem_bytes, stream>>>(y_maps, x, lut, w, scale, shift, b, n_agents, c_total,
                                                                   c_first, h, wpx, act, num_tiles);

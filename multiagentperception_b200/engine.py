@@ -36,12 +36,6 @@ _TS = os.environ.get("W2C_TWO_STREAMS")
 TWO_STREAMS = None if _TS is None else _TS == "1"
 
 
-# W2C_DECONV_DENSE=1 runs the 64-channel transposed conv as one dense 256-wide GEMM per input tile (kind 5). Measured:
-# 3.3x less L2->SM traffic and no gain in time (0.548 vs 0.543 ms; 3536 vs 3520 agent-frames/s, within run-to-run
-# noise) - that layer is bound by its 1.34 GB of parity-strided output writes - so the default stays the four-class form.
-DENSE_DECONV = os.environ.get("W2C_DECONV_DENSE", "0") == "1"
-
-
 def use_graphs_default():
     return os.environ.get("W2C_CUDA_GRAPH", "1") != "0"
 
@@ -110,12 +104,7 @@ class WeightCache:
         if kind is None:
             raise NotImplementedError("no sm_100a kernel for conv k=%s stride=%s" % ((kh, kw), stride))
         pc = PackedConv()
-        if transposed and conv.out_channels == 64 and cin == 64 and DENSE_DECONV:
-            # 64 -> 64 transposed conv (decoder deconv11, 256 -> 512): one dense 256-wide GEMM per input tile
-            kind = ops.DECONV3X3_S2_DENSE
-            pc.w = ops.pack_deconv_dense_weight(w, cin, self.act)
-        else:
-            pc.w = ops.pack_conv_weight(w, cin, transposed, self.act)
+        pc.w = ops.pack_conv_weight(w, cin, transposed, self.act)
         pc.cin, pc.cout, pc.kind, pc.relu = cin, conv.out_channels, kind, bool(relu)
         pc.subsample = 2 if (not transposed and stride == 4) else 1
         pc.scale, pc.shift = self._fold(conv, bn)
@@ -268,7 +257,7 @@ class Program:
             return out
         if pc.kind in (ops.CONV3X3_S2, ops.CONV1X1_S2):
             ho, wo = x.h // 2, x.w // 2
-        elif pc.kind in (ops.DECONV3X3_S2, ops.DECONV3X3_S2_DENSE):
+        elif pc.kind == ops.DECONV3X3_S2:
             ho, wo = x.h * 2, x.w * 2
         else:
             ho, wo = x.h, x.w

@@ -10,8 +10,8 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_BF16, ACT_BF16X2, ACT_FP16, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_HALO, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
-                   DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, DECONV3X3_S2_DENSE, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX, GT_U8, GT_I64)
+from ._lib import (ACT_BF16, ACT_BF16X2, ACT_FP16, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
+                   DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX, GT_U8, GT_I64)
 
 # airsim_loader.py:191 (mean_rgb['airsim'], indexed by BGR channel after the loader's flip)
 LOADER_MEAN_BGR = (103.939, 116.779, 123.68)
@@ -73,18 +73,6 @@ def pack_conv_weight(w, cin_pad, transposed, act):
     packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
     _lib.check(lib.w2c_pack_conv_weight(_ptr(w), cout, cin_real, cin_pad, ntaps, int(bool(transposed)), act,
                                         _ptr(packed), _stream()), "w2c_pack_conv_weight")
-    return packed
-
-
-def pack_deconv_dense_weight(w, cin_pad, act):
-    """ConvTranspose2d.weight [ci, 64, 3, 3] -> the dense [4*64][4*cin] operand of DECONV3X3_S2_DENSE."""
-    lib = _lib.load()
-    w = w.detach().to(dtype=torch.float32).contiguous()
-    cin_real, cout = w.shape[0], w.shape[1]
-    nbytes = lib.w2c_packed_deconv_dense_bytes(cout, cin_pad, act)
-    packed = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
-    _lib.check(lib.w2c_pack_deconv_dense_weight(_ptr(w), cout, cin_real, cin_pad, act, _ptr(packed), _stream()),
-               "w2c_pack_deconv_dense_weight")
     return packed
 
 

@@ -1,6 +1,6 @@
 """GPU: every C-ABI kernel entry point against a float64 torch evaluation of the same op (the bring-up cases of
 tools/gpu_kernel_check.py, run in-process). Covers all conv kinds in the three tensor-core kernels (one-tile,
-persistent incl. row-halo stages / dual epilogue groups / multi-CTA logits path, halo experiment), both activation
+persistent incl. row-halo stages / dual epilogue groups / multi-CTA logits path), the activation
 storages, slices, residuals, ragged edges, the stems, pooling, up-sampling, the MLP heads and the attention kernel."""
 import pytest
 
@@ -8,8 +8,7 @@ from tools import gpu_kernel_check as kc
 
 pytestmark = pytest.mark.gpu
 
-# the halo experiment is only correct with its default base-offset mode; keep a few of its cases as regression
-_CONV = [n for n in kc.CONV_CASES if not n.startswith("halo_")] + ["halo_s1_multi", "halo_deconv_c64", "halo_nchw_c11"]
+_CONV = list(kc.CONV_CASES)
 
 
 @pytest.mark.parametrize("name", _CONV)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-layer kernel sweep on a B200: every distinct conv / deconv shape of the n_segnet MIMOcom forward at the bench
-batch (40 agent-frames), timed with CUDA events for each tensor-core kernel variant (per-tap vs halo, BLOCK_N).
+batch (40 agent-frames), timed with CUDA events for each tensor-core kernel variant (one-tile vs persistent, tuning flags, BLOCK_N).
 Used to pick the dispatch heuristic; writes gpurun_out/conv_sweep.md."""
 import os
 import sys
@@ -61,77 +61,29 @@ def main():
             y = torch.empty(N, ho, ho, ops.planes_of(act) * cout, device=dev, dtype=torch.bfloat16)
         m = N * (ho * ho if kind != 2 else h * h)
         flop = 2.0 * m * cin * cout * 9
+        # variants: the one-tile kernel, the persistent kernel and its tuning flags (bits 8.. of impl: 1 no row-halo
+        # stages, 2 one epilogue group, 4 / 8 two / three CTAs per SM, 16 one, 32 no resident weights, 64 resident
+        # opt-ins, 128 class-major transposed-conv order, 256 per-thread logits stores)
         variants = [("taps", ops.IMPL_TC_TAPS, 0), ("pers", ops.IMPL_TC_PERSIST, 0),
                     ("pers 1-epi-group", ops.IMPL_TC_PERSIST | (2 << 8), 0)]
-        ab = os.environ.get("SWEEP_AB") == "1"
-        if ab:
-            # A/B of the round-1 late changes: resident weights (flag 32 = off, 64 = opt-in variants) and the
-            # class-inner tile order of transposed convs (flag 128 = old class-major order)
-            if cin * cout * 9 * 2 > 147456 and kind != 2:
-                continue
-            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-resident", ops.IMPL_TC_PERSIST | (32 << 8), 0)]
-            if (kind == 0 and cin == 128 and cout == 64) or cout <= 16 or (cin == 64 and cout == 64):
-                variants.append(("pers resident opt-in", ops.IMPL_TC_PERSIST | (64 << 8), 0))
-            if kind == 2:
-                variants.append(("pers class-major", ops.IMPL_TC_PERSIST | (128 << 8), 0))
-        if cout == 64 and not ab:
-            variants += [("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0)]
-        if cout <= 16 and not ab:
+        if kind == 2:
+            variants.append(("pers class-major", ops.IMPL_TC_PERSIST | (128 << 8), 0))
+        if cout == 64:
+            variants.append(("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0))
+        if cout <= 16:
             variants += [("pers 1cta/sm", ops.IMPL_TC_PERSIST | (16 << 8), 0),
-                         ("pers 2cta/sm", ops.IMPL_TC_PERSIST | (4 << 8), 0),
-                         ("pers direct stores", ops.IMPL_TC_PERSIST | (256 << 8), 0),
-                         ("pers 1cta/sm 1-epi-group", ops.IMPL_TC_PERSIST | ((16 | 2) << 8), 0)]
-        cp = 1 if ab else ops.cout_pad(cout)
-        if cp % 256 == 0:
-            variants.append(("pers bn128", ops.IMPL_TC_PERSIST, 128))
-        if os.environ.get("SWEEP_FLAGS"):
-            # persistent-kernel tuning flags (bits 8.. of impl): 1 no row-halo, 2 no resident weights, 4 two CTAs/SM,
-            # 8 no chunk merge
-            variants = [("taps", ops.IMPL_TC_TAPS, 0)]
-            for fl in [int(v) for v in os.environ["SWEEP_FLAGS"].split(",")]:
-                variants.append(("exp f%d" % fl, 5 | (fl << 8) | (1 << 16), 0))  # experimental conv_pers.cu
-            cp = 1
-        if os.environ.get("SWEEP_QUICK") == "1":
-            variants = variants[:3]
-            cp = 1
+                         ("pers 3cta/sm", ops.IMPL_TC_PERSIST | (8 << 8), 0),
+                         ("pers per-thread stores", ops.IMPL_TC_PERSIST | (256 << 8), 0)]
+        cp = ops.cout_pad(cout)
         if os.environ.get("SWEEP_PROD") == "1":  # only the production dispatch (for ncu captures)
             variants = [("production dispatch", ops.IMPL_TCGEN05, 0)]
             cp = 1
-        if os.environ.get("SWEEP_DIRECT") == "1":  # A/B of direct coalesced stores (flag 1024 on / 2048 off)
-            variants = [("pers tma-store", ops.IMPL_TC_PERSIST | (2048 << 8), 0),
-                        ("pers direct-store", ops.IMPL_TC_PERSIST | (1024 << 8), 0)]
-            if kind == 2 and cin == 64 and cout == 64:
-                variants += [("dense tma-store", ops.IMPL_TCGEN05 | (2048 << 8), 0),
-                             ("dense direct-store", ops.IMPL_TCGEN05 | (1024 << 8), 0)]
-                wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
-            cp = 1
-        if os.environ.get("SWEEP_ROT") == "1":  # A/B of the per-CTA class rotation of transposed convs (flag 4096)
-            if kind != 2:
-                continue
-            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers class-rotate", ops.IMPL_TC_PERSIST | (4096 << 8), 0),
-                        ("pers", ops.IMPL_TC_PERSIST, 0), ("pers class-rotate", ops.IMPL_TC_PERSIST | (4096 << 8), 0)]
-            cp = 1
-        if os.environ.get("SWEEP_PF") == "1":  # A/B of the L2 prefetch (impl flag 512 = off)
-            variants = [("pers", ops.IMPL_TC_PERSIST, 0), ("pers no-prefetch", ops.IMPL_TC_PERSIST | (512 << 8), 0)]
-            cp = 1
         if cp % 256 == 0:
-            variants.append(("taps bn256", ops.IMPL_TC_TAPS, 256))
+            variants += [("pers bn128", ops.IMPL_TC_PERSIST, 128), ("taps bn256", ops.IMPL_TC_TAPS, 256)]
         if cp % 128 == 0:
             variants.append(("taps bn64", ops.IMPL_TC_TAPS, 64))
-        if (kind != 1 and not os.environ.get("SWEEP_FLAGS") and os.environ.get("SWEEP_AB") != "1"
-                and os.environ.get("SWEEP_PROD") != "1" and os.environ.get("SWEEP_PF") != "1"
-                and os.environ.get("SWEEP_DIRECT") != "1" and os.environ.get("SWEEP_ROT") != "1"):
-            variants.append(("halo", ops.IMPL_TC_HALO, 0))
-            if cp % 128 == 0 and kind == 0:
-                variants.append(("halo bn64", ops.IMPL_TC_HALO, 64))
-            if cp % 128 == 0 and kind == 2:
-                variants.append(("halo bn128", ops.IMPL_TC_HALO, 128))
-        if (kind == 2 and cin == 64 and cout == 64 and os.environ.get("SWEEP_DIRECT") != "1"
-                and os.environ.get("SWEEP_ROT") != "1"):
-            variants.append(("dense deconv", ops.IMPL_TCGEN05, 0))
-            wp_dense = ops.pack_deconv_dense_weight(wt, cin, act)
         for name, impl, bn in variants:
-            k2, w2 = (5, wp_dense) if name.startswith("dense") else (kind, wp)
+            k2, w2 = kind, wp
 
             def run(k2=k2, w2=w2, impl=impl, bn=bn):
                 ops.conv_bnrelu(x, w2, scale, shift, y, n=N, h_in=h, w_in=h, cin=cin, cout=cout, kind=k2, relu=True,

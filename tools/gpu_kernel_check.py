@@ -49,7 +49,7 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     cin_real = cin_real or cin
     ksz = 1 if kind in (ops.CONV1X1_S1, ops.CONV1X1_S2) else 3
     x = torch.randn(n, cin_real, h, w, generator=g)
-    transposed = kind in (ops.DECONV3X3_S2, ops.DECONV3X3_S2_DENSE)
+    transposed = kind == ops.DECONV3X3_S2
     wshape = (cin_real, cout, ksz, ksz) if transposed else (cout, cin_real, ksz, ksz)
     wt = torch.randn(*wshape, generator=g) / (cin_real * ksz * ksz) ** 0.5
     scale = torch.rand(cout, generator=g) + 0.5
@@ -60,14 +60,13 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     xa = ops.nchw_to_act(x, act, cstride=x_cs_eff, coffset=x_co)      # zero-filled outside the slice
     if cin_real < cin or x_cs:
         pass  # padded channels are zero in xa by construction (nchw_to_act zero-initialises)
-    wp = (ops.pack_deconv_dense_weight(wt, cin, act) if kind == ops.DECONV3X3_S2_DENSE
-          else ops.pack_conv_weight(wt, cin, transposed, act))
+    wp = ops.pack_conv_weight(wt, cin, transposed, act)
     xq, wq = _quant(x, act), _quant(wt, act)
     if kind == ops.CONV3X3_S1:
         ref = F.conv2d(xq, wq, padding=1)
     elif kind == ops.CONV3X3_S2:
         ref = F.conv2d(xq, wq, padding=1, stride=2)
-    elif kind in (ops.DECONV3X3_S2, ops.DECONV3X3_S2_DENSE):
+    elif kind == ops.DECONV3X3_S2:
         ref = F.conv_transpose2d(xq, wq, stride=2, padding=1, output_padding=1)
     elif kind == ops.CONV1X1_S1:
         ref = F.conv2d(xq, wq)
@@ -162,14 +161,6 @@ CONV_CASES = {
     "f16_pers_bn256": (0, 2, 32, 32, 256, 256, 2, dict(impl=4)),
     "f16_pers_nchw_c11": (0, 2, 32, 32, 64, 11, 2, dict(impl=4, nchw_out=True)),
     "f16_pers_ragged": (0, 3, 13, 21, 64, 72, 2, dict(impl=4)),
-    "f16_dense_deconv": (5, 2, 16, 32, 64, 64, 2, dict()),
-    # dense transposed conv (kind 5): resident weights (bf16), streamed (bf16x3), ragged edges, cin 128, slices
-    "dense_deconv": (5, 2, 16, 32, 64, 64, 0, dict()),
-    "dense_deconv_x2": (5, 2, 8, 16, 64, 64, 1, dict()),
-    "dense_deconv_ragged": (5, 3, 13, 21, 64, 64, 0, dict(relu=False)),
-    "dense_deconv_cin128": (5, 2, 16, 16, 128, 64, 0, dict()),
-    "dense_deconv_slices": (5, 2, 16, 16, 64, 64, 0, dict(x_cs=128, x_co=64, y_cs=192, y_co=64)),
-    "dense_deconv_many": (5, 6, 64, 64, 64, 64, 0, dict()),
     "pers_1x1s2_res": (4, 2, 16, 16, 64, 128, 0, dict(impl=4, residual=True)),
     "pers_res_x2": (0, 2, 16, 16, 64, 128, 1, dict(impl=4, residual=True)),
     "pers_small_8x8": (0, 5, 8, 8, 256, 256, 0, dict(impl=4)),
@@ -180,18 +171,6 @@ CONV_CASES = {
     "pers_ragged": (0, 3, 13, 21, 64, 72, 0, dict(impl=4)),
     "pers_ragged_c64": (0, 3, 13, 21, 64, 64, 0, dict(impl=4)),
     "pers_many_tiles": (0, 8, 64, 64, 64, 128, 0, dict(impl=4)),
-    # halo-reuse kernel (impl=3): 3x3 s1 conv and 3x3 s2 deconv
-    "halo_s1_min": (0, 1, 7, 16, 64, 64, 0, dict(impl=3)),
-    "halo_s1_multi": (0, 3, 24, 40, 128, 128, 0, dict(impl=3)),
-    "halo_s1_k512": (0, 2, 16, 16, 512, 192, 0, dict(impl=3, block_n=64)),
-    "halo_s1_x2": (0, 2, 16, 16, 128, 64, 1, dict(impl=3)),
-    "halo_deconv": (2, 2, 16, 16, 128, 128, 0, dict(impl=3)),
-    "halo_deconv_x2": (2, 1, 8, 8, 64, 64, 1, dict(impl=3)),
-    "halo_deconv_c64": (2, 2, 40, 24, 64, 64, 0, dict(impl=3)),
-    "halo_nchw_c11": (0, 2, 32, 32, 64, 11, 0, dict(impl=3, nchw_out=True)),
-    "halo_nchw_c11_x2": (0, 2, 16, 32, 64, 11, 1, dict(impl=3, nchw_out=True, relu=False)),
-    "halo_slices_res": (0, 2, 16, 16, 64, 64, 0, dict(impl=3, x_cs=128, x_co=64, y_cs=192, y_co=64, residual=True)),
-    "halo_ragged": (0, 3, 13, 21, 64, 72, 0, dict(impl=3)),
 }
 
 
