@@ -168,6 +168,22 @@ enum { W2C_GT_U8 = 0, W2C_GT_I64 = 1 };
 int w2c_confusion_update(const uint8_t* pred, const void* gt, int32_t gt_dtype, int64_t count, int32_t n_class,
                          int64_t* hist, w2c_stream_t stream);
 
+/* runningScore.update_div (metrics.py:70-97): the same histogram split per IMAGE into the "normal" and the "noisy"
+ * matrix (confusion_matrix_pos / _neg).  pred / gt hold n_img images of px_per_img pixels; img_flag uint8 [n_img]:
+ * 1 -> hist_pos, 0 -> hist_neg (the caller derives it from commun_label exactly as update_div does: 'mimo'
+ * commun_label[:,0,:] == 0 transposed to agent-major, 'when2com' commun_label == -1). */
+int w2c_confusion_update_div(const uint8_t* pred, const void* gt, int32_t gt_dtype, const uint8_t* img_flag,
+                             int32_t n_img, int64_t px_per_img, int32_t n_class, int64_t* hist_pos, int64_t* hist_neg,
+                             w2c_stream_t stream);
+
+/* runningScore.update_selection (metrics.py:23-68) accumulated on the device: counters int64 [3] =
+ * {total_agent, correct_when2com, correct_who2com}, caller-zeroed.
+ *   mode 0 'mimo':     action int64 [b][n] (forward()'s action_argmax), commun_label int64 [b][2][n]
+ *   mode 1 'when2com': action int64 [b] (arg-max link), commun_label int64 [b] in -1 .. n-2
+ *   mode 2 'when2com': action fp32 [b][n] (the thresholded weights 'activated' returns), commun_label int64 [b] */
+int w2c_selection_update(const void* action, const int64_t* commun_label, int32_t b_sz, int32_t n, int32_t mode,
+                         int64_t* counters, w2c_stream_t stream);
+
 /*
  * Key / query heads: flatten -> Linear -> ReLU -> Linear -> ReLU -> Linear.  Replaces km_generator.forward and
  * linear.forward (agent.py:145-178).  feat is the NHWC policy feature map [m][s][s][256]; w0 must already be

@@ -71,6 +71,8 @@ _SIGNATURES = {
     "w2c_stem_conv3x3_u8_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_argmax_labels_fwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, c_vp]),
     "w2c_confusion_update": (ctypes.c_int, [c_vp, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp]),
+    "w2c_confusion_update_div": (ctypes.c_int, [c_vp, c_vp, c_i32, c_vp, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_vp]),
+    "w2c_selection_update": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "w2c_kq_mlp_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp]),
     "w2c_kq_mlp_heads_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(MlpHead), c_i32, c_vp, c_vp]),
     "w2c_attn_fuse_fwd": (ctypes.c_int, [ctypes.POINTER(AttnArgs), c_vp]),

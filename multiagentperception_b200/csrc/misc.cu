@@ -399,6 +399,77 @@ __global__ void __launch_bounds__(256) confusion_kernel(const uint8_t* __restric
     if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
 }
 
+// runningScore.update_div (metrics.py:70-97): the same histogram routed per IMAGE into one of two matrices by a
+// per-image flag (1 = "normal" image -> hist_pos, 0 = noisy -> hist_neg). One CTA never straddles two images.
+template <typename GT>
+__global__ void __launch_bounds__(256) confusion_div_kernel(const uint8_t* __restrict__ pred, const GT* __restrict__ gt,
+                                                            const uint8_t* __restrict__ img_flag, int n_img,
+                                                            size_t px_per_img, int ctas_per_img, int n_class,
+                                                            unsigned long long* __restrict__ hist_pos,
+                                                            unsigned long long* __restrict__ hist_neg) {
+  extern __shared__ unsigned int s_hist[];
+  const int bins = n_class * n_class;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_hist[i] = 0;
+  __syncthreads();
+  const int img = blockIdx.x / ctas_per_img, part = blockIdx.x % ctas_per_img;
+  if (img >= n_img) return;
+  const size_t base = static_cast<size_t>(img) * px_per_img;
+  for (size_t i = static_cast<size_t>(part) * blockDim.x + threadIdx.x; i < px_per_img;
+       i += static_cast<size_t>(ctas_per_img) * blockDim.x) {
+    const long long g = static_cast<long long>(gt[base + i]);
+    const int pr = pred[base + i];
+    if (g >= 0 && g < n_class && pr < n_class) atomicAdd(&s_hist[static_cast<int>(g) * n_class + pr], 1u);
+  }
+  __syncthreads();
+  unsigned long long* hist = img_flag[img] ? hist_pos : hist_neg;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x)
+    if (s_hist[i]) atomicAdd(&hist[i], static_cast<unsigned long long>(s_hist[i]));
+}
+
+// runningScore.update_selection (metrics.py:23-68) on the device. counters = {total_agent, correct_when2com,
+// correct_who2com}.
+//   mode 0 'mimo'      action int64 [B][N], commun_label int64 [B][2][N]  (row 0: needs communication, row 1: with whom)
+//   mode 1 'when2com'  action int64 [B] (arg-max link), commun_label int64 [B] in -1..N-2
+//   mode 2 'when2com'  action fp32 [B][N] (thresholded weights, 'activated'), commun_label int64 [B]
+__global__ void selection_kernel(const void* __restrict__ action, const long long* __restrict__ label, int b_sz, int n,
+                                 int mode, unsigned long long* __restrict__ counters) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long when_ok = 0, who_ok = 0, agents = 0;
+  if (mode == 0) {
+    if (i < b_sz * n) {
+      const int b = i / n, j = i % n;
+      const long long need = label[(static_cast<size_t>(b) * 2 + 0) * n + j];
+      const long long who = label[(static_cast<size_t>(b) * 2 + 1) * n + j];
+      const long long act = static_cast<const long long*>(action)[i];
+      agents = 1;
+      // when2com: (action != own id) == uint8(need)   (commun_label[:,0,:].type(ByteTensor))
+      when_ok = (static_cast<unsigned char>(act != j) == static_cast<unsigned char>(need)) ? 1 : 0;
+      who_ok = (act == who * need + static_cast<long long>(j) * (1 - need)) ? 1 : 0;
+    }
+  } else if (i < b_sz) {
+    const long long lab = label[i] + 1;  // -1,0,1,.. -> 0,1,2,..
+    agents = 1;
+    if (mode == 1) {
+      const long long act = static_cast<const long long*>(action)[i];
+      when_ok = ((act == 0) == (lab == 0)) ? 1 : 0;
+      who_ok = (act == lab) ? 1 : 0;
+    } else {
+      const float* row = static_cast<const float*>(action) + static_cast<size_t>(i) * n;
+      bool pred_comm = false;
+      for (int l = 0; l < n; ++l)
+        if (row[l] > 0.2f) {
+          if (l == lab) ++who_ok;
+          if (l != 0) pred_comm = true;
+        }
+      // the reference compares an int8 "communicates" flag with the (label == 0) mask as written (metrics.py:44)
+      when_ok = (pred_comm == (lab == 0)) ? 1 : 0;
+    }
+  }
+  if (agents) atomicAdd(&counters[0], agents);
+  if (when_ok) atomicAdd(&counters[1], when_ok);
+  if (who_ok) atomicAdd(&counters[2], who_ok);
+}
+
 }  // namespace
 }  // namespace w2c
 
@@ -502,6 +573,43 @@ int w2c_confusion_update(const uint8_t* pred, const void* gt, int32_t gt_dtype, 
   else
     confusion_kernel<long long><<<grid, 256, smem, s>>>(pred, static_cast<const long long*>(gt), count, n_class, h);
   W2C_CHECK_LAUNCH("confusion_kernel");
+  return W2C_OK;
+}
+
+int w2c_confusion_update_div(const uint8_t* pred, const void* gt, int32_t gt_dtype, const uint8_t* img_flag,
+                             int32_t n_img, int64_t px_per_img, int32_t n_class, int64_t* hist_pos, int64_t* hist_neg,
+                             w2c_stream_t stream) {
+  W2C_CHECK_ARG(pred && gt && img_flag && hist_pos && hist_neg && n_img > 0 && px_per_img > 0,
+                "confusion_div: bad arguments");
+  W2C_CHECK_ARG(n_class > 0 && n_class <= 64, "confusion_div: n_class=%d (1..64)", n_class);
+  W2C_CHECK_ARG(gt_dtype == W2C_GT_U8 || gt_dtype == W2C_GT_I64, "confusion_div: gt_dtype=%d", gt_dtype);
+  const size_t smem = static_cast<size_t>(n_class) * n_class * sizeof(unsigned int);
+  int ctas_per_img = static_cast<int>((px_per_img + 256 * 16 - 1) / (256 * 16));
+  const int cap = (device_sm_count() * 8 + n_img - 1) / n_img;
+  if (ctas_per_img > cap) ctas_per_img = cap;
+  if (ctas_per_img < 1) ctas_per_img = 1;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned long long* hp = reinterpret_cast<unsigned long long*>(hist_pos);
+  unsigned long long* hn = reinterpret_cast<unsigned long long*>(hist_neg);
+  if (gt_dtype == W2C_GT_U8)
+    confusion_div_kernel<uint8_t><<<n_img * ctas_per_img, 256, smem, s>>>(
+        pred, static_cast<const uint8_t*>(gt), img_flag, n_img, static_cast<size_t>(px_per_img), ctas_per_img, n_class, hp, hn);
+  else
+    confusion_div_kernel<long long><<<n_img * ctas_per_img, 256, smem, s>>>(
+        pred, static_cast<const long long*>(gt), img_flag, n_img, static_cast<size_t>(px_per_img), ctas_per_img, n_class, hp, hn);
+  W2C_CHECK_LAUNCH("confusion_div_kernel");
+  return W2C_OK;
+}
+
+int w2c_selection_update(const void* action, const int64_t* commun_label, int32_t b_sz, int32_t n, int32_t mode,
+                         int64_t* counters, w2c_stream_t stream) {
+  W2C_CHECK_ARG(action && commun_label && counters && b_sz > 0 && n > 0, "selection: bad arguments");
+  W2C_CHECK_ARG(mode >= 0 && mode <= 2, "selection: mode=%d (0 mimo, 1 when2com arg-max, 2 when2com weights)", mode);
+  const int total = mode == 0 ? b_sz * n : b_sz;
+  selection_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      action, reinterpret_cast<const long long*>(commun_label), b_sz, n, mode,
+      reinterpret_cast<unsigned long long*>(counters));
+  W2C_CHECK_LAUNCH("selection_kernel");
   return W2C_OK;
 }
 

@@ -245,6 +245,8 @@ class Program:
             full = self.conv(x, _stride2_view(pc))                      # (h/2, w/2) map
             if out is None:
                 out = self.act_buf(x.n, x.h // 4, x.w // 4, pc.cout)
+            elif (out.n, out.h, out.w, out.c) != (x.n, x.h // 4, x.w // 4, pc.cout):
+                raise ValueError("conv (stride 4): the caller's output map does not match the layer's output")
             planes = self.planes
 
             def run(_stream, full=full, out=out):
@@ -270,6 +272,9 @@ class Program:
         else:
             if out is None:
                 out = self.act_buf(x.n, ho, wo, pc.cout)
+            elif (out.n, out.h, out.w, out.c) != (x.n, ho, wo, pc.cout):
+                raise ValueError("conv: the caller's output map is %dx%dx%dx%d but the layer produces %dx%dx%dx%d"
+                                 % (out.n, out.h, out.w, out.c, x.n, ho, wo, pc.cout))
             y_ptr, out_fmt, ycs, yco, ret = out.buf.data_ptr(), ops.OUT_NHWC, out.cstride, out.coffset, out
         a = _lib.ConvArgs(x=x.buf.data_ptr(), w=pc.w.data_ptr(), scale=pc.scale.data_ptr(), shift=pc.shift.data_ptr(),
                           residual=residual.buf.data_ptr() if residual is not None else None, y=y_ptr, n=x.n,

@@ -15,6 +15,7 @@ import torch
 import torch.nn as nn
 
 from .. import engine, ops
+from ..lazy import DeviceScalar
 from .layers import (_Container, conv2DBatchNormRelu, deconv2DBatchNormRelu, get_decoder, get_encoder,
                      n_segnet_decoder, n_segnet_encoder, resnet_encoder, simple_decoder)
 
@@ -473,7 +474,7 @@ class _AttentionModel(_W2CModel):
         queries, val) tensors to write into (the rank's slot of the exchange buffer when agents are sharded)."""
         val_out = None
         if dst is not None:
-            val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], FEATURE_CHANNELS)
+            val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], dst[2].shape[3] // prog.planes)
         encs = self._value_encoders()
         if encs is None:
             stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
@@ -550,6 +551,8 @@ class MIMOcom(_AttentionModel):
         return self
 
     def forward(self, inputs, training=True, MO_flag=False, inference="argmax"):
+        if self.shared_img_encoder != "unified":
+            raise ValueError("Incorrect encoder")  # agent.py:1116-1118,1335-1337: only the unified encoder exists
         if self._w2c.get("shard") is not None:
             return self._forward_sharded(inputs, training, MO_flag, inference)
         n = self.agent_num
@@ -595,8 +598,8 @@ class MIMOcom(_AttentionModel):
             action = self._ret(out["action"])
         if mode == "softmax":
             num_connect = n - 1
-        else:
-            num_connect = int(out["connect"].item()) / (n * b)
+        else:  # counted by the attention kernel; stays on the device until somebody reads it (lazy.DeviceScalar)
+            num_connect = DeviceScalar.from_count(out["connect"], n * b)
         return self._ret(out["pred"]), prob, action, num_connect
 
 
@@ -617,28 +620,32 @@ class MIMOcom(_AttentionModel):
         b, h, w = _bhw(inputs)
 
         def build(prog, x):
-            fh, fw = h // 32, w // 32
-            lay = sharding.AgentShardLayout(n, world, rank, b, self.key_size, self.query_size, fh, fw,
-                                            FEATURE_CHANNELS, prog.planes)
+            # feature-map geometry as the encoder really produces it: the squeezer may stride (feat_squeezer 2 / 4,
+            # agent.py:49-54) and sets the channel count (feat_channel)
+            sq = {2: 2, 4: 4}.get(self.u_encoder.feat_squeezer, 1)
+            fh, fw = h // 32 // sq, w // 32 // sq
+            fc = self.u_encoder.squeezer.conv.out_channels
+            lay = sharding.AgentShardLayout(n, world, rank, b, self.key_size, self.query_size, fh, fw, fc,
+                                            prog.planes)
             exchange = lay.allocate(prog.device)
             prog.keep.append(exchange)
             k_loc, q_loc, v_loc = lay.views(exchange)
             self._keys_queries(prog, x, b, apr, h, w, dst=(k_loc, q_loc, v_loc))
             prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group))   # the one collective
             k0, q0, v0 = lay.views(exchange, 0)
-            val = engine.ActMap(v0, apr * b, fh, fw, FEATURE_CHANNELS)
+            val = engine.ActMap(v0, apr * b, fh, fw, fc)
             wq, bq, temp = self._attn_weights(prog)
             prob = prog.f32_buf(b, n, n)
             coef = prog.f32_buf(b, n, n)
             action = prog.f32_buf(b, n, dtype=torch.int64)
             connect = prog.f32_buf(1, dtype=torch.int32, zero=True)
             if self.who:
-                cat = prog.act_buf(apr * b, fh, fw, 2 * FEATURE_CHANNELS)
-                fused = cat.slice(0, FEATURE_CHANNELS)
-                prog.copy_channels(engine.ActMap(v_loc, apr * b, fh, fw, FEATURE_CHANNELS),
-                                   cat.slice(FEATURE_CHANNELS, FEATURE_CHANNELS))
+                cat = prog.act_buf(apr * b, fh, fw, 2 * fc)
+                fused = cat.slice(0, fc)
+                prog.copy_channels(engine.ActMap(v_loc, apr * b, fh, fw, fc),
+                                   cat.slice(fc, fc))
             else:
-                cat = fused = prog.act_buf(apr * b, fh, fw, FEATURE_CHANNELS)
+                cat = fused = prog.act_buf(apr * b, fh, fw, fc)
             prog.memset(connect)
             prog.attn(k0, q0, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=n,
                       k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], mask_self=self.who,
@@ -651,7 +658,7 @@ class MIMOcom(_AttentionModel):
         out = self._compiled(inputs, ("shard", rank, world, mode), build).out
         prob = self._ret(out["prob"])
         action = torch.argmax(prob, dim=1) if self.who else self._ret(out["action"])
-        num_connect = n - 1 if mode == "softmax" else int(out["connect"].item()) / (n * b)
+        num_connect = n - 1 if mode == "softmax" else DeviceScalar.from_count(out["connect"], n * b)
         return self._ret(out["pred"]), prob, action, num_connect
 
 
@@ -712,7 +719,7 @@ class LearnWhen2Com(_AttentionModel):
             return pred, prob, action
         if mode == "softmax":
             return pred, prob, action, 4
-        num_connect = int(out["connect"].item()) / b
+        num_connect = DeviceScalar.from_count(out["connect"], b)
         if mode == "activated":
             return pred, prob, out["coef"].transpose(1, 2).clone(), num_connect  # action = thresholded weights
         return pred, prob, action, num_connect

@@ -149,6 +149,53 @@ def confusion_update(pred_labels, gt, n_classes, hist):
     return hist
 
 
+def confusion_update_div(pred_labels, gt, img_flag, n_classes, hist_pos, hist_neg):
+    """runningScore.update_div (metrics.py:70-97) on the device: image i of pred / gt (uint8 [n_img, H, W] / uint8 or
+    int64) is histogrammed into hist_pos when img_flag[i] != 0 ("normal"), else into hist_neg ("noisy")."""
+    lib = _lib.load()
+    n_img = img_flag.numel()
+    if pred_labels.dtype != torch.uint8 or pred_labels.numel() != gt.numel() or pred_labels.numel() % n_img:
+        raise ValueError("confusion_update_div: pred must be uint8 [n_img, ...] with as many elements as gt")
+    if img_flag.dtype != torch.uint8:
+        raise ValueError("confusion_update_div: img_flag must be uint8 [n_img]")
+    for h in (hist_pos, hist_neg):
+        if h.dtype != torch.int64 or h.numel() != n_classes * n_classes:
+            raise ValueError("confusion_update_div: hist must be int64 [%d, %d]" % (n_classes, n_classes))
+    dt = {torch.uint8: GT_U8, torch.int64: GT_I64}.get(gt.dtype)
+    if dt is None:
+        raise ValueError("confusion_update_div: gt must be uint8 or int64 (got %s)" % gt.dtype)
+    _lib.check(lib.w2c_confusion_update_div(_ptr(pred_labels), _ptr(gt), dt, _ptr(img_flag), n_img,
+                                            pred_labels.numel() // n_img, n_classes, _ptr(hist_pos), _ptr(hist_neg),
+                                            _stream()), "w2c_confusion_update_div")
+
+
+def selection_update(action, commun_label, mode, counters):
+    """runningScore.update_selection (metrics.py:23-68) on the device; counters int64 [3] = {total_agent,
+    correct_when2com, correct_who2com}. mode 'mimo': action int64 [B, N], commun_label int64 [B, 2, N]; 'when2com':
+    action int64 [B] (arg-max) or fp32 [B, N] (thresholded weights), commun_label int64 [B]."""
+    lib = _lib.load()
+    if counters.dtype != torch.int64 or counters.numel() != 3 or commun_label.dtype != torch.int64:
+        raise ValueError("selection_update: counters int64 [3], commun_label int64")
+    if mode == "mimo":
+        b, n = action.shape
+        if action.dtype != torch.int64 or tuple(commun_label.shape) != (b, 2, n):
+            raise ValueError("selection_update('mimo'): action int64 [B, N], commun_label [B, 2, N]")
+        m = 0
+    elif mode == "when2com":
+        if action.dim() == 1 and action.dtype == torch.int64:
+            b, n, m = action.shape[0], 1, 1
+        elif action.dim() == 2 and action.dtype == torch.float32:
+            (b, n), m = action.shape, 2
+        else:
+            raise ValueError("selection_update('when2com'): action int64 [B] or fp32 [B, N]")
+        if commun_label.numel() != b:
+            raise ValueError("selection_update('when2com'): commun_label [B]")
+    else:
+        raise ValueError("selection_update: mode must be 'mimo' or 'when2com'")
+    _lib.check(lib.w2c_selection_update(_ptr(action.contiguous()), _ptr(commun_label.contiguous()), b, n, m,
+                                        _ptr(counters), _stream()), "w2c_selection_update")
+
+
 def stem_conv7x7s2(x_nchw, w147, scale, shift, y, *, b, n_agents, h, w, act, c_total=0, c_first=0, cout=64, n_split=1):
     lib = _lib.load()
     _lib.check(lib.w2c_stem_conv7x7s2_fwd(_ptr(x_nchw), _ptr(w147), _ptr(scale), _ptr(shift), _ptr(y), b, n_agents,

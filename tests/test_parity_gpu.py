@@ -185,7 +185,8 @@ def test_single_agent_ragged_sizes_against_oracle(hw, cuda_device):
 
 
 def test_single_agent_1024_against_oracle(cuda_device):
-    """BASELINE config 4 shape (Single_agent, n_segnet pair, 1024x1024; one view - the oracle takes ~10 s for it)."""
+    """BASELINE config 4 shape (Single_agent, n_segnet pair, 1024x1024; one view - the oracle takes ~10 s for it), in
+    config 4's own dtype (fp16) as well as the parity and bf16 precisions."""
     dev = cuda_device
     cfg = configs.make_config("Single_agent", img_size=1024)
     model = get_model(cfg, 11)
@@ -193,7 +194,8 @@ def test_single_agent_1024_against_oracle(cuda_device):
     x = synth.synthetic_views(1, 1, 1024, 1024, seed=5)
     ref = orc.forward(model.state_dict(), cfg, x)
     model = model.to(dev).eval()
-    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU)):
+    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU),
+                            ("fp16", FP16_LOGIT_TOL, FP16_MIOU)):
         pred = model.set_precision(prec)(x.to(dev))
         assert pred.shape == (1, 11, 1024, 1024)
         assert _rel(pred, ref) <= tol
