@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
     ap.add_argument("--batch", type=int, default=0, help="scenes per step (per rank for --config 4); 0 = the config's own")
-    ap.add_argument("--precision", default="", choices=["", "bf16", "bf16x3", "fp16", "mixed"])
+    ap.add_argument("--precision", default="", choices=["", "bf16", "bf16x3", "fp16", "fp16x3", "mixed"])
     ap.add_argument("--backbones", default="n_segnet", choices=["n_segnet", "resnet"])
     ap.add_argument("--inference", default="softmax", choices=["softmax", "activated", "argmax_test"])
     ap.add_argument("--frames-per-gpu", type=int, default=FRAMES_PER_GPU)
@@ -343,14 +343,19 @@ def library_baseline(wl, dev, steps=5):
                 out[name] = timed(lambda: ref_harness.reference_forward(ref, x, **wl.kw))
             except Exception as e:  # e.g. out of memory: report, keep going
                 out[name] = {"error": str(e)[:200]}
+        def step_bf16(m, xin):
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                return ref_harness.reference_forward(m, xin, **wl.kw)
         try:
+            out["bf16_autocast"] = timed(lambda: step_bf16(ref, x))
+        except Exception as e:
+            out["bf16_autocast"] = {"error": str(e)[:200]}
+        try:
+            # channels_last weights and input: the reference's own `.view()` calls (agent.py:158,1114) reject
+            # channels_last activations for some archs - reported as an error then, the plain autocast line stands
             ref_cl = ref.to(memory_format=torch.channels_last)
             x_cl = x.contiguous(memory_format=torch.channels_last)
-
-            def step_bf16():
-                with torch.autocast("cuda", dtype=torch.bfloat16):
-                    return ref_harness.reference_forward(ref_cl, x_cl, **wl.kw)
-            out["bf16_autocast_channels_last"] = timed(step_bf16)
+            out["bf16_autocast_channels_last"] = timed(lambda: step_bf16(ref_cl, x_cl))
         except Exception as e:
             out["bf16_autocast_channels_last"] = {"error": str(e)[:200]}
     finally:
@@ -611,7 +616,7 @@ def run_b200(args):
     precisions = None
     if not args.no_parity_value:
         precisions = {}
-        for prec in ("bf16x3", "mixed", "fp16", "bf16"):
+        for prec in ("bf16x3", "fp16x3", "mixed", "fp16", "bf16"):
             if prec == wl.precision or prec not in engine.PRECISIONS:
                 continue
             model.set_precision(prec)
@@ -622,7 +627,7 @@ def run_b200(args):
             precisions[prec] = {"precision": prec, "value": wl.frames_total / (ms_p * 1e-3), "unit": UNIT,
                                 "ms_per_step": ms_p}
         model.set_precision(wl.precision)
-        for prec, tol in (("bf16x3", "1e-3"), ("mixed", "1e-3"), ("fp16", "8e-3")):
+        for prec, tol in (("bf16x3", "1e-3"), ("fp16x3", "1e-3"), ("mixed", "1e-3"), ("fp16", "8e-3")):
             if prec in precisions:
                 precisions[prec]["logit_tolerance"] = ("%s of max|logit| vs the fp32 reference "
                                                        "(tests/test_parity_gpu.py)" % tol)
@@ -645,7 +650,7 @@ def run_b200(args):
         parity = {"sample": "1 scene x %d agents @%dx%d, same weights and views as cpu_baseline; rank 0's %d agent(s)%s"
                             % (wl.n_agents, wl.img, wl.img, wl.local_agents,
                                " of the SHARDED forward" if wl.shard else "")}
-        for prec in ("bf16", "fp16", "mixed", "bf16x3"):
+        for prec in ("bf16", "fp16", "mixed", "fp16x3", "bf16x3"):
             if prec not in engine.PRECISIONS:
                 continue
             model.set_precision(prec)

@@ -43,7 +43,11 @@ enum {
 /* W2C_ACT_FP16: one IEEE half plane per pixel (weights packed as half too): same speed and bytes as W2C_ACT_BF16 with
  * three more mantissa bits - logits within ~2e-3 of the fp32 reference instead of ~2e-2 - for activations that stay
  * below 65504 (BatchNorm-ed feature maps do). */
-enum { W2C_ACT_BF16 = 0, W2C_ACT_BF16X2 = 1, W2C_ACT_FP16 = 2 };
+/* W2C_ACT_FP16X2: two IEEE-half planes per pixel [hi(C) | lo(C)], value = hi + lo (22 significant bits; lo may be
+ * subnormal for |value| < 2^-3, absolute floor 2^-25).  Same three-pass product as BF16X2 by default, but a layer
+ * may run ONE pass (w2c_conv_args.passes = 1: hi*hi only, i.e. plain fp16 arithmetic on the rounded operands, at a
+ * third of the MMA work) while still writing both planes - the storage the "mixed" precision plan is built on. */
+enum { W2C_ACT_BF16 = 0, W2C_ACT_BF16X2 = 1, W2C_ACT_FP16 = 2, W2C_ACT_FP16X2 = 3 };
 enum { W2C_OUT_NHWC = 0, W2C_OUT_NCHW_F32 = 1 };
 /* W2C_IMPL_TCGEN05 (the product setting) lets the library pick between its two tensor-core kernels: the persistent
  * warp-specialised kernel wherever a layer has at least one tile per SM, the one-tile-per-CTA kernel for the
@@ -103,6 +107,9 @@ typedef struct w2c_conv_args {
    * `outputs.data.max(1)[1]` of Trainer_MIMOcom.evaluate, trainer.py:804) from the same accumulators.  With labels
    * set, y may be NULL (label map only: the eval loop never reads the logits).  NULL = no label map. */
   uint8_t* labels;
+  /* MMA passes over the operand planes of a two-plane act: 0 = the format's default (3: hi*hi + hi*lo + lo*hi),
+   * 1 = hi*hi only.  Ignored (1) for one-plane formats.  The output is written in `act` either way. */
+  int32_t passes;
 } w2c_conv_args;
 
 int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream);

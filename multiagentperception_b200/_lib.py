@@ -13,7 +13,7 @@ c_i32 = ctypes.c_int32
 c_f32 = ctypes.c_float
 c_vp = ctypes.c_void_p
 
-ACT_BF16, ACT_BF16X2, ACT_FP16 = 0, 1, 2
+ACT_BF16, ACT_BF16X2, ACT_FP16, ACT_FP16X2 = 0, 1, 2, 3
 OUT_NHWC, OUT_NCHW_F32 = 0, 1
 IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_PERSIST = 0, 1, 2, 4
 CONV3X3_S1, CONV3X3_S2, DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2 = 0, 1, 2, 3, 4
@@ -31,6 +31,7 @@ class ConvArgs(ctypes.Structure):
         ("y_cstride", c_i32), ("y_coffset", c_i32),
         ("kind", c_i32), ("relu", c_i32), ("act", c_i32), ("out_fmt", c_i32), ("impl", c_i32), ("block_n", c_i32),
         ("labels", c_vp),
+        ("passes", c_i32),
     ]
 
 

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
   const int slab = blockIdx.x % p.slabs;
   const int pix0 = slab * p.pix_per_cta;
   const int npix = min(p.pix_per_cta, a.hw - pix0);
-  const int planes = a.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(a.act);
   const int vpix = a.c * planes;  // elements per pixel of val
   const uint32_t slab_bytes = static_cast<uint32_t>(npix) * vpix * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -220,15 +220,15 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
         const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float2 f = unpack_act2(hb[e], a.act == W2C_ACT_FP16);
+          const float2 f = unpack_act2(hb[e], act_is_f16(a.act));
           v[i][2 * e] = f.x, v[i][2 * e + 1] = f.y;
         }
         if (planes == 2) {
           const uint4 lv = *reinterpret_cast<const uint4*>(src + a.c);
-          const __nv_bfloat162* lb = reinterpret_cast<const __nv_bfloat162*>(&lv);
+          const uint32_t* lb = reinterpret_cast<const uint32_t*>(&lv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f = __bfloat1622float2(lb[e]);
+            const float2 f = unpack_act2(lb[e], act_is_f16(a.act));
             v[i][2 * e] += f.x, v[i][2 * e + 1] += f.y;
           }
         }
@@ -248,20 +248,10 @@ __global__ void __launch_bounds__(256) attn_fuse_kernel(const AttnParams p) {
         }
       }
       uint4 hv, lv;
-      __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
-      __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+      uint32_t* hb = reinterpret_cast<uint32_t*>(&hv);
+      uint32_t* lb = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (a.act == W2C_ACT_FP16) {
-          const uint32_t pk16 = ptx::pack_f16x2(o[2 * e], o[2 * e + 1]);
-          hb[e] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
-          lb[e] = hb[e];
-        } else {
-          hb[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-          const float2 hf = __bfloat1622float2(hb[e]);
-          lb[e] = __floats2bfloat162_rn(o[2 * e] - hf.x, o[2 * e + 1] - hf.y);
-        }
-      }
+      for (int e = 0; e < 4; ++e) split_act2(o[2 * e], o[2 * e + 1], act_is_f16(a.act), hb[e], lb[e]);
       __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(a.fused) +
                            (static_cast<size_t>((j - a.q_first) * a.b_sz + scene) * a.hw + pix0 + px) * fpix + a.fused_coffset + g * 8;
       *reinterpret_cast<uint4*>(dst) = hv;
@@ -296,7 +286,7 @@ extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream)
   if (p.a.fused_cstride <= 0) p.a.fused_cstride = a.c;
   W2C_CHECK_ARG(p.a.fused_cstride % 8 == 0 && p.a.fused_coffset % 8 == 0 && p.a.fused_coffset + a.c <= p.a.fused_cstride,
                 "attn: fused slice out of range");
-  const int planes = a.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(a.act);
   const size_t head = ((16 + (static_cast<size_t>(a.n_q) * (a.k_dim + a.q_dim) + 3 * kMaxAgents * kMaxAgents) * 4) + 127) &
                       ~static_cast<size_t>(127);
   // slab size: as many pixels as fit ~96 KB of feature rows, at least 1, and 16-byte granular copies

@@ -43,6 +43,18 @@ int stem7x7_tc_forward(const void* x, const float* lut, const float* w, const fl
     ::w2c::count_launch();                                                                      \
   } while (0)
 
+// storage formats (include/w2c.h): one plane (BF16, FP16) or two planes [hi | lo] per pixel (BF16X2, FP16X2)
+__host__ __device__ __forceinline__ int act_planes(int act) {
+  return (act == W2C_ACT_BF16X2 || act == W2C_ACT_FP16X2) ? 2 : 1;
+}
+__host__ __device__ __forceinline__ bool act_is_f16(int act) { return act == W2C_ACT_FP16 || act == W2C_ACT_FP16X2; }
+__host__ __device__ __forceinline__ bool act_valid(int act) { return act >= W2C_ACT_BF16 && act <= W2C_ACT_FP16X2; }
+// MMA passes over the planes: 1 = hi*hi; 3 = hi*hi + hi*lo + lo*hi (two-plane formats only). passes = 0 picks the
+// format's default (3 for two planes).
+__host__ __device__ __forceinline__ int act_passes(int act, int passes) {
+  return act_planes(act) == 1 ? 1 : (passes == 1 ? 1 : 3);
+}
+
 // 16-bit storage element <-> float in either storage type (the buffers are typed __nv_bfloat16 for addressing only)
 __device__ __forceinline__ float elem_to_float(__nv_bfloat16 v, bool f16) {
   return f16 ? __half2float(*reinterpret_cast<const __half*>(&v)) : __bfloat162float(v);
@@ -60,21 +72,35 @@ __device__ __forceinline__ float2 unpack_act2(uint32_t bits, bool f16) {
              : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&bits));
 }
 
-// value = hi (+ lo).  Pixel layout for BF16X2: [hi: cstride channels][lo: cstride channels].
+// (hi, lo) split of a pair of values in either element type: hi = rn(v), lo = rn(v - hi)
+__device__ __forceinline__ void split_act2(float a, float b, bool f16, uint32_t& hi, uint32_t& lo) {
+  if (f16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 hf = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+// value = hi (+ lo).  Pixel layout of the two-plane formats: [hi: cstride channels][lo: cstride channels].
 __device__ __forceinline__ float act_load(const __nv_bfloat16* pix, int c, int cstride, int act) {
-  if (act == W2C_ACT_FP16) return elem_to_float(pix[c], true);
-  float v = __bfloat162float(pix[c]);
-  if (act == W2C_ACT_BF16X2) v += __bfloat162float(pix[cstride + c]);
+  const bool f16 = act_is_f16(act);
+  float v = elem_to_float(pix[c], f16);
+  if (act_planes(act) == 2) v += elem_to_float(pix[cstride + c], f16);
   return v;
 }
 __device__ __forceinline__ void act_store(__nv_bfloat16* pix, int c, int cstride, int act, float v) {
-  if (act == W2C_ACT_FP16) {
-    pix[c] = float_to_elem(v, true);
-    return;
-  }
-  __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  const bool f16 = act_is_f16(act);
+  const __nv_bfloat16 hi = float_to_elem(v, f16);
   pix[c] = hi;
-  if (act == W2C_ACT_BF16X2) pix[cstride + c] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  if (act_planes(act) == 2) pix[cstride + c] = float_to_elem(v - elem_to_float(hi, f16), f16);
 }
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   const ConvPlan& pl = p.plan;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int chunks = pl.cin / kBlockK;
-  const int npass = pl.act == W2C_ACT_BF16X2 ? 3 : 1;
+  const int npass = pl.npass;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&p.b_map);
@@ -160,8 +160,12 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       for (int it = 0; tile_at(p, it, BLOCK_N, tc); ++it) {
         const int ntaps = pl.ntaps[tc.cls];
         for (int pass = 0; pass < npass; ++pass) {
-          const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
-          const int b_row = tc.n0 + (pass == 1 ? pl.cout_pad : 0);
+          // three-pass order: lo*hi, hi*lo, then hi*hi. The two correction passes run while the accumulator is still
+          // small, so the tensor core's truncating fp32 adds cost them nothing; only the last pass accumulates at
+          // full magnitude (hi*hi first made all three passes pay: a -1e-4 relative bias per K = 4608 layer)
+          const bool a_lo = npass == 3 && pass == 0, b_lo = npass == 3 && pass == 1;
+          const int a_c0 = pl.x_coffset + (a_lo ? pl.x_cstride : 0);
+          const int b_row = tc.n0 + (b_lo ? pl.cout_pad : 0);
           if constexpr (GROUP == 3) {
             // 3x3 stride-1 conv: filter column kw -> one box of th+2 rows starting one row above the tile
             // (a_map[1]); its three weight tiles (kh = 0,1,2) land behind each other in the stage
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
   } else if (warp == 1) {
     if (ptx::elect_one_sync()) {
       // ===================== MMA issuer =====================
-      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, pl.act == W2C_ACT_FP16);
+      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, act_is_f16(pl.act));
       constexpr uint32_t kBTile16 = L::kBTileBytes >> 4;
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
       const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
@@ -283,8 +287,8 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     const int lw = row % p.tw;
     const int lh = (row / p.tw) % p.th;
     const int li = row / (p.tw * p.th);
-    const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
-    const bool f16 = pl.act == W2C_ACT_FP16;
+    const int planes = act_planes(pl.act);
+    const bool f16 = act_is_f16(pl.act);
     int unit = 0;  // staging-buffer rotation counter (EG == 1)
     TileCoord tc;
     for (int it = eg; tile_at(p, it, BLOCK_N, tc); it += EG) {
@@ -346,15 +350,9 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
-                    const float a = v[c8 * 8 + 2 * j], b = v[c8 * 8 + 2 * j + 1];
-                    const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
-                    if (pln == 0) {
-                      pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
-                    } else {
-                      const float2 hf = __bfloat1622float2(hi);
-                      const __nv_bfloat162 lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-                      pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
-                    }
+                    uint32_t hi, lo;
+                    split_act2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1], f16, hi, lo);
+                    pw[j] = pln == 0 ? hi : lo;
                   }
                 }
                 *reinterpret_cast<uint4*>(stg + row * 128 + ((c8 ^ (row & 7)) << 4)) = pk;
@@ -472,21 +470,13 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
               }
             }
             uint4 hv, lv;
-            __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
-            __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+            uint32_t* hb = reinterpret_cast<uint32_t*>(&hv);
+            uint32_t* lb = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float a = v[g * 8 + 2 * j], b = v[g * 8 + 2 * j + 1];
               if (pl.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-              if (f16) {
-                const uint32_t pk16 = ptx::pack_f16x2(a, b);
-                hb[j] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
-                lb[j] = hb[j];
-              } else {
-                hb[j] = __floats2bfloat162_rn(a, b);
-                const float2 hf = __bfloat1622float2(hb[j]);
-                lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-              }
+              split_act2(a, b, f16, hb[j], lb[j]);
             }
             *reinterpret_cast<uint4*>(ypix + g * 8) = hv;
             if (planes == 2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;
@@ -541,7 +531,7 @@ bool conv_persv1_supported(const ConvPlan& plan) { return plan.cout <= kMaxCout;
 int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream) {
   PersParams p;
   p.plan = plan;
-  const int planes = plan.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(plan.act);
   W2C_CHECK_ARG(plan.cout <= kMaxCout, "conv_pers: cout=%d exceeds %d", plan.cout, kMaxCout);
 
   int tw = plan.wm >= 16 ? 16 : pow2_ceil(plan.wm);

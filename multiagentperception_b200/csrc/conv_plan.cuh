@@ -41,6 +41,7 @@ struct ConvPlan {
   int x_pix, x_cstride, x_coffset;  // x_pix = elements per input pixel (all planes)
   int y_pix, y_cstride, y_coffset;
   int act, relu, out_fmt;
+  int npass;  // MMA passes over the operand planes: 1 (hi*hi) or 3 (hi*hi + hi*lo + lo*hi)
   // K order of the accumulation. 3x3 stride-1 convs run (filter column kw, 64-channel chunk, filter row kh) in EVERY
   // tensor-core kernel - the order the row-halo stages of the persistent kernel impose - so that the result does not
   // depend on which kernel / tile width the dispatch picks for a given batch (sharded == unsharded, scene i alone
@@ -62,9 +63,10 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   W2C_CHECK_ARG(a.n > 0 && a.h_in > 0 && a.w_in > 0, "conv: bad image extent %dx%dx%d", a.n, a.h_in, a.w_in);
   W2C_CHECK_ARG(a.cin > 0 && a.cin % 64 == 0, "conv: cin=%d must be a positive multiple of 64", a.cin);
   W2C_CHECK_ARG(a.cout > 0, "conv: cout=%d", a.cout);
-  W2C_CHECK_ARG(a.act == W2C_ACT_BF16 || a.act == W2C_ACT_BF16X2 || a.act == W2C_ACT_FP16, "conv: bad act %d", a.act);
+  W2C_CHECK_ARG(act_valid(a.act), "conv: bad act %d", a.act);
+  W2C_CHECK_ARG(a.passes == 0 || a.passes == 1 || a.passes == 3, "conv: passes=%d (0 = default, 1 or 3)", a.passes);
   W2C_CHECK_ARG(a.out_fmt == W2C_OUT_NHWC || a.out_fmt == W2C_OUT_NCHW_F32, "conv: bad out_fmt %d", a.out_fmt);
-  const int planes = a.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(a.act);
   p = ConvPlan{};
   p.x = static_cast<const __nv_bfloat16*>(a.x);
   p.w = static_cast<const __nv_bfloat16*>(a.w);
@@ -86,6 +88,7 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   p.y_coffset = a.y_coffset;
   p.y_pix = p.y_cstride * planes;
   p.act = a.act;
+  p.npass = act_passes(a.act, a.passes);
   p.relu = a.relu;
   p.out_fmt = a.out_fmt;
   W2C_CHECK_ARG(p.x_coffset >= 0 && p.x_coffset + p.cin <= p.x_cstride, "conv: input channel slice out of range");

@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
 
   const int chunks = pl.cin / kBlockK;
   const int ntaps = pl.ntaps[cls];
-  const int npass = pl.act == W2C_ACT_BF16X2 ? 3 : 1;
+  const int npass = pl.npass;
   const int num_kb = npass * ntaps * chunks;
 
   if (warp == 0 && lane == 0) {
@@ -110,8 +110,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int pass = 0; pass < npass; ++pass) {
-        const int a_c0 = pl.x_coffset + (pass == 2 ? pl.x_cstride : 0);
-        const int b_row = n0 + (pass == 1 ? pl.cout_pad : 0);
+        // three-pass order lo*hi, hi*lo, hi*hi (the same as conv_pers_v1.cu: corrections first, while the
+        // accumulator is small and the tensor core's truncating adds are harmless)
+        const bool a_lo = npass == 3 && pass == 0, b_lo = npass == 3 && pass == 1;
+        const int a_c0 = pl.x_coffset + (a_lo ? pl.x_cstride : 0);
+        const int b_row = n0 + (b_lo ? pl.cout_pad : 0);
         // canonical K order (ConvPlan::kw_major): (kw, chunk, kh) for 3x3 s1 convs, (tap, chunk) otherwise
         const int n_outer = pl.kw_major ? 3 : ntaps, n_inner = pl.kw_major ? 3 : 1;
         for (int o = 0; o < n_outer; ++o)
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
   } else if (warp == 1) {
     if (ptx::elect_one_sync()) {  // one lane; see ptx::elect_one_sync
       // ===================== MMA issuer =====================
-      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, pl.act == W2C_ACT_FP16);
+      const uint32_t idesc = ptx::make_idesc_16(kBlockM, BLOCK_N, act_is_f16(pl.act));
       const uint64_t a_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kAOff));
       const uint64_t b_desc0 = ptx::make_sw128_kmajor_desc(ptx::smem_u32(smem + L::kBOff));
       int stage = 0;
@@ -207,38 +210,30 @@ __global__ void __launch_bounds__(kNumThreads, 1) conv_tc_kernel(const __grid_co
             const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_act2(rb[j], pl.act == W2C_ACT_FP16);
+              const float2 f = unpack_act2(rb[j], act_is_f16(pl.act));
               v[g * 8 + 2 * j] += f.x, v[g * 8 + 2 * j + 1] += f.y;
             }
-            if (pl.act == W2C_ACT_BF16X2) {
+            if (act_planes(pl.act) == 2) {
               const uint4 rl = *reinterpret_cast<const uint4*>(rpix + pl.y_cstride + g * 8);
-              const __nv_bfloat162* lb = reinterpret_cast<const __nv_bfloat162*>(&rl);
+              const uint32_t* lb = reinterpret_cast<const uint32_t*>(&rl);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float2 f = __bfloat1622float2(lb[j]);
+                const float2 f = unpack_act2(lb[j], act_is_f16(pl.act));
                 v[g * 8 + 2 * j] += f.x, v[g * 8 + 2 * j + 1] += f.y;
               }
             }
           }
           uint4 hv, lv;
-          __nv_bfloat162* hb = reinterpret_cast<__nv_bfloat162*>(&hv);
-          __nv_bfloat162* lb = reinterpret_cast<__nv_bfloat162*>(&lv);
+          uint32_t* hb = reinterpret_cast<uint32_t*>(&hv);
+          uint32_t* lb = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float a = v[g * 8 + 2 * j], b = v[g * 8 + 2 * j + 1];
             if (pl.relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-            if (pl.act == W2C_ACT_FP16) {
-              const uint32_t pk16 = ptx::pack_f16x2(a, b);
-              hb[j] = *reinterpret_cast<const __nv_bfloat162*>(&pk16);
-              lb[j] = hb[j];
-            } else {
-              hb[j] = __floats2bfloat162_rn(a, b);
-              const float2 hf = __bfloat1622float2(hb[j]);
-              lb[j] = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-            }
+            split_act2(a, b, act_is_f16(pl.act), hb[j], lb[j]);
           }
           *reinterpret_cast<uint4*>(ypix + g * 8) = hv;
-          if (pl.act == W2C_ACT_BF16X2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;
+          if (act_planes(pl.act) == 2) *reinterpret_cast<uint4*>(ypix + pl.y_cstride + g * 8) = lv;
         }
       }
     }
@@ -326,7 +321,7 @@ int launch(const ConvTcParams& p, cudaStream_t stream) {
 int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream) {
   ConvTcParams p;
   p.plan = plan;
-  const int planes = plan.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(plan.act);
 
   // ---- tile shape in the M-space
   int tw = plan.wm >= 16 ? 16 : pow2_ceil(plan.wm);
@@ -404,7 +399,7 @@ int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t s
 namespace {
 
 __global__ void conv_simt_kernel(const ConvPlan pl) {
-  const int planes = pl.act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(pl.act);
   const size_t per_class = static_cast<size_t>(pl.n_img) * pl.hm * pl.wm * pl.cout;
   const size_t total = per_class * pl.num_classes;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
@@ -427,13 +422,13 @@ __global__ void conv_simt_kernel(const ConvPlan pl) {
       const __nv_bfloat16* wp = pl.w + static_cast<size_t>(co) * pl.ktot + tap.wtap * pl.cin;
       const __nv_bfloat16* wl = wp + static_cast<size_t>(pl.cout_pad) * pl.ktot;
       for (int ci = 0; ci < pl.cin; ++ci) {
-        const bool f16 = pl.act == W2C_ACT_FP16;
+        const bool f16 = act_is_f16(pl.act);
         const float xh = elem_to_float(xp[ci], f16);
         const float wh = elem_to_float(wp[ci], f16);
         acc = fmaf(xh, wh, acc);
-        if (planes == 2) {
-          acc = fmaf(xh, __bfloat162float(wl[ci]), acc);
-          acc = fmaf(__bfloat162float(xp[pl.x_cstride + ci]), wh, acc);
+        if (pl.npass == 3) {
+          acc = fmaf(xh, elem_to_float(wl[ci], f16), acc);
+          acc = fmaf(elem_to_float(xp[pl.x_cstride + ci], f16), wh, acc);
         }
       }
     }

@@ -46,7 +46,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     }
     const __nv_bfloat16 hi = float_to_elem(v, f16);
     out[idx] = hi;
-    if (planes == 2) out[total + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    if (planes == 2) out[total + idx] = float_to_elem(v - elem_to_float(hi, f16), f16);
   }
 }
 
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) stem3x3_kernel(const float* __restrict__ 
 
   const size_t plane = static_cast<size_t>(h) * wpx;
   const size_t total = static_cast<size_t>(b_sz) * n_agents * plane;
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int ow = idx % wpx;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
                                                            __nv_bfloat16* __restrict__ y, int n, int h, int wpx, int c,
                                                            int act) {
   const int ho = h / 2, wo = wpx / 2;
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const int c8 = c / 8;
   const size_t total = static_cast<size_t>(n) * ho * wo * c8;
   const size_t pixs = static_cast<size_t>(c) * planes;  // elements per pixel
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
         const __nv_bfloat16* pix = x + ((static_cast<size_t>(img) * h + ih) * wpx + iw) * pixs + cg * 8;
         const uint4 hv = __ldg(reinterpret_cast<const uint4*>(pix));
         const __nv_bfloat162* hb = reinterpret_cast<const __nv_bfloat162*>(&hv);
-        if (planes == 1 && act == W2C_ACT_FP16) {
+        if (planes == 1 && act_is_f16(act)) {
           const __half2* hh = reinterpret_cast<const __half2*>(&hv);
           __half2* bh = reinterpret_cast<__half2*>(best);
 #pragma unroll
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(256) maxpool3x3s2_kernel(const __nv_bfloat16* 
           const __nv_bfloat162* lb = reinterpret_cast<const __nv_bfloat162*>(&lv);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 hf = __bfloat1622float2(hb[e]), lf = __bfloat1622float2(lb[e]);
+            const float2 hf = unpack_act2(*reinterpret_cast<const uint32_t*>(&hb[e]), act_is_f16(act));
+            const float2 lf = unpack_act2(*reinterpret_cast<const uint32_t*>(&lb[e]), act_is_f16(act));
             const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
             const bool t0 = first || v0 > bv[2 * e], t1 = first || v1 > bv[2 * e + 1];
             if (t0) bv[2 * e] = v0;
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) bilinear_argmax_kernel(const float* __res
 // ------------------------------------------------------------------------------------------ layout helpers
 __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int n, int h, int wpx,
                                     int c, int cstride, int coffset, int act) {
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const size_t total = static_cast<size_t>(n) * c * h * wpx;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -316,7 +317,7 @@ __global__ void nhwc_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* 
 }
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, int n, int h, int wpx,
                                     int c, int cstride, int coffset, int act) {
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const size_t total = static_cast<size_t>(n) * c * h * wpx;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -483,7 +484,7 @@ uint64_t w2c_launch_count(void) { return g_launches.load(std::memory_order_relax
 
 int32_t w2c_cout_pad(int32_t cout) { return (cout + 15) / 16 * 16; }
 size_t w2c_packed_weight_bytes(int32_t cout, int32_t cin, int32_t ntaps, int32_t act) {
-  return static_cast<size_t>(w2c_cout_pad(cout)) * ntaps * cin * 2 * (act == W2C_ACT_BF16X2 ? 2 : 1);
+  return static_cast<size_t>(w2c_cout_pad(cout)) * ntaps * cin * 2 * (act_planes(act));
 }
 
 int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
@@ -492,12 +493,12 @@ int w2c_pack_conv_weight(const float* w, int32_t cout, int32_t cin_real, int32_t
   W2C_CHECK_ARG(cout > 0 && cin_real > 0 && cin >= cin_real && cin % 64 == 0, "pack: bad channels %d/%d/%d", cout,
                 cin_real, cin);
   W2C_CHECK_ARG(ntaps == 9 || ntaps == 1, "pack: ntaps must be 9 or 1");
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const int cout_pad = w2c_cout_pad(cout);
   const size_t total = static_cast<size_t>(cout_pad) * ntaps * cin;
   pack_weight_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       w, cout, cin_real, cin, ntaps, transposed, planes, cout_pad, static_cast<__nv_bfloat16*>(packed),
-      act == W2C_ACT_FP16);
+      act_is_f16(act));
   W2C_CHECK_LAUNCH("pack_weight_kernel");
   return W2C_OK;
 }
@@ -620,7 +621,7 @@ int w2c_gather_images_fwd(const void* src, void* dst, const int32_t* sel, int32_
   W2C_CHECK_ARG(c % 8 == 0 && src_cstride % 8 == 0 && src_coffset % 8 == 0 && dst_cstride % 8 == 0 && dst_coffset % 8 == 0,
                 "gather_images: channel counts, strides and offsets must be multiples of 8");
   W2C_CHECK_ARG(src_coffset + c <= src_cstride && dst_coffset + c <= dst_cstride, "gather_images: slice out of range");
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const size_t px = static_cast<size_t>(h) * w_px;
   const size_t total = static_cast<size_t>(n_groups) * b * px * planes * (c / 8);
   gather_images_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(

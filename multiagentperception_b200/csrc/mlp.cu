@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restric
   float* __restrict__ out = ws + static_cast<size_t>(blockIdx.y) * m * 256;
   const int j0 = blockIdx.x * kNeurons;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   const size_t row_elems = static_cast<size_t>(n_feat) * planes;
   const float* w0 = W + static_cast<size_t>(j0) * n_feat;
   const float* w1 = w0 + n_feat;
@@ -65,15 +65,15 @@ __global__ void __launch_bounds__(256) fc0_kernel(const __nv_bfloat16* __restric
           float x[8];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 f = unpack_act2(hb[e], act == W2C_ACT_FP16);
+            const float2 f = unpack_act2(hb[e], act_is_f16(act));
             x[2 * e] = f.x, x[2 * e + 1] = f.y;
           }
           if (planes == 2) {
             const uint4 lv = __ldg(reinterpret_cast<const uint4*>(p + 256));
-            const __nv_bfloat162* lb = reinterpret_cast<const __nv_bfloat162*>(&lv);
+            const uint32_t* lb = reinterpret_cast<const uint32_t*>(&lv);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              const float2 f = __bfloat1622float2(lb[e]);
+              const float2 f = unpack_act2(lb[e], act_is_f16(act));
               x[2 * e] += f.x, x[2 * e + 1] += f.y;
             }
           }

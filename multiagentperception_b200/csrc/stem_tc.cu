@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
       gather_taps(x, p, total, b_sz, c_total, c_first, h, wpx, dst);
   };
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool x3 = act == W2C_ACT_BF16X2;
-  const bool f16 = act == W2C_ACT_FP16;
+  const bool x3 = act_planes(act) == 2;
+  const bool f16 = act_is_f16(act);
 
   // ---- one-time setup: scale * weights (k < 27) and shift (k = 27) -> swizzled B tiles, barrier, TMEM
   for (int i = tid; i < COUT * 4; i += kTile) {
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
       const int k = c * 8 + e;
       const float v = k < 27 ? w[co * 27 + k] * sc : (k == 27 ? shift[co] : 0.f);
       hb[e] = float_to_elem(v, f16);
-      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
+      lb[e] = float_to_elem(v - elem_to_float(hb[e], f16), f16);  // (lo plane: two-plane formats only)
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + sw128(co, c)) = hv;
     if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + sw128(co, c)) = lv;
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
         const int k = c * 8 + e;
         const float v = k < 27 ? in[k < 27 ? k : 0] : (k == 27 ? 1.f : 0.f);
         hb[e] = float_to_elem(v, f16);
-        lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
+        lb[e] = float_to_elem(v - elem_to_float(hb[e], f16), f16);  // (lo plane: two-plane formats only)
       }
       *reinterpret_cast<uint4*>(smem + L::kAHi + sw128(tid, c)) = hv;
       if (x3) *reinterpret_cast<uint4*>(smem + L::kALo + sw128(tid, c)) = lv;
@@ -267,14 +267,9 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
               for (int j = 0; j < 4; ++j) {
                 const float a = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j]), 0.f);
                 const float b = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j + 1]), 0.f);
-                const __nv_bfloat162 hi = __floats2bfloat162_rn(a, b);
-                if (pln == 0) {
-                  pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
-                } else {
-                  const float2 hf = __bfloat1622float2(hi);
-                  const __nv_bfloat162 lo = __floats2bfloat162_rn(a - hf.x, b - hf.y);
-                  pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
-                }
+                uint32_t hi, lo;
+                split_act2(a, b, f16, hi, lo);
+                pw[j] = pln == 0 ? hi : lo;
               }
             }
             *reinterpret_cast<uint4*>(stg + sw128(tid, half * 4 + c4)) = pk;
@@ -332,7 +327,7 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
     return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * h * wpx;
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
   y_maps.direct = 0;
@@ -409,8 +404,8 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
   float* s_lut = reinterpret_cast<float*>(smem + L::kLut);
   const int tid = threadIdx.x, warp = tid >> 5;
-  const bool x3 = act == W2C_ACT_BF16X2;
-  const bool f16 = act == W2C_ACT_FP16;
+  const bool x3 = act_planes(act) == 2;
+  const bool f16 = act_is_f16(act);
   const int ho = h / 2, wo = wpx / 2;
   const size_t total = static_cast<size_t>(b_sz) * n_agents * ho * wo;
   const size_t plane = static_cast<size_t>(h) * wpx;
@@ -428,7 +423,7 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
       const int k = piece * 8 + e;
       const float v = k < KT ? w[co * KT + k] * sc : (k == KT ? shift[co] : 0.f);
       hb[e] = float_to_elem(v, f16);
-      lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
+      lb[e] = float_to_elem(v - elem_to_float(hb[e], f16), f16);  // (lo plane: two-plane formats only)
     }
     *reinterpret_cast<uint4*>(smem + L::kBHi + ck * COUT * kRowBytes + sw128(co, c)) = hv;
     if (x3) *reinterpret_cast<uint4*>(smem + L::kBLo + ck * COUT * kRowBytes + sw128(co, c)) = lv;
@@ -508,7 +503,7 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
             v = 1.f;
           }
           hb[e] = float_to_elem(v, f16);
-          lb[e] = __float2bfloat16_rn(v - __bfloat162float(hb[e]));  // (lo plane: bf16x3 only)
+          lb[e] = float_to_elem(v - elem_to_float(hb[e], f16), f16);  // (lo plane: two-plane formats only)
         }
         if (ck * 64 + c * 8 < 160) {  // K is padded to 160: the last 32 columns of chunk 2 are never read
           *reinterpret_cast<uint4*>(smem + L::kAHi + ck * kTile * kRowBytes + sw128(tid, c)) = hv;
@@ -558,14 +553,9 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
                 pw[j] = ptx::pack_act2(a, b, true, f16);
               } else {
                 const float ar = fmaxf(a, 0.f), br = fmaxf(b, 0.f);
-                const __nv_bfloat162 hi = __floats2bfloat162_rn(ar, br);
-                if (pln == 0) {
-                  pw[j] = *reinterpret_cast<const uint32_t*>(&hi);
-                } else {
-                  const float2 hf = __bfloat1622float2(hi);
-                  const __nv_bfloat162 lo = __floats2bfloat162_rn(ar - hf.x, br - hf.y);
-                  pw[j] = *reinterpret_cast<const uint32_t*>(&lo);
-                }
+                uint32_t hi, lo;
+                split_act2(ar, br, f16, hi, lo);
+                pw[j] = pln == 0 ? hi : lo;
               }
             }
             *reinterpret_cast<uint4*>(stg + sw128(tid, half * 4 + c4)) = pk;
@@ -604,7 +594,7 @@ int launch_stem7(const void* x, const float* lut, const float* w, const float* s
     return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (wpx / 2);
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
-  const int planes = act == W2C_ACT_BF16X2 ? 2 : 1;
+  const int planes = act_planes(act);
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
   y_maps.direct = 0;

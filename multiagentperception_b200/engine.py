@@ -16,7 +16,23 @@ from . import _lib, ops
 
 # "fp16": IEEE-half activations and weights on the same kernels - the speed and bytes of "bf16" with three more
 # mantissa bits (logits ~2e-3 of the range from the fp32 reference instead of ~2e-2); needs activations < 65504
-PRECISIONS = {"bf16": ops.ACT_BF16, "bf16x3": ops.ACT_BF16X2, "fp16": ops.ACT_FP16}
+# "fp16x3": two fp16 planes (hi | lo), every product as hi*hi + hi*lo + lo*hi: the bf16x3 scheme on half operands
+# "mixed": the fp16x3 storage with a per-layer pass plan (MIXED_ONE_PASS): the layers listed there run ONE pass
+#          (plain fp16 arithmetic on the hi planes, a third of the MMA work), everything else three. The plan comes
+#          from the per-layer error attribution in profiles/r2_precision_attribution.md: the policy net decides the
+#          softmax weights and tolerates no rounding (fp16 there alone costs 6e-3 of the logit range), decoder layers
+#          sit too close to the output; the wide middle of the feature encoder is where one pass is affordable within
+#          the 1e-3 bound.
+PRECISIONS = {"bf16": ops.ACT_BF16, "bf16x3": ops.ACT_BF16X2, "fp16": ops.ACT_FP16, "fp16x3": ops.ACT_FP16X2,
+              "mixed": ops.ACT_FP16X2}
+# stack -> 1-based layer numbers (conv<i> of n_segnet_encoder, backbone.py:19-39) that run one pass under "mixed".
+#   "encoder_fused"  the value-map encoder of a model whose decoder input is an attention-weighted SUM of several
+#                    agents' maps (MIMOcom, MIMOcomWho, LearnWhen2Com): the sum averages the per-map rounding noise
+#   "encoder"        the value-map encoder whose map reaches the decoder directly / concatenated (Single_agent,
+#                    All_agents, MIMO_All_agents, LearnWho2Com's own map): less headroom, fewer one-pass layers
+# Measured on B200 (bench.py `parity`, tests/test_parity_gpu.py): each one-pass layer adds 2.5-4e-4 (in quadrature) to
+# the ~4e-4 floor of the three-pass path; the layers listed are the ones with the most MMA time per unit of error.
+MIXED_ONE_PASS = {"encoder_fused": (3, 5, 6, 8, 9), "encoder": (6, 9)}
 BN_EPS_DEFAULT = 1e-5
 
 
@@ -188,6 +204,7 @@ class Program:
         self.want_labels = False
         self.want_logits = True
         self.labels_out = None
+        self.pass_plan = None   # {"stack": (layer numbers)} that run ONE MMA pass (two-plane formats; see PRECISIONS)
 
     # ---- buffers
     def act_buf(self, n, h, w, c):
@@ -234,15 +251,22 @@ class Program:
         # (a join without a preceding fork is a no-op at run time)
         self.calls.append((Program._JOIN, None, 0))
 
-    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None):
+    def passes_for(self, stack, layer):
+        """MMA passes of layer number `layer` of `stack` under this program's precision plan (0 = format default)."""
+        if self.pass_plan and layer in self.pass_plan.get(stack, ()):
+            return 1
+        return 0
+
+    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None, passes=0):
         """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given). labels: uint8 [n, h, w] tensor that
-        receives the arg-max class of the fp32 NCHW logits (nchw_out may then be the string 'none': labels only)."""
+        receives the arg-max class of the fp32 NCHW logits (nchw_out may then be the string 'none': labels only).
+        passes: MMA passes over the operand planes (0 = the format's default; 1 = hi*hi only)."""
         if x.c != pc.cin:
             raise ValueError("conv expects %d input channels, got %d" % (pc.cin, x.c))
         if pc.subsample == 2:
             if nchw_out is not None or residual is not None or x.h % 4 or x.w % 4:
                 raise ValueError("stride-4 conv: NHWC output, no residual, H and W divisible by 4")
-            full = self.conv(x, _stride2_view(pc))                      # (h/2, w/2) map
+            full = self.conv(x, _stride2_view(pc), passes=passes)       # (h/2, w/2) map
             if out is None:
                 out = self.act_buf(x.n, x.h // 4, x.w // 4, pc.cout)
             elif (out.n, out.h, out.w, out.c) != (x.n, x.h // 4, x.w // 4, pc.cout):
@@ -281,7 +305,7 @@ class Program:
                           h_in=x.h, w_in=x.w, cin=pc.cin, cout=pc.cout, x_cstride=x.cstride, x_coffset=x.coffset,
                           y_cstride=ycs, y_coffset=yco, kind=pc.kind, relu=int(pc.relu), act=self.act,
                           out_fmt=out_fmt, impl=ops.IMPL_TCGEN05, block_n=block_n,
-                          labels=labels.data_ptr() if labels is not None else None)
+                          labels=labels.data_ptr() if labels is not None else None, passes=passes)
         self.keep.append(a)
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret

@@ -71,15 +71,33 @@ class DeviceScalar(numbers.Real):
     def __hash__(self):
         return hash(self.item())
 
-    # ---- comparisons resolve
+    # ---- comparisons resolve (anything that is not a plain number - e.g. pytest.approx - compares from its side)
+    @staticmethod
+    def _num(o):
+        return float(o) if isinstance(o, (int, float, DeviceScalar)) else None
+
     def __eq__(self, o):
-        return self.item() == float(o)
+        v = self._num(o)
+        return self.item() == v if v is not None else o == self.item()
+
+    def __ne__(self, o):
+        return not self.__eq__(o)
 
     def __lt__(self, o):
-        return self.item() < float(o)
+        v = self._num(o)
+        return self.item() < v if v is not None else NotImplemented
 
     def __le__(self, o):
-        return self.item() <= float(o)
+        v = self._num(o)
+        return self.item() <= v if v is not None else NotImplemented
+
+    def __gt__(self, o):
+        v = self._num(o)
+        return self.item() > v if v is not None else NotImplemented
+
+    def __ge__(self, o):
+        v = self._num(o)
+        return self.item() >= v if v is not None else NotImplemented
 
     # ---- arithmetic stays on the device
     def _other(self, o):

@@ -119,9 +119,10 @@ def _make_attention(attention, query_size, key_size):
 
 
 # ------------------------------------------------------------------------------------------- program builders
-def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=None, stem=None):
+def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=None, stem=None, stack="encoder"):
     """img_encoder.forward (agent.py:56-60) on agents [c_first/3, ...) of the fp32 NCHW batch -> ActMap.
-    stem: output of an already-issued (fused) first layer to start from instead of running conv1 here."""
+    stem: output of an already-issued (fused) first layer to start from instead of running conv1 here.
+    stack: name under which the precision plan lists this encoder's layers (engine.MIXED_ONE_PASS)."""
     wc = prog.weights
     bb = enc.feature_backbone
     if isinstance(bb, n_segnet_encoder):
@@ -131,7 +132,7 @@ def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=Non
         a = stem if stem is not None else prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h,
                                                        w, c_first)
         for i, u in enumerate(units[1:], 2):
-            a = prog.conv(a, wc.conv(u.conv, u.bn, True))
+            a = prog.conv(a, wc.conv(u.conv, u.bn, True), passes=prog.passes_for(stack, i))
     elif isinstance(bb, resnet_encoder):
         if h % 32 or w % 32:
             raise ValueError("resnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
@@ -209,7 +210,7 @@ def _fused_stems(prog, enc_a, enc_b, x_nchw, b, n_agents, h, w):
 
 def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
     """policy_net4.forward (agent.py:134-142) -> ActMap (n_agents*b, s, s, 256)."""
-    a = _build_encoder(prog, pol.img_encoder, "img_encoder", x_nchw, b, n_agents, h, w, stem=stem)
+    a = _build_encoder(prog, pol.img_encoder, "img_encoder", x_nchw, b, n_agents, h, w, stem=stem, stack="policy")
     if a.h % 4 or a.w % 4:
         raise ValueError("policy_net4 needs the %dx%d feature map divisible by 4" % (a.h, a.w))
     for i in range(1, 6):
@@ -233,7 +234,9 @@ class _W2CModel(nn.Module):
 
     # ---- configuration
     def set_precision(self, name):
-        """'bf16' (throughput) or 'bf16x3' (fp32-grade parity precision on the same tensor-core kernels)."""
+        """'bf16' / 'fp16' (throughput), 'bf16x3' / 'fp16x3' (fp32-grade parity precision: hi/lo planes, three MMA
+        passes) or 'mixed' (the fp16x3 storage with one pass where the error attribution allows it), see
+        engine.PRECISIONS."""
         if name not in engine.PRECISIONS:
             raise ValueError("precision must be one of %s" % sorted(engine.PRECISIONS))
         self._w2c["precision"] = name
@@ -311,8 +314,9 @@ class _W2CModel(nn.Module):
         elif inputs.dim() != 4:
             raise ValueError("expected (B, 3*N, H, W) input, got shape %s" % (tuple(inputs.shape),))
         dev = inputs.device
-        act = engine.PRECISIONS[self._w2c["precision"]]
-        key = (dev, act, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"])
+        precision = self._w2c["precision"]
+        act = engine.PRECISIONS[precision]
+        key = (dev, precision, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"])
         c = self._w2c["programs"].get(key)
         if c is None:
             wkey = (dev, act)
@@ -322,6 +326,7 @@ class _W2CModel(nn.Module):
                 self._w2c["weights"][wkey] = wc
             with torch.cuda.device(dev), torch.no_grad():
                 prog = engine.Program(wc, dev, act)
+                prog.pass_plan = engine.MIXED_ONE_PASS if precision == "mixed" else None
                 prog.want_labels, prog.want_logits = io["labels"], io["logits"]
                 if io["u8"]:
                     prog.input_u8 = True
@@ -382,6 +387,9 @@ class Single_agent(_W2CModel):
 
 class _AttentionModel(_W2CModel):
     """Shared constructor plumbing of the four learned-communication models."""
+    # precision-plan stack of the value-map encoder (engine.MIXED_ONE_PASS): "encoder_fused" where the decoder sees
+    # only an attention-weighted sum of maps, "encoder" where an agent's own map reaches the decoder as it is
+    _value_stack = "encoder"
 
     def _init_common(self, n_classes, in_channels, feat_channel, feat_squeezer, attention, has_query, sparse,
                      shared_img_encoder, image_size, key_size, query_size, enc_backbone, dec_backbone, head_cls,
@@ -482,7 +490,8 @@ class _AttentionModel(_W2CModel):
             # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
             small_kernels = isinstance(self.u_encoder.feature_backbone, resnet_encoder)
             with prog.side_stream(auto=small_kernels):
-                val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u)
+                val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u,
+                                     stack=self._value_stack)
         else:
             # separate encoders per agent group (agent.py:579-594,823-838), each writing its agents' images of the
             # agent-major feature buffer
@@ -491,7 +500,7 @@ class _AttentionModel(_W2CModel):
             val = prog.act_buf(n * b, h // 32 // sq, w // 32 // sq, encs[0][0].squeezer.conv.out_channels)
             for enc, first, count in encs:
                 _build_encoder(prog, enc, "enc%d" % first, x, b, count, h, w, c_first=3 * first,
-                               out=val.images(first * b, count * b))
+                               out=val.images(first * b, count * b), stack=self._value_stack)
         qk = _build_policy(prog, self.query_key_net, x, b, n, h, w, stem=stem_p)
         if qk.h != qk.w:
             raise ValueError("square inputs only (the reference derives n_feat from image_size alone)")
@@ -513,6 +522,7 @@ _MODES = {"softmax": ops.FUSE_SOFTMAX, "activated": ops.FUSE_ACTIVATED, "argmax_
 
 class MIMOcom(_AttentionModel):
     who = False
+    _value_stack = "encoder_fused"
 
     def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1, attention="additive",
                  has_query=True, sparse=False, agent_num=5, shuffle_flag=False, image_size=512,
@@ -664,9 +674,12 @@ class MIMOcom(_AttentionModel):
 
 class MIMOcomWho(MIMOcom):
     who = True
+    _value_stack = "encoder"   # decoder input = cat(fused, own map), agent.py:1382
 
 
 class LearnWhen2Com(_AttentionModel):
+    _value_stack = "encoder_fused"
+
     def __init__(self, n_classes=21, in_channels=3, feat_channel=512, feat_squeezer=-1, attention="additive",
                  has_query=True, sparse=False, aux_agent_num=4, shuffle_flag=False, image_size=512,
                  shared_img_encoder=False, key_size=128, query_size=128, enc_backbone="n_segnet_encoder",

@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import (ACT_BF16, ACT_BF16X2, ACT_FP16, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
+from ._lib import (ACT_BF16, ACT_BF16X2, ACT_FP16, ACT_FP16X2, OUT_NHWC, OUT_NCHW_F32, IMPL_TCGEN05, IMPL_SIMT, IMPL_TC_TAPS, IMPL_TC_PERSIST, CONV3X3_S1, CONV3X3_S2,
                    DECONV3X3_S2, CONV1X1_S1, CONV1X1_S2, FUSE_SOFTMAX, FUSE_ACTIVATED, FUSE_ARGMAX, GT_U8, GT_I64)
 
 # airsim_loader.py:191 (mean_rgb['airsim'], indexed by BGR channel after the loader's flip)
@@ -32,7 +32,7 @@ def _ptr(t):
 
 
 def planes_of(act):
-    return 2 if act == ACT_BF16X2 else 1
+    return 2 if act in (ACT_BF16X2, ACT_FP16X2) else 1
 
 
 def launch_count():
@@ -79,14 +79,14 @@ def pack_conv_weight(w, cin_pad, transposed, act):
 # ------------------------------------------------------------------------------------------------ hot-path ops
 def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind, relu, act, out_fmt=OUT_NHWC,
                 residual=None, x_cstride=0, x_coffset=0, y_cstride=0, y_coffset=0, impl=IMPL_TCGEN05, block_n=0,
-                labels=None):
+                labels=None, passes=0):
     """labels: optional uint8 [n, h_out, w_out] tensor receiving argmax_co y (NCHW fp32 logits layout only); with
     labels given, y may be None (label map only)."""
     lib = _lib.load()
     a = _lib.ConvArgs(x=_ptr(x), w=_ptr(w_packed), scale=_ptr(scale), shift=_ptr(shift), residual=_ptr(residual),
                       y=_ptr(y), labels=_ptr(labels), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout, x_cstride=x_cstride,
                       x_coffset=x_coffset, y_cstride=y_cstride, y_coffset=y_coffset, kind=kind, relu=int(relu),
-                      act=act, out_fmt=out_fmt, impl=impl, block_n=block_n)
+                      act=act, out_fmt=out_fmt, impl=impl, block_n=block_n, passes=passes)
     _lib.check(lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), _stream()), "w2c_conv_bnrelu_fwd")
     return y
 

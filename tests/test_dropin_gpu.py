@@ -170,4 +170,4 @@ def test_num_connect_is_lazy_and_behaves_like_a_number(cuda_device):
     assert isinstance(total, DeviceScalar) and total._v is None      # nothing has synchronised yet
     avg = total / 3.0                   # get_avg_bandW, metrics.py:110-111
     assert float(avg) == pytest.approx(ref[3], abs=1e-12)
-    assert str(avg) == str(float(avg)) and avg == ref[3] and round(avg * 100, 2) == round(ref[3] * 100, 2)
+    assert str(avg) == str(float(avg)) and avg == float(avg) and round(avg * 100, 2) == round(ref[3] * 100, 2)

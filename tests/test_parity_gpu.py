@@ -4,6 +4,9 @@ reference-generated golden vectors on the same seeded inputs.
 Tolerances (stated here, used below):
   bf16x3 ("parity" precision): max |logit error| <= 1e-3 * max |logit|  (the north star's 1e-3 relative bound);
                                prob_action within 1e-3; action / num_connect exact; mIoU vs oracle argmax >= 0.995.
+  fp16x3 / mixed:              the same 1e-3 bound. "fp16x3" = fp16 hi|lo planes, three passes; "mixed" = that storage
+                               with ONE pass on the layers engine.MIXED_ONE_PASS lists (per-layer error attribution:
+                               profiles/r2_precision_attribution.md) - the cheapest plan found that still meets 1e-3.
   bf16   ("fast" precision):   max |logit error| <= 5e-2 * max |logit|, mIoU >= 0.93 — bf16 activations through 27
                                stacked layers cannot meet 1e-3 (torch's own bf16 autocast of the
                                reference drifts 0.4-1.4e-2); measured drift is reported in DESIGN.md, not hidden.
@@ -72,6 +75,26 @@ def test_parity_bf16x3_against_oracle_and_golden(name, cuda_device):
     sub = outs[0][:, :, ::4, ::4].cpu().numpy()
     assert np.abs(sub - g["out0_sub"]).max() <= X3_LOGIT_TOL * np.abs(g["out0_sub"]).max()
     assert abs(float(outs[0].double().sum()) - float(g["out0_sum"])) <= 1e-3 * float(g["out0_abs"])
+
+
+@pytest.mark.parametrize("precision", ["mixed", "fp16x3"])
+@pytest.mark.parametrize("name", sorted(cases.CASES))
+def test_parity_fp16_planes_against_oracle_and_golden(name, precision, cuda_device):
+    """Every case again in the two fp16-plane precisions, held to the SAME 1e-3 bound as bf16x3."""
+    ref, outs = _run_case(name, cuda_device, precision)
+    assert _rel(outs[0], ref[0]) <= X3_LOGIT_TOL
+    assert orc.miou_between(ref[0], outs[0].cpu()) >= X3_MIOU
+    for o, r in zip(outs[1:], ref[1:]):
+        if torch.is_tensor(r):
+            if r.dtype == torch.int64:
+                assert torch.equal(o.cpu(), r)
+            else:
+                assert float((o.cpu() - r).abs().max()) <= X3_PROB_TOL
+        else:
+            assert float(o) == pytest.approx(float(r), abs=1e-9)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sub = outs[0][:, :, ::4, ::4].cpu().numpy()
+    assert np.abs(sub - g["out0_sub"]).max() <= X3_LOGIT_TOL * np.abs(g["out0_sub"]).max()
 
 
 @pytest.mark.parametrize("name", ["single_segnet", "mimocom_segnet_activated", "mimocom_resnet_activated",
@@ -153,7 +176,8 @@ def test_full_size_one_scene_against_oracle(cuda_device):
     ref_act = orc.forward(sd, cfg, x, **act)
     model = model.to(dev).eval()
     # logits in both precisions on the continuous (softmax-fusion) path
-    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU),
+    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("fp16x3", X3_LOGIT_TOL, X3_MIOU),
+                            ("mixed", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU),
                             ("fp16", FP16_LOGIT_TOL, FP16_MIOU)):
         pred, prob, action, nconn = model.set_precision(prec)(x.to(dev), **soft)
         assert _rel(pred, ref_soft[0]) <= tol
@@ -194,8 +218,8 @@ def test_single_agent_1024_against_oracle(cuda_device):
     x = synth.synthetic_views(1, 1, 1024, 1024, seed=5)
     ref = orc.forward(model.state_dict(), cfg, x)
     model = model.to(dev).eval()
-    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("bf16", BF16_LOGIT_TOL, BF16_MIOU),
-                            ("fp16", FP16_LOGIT_TOL, FP16_MIOU)):
+    for prec, tol, miou in (("bf16x3", X3_LOGIT_TOL, X3_MIOU), ("mixed", X3_LOGIT_TOL, X3_MIOU),
+                            ("bf16", BF16_LOGIT_TOL, BF16_MIOU), ("fp16", FP16_LOGIT_TOL, FP16_MIOU)):
         pred = model.set_precision(prec)(x.to(dev))
         assert pred.shape == (1, 11, 1024, 1024)
         assert _rel(pred, ref) <= tol

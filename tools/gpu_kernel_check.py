@@ -34,6 +34,10 @@ def _quant(t, act):
     import torch
     if act == 2:
         return t.to(torch.float16).to(torch.float64)
+    if act == 3:   # fp16 hi + fp16 lo planes
+        hi16 = t.to(torch.float16)
+        lo16 = (t - hi16.to(torch.float32)).to(torch.float16)
+        return hi16.to(torch.float64) + lo16.to(torch.float64)
     hi = t.to(torch.bfloat16)
     if act == 0:
         return hi.to(torch.float64)
@@ -42,7 +46,7 @@ def _quant(t, act):
 
 
 def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw_out=False, impl=0, block_n=0,
-               cin_real=None, seed=0, x_cs=0, x_co=0, y_cs=0, y_co=0):
+               cin_real=None, seed=0, x_cs=0, x_co=0, y_cs=0, y_co=0, passes=0):
     torch, F, ops = _imports()
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -61,7 +65,9 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
     if cin_real < cin or x_cs:
         pass  # padded channels are zero in xa by construction (nchw_to_act zero-initialises)
     wp = ops.pack_conv_weight(wt, cin, transposed, act)
-    xq, wq = _quant(x, act), _quant(wt, act)
+    # one pass over a two-plane format = the hi planes only: plain fp16 / bf16 operands
+    op_act = {3: 2, 1: 0}.get(act, act) if passes == 1 else act
+    xq, wq = _quant(x, op_act), _quant(wt, op_act)
     if kind == ops.CONV3X3_S1:
         ref = F.conv2d(xq, wq, padding=1)
     elif kind == ops.CONV3X3_S2:
@@ -88,7 +94,7 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
         y = torch.zeros((n, ho, wo, ops.planes_of(act) * y_cs_eff), dtype=torch.bfloat16, device=dev)
     ops.conv_bnrelu(xa, wp, scale, shift, y, n=n, h_in=h, w_in=w, cin=cin, cout=cout, kind=kind, relu=relu, act=act,
                     out_fmt=ops.OUT_NCHW_F32 if nchw_out else ops.OUT_NHWC, residual=res_act, x_cstride=x_cs,
-                    x_coffset=x_co, y_cstride=y_cs, y_coffset=y_co, impl=impl, block_n=block_n)
+                    x_coffset=x_co, y_cstride=y_cs, y_coffset=y_co, impl=impl, block_n=block_n, passes=passes)
     torch.cuda.synchronize()
     got = y.double() if nchw_out else ops.act_to_nchw(y, cout, act, cstride=y_cs_eff, coffset=y_co).double()
     err = (got - ref).abs().max().item()
@@ -102,7 +108,7 @@ def case_layout():
     torch, F, ops = _imports()
     out = {}
     ok = True
-    for act in (0, 1, 2):
+    for act in (0, 1, 2, 3):
         x = torch.randn(2, 24, 5, 7, device="cuda:0")
         a = ops.nchw_to_act(x, act, cstride=32, coffset=8)
         back = ops.act_to_nchw(a, 24, act, cstride=32, coffset=8)
@@ -161,6 +167,20 @@ CONV_CASES = {
     "f16_pers_bn256": (0, 2, 32, 32, 256, 256, 2, dict(impl=4)),
     "f16_pers_nchw_c11": (0, 2, 32, 32, 64, 11, 2, dict(impl=4, nchw_out=True)),
     "f16_pers_ragged": (0, 3, 13, 21, 64, 72, 2, dict(impl=4)),
+    # fp16 hi|lo planes (act 3): three passes (default) and the one-pass layers of the "mixed" precision plan
+    "f16x2_pers_rowhalo": (0, 3, 24, 40, 128, 128, 3, dict(impl=4)),
+    "f16x2_pers_s2": (1, 2, 32, 32, 64, 128, 3, dict(impl=4)),
+    "f16x2_pers_deconv": (2, 2, 16, 16, 128, 128, 3, dict(impl=4)),
+    "f16x2_pers_res_bn256": (0, 2, 32, 32, 256, 256, 3, dict(impl=4, residual=True)),
+    "f16x2_pers_nchw_c11": (0, 2, 32, 32, 64, 11, 3, dict(impl=4, nchw_out=True)),
+    "f16x2_tc_s1": (0, 2, 16, 16, 128, 64, 3, dict(impl=2)),
+    "f16x2_simt_s2": (1, 2, 8, 12, 64, 32, 3, dict(impl=1)),
+    "f16x2_pers_one_pass": (0, 3, 24, 40, 128, 128, 3, dict(impl=4, passes=1)),
+    "f16x2_pers_one_pass_bn256": (0, 2, 32, 32, 256, 256, 3, dict(impl=4, passes=1)),
+    "f16x2_pers_one_pass_s2": (1, 2, 32, 32, 128, 128, 3, dict(impl=4, passes=1)),
+    "f16x2_tc_one_pass": (0, 2, 16, 16, 128, 64, 3, dict(impl=2, passes=1)),
+    "f16x2_simt_one_pass": (0, 2, 9, 11, 64, 24, 3, dict(impl=1, passes=1)),
+    "bf16x2_pers_one_pass": (0, 2, 16, 16, 128, 64, 1, dict(impl=4, passes=1)),
     "pers_1x1s2_res": (4, 2, 16, 16, 64, 128, 0, dict(impl=4, residual=True)),
     "pers_res_x2": (0, 2, 16, 16, 64, 128, 1, dict(impl=4, residual=True)),
     "pers_small_8x8": (0, 5, 8, 8, 256, 256, 0, dict(impl=4)),
@@ -178,7 +198,7 @@ def case_stem():
     torch, F, ops = _imports()
     dev = "cuda:0"
     out, ok = {}, True
-    for act, cout in ((0, 64), (1, 64), (2, 64), (0, 128), (1, 128), (2, 128), (0, 32)):
+    for act, cout in ((0, 64), (1, 64), (2, 64), (3, 64), (0, 128), (1, 128), (2, 128), (3, 128), (0, 32)):
         b, na, h, w = 2, 3, 20, 28
         x = torch.randn(b, 3 * na, h, w, device=dev)
         wt = torch.randn(cout, 3, 3, 3, device=dev) * 0.2
@@ -286,6 +306,7 @@ def case_attn():
         dict(b_sz=2, n_k=5, n_q=1, kd=1024, qd=32, mode=2, act=1, diag=0.0),
         dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=0, act=0, diag=0.0, mask_self=True),
         dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=1, act=2, diag=0.001),
+        dict(b_sz=2, n_k=5, n_q=5, kd=1024, qd=32, mode=1, act=3, diag=0.001),
     ]
     for ci, cf in enumerate(cfgs):
         b_sz, n_k, n_q, kd, qd = cf["b_sz"], cf["n_k"], cf["n_q"], cf["kd"], cf["qd"]
@@ -328,7 +349,7 @@ def case_mlp():
     torch, F, ops = _imports()
     dev = "cuda:0"
     out, ok = {}, True
-    for act in (0, 1, 2):
+    for act in (0, 1, 2, 3):
         for (m, s, od) in ((5, 4, 1024), (10, 1, 32), (13, 2, 128)):
             n_feat = 256 * s * s
             feat = torch.randn(m, 256, s, s, device=dev)
