@@ -114,6 +114,43 @@ typedef struct w2c_conv_args {
 
 int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream);
 
+/*
+ * Fused head of n_segnet_encoder: conv1 (3 -> 64, k3 s1) + BN + ReLU followed by conv2 (64 -> 64, k3 s2) + BN + ReLU
+ * in ONE kernel, including the divide_inputs / cat regrouping of the views.  Replaces the first two layers of
+ * n_segnet_encoder.forward (ptsemseg/models/backbone.py:19-20,42-43) under img_encoder.forward (agent.py:56-60) on
+ * the input regrouped per agent.py:1088-1108, i.e. w2c_stem_conv3x3_fwd + w2c_conv_bnrelu_fwd(W2C_CONV3X3_S2) without
+ * the 64-channel full-resolution map ever reaching HBM (csrc/enc_head.cu).  Results are bit-identical to that
+ * pair of calls in the one-plane formats.
+ *
+ *   x        x_u8 = 0: the fp32 views (B, c_total, H, W); agents' channels [c_first, c_first + 3*n_agents)
+ *            x_u8 = 1: the loader's raw frames, uint8 RGB (B, c_total = agents_total, H, W, 3), agents
+ *                      [c_first, c_first + n_agents), mapped through lut (fp32 [3][256], see w2c_stem_conv3x3_u8_fwd)
+ *   w1       conv1.weight fp32 [64][27]; scale1 / shift1: its folded BatchNorm (w2c_fold_bn)
+ *   w2       conv2 weight packed by w2c_pack_conv_weight(cout 64, cin 64, 9 taps, act); scale2 / shift2 likewise
+ *   y        NHWC (B*n_agents, H/2, W/2, y_cstride) in `act`, written at channel y_coffset; images agent-major
+ *   act      W2C_ACT_BF16 / W2C_ACT_FP16, or a two-plane format: the conv1 map inside the kernel is ONE plane of the
+ *            format's element type and both convs run one MMA pass (the "mixed" precision's one-pass layers); the
+ *            output is written in both planes.  H and W must be even.
+ */
+typedef struct w2c_enc_head_args {
+  const void* x;
+  const float* lut;
+  const float* w1;
+  const float* scale1;
+  const float* shift1;
+  const void* w2;
+  const float* scale2;
+  const float* shift2;
+  void* y;
+  int32_t x_u8;
+  int32_t b, n_agents, c_total, c_first;
+  int32_t h, w;
+  int32_t act;
+  int32_t y_cstride, y_coffset;
+} w2c_enc_head_args;
+
+int w2c_enc_head_fwd(const w2c_enc_head_args* args, w2c_stream_t stream);
+
 /* cout rounded up to the row padding the packed weight layout uses. */
 int32_t w2c_cout_pad(int32_t cout);
 /* Bytes of the packed weight buffer for a conv of the given geometry. */

@@ -35,6 +35,16 @@ class ConvArgs(ctypes.Structure):
     ]
 
 
+class EncHeadArgs(ctypes.Structure):
+    """struct w2c_enc_head_args (include/w2c.h)."""
+    _fields_ = [
+        ("x", c_vp), ("lut", c_vp), ("w1", c_vp), ("scale1", c_vp), ("shift1", c_vp), ("w2", c_vp), ("scale2", c_vp),
+        ("shift2", c_vp), ("y", c_vp),
+        ("x_u8", c_i32), ("b", c_i32), ("n_agents", c_i32), ("c_total", c_i32), ("c_first", c_i32),
+        ("h", c_i32), ("w", c_i32), ("act", c_i32), ("y_cstride", c_i32), ("y_coffset", c_i32),
+    ]
+
+
 class AttnArgs(ctypes.Structure):
     """struct w2c_attn_args (include/w2c.h)."""
     _fields_ = [
@@ -64,6 +74,7 @@ _SIGNATURES = {
     "w2c_last_error": (ctypes.c_char_p, []),
     "w2c_launch_count": (ctypes.c_uint64, []),
     "w2c_conv_bnrelu_fwd": (ctypes.c_int, [ctypes.POINTER(ConvArgs), c_vp]),
+    "w2c_enc_head_fwd": (ctypes.c_int, [ctypes.POINTER(EncHeadArgs), c_vp]),
     "w2c_cout_pad": (c_i32, [c_i32]),
     "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

@@ -52,6 +52,11 @@ _TS = os.environ.get("W2C_TWO_STREAMS")
 TWO_STREAMS = None if _TS is None else _TS == "1"
 
 
+# Fused encoder head (csrc/enc_head.cu: conv1 + conv2 of n_segnet_encoder in one kernel, the 64-channel full-resolution
+# map stays in shared memory). bench.py --no-fused-ends / tests flip this for the A/B against the two-kernel path.
+FUSE_ENCODER_HEAD = os.environ.get("W2C_FUSE_ENDS", "1") != "0"
+
+
 def use_graphs_default():
     return os.environ.get("W2C_CUDA_GRAPH", "1") != "0"
 
@@ -310,6 +315,32 @@ class Program:
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret
 
+    def can_fuse_head(self, stack):
+        """True when conv1 + conv2 of an n_segnet encoder in `stack` may run as the fused head kernel: always in the
+        one-plane formats; in a two-plane format only where the precision plan runs BOTH layers in one pass (the
+        conv1 map inside the kernel is a single plane)."""
+        if not FUSE_ENCODER_HEAD:
+            return False
+        if self.planes == 1:
+            return True
+        return self.passes_for(stack, 1) == 1 and self.passes_for(stack, 2) == 1
+
+    def enc_head(self, x_in, st1, pc2, b, n_agents, h, w, c_first=0):
+        """conv1 (stem operands st1 = (w [64][27], scale, shift)) + conv2 (PackedConv pc2) -> ActMap (h/2, w/2, 64)."""
+        w1, scale1, shift1 = st1
+        if w1.shape[0] != 64 or pc2.cin != 64 or pc2.cout != 64 or pc2.kind != ops.CONV3X3_S2 or not pc2.relu:
+            raise ValueError("enc_head covers conv1 3->64 followed by conv2 64->64 stride 2 with ReLU")
+        out = self.act_buf(b * n_agents, h // 2, w // 2, 64)
+        a = _lib.EncHeadArgs(x=x_in.data_ptr(), lut=self.lut.data_ptr() if self.input_u8 else None, w1=w1.data_ptr(),
+                             scale1=scale1.data_ptr(), shift1=shift1.data_ptr(), w2=pc2.w.data_ptr(),
+                             scale2=pc2.scale.data_ptr(), shift2=pc2.shift.data_ptr(), y=out.buf.data_ptr(),
+                             x_u8=int(self.input_u8), b=b, n_agents=n_agents, c_total=x_in.shape[1],
+                             c_first=c_first // 3 if self.input_u8 else c_first, h=h, w=w, act=self.act,
+                             y_cstride=out.cstride, y_coffset=out.coffset)
+        self.keep.append(a)
+        self._record(self._lib.w2c_enc_head_fwd, ctypes.byref(a))
+        return out
+
     def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False):
         """split=True (a fused pair of 64-channel first layers): returns TWO dense 64-channel maps."""
         wt, scale, shift = st
@@ -553,6 +584,6 @@ class Program:
         time the dominant kernel in isolation from the stems / attention / layout kernels."""
         sub = Program(self.weights, self.device, self.act)
         sub.keep = self.keep
-        sub.calls = [c for c in self.calls if c[0] is self._lib.w2c_conv_bnrelu_fwd or c[0] in (Program._FORK,
-                                                                                                  Program._JOIN)]
+        convs = (self._lib.w2c_conv_bnrelu_fwd, self._lib.w2c_enc_head_fwd)
+        sub.calls = [c for c in self.calls if c[0] in convs or c[0] in (Program._FORK, Program._JOIN)]
         return sub

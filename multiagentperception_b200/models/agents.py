@@ -129,9 +129,17 @@ def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=Non
         if h % 32 or w % 32:
             raise ValueError("n_segnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
         units = bb.units()
-        a = stem if stem is not None else prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h,
-                                                       w, c_first)
-        for i, u in enumerate(units[1:], 2):
+        first = 1   # index into units of the next layer to run
+        if stem is not None:
+            a = stem
+        elif prog.can_fuse_head(stack):
+            # conv1 + conv2 in one kernel: the 64-channel full-resolution map never reaches HBM (csrc/enc_head.cu)
+            a = prog.enc_head(x_nchw, wc.stem(units[0].conv, units[0].bn), wc.conv(units[1].conv, units[1].bn, True),
+                              b, n_agents, h, w, c_first)
+            first = 2
+        else:
+            a = prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h, w, c_first)
+        for i, u in enumerate(units[first:], first + 1):
             a = prog.conv(a, wc.conv(u.conv, u.bn, True), passes=prog.passes_for(stack, i))
     elif isinstance(bb, resnet_encoder):
         if h % 32 or w % 32:
@@ -485,7 +493,13 @@ class _AttentionModel(_W2CModel):
             val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], dst[2].shape[3] // prog.planes)
         encs = self._value_encoders()
         if encs is None:
-            stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
+            segnet = isinstance(self.u_encoder.feature_backbone, n_segnet_encoder)
+            if segnet and prog.can_fuse_head(self._value_stack):
+                # each encoder starts with its own fused conv1 + conv2 head kernel (under the "mixed" precision only
+                # the value encoder does: the policy net keeps three passes and runs its own first layer)
+                stem_u = stem_p = None
+            else:
+                stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
             # the feature encoder runs beside the policy net + heads (independent chains); worth it for the resnet
             # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
             small_kernels = isinstance(self.u_encoder.feature_backbone, resnet_encoder)

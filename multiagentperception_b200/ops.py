@@ -91,6 +91,20 @@ def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind,
     return y
 
 
+def enc_head(x, w1, scale1, shift1, w2_packed, scale2, shift2, y, *, b, n_agents, h, w, act, c_total=0, c_first=0,
+             lut=None, y_cstride=0, y_coffset=0):
+    """Fused conv1 + conv2 of n_segnet_encoder (csrc/enc_head.cu). x: fp32 views (B, c_total, H, W), or - with `lut`
+    given - the raw uint8 frames (B, agents_total, H, W, 3); y: NHWC (b*n_agents, H/2, W/2, planes*y_cstride)."""
+    lib = _lib.load()
+    u8 = lut is not None
+    a = _lib.EncHeadArgs(x=_ptr(x), lut=_ptr(lut), w1=_ptr(w1), scale1=_ptr(scale1), shift1=_ptr(shift1),
+                         w2=_ptr(w2_packed), scale2=_ptr(scale2), shift2=_ptr(shift2), y=_ptr(y), x_u8=int(u8), b=b,
+                         n_agents=n_agents, c_total=c_total or (n_agents if u8 else 3 * n_agents), c_first=c_first,
+                         h=h, w=w, act=act, y_cstride=y_cstride, y_coffset=y_coffset)
+    _lib.check(lib.w2c_enc_head_fwd(ctypes.byref(a), _stream()), "w2c_enc_head_fwd")
+    return y
+
+
 def stem_conv3x3(x_nchw, w27, scale, shift, y, *, b, n_agents, h, w, cout, act, c_total=0, c_first=0, n_split=1):
     """n_split=2 (cout=128): y holds two dense 64-channel NHWC maps, [2, n, h, w, planes*64]."""
     lib = _lib.load()

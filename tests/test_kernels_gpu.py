@@ -18,7 +18,7 @@ def test_conv_kernel_case(name, cuda_device):
     assert r["ok"], r
 
 
-@pytest.mark.parametrize("name", ["layout", "stem", "mlp", "attn"])
+@pytest.mark.parametrize("name", ["layout", "stem", "mlp", "attn", "enc_head"])
 def test_other_kernels(name, cuda_device):
     r = kc.run_case(name)
     assert r["ok"], r

@@ -256,6 +256,66 @@ def case_stem():
     return out
 
 
+def case_enc_head():
+    """Fused conv1 + conv2 head kernel against the two-kernel path it replaces (stem, then the stride-2 conv): bit for
+    bit in the one-plane formats, full tiles and ragged edges, fp32 views and raw uint8 frames, channel slices."""
+    torch, F, ops = _imports()
+    dev = torch.device("cuda:0")
+    out, ok = {}, True
+    g = torch.Generator().manual_seed(3)
+    for ci, (b, na, h, w, act, u8, first) in enumerate([
+            (1, 1, 32, 64, 0, False, 0), (2, 3, 64, 96, 0, False, 0), (1, 2, 48, 80, 2, False, 0),
+            (2, 2, 34, 54, 0, False, 0), (1, 3, 64, 64, 0, False, 1), (2, 2, 64, 96, 0, True, 0),
+            (1, 3, 40, 72, 2, True, 1), (1, 1, 128, 160, 0, False, 0), (3, 5, 96, 128, 0, False, 0),
+            (1, 2, 64, 64, 3, False, 0)]):
+        n_total = na + first + 1
+        w1 = (torch.randn(64, 3, 3, 3, generator=g) * 0.3).to(dev)
+        w2 = (torch.randn(64, 64, 3, 3, generator=g) / 24).to(dev)
+        s1, t1 = (torch.rand(64, generator=g) + 0.5).to(dev), (torch.randn(64, generator=g) * 0.1).to(dev)
+        s2, t2 = (torch.rand(64, generator=g) + 0.5).to(dev), (torch.randn(64, generator=g) * 0.1).to(dev)
+        base_act = 2 if act == 3 else act      # the two-kernel reference runs in the one-plane element type
+        if u8:
+            x = torch.randint(0, 256, (b, n_total, h, w, 3), generator=g, dtype=torch.uint8).to(dev)
+            lut = ops.loader_lut(ops.LOADER_MEAN_BGR, True, dev)
+        else:
+            x = torch.randn(b, 3 * n_total, h, w, generator=g).to(dev)
+            lut = None
+        wp2 = ops.pack_conv_weight(w2, 64, False, act)
+        wp2_base = ops.pack_conv_weight(w2, 64, False, base_act)
+        w27 = w1.reshape(64, 27).contiguous()
+        # reference: stem -> conv2
+        y1 = ops.new_act(b * na, h, w, 64, base_act, dev)
+        if u8:
+            ops.stem_conv3x3_u8(x, lut, w27, s1, t1, y1, b=b, n_agents=na, h=h, w=w, cout=64, act=base_act,
+                                agents_total=n_total, agent_first=first)
+        else:
+            ops.stem_conv3x3(x, w27, s1, t1, y1, b=b, n_agents=na, h=h, w=w, cout=64, act=base_act,
+                             c_total=3 * n_total, c_first=3 * first)
+        ref = ops.new_act(b * na, h // 2, w // 2, 64, base_act, dev)
+        ops.conv_bnrelu(y1, wp2_base, s2, t2, ref, n=b * na, h_in=h, w_in=w, cin=64, cout=64, kind=ops.CONV3X3_S2,
+                        relu=True, act=base_act)
+        # fused, written into a channel slice of a wider map
+        cs = 128
+        got = torch.full((b * na, h // 2, w // 2, ops.planes_of(act) * cs), 7.0, dtype=torch.bfloat16, device=dev)
+        ops.enc_head(x, w27, s1, t1, wp2, s2, t2, got, b=b, n_agents=na, h=h, w=w, act=act,
+                     c_total=n_total if u8 else 3 * n_total, c_first=first if u8 else 3 * first, lut=lut,
+                     y_cstride=cs, y_coffset=64)
+        torch.cuda.synchronize()
+        hi = got[..., 64:128]
+        same = bool(torch.equal(hi.contiguous().view(torch.int16), ref.view(torch.int16)))
+        untouched = bool((got[..., :64] == 7.0).all())
+        rec = {"hi_plane_bit_identical": same, "neighbour_channels_untouched": untouched}
+        if act == 3:   # lo plane: what fp16 rounding left of the fp32 conv2 result - small and mostly non-zero
+            lo = got[..., cs + 64:cs + 128].contiguous().view(torch.float16).float()
+            hi_f = hi.contiguous().view(torch.float16).float()
+            rec["lo_small"] = bool((lo.abs() <= hi_f.abs() * 2.0 ** -10 + 1e-7).all())
+            same = same and rec["lo_small"]
+        out["cfg%d" % ci] = rec
+        ok &= same and untouched
+    out["ok"] = bool(ok)
+    return out
+
+
 def _attn_ref(keys, queries, wq, bq, val, b_sz, n_k, n_q, mode, sparse, mask_self, temperature, diag_bias, thresh):
     import torch
     k = keys.double().view(n_k, b_sz, -1).transpose(0, 1)       # (B, n_k, kd)
@@ -386,6 +446,8 @@ def run_case(name):
         r = case_attn()
     elif name == "mlp":
         r = case_mlp()
+    elif name == "enc_head":
+        r = case_enc_head()
     elif name in CONV_CASES:
         kind, n, h, w, cin, cout, act, kw = CONV_CASES[name]
         r = _conv_case(kind, n, h, w, cin, cout, act, **kw)
