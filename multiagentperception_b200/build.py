@@ -41,9 +41,16 @@ def _fingerprint(extra_flags):
     return h.hexdigest()
 
 
-def build(force=False, verbose=False, extra_flags=()):
-    """Compile every CUDA source for sm_100a into lib/libw2c.so. Returns the library path."""
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile every CUDA source for sm_100a into lib/libw2c.so (or `out`: a variant build, e.g. the instrumented one
+    tools/time_enc_head.py makes with -DW2C_HEAD_TIMING; variants are never stamped). Returns the library path."""
     os.makedirs(LIB_DIR, exist_ok=True)
+    if out is not None:
+        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + "\n" + res.stderr)
+        return out
     fp = _fingerprint(extra_flags)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
         with open(STAMP) as f:

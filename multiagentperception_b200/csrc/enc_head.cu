@@ -22,7 +22,7 @@
 // writes 336 MB. Accumulation order and operand rounding are those of the unfused kernels (stem_tc.cu followed by
 // conv_pers_v1.cu): results are bit-identical to that path, which is how the tests pin it.
 //
-// warps 0-3: patch + im2col ("front")    warp 4: MMA issuer, TMEM owner    warps 5-8: both epilogues
+// warps 0-3: patch + im2col ("front")    warp 4: MMA issuer, TMEM owner    warps 5-8 / 9-12: two epilogue warpgroups
 #include <cuda.h>
 
 #include "common.cuh"
@@ -41,10 +41,11 @@ constexpr int kY1Cols = 33;        // conv1 outputs under an 8x16 conv2 tile: 17
 constexpr int kY1Px = 17 * kY1Cols;
 constexpr int kMTiles = 5;         // ceil(561 / 128)
 constexpr int kPatchRows = 19, kPatchCols = 35, kPatchPitch = 36;
-constexpr int kPatchElems = 3 * kPatchRows * kPatchCols;   // 1995
-constexpr int kPatchPerThread = 16;                        // ceil(1995 / 128)
-constexpr int kFront = 128, kEpi = 128;
-constexpr int kThreads = kFront + 32 + kEpi;               // 288
+constexpr int kFront = 128;
+constexpr int kEpiGroup = 128;                             // one epilogue warpgroup (TMEM lane quadrants 0..3)
+constexpr int kEpiGroups = 2;                              // group 0: conv1 tiles 0-2; group 1: conv1 tiles 3-4 + conv2
+constexpr int kEpi = kEpiGroups * kEpiGroup;
+constexpr int kThreads = kFront + 32 + kEpi;               // 416 (13 warps: registers are allocated as for 16)
 constexpr int kTmemCols = 512;                             // 5 x 64 (conv1) + 2 x 64 (conv2) = 448 -> 512
 constexpr int kAcc2Col = kMTiles * 64;
 
@@ -65,9 +66,9 @@ struct HeadSmem {
   static constexpr int kPatchBytes = 3 * kPatchRows * kPatchPitch * 4;
   static constexpr int kLut = kPatch + kPatchBytes;         // fp32 [3][256] (uint8 input only)
   static constexpr int kBar = (kLut + 3 * 256 * 4 + 7) / 8 * 8;
-  static constexpr int kNumBars = 10;
+  static constexpr int kNumBars = 14;
   static constexpr int kTmemPtr = kBar + kNumBars * 8;
-  static constexpr int kScale = kTmemPtr + 8;               // conv2 scale[64], shift[64]
+  static constexpr int kScale = (kTmemPtr + 8 + 15) / 16 * 16;   // conv2 scale[64], shift[64] (read as float4)
   static constexpr int kTotal = kScale + 128 * 4;
   static constexpr int kDynamic = kTotal + 1024;
 };
@@ -77,8 +78,8 @@ static_assert(HeadSmem::kW2 % 1024 == 0 && HeadSmem::kA1 % 1024 == 0 && HeadSmem
               "enc_head: operand tiles must sit on 1024-byte boundaries");
 
 // barrier indices
-enum { B_W = 0, B_A1_FULL, B_A1_EMPTY, B_ACC1_FULL, B_ACC1_EMPTY, B_Y1_FULL, B_ACC2_FULL0, B_ACC2_FULL1, B_ACC2_EMPTY0,
-       B_ACC2_EMPTY1 };
+enum { B_W = 0, B_A1_FULL, B_A1_EMPTY, B_ACC1_FULL, B_Y1_FULL, B_ACC2_FULL0, B_ACC2_FULL1, B_ACC2_EMPTY0, B_ACC2_EMPTY1,
+       B_ACC1_EMPTY0 /* .. +4: one per conv1 accumulator */ };
 
 struct HeadParams {
   CUtensorMap w2_map;   // packed conv2 weight [rows][576], box [64][64]
@@ -95,7 +96,18 @@ struct HeadParams {
   int tiles_w, tiles_h, num_tiles;
   int act;              // output storage (and operand element type); y1 is always ONE plane of that element type
   int y_cstride, y_coffset;
+  long long* dbg;       // optional [32] cycle counters of CTA 0 (w2c_debug_enc_head_timing), else NULL
 };
+
+// cycle counters of CTA 0's warp roles: compiled in only with -DW2C_HEAD_TIMING (tools/time_enc_head.py builds that
+// variant); the product build carries none of it
+#ifdef W2C_HEAD_TIMING
+#define TICK() clock64()
+#define TIMING(...) __VA_ARGS__
+#else
+#define TICK() 0ll
+#define TIMING(...)
+#endif
 
 __device__ __forceinline__ uint32_t sw_chunk(uint32_t row, uint32_t chunk) { return row * kRow + ((chunk ^ (row & 7u)) << 4); }
 
@@ -114,6 +126,76 @@ __device__ __forceinline__ TileAt tile_at(const HeadParams& p, int tile) {
   t.oh0 = (r % p.tiles_h) * 8;
   t.img = r / p.tiles_h;
   return t;
+}
+
+// Where conv1 pixel q (0..560, even rows first) of a tile lives in the y1 planes: dst0 / dst1 = byte offset of the pixel
+// row in its plane(s) with +16 * (idx & 7) folded in for the swizzle (dst1 < 0: one destination only; both < 0: no
+// pixel), drc = (dr << 8) | dc with image row R = 2*oh0 - 1 + dr and column C = 2*ow0 - 1 + dc.
+struct Y1Slot {
+  int dst0, dst1, drc;
+};
+// conv1 pixel q of a tile -> (row order ro: 0-7 the even image rows, 8-16 the odd ones; column cq = image column -
+// (2*ow0 - 1)). Within a row the 16 even image columns (cq odd) come first, then the 17 odd ones: consecutive lanes
+// then write consecutive pixels of ONE y1 plane (distinct bank groups within every quarter warp - enumerating the
+// columns in image order put an even-plane and an odd-plane pixel with the same swizzle phase next to each other: two
+// wavefronts per quarter warp on every 16-byte store) and read consecutive words of one column-parity half of the patch.
+__device__ __forceinline__ void y1_pixel(int q, int& ro, int& cq) {
+  ro = q / kY1Cols;
+  const int j = q % kY1Cols;
+  cq = j < 16 ? 2 * j + 1 : 2 * (j - 16);
+}
+__device__ __forceinline__ Y1Slot y1_slot(int q) {
+  Y1Slot s{-1, -1, 0};
+  if (q < kY1Px) {
+    int ro, cq;
+    y1_pixel(q, ro, cq);
+    const int rp = ro < 8 ? 0 : 1, pri = ro < 8 ? ro : ro - 8;
+    const int dr = ro < 8 ? 2 * ro + 1 : 2 * pri;
+    s.drc = (dr << 8) | cq;
+    if (cq & 1) {   // even image column -> the even-column plane
+      const int idx = (cq - 1) >> 1;
+      s.dst0 = plane_off(rp, 0) + (pri * 16 + idx) * kRow + ((idx & 7) << 4);
+    } else {        // odd image column jj = cq / 2 of 0..16: left variant holds 0..15, right variant 1..16
+      const int jj = cq >> 1;
+      if (jj < 16) s.dst0 = plane_off(rp, 1) + (pri * 16 + jj) * kRow + ((jj & 7) << 4);
+      if (jj >= 1) {
+        const int d = plane_off(rp, 2) + (pri * 16 + jj - 1) * kRow + (((jj - 1) & 7) << 4);
+        if (s.dst0 < 0) s.dst0 = d; else s.dst1 = d;
+      }
+    }
+  }
+  return s;
+}
+
+// One conv1 accumulator row (64 fp32 columns at TMEM address taddr) -> ReLU -> 16 bit -> its slot(s) in the y1 planes.
+__device__ __forceinline__ void drain_conv1_row(uint8_t* smem, uint32_t taddr, const Y1Slot s, int Rb, int Cb, int h,
+                                                int w, bool f16, uint64_t* empty_bar) {
+  uint32_t r[64];
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+  ptx::tmem_ld_32x32b_x32(taddr + 32, r + 32);
+  ptx::tmem_ld_wait();
+  ptx::tc_fence_before();
+  ptx::mbar_arrive(empty_bar);   // the accumulator is in registers: conv1 of the next tile may overwrite it
+  if (s.dst0 < 0) return;
+  const int R = Rb + (s.drc >> 8), C = Cb + (s.drc & 255);
+  // conv2 zero-pads ITS input: conv1 outputs outside the image are zeros, not conv1 of the padded image
+  const bool inside = R >= 0 && R < h && C >= 0 && C < w;
+  // convert everything first (32 distinct registers), then issue the stores back to back: reusing four registers
+  // per chunk made every conversion wait for the previous store to read them (ncu: short-scoreboard stalls)
+  uint32_t pk[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    pk[j] = inside ? ptx::pack_act2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]), true, f16) : 0u;
+#pragma unroll
+  for (int c8 = 0; c8 < 8; ++c8)
+    *reinterpret_cast<uint4*>(smem + (static_cast<uint32_t>(s.dst0) ^ (c8 << 4))) =
+        make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+  if (s.dst1 >= 0) {
+#pragma unroll
+    for (int c8 = 0; c8 < 8; ++c8)
+      *reinterpret_cast<uint4*>(smem + (static_cast<uint32_t>(s.dst1) ^ (c8 << 4))) =
+          make_uint4(pk[4 * c8], pk[4 * c8 + 1], pk[4 * c8 + 2], pk[4 * c8 + 3]);
+  }
 }
 
 template <bool U8>
@@ -160,12 +242,12 @@ __global__ void __launch_bounds__(kThreads, 1) enc_head_kernel(const __grid_cons
     ptx::mbar_init(&bars[B_A1_FULL], kFront);
     ptx::mbar_init(&bars[B_A1_EMPTY], 1);
     ptx::mbar_init(&bars[B_ACC1_FULL], 1);
-    ptx::mbar_init(&bars[B_ACC1_EMPTY], kEpi);
+    for (int i = 0; i < kMTiles; ++i) ptx::mbar_init(&bars[B_ACC1_EMPTY0 + i], kEpiGroup);
     ptx::mbar_init(&bars[B_Y1_FULL], kEpi);
     ptx::mbar_init(&bars[B_ACC2_FULL0], 1);
     ptx::mbar_init(&bars[B_ACC2_FULL1], 1);
-    ptx::mbar_init(&bars[B_ACC2_EMPTY0], kEpi);
-    ptx::mbar_init(&bars[B_ACC2_EMPTY1], kEpi);
+    ptx::mbar_init(&bars[B_ACC2_EMPTY0], kEpiGroup);
+    ptx::mbar_init(&bars[B_ACC2_EMPTY1], kEpiGroup);
     ptx::fence_barrier_init();
   }
   if (warp == 4) {
@@ -184,110 +266,114 @@ __global__ void __launch_bounds__(kThreads, 1) enc_head_kernel(const __grid_cons
       ptx::mbar_arrive_expect_tx(&bars[B_W], L::kW2Bytes);
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(&p.w2_map, &bars[B_W], smem + L::kW2 + t * 64 * kRow, t * 64, 0);
     }
+    // patch loader: thread <-> (channel, patch column), looping over the 19 patch rows with plain pointer increments
+    // (uint8 frames: thread <-> byte of the 105-byte RGB row, channel = BGR index of that byte, airsim_loader.py:521)
     const size_t plane = static_cast<size_t>(p.h) * p.w;
-    float pre[kPatchPerThread];
-    // the patch of `tile` into registers (loads only; stored to shared memory once the previous tile's im2col is done)
+    const int l_ch = U8 ? 2 - tid % 3 : tid / kPatchPitch;
+    const int l_pc = U8 ? tid / 3 : tid % kPatchPitch;
+    const bool l_on = U8 ? tid < kPatchCols * 3 : (tid < 3 * kPatchPitch && l_pc < kPatchCols);
+    float pre[kPatchRows];
     auto load_patch = [&](int tile) {
       const TileAt t = tile_at(p, tile);
       const int agent = t.img / p.b_sz, bat = t.img % p.b_sz;
-      const int r0 = 2 * t.oh0 - 2, c0 = 2 * t.ow0 - 2;
+      const int r0 = 2 * t.oh0 - 2, C = 2 * t.ow0 - 2 + l_pc;
+      const bool col_ok = l_on && C >= 0 && C < p.w;
+      if constexpr (U8) {
+        const uint8_t* xin = static_cast<const uint8_t*>(p.x) +
+                             (static_cast<size_t>(bat) * p.c_total + p.c_first + agent) * plane * 3 +
+                             static_cast<size_t>(C) * 3 + (tid % 3);
+        const float* lut = s_lut + l_ch * 256;
 #pragma unroll
-      for (int i = 0; i < kPatchPerThread; ++i) {
-        const int e = tid + i * kFront;
-        float v = 0.f;
-        if (e < kPatchElems) {
-          if constexpr (U8) {
-            const int pr = e / (kPatchCols * 3), rem = e % (kPatchCols * 3);
-            const int pc = rem / 3, cb = rem % 3;
-            const int R = r0 + pr, C = c0 + pc;
-            if (R >= 0 && R < p.h && C >= 0 && C < p.w) {
-              const uint8_t* xin = static_cast<const uint8_t*>(p.x) +
-                                   (static_cast<size_t>(bat) * p.c_total + p.c_first + agent) * plane * 3;
-              v = s_lut[(2 - cb) * 256 + __ldg(xin + (static_cast<size_t>(R) * p.w + C) * 3 + cb)];
-            }
-          } else {
-            const int ch = e / (kPatchRows * kPatchCols), rem = e % (kPatchRows * kPatchCols);
-            const int pr = rem / kPatchCols, pc = rem % kPatchCols;
-            const int R = r0 + pr, C = c0 + pc;
-            if (R >= 0 && R < p.h && C >= 0 && C < p.w) {
-              const float* xin = static_cast<const float*>(p.x) +
-                                 (static_cast<size_t>(bat) * p.c_total + p.c_first + 3 * agent + ch) * plane;
-              v = __ldg(xin + static_cast<size_t>(R) * p.w + C);
-            }
-          }
+        for (int pr = 0; pr < kPatchRows; ++pr) {
+          const int R = r0 + pr;
+          pre[pr] = (col_ok && R >= 0 && R < p.h) ? lut[__ldg(xin + static_cast<size_t>(R) * p.w * 3)] : 0.f;
         }
-        pre[i] = v;
+      } else {
+        const float* xin = static_cast<const float*>(p.x) +
+                           (static_cast<size_t>(bat) * p.c_total + p.c_first + 3 * agent + l_ch) * plane + C;
+#pragma unroll
+        for (int pr = 0; pr < kPatchRows; ++pr) {
+          const int R = r0 + pr;
+          pre[pr] = (col_ok && R >= 0 && R < p.h) ? __ldg(xin + static_cast<size_t>(R) * p.w) : 0.f;
+        }
       }
     };
+    // patch layout: [channel][row][column parity][18] (a row is still 36 words): for a fixed filter column the lanes of
+    // a warp - consecutive pixels of one column parity, see y1_pixel - read consecutive words
     auto store_patch = [&]() {
+      if (l_on) {
+        float* dst = s_patch + l_ch * kPatchRows * kPatchPitch + (l_pc & 1) * (kPatchPitch / 2) + (l_pc >> 1);
 #pragma unroll
-      for (int i = 0; i < kPatchPerThread; ++i) {
-        const int e = tid + i * kFront;
-        if (e < kPatchElems) {
-          int ch, pr, pc;
-          if constexpr (U8) {
-            pr = e / (kPatchCols * 3);
-            const int rem = e % (kPatchCols * 3);
-            pc = rem / 3;
-            ch = 2 - rem % 3;   // BGR channel of RGB byte cb (airsim_loader.py:521)
-          } else {
-            ch = e / (kPatchRows * kPatchCols);
-            const int rem = e % (kPatchRows * kPatchCols);
-            pr = rem / kPatchCols, pc = rem % kPatchCols;
-          }
-          s_patch[(ch * kPatchRows + pr) * kPatchPitch + pc] = pre[i];
-        }
+        for (int pr = 0; pr < kPatchRows; ++pr) dst[pr * kPatchPitch] = pre[pr];
       }
     };
+    // this thread's conv1 pixel in each of the five M tiles: word offsets of its window's filter columns 0 and 1 in
+    // the patch (column 2 = column 0 + one word: same parity, next pixel pair). Rows without a pixel reuse window 0.
+    auto patch_col = [](int c) { return (c & 1) * (kPatchPitch / 2) + (c >> 1); };
+    int win0[kMTiles], win1[kMTiles];
+#pragma unroll
+    for (int mt = 0; mt < kMTiles; ++mt) {
+      const int q = mt * kM + tid;
+      int ro, cq;
+      y1_pixel(q < kY1Px ? q : 0, ro, cq);
+      const int prow = ro < 8 ? 2 * ro + 1 : 2 * (ro - 8);
+      win0[mt] = prow * kPatchPitch + patch_col(cq);
+      win1[mt] = prow * kPatchPitch + patch_col(cq + 1);
+    }
 
     int tile = blockIdx.x;
     if (tile < p.num_tiles) load_patch(tile);
     uint32_t n = 0;  // A1 fill counter (three per tile)
+    TIMING(long long d_wait = 0; long long d_im2col = 0; long long d_patch = 0; long long t0;)
     for (; tile < p.num_tiles; tile += gridDim.x) {
+      TIMING(t0 = TICK();)
       store_patch();
       ptx::named_bar_sync(1, kFront);
       const int next = tile + gridDim.x;
       if (next < p.num_tiles) load_patch(next);   // in flight during the im2col below
-#pragma unroll 1
+      TIMING(d_patch += TICK() - t0;)
+#pragma unroll
       for (int g = 0; g < 3; ++g, ++n) {
+        TIMING(t0 = TICK();)
         if (n > 0) ptx::mbar_wait(&bars[B_A1_EMPTY], (n - 1) & 1);   // the MMAs that read the previous fill are done
-#pragma unroll 1
+        TIMING(d_wait += TICK() - t0;)
+        TIMING(t0 = TICK();)
+#pragma unroll
         for (int s = 0; s < (g < 2 ? 2 : 1); ++s) {
-          const int q = (2 * g + s) * kM + tid;
+          const float* p0 = s_patch + win0[2 * g + s];
+          const float* p1 = s_patch + win1[2 * g + s];
           float in[27];
-          if (q < kY1Px) {
-            const int ro = q / kY1Cols, cq = q % kY1Cols;
-            const int prow = ro < 8 ? 2 * ro + 1 : 2 * (ro - 8);
-            const float* pp = s_patch + prow * kPatchPitch + cq;
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci)
+          for (int ci = 0; ci < 3; ++ci)
 #pragma unroll
-              for (int kh = 0; kh < 3; ++kh)
-#pragma unroll
-                for (int kw = 0; kw < 3; ++kw)
-                  in[ci * 9 + kh * 3 + kw] = pp[(ci * kPatchRows + kh) * kPatchPitch + kw];
-          } else {
-#pragma unroll
-            for (int k = 0; k < 27; ++k) in[k] = 0.f;
-          }
+            for (int kh = 0; kh < 3; ++kh) {
+              const int ro = (ci * kPatchRows + kh) * kPatchPitch;
+              in[ci * 9 + kh * 3 + 0] = p0[ro];
+              in[ci * 9 + kh * 3 + 1] = p1[ro];
+              in[ci * 9 + kh * 3 + 2] = p0[ro + 1];
+            }
+          // (a row without a pixel computes on window 0; its accumulator row is never read)
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             uint4 hv;
-            __nv_bfloat16* hb = reinterpret_cast<__nv_bfloat16*>(&hv);
+            uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              const int k = c * 8 + e;
-              const float v = k < 27 ? in[k < 27 ? k : 0] : (k == 27 ? 1.f : 0.f);
-              hb[e] = float_to_elem(v, f16);
+            for (int e2 = 0; e2 < 4; ++e2) {
+              const int k = c * 8 + 2 * e2;
+              const float v0 = k < 27 ? in[k < 27 ? k : 0] : (k == 27 ? 1.f : 0.f);
+              const float v1 = k + 1 < 27 ? in[k + 1 < 27 ? k + 1 : 0] : (k + 1 == 27 ? 1.f : 0.f);
+              hw[e2] = ptx::pack_act2(v0, v1, false, f16);
             }
             *reinterpret_cast<uint4*>(smem + L::kA1 + sw_chunk(tid, 4 * s + c)) = hv;
           }
         }
         ptx::fence_proxy_async();
         ptx::mbar_arrive(&bars[B_A1_FULL]);
+        TIMING(d_im2col += TICK() - t0;)
       }
       ptx::named_bar_sync(1, kFront);   // every thread has read the patch before the next one is stored
     }
+    TIMING(if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[0] = d_patch, p.dbg[1] = d_wait, p.dbg[2] = d_im2col;)
   } else if (warp == 4) {
     // ================================================================ MMA issuer
     if (ptx::elect_one_sync()) {
@@ -299,29 +385,43 @@ __global__ void __launch_bounds__(kThreads, 1) enc_head_kernel(const __grid_cons
       ptx::mbar_wait(&bars[B_W], 0);
       ptx::tc_fence_after();
       uint32_t n = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
-        if (it > 0) {
-          ptx::mbar_wait(&bars[B_ACC1_EMPTY], (it - 1) & 1);   // epilogue has drained the conv1 accumulators
-          ptx::tc_fence_after();
-        }
-        // ---- conv1: five M tiles, K = 32 = two k-steps, each into its own accumulator
+      // conv1 of local tile jt: five M tiles, K = 32 = two k-steps, each into its own accumulator as soon as the
+      // epilogue has drained that accumulator's previous contents
+      TIMING(long long m_a1 = 0; long long m_acc1 = 0; long long m_y1 = 0; long long m_acc2 = 0; long long t0;)
+      auto conv1 = [&](int jt) {
 #pragma unroll 1
         for (int g = 0; g < 3; ++g, ++n) {
+          TIMING(t0 = TICK();)
           ptx::mbar_wait(&bars[B_A1_FULL], n & 1);
-          ptx::tc_fence_after();
+          TIMING(m_a1 += TICK() - t0;)
           for (int s = 0; s < (g < 2 ? 2 : 1); ++s) {
-            const uint32_t d = tmem_base + (2 * g + s) * 64;
+            const int mt = 2 * g + s;
+            TIMING(t0 = TICK();)
+            if (jt > 0) ptx::mbar_wait(&bars[B_ACC1_EMPTY0 + mt], (jt - 1) & 1);
+            TIMING(m_acc1 += TICK() - t0;)
+            ptx::tc_fence_after();
+            const uint32_t d = tmem_base + mt * 64;
             ptx::umma_bf16(d, a1 + 4 * s, w1, idesc, 0);
             ptx::umma_bf16(d, a1 + 4 * s + 2, w1 + 2, idesc, 1);
           }
           ptx::umma_commit(&bars[B_A1_EMPTY]);
         }
         ptx::umma_commit(&bars[B_ACC1_FULL]);
+      };
+      int it = 0;
+      if (blockIdx.x < p.num_tiles) conv1(0);
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        // conv1 of the NEXT tile goes first: its im2col and MMAs overlap this tile's first epilogue, and the front
+        // warps are not held up behind the wait for y1 below
+        if (tile + static_cast<int>(gridDim.x) < p.num_tiles) conv1(it + 1);
         // ---- conv2: 9 taps x 4 k-steps on the y1 planes
+        TIMING(t0 = TICK();)
         ptx::mbar_wait(&bars[B_Y1_FULL], it & 1);
+        TIMING(m_y1 += TICK() - t0;)
         const int b = it & 1;
+        TIMING(t0 = TICK();)
         if (it >= 2) ptx::mbar_wait(&bars[B_ACC2_EMPTY0 + b], ((it >> 1) & 1) ^ 1);
+        TIMING(m_acc2 += TICK() - t0;)
         ptx::tc_fence_after();
         const uint32_t d2 = tmem_base + kAcc2Col + b * 64;
 #pragma unroll
@@ -337,44 +437,67 @@ __global__ void __launch_bounds__(kThreads, 1) enc_head_kernel(const __grid_cons
           }
         ptx::umma_commit(&bars[B_ACC2_FULL0 + b]);
       }
+      TIMING(if (p.dbg && blockIdx.x == 0) p.dbg[4] = m_a1, p.dbg[5] = m_acc1, p.dbg[6] = m_y1, p.dbg[7] = m_acc2;)
     }
   } else {
-    // ================================================================ epilogues (warps 5-8)
+    // ================================================================ epilogues (two warpgroups: warps 5-8, 9-12)
+    // Everything here sits on the critical path between conv2 of one tile and conv2 of the next (y1 exists once), so
+    // the five conv1 tiles are split over two warpgroups (3 + 2; the second also drains conv2), and everything that
+    // does not depend on the tile is precomputed per thread.
+    const int grp = (warp - 5) >> 2;            // 0, 1
     const int wq = warp & 3;                    // TMEM lane quadrant this warp may read
     const int m = wq * 32 + lane;               // accumulator row of this thread
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(wq * 32) << 16);
-    const bool lead = warp == 5;
+    const bool lead = warp == 9;                // issues the TMA stores (group 1)
     const int planes = act_planes(p.act);
+    const int mt0 = grp == 0 ? 0 : 3;
+    // this thread's pixel in the group's conv1 tiles (scalars, not arrays: an indexed array here ended up in local
+    // memory, and with the L1 carved down to nothing by 227 KB of shared memory every access cost an L2 trip)
+    const Y1Slot slot_a = y1_slot(mt0 * kM + m);
+    const Y1Slot slot_b = y1_slot((mt0 + 1) * kM + m);
+    const Y1Slot slot_c = grp == 0 ? y1_slot(2 * kM + m) : Y1Slot{-1, -1, 0};
+    const uint32_t stg_row = L::kStg + m * kRow + ((m & 7) << 4);
 
-    auto epilogue2 = [&](int jt, int jtile) {   // conv2 accumulator of local tile jt -> staging -> TMA store
+    auto epilogue2 = [&](int jt, int jtile) {   // conv2 accumulator of local tile jt -> staging -> TMA store (group B)
       const int b = jt & 1;
       const TileAt t = tile_at(p, jtile);
-      uint32_t r[64];
-      ptx::tmem_ld_32x32b_x32(t_row + kAcc2Col + b * 64, r);
-      ptx::tmem_ld_32x32b_x32(t_row + kAcc2Col + b * 64 + 32, r + 32);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&bars[B_ACC2_EMPTY0 + b]);
-      float v[64];
-#pragma unroll
-      for (int j = 0; j < 64; ++j) v[j] = fmaxf(fmaf(__uint_as_float(r[j]), s_scale[j], s_shift[j]), 0.f);
       for (int pln = 0; pln < planes; ++pln) {
         if (lead && ptx::elect_one_sync()) ptx::bulk_wait_group_read<0>();   // the previous store has read the tile
-        ptx::named_bar_sync(2, kEpi);
+        ptx::named_bar_sync(2, kEpiGroup);
+        uint32_t r[64];
+        ptx::tmem_ld_32x32b_x32(t_row + kAcc2Col + b * 64, r);
+        ptx::tmem_ld_32x32b_x32(t_row + kAcc2Col + b * 64 + 32, r + 32);
+        ptx::tmem_ld_wait();
 #pragma unroll
         for (int c8 = 0; c8 < 8; ++c8) {
           uint4 pk;
           uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
+          float sc[8], sh[8];
+          *reinterpret_cast<float4*>(sc) = reinterpret_cast<const float4*>(s_scale)[2 * c8];
+          *reinterpret_cast<float4*>(sc + 4) = reinterpret_cast<const float4*>(s_scale)[2 * c8 + 1];
+          *reinterpret_cast<float4*>(sh) = reinterpret_cast<const float4*>(s_shift)[2 * c8];
+          *reinterpret_cast<float4*>(sh + 4) = reinterpret_cast<const float4*>(s_shift)[2 * c8 + 1];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t hi, lo;
-            split_act2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1], f16, hi, lo);
-            pw[j] = pln == 0 ? hi : lo;
+            const int c = c8 * 8 + 2 * j;
+            const float v0 = fmaf(__uint_as_float(r[c]), sc[2 * j], sh[2 * j]);
+            const float v1 = fmaf(__uint_as_float(r[c + 1]), sc[2 * j + 1], sh[2 * j + 1]);
+            if (planes == 1) {
+              pw[j] = ptx::pack_act2(v0, v1, true, f16);
+            } else {
+              uint32_t hi, lo;
+              split_act2(fmaxf(v0, 0.f), fmaxf(v1, 0.f), f16, hi, lo);
+              pw[j] = pln == 0 ? hi : lo;
+            }
           }
-          *reinterpret_cast<uint4*>(smem + L::kStg + sw_chunk(m, c8)) = pk;
+          *reinterpret_cast<uint4*>(smem + (stg_row ^ (c8 << 4))) = pk;
+        }
+        if (pln == planes - 1) {   // the accumulator has been read for the last time
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&bars[B_ACC2_EMPTY0 + b]);
         }
         ptx::fence_proxy_async();
-        ptx::named_bar_sync(2, kEpi);
+        ptx::named_bar_sync(2, kEpiGroup);
         if (lead && ptx::elect_one_sync()) {
           ptx::tma_store_4d(&p.y_map, smem + L::kStg, p.y_coffset + pln * p.y_cstride, t.ow0, t.oh0, t.img);
           ptx::bulk_commit_group();
@@ -383,65 +506,39 @@ __global__ void __launch_bounds__(kThreads, 1) enc_head_kernel(const __grid_cons
     };
 
     int it = 0, prev_tile = -1;
+    TIMING(long long e_w1 = 0; long long e_w2 = 0; long long e_e1 = 0; long long e_e2 = 0; long long e_ld = 0;
+           long long e_fence = 0; long long t0; const long long t_start = TICK();)
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       const TileAt t = tile_at(p, tile);
+      const int Rb = 2 * t.oh0 - 1, Cb = 2 * t.ow0 - 1;
+      TIMING(t0 = TICK();)
       ptx::mbar_wait(&bars[B_ACC1_FULL], it & 1);
+      TIMING(e_w1 += TICK() - t0;)
+      TIMING(t0 = TICK();)
       if (it > 0) ptx::mbar_wait(&bars[B_ACC2_FULL0 + ((it - 1) & 1)], ((it - 1) >> 1) & 1);   // conv2 of the previous tile has read y1
+      TIMING(e_w2 += TICK() - t0;)
       ptx::tc_fence_after();
-      // ---- epilogue 1: conv1 accumulators -> ReLU -> 16 bit -> the six y1 planes
-#pragma unroll 1
-      for (int mt = 0; mt < kMTiles; ++mt) {
-        const int q = mt * kM + m;
-        uint32_t r[64];
-        ptx::tmem_ld_32x32b_x32(t_row + mt * 64, r);
-        ptx::tmem_ld_32x32b_x32(t_row + mt * 64 + 32, r + 32);
-        ptx::tmem_ld_wait();
-        if (q < kY1Px) {
-          const int ro = q / kY1Cols, cq = q % kY1Cols;
-          const int rp = ro < 8 ? 0 : 1, pri = ro < 8 ? ro : ro - 8;
-          const int R = ro < 8 ? 2 * (t.oh0 + ro) : 2 * (t.oh0 - 1 + pri) + 1;
-          const int C = 2 * t.ow0 - 1 + cq;
-          // conv2 zero-pads ITS input: conv1 outputs outside the image are zeros, not conv1 of the padded image
-          const bool inside = R >= 0 && R < p.h && C >= 0 && C < p.w;
-          uint4 pk[8];
-#pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) {
-            uint32_t* pw = reinterpret_cast<uint32_t*>(&pk[c8]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              pw[j] = inside ? ptx::pack_act2(__uint_as_float(r[c8 * 8 + 2 * j]), __uint_as_float(r[c8 * 8 + 2 * j + 1]), true, f16)
-                             : 0u;
-          }
-          if (cq & 1) {   // even image column -> the even-column plane
-            const int idx = (cq - 1) >> 1;
-            uint8_t* dst = smem + plane_off(rp, 0) + (pri * 16 + idx) * kRow;
-#pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(dst + ((c8 ^ (idx & 7)) << 4)) = pk[c8];
-          } else {        // odd image column jj = cq / 2 of 0..16: left variant holds 0..15, right variant 1..16
-            const int jj = cq >> 1;
-            if (jj < 16) {
-              uint8_t* dst = smem + plane_off(rp, 1) + (pri * 16 + jj) * kRow;
-#pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(dst + ((c8 ^ (jj & 7)) << 4)) = pk[c8];
-            }
-            if (jj >= 1) {
-              const int idx = jj - 1;
-              uint8_t* dst = smem + plane_off(rp, 2) + (pri * 16 + idx) * kRow;
-#pragma unroll
-              for (int c8 = 0; c8 < 8; ++c8) *reinterpret_cast<uint4*>(dst + ((c8 ^ (idx & 7)) << 4)) = pk[c8];
-            }
-          }
-        }
-      }
+      TIMING(t0 = TICK();)
+      // ---- epilogue 1: this group's conv1 accumulators -> ReLU -> 16 bit -> the y1 planes
+      drain_conv1_row(smem, t_row + mt0 * 64, slot_a, Rb, Cb, p.h, p.w, f16, &bars[B_ACC1_EMPTY0 + mt0]);
+      drain_conv1_row(smem, t_row + (mt0 + 1) * 64, slot_b, Rb, Cb, p.h, p.w, f16, &bars[B_ACC1_EMPTY0 + mt0 + 1]);
+      if (grp == 0) drain_conv1_row(smem, t_row + 2 * 64, slot_c, Rb, Cb, p.h, p.w, f16, &bars[B_ACC1_EMPTY0 + 2]);
+      TIMING(const long long tf = TICK();)
       ptx::fence_proxy_async();
-      ptx::tc_fence_before();
       ptx::mbar_arrive(&bars[B_Y1_FULL]);
-      ptx::mbar_arrive(&bars[B_ACC1_EMPTY]);
+      TIMING(e_fence += TICK() - tf;)
+      TIMING(e_e1 += TICK() - t0;)
+      TIMING(t0 = TICK();)
       // ---- epilogue 2 of the PREVIOUS tile (its conv2 completion was waited for above); overlaps this tile's conv2
-      if (it > 0) epilogue2(it - 1, prev_tile);
+      if (grp == 1 && it > 0) epilogue2(it - 1, prev_tile);
+      TIMING(e_e2 += TICK() - t0;)
       prev_tile = tile;
     }
-    if (it > 0) {
+    TIMING(if (p.dbg && blockIdx.x == 0 && lane == 0 && (warp == 5 || warp == 9)) {
+      long long* d = p.dbg + (warp == 5 ? 8 : 16);
+      d[0] = e_w1, d[1] = e_w2, d[2] = e_e1, d[3] = e_e2, d[4] = TICK() - t_start, d[5] = it, d[6] = e_ld, d[7] = e_fence;
+    })
+    if (grp == 1 && it > 0) {
       ptx::mbar_wait(&bars[B_ACC2_FULL0 + ((it - 1) & 1)], ((it - 1) >> 1) & 1);
       ptx::tc_fence_after();
       epilogue2(it - 1, prev_tile);
@@ -473,10 +570,16 @@ int launch_head(const HeadParams& p, cudaStream_t stream) {
   return W2C_OK;
 }
 
+long long* g_head_dbg = nullptr;
+
 }  // namespace
 }  // namespace w2c
 
 using namespace w2c;
+
+// Debug aid (not part of the product path): cycle counters of CTA 0's warp roles are written to `buf` (device memory,
+// 32 x int64) by every later w2c_enc_head_fwd launch; NULL switches it off again.
+extern "C" void w2c_debug_enc_head_timing(long long* buf) { g_head_dbg = buf; }
 
 extern "C" int w2c_enc_head_fwd(const w2c_enc_head_args* a, w2c_stream_t stream) {
   if (!a) return set_error(W2C_ERR_INVALID, "enc_head: args is NULL");
@@ -505,6 +608,7 @@ extern "C" int w2c_enc_head_fwd(const w2c_enc_head_args* a, w2c_stream_t stream)
   W2C_CHECK_ARG(tiles < (1ll << 31), "enc_head: too many tiles");
   p.num_tiles = static_cast<int>(tiles);
   p.act = a->act, p.y_cstride = y_cstride, p.y_coffset = a->y_coffset;
+  p.dbg = g_head_dbg;
   const cuuint64_t esz = 2;
   {
     // conv2 weight as packed by w2c_pack_conv_weight (cout = 64, cin = 64, 9 taps): [planes * 64][576]; the hi plane

@@ -70,6 +70,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // deadlocked pipeline then surfaces as a launch failure the host can report.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifndef W2C_UNBOUNDED_WAIT
+  // (unroll 1: ptxas otherwise replicates the try_wait dozens of times per call site - the fused encoder-head kernel
+  // grew to 118 KB of SASS and ncu showed its warps starved by instruction-cache misses, stall_no_inst)
+#pragma unroll 1
   for (uint32_t i = 0; i < (1u << 26); ++i)
     if (mbar_try_wait(bar, parity)) return;
   asm volatile("trap;");

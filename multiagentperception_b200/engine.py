@@ -32,7 +32,7 @@ PRECISIONS = {"bf16": ops.ACT_BF16, "bf16x3": ops.ACT_BF16X2, "fp16": ops.ACT_FP
 #                    All_agents, MIMO_All_agents, LearnWho2Com's own map): less headroom, fewer one-pass layers
 # Measured on B200 (bench.py `parity`, tests/test_parity_gpu.py): each one-pass layer adds 2.5-4e-4 (in quadrature) to
 # the ~4e-4 floor of the three-pass path; the layers listed are the ones with the most MMA time per unit of error.
-MIXED_ONE_PASS = {"encoder_fused": (3, 5, 6, 8, 9), "encoder": (6, 9)}
+MIXED_ONE_PASS = {"encoder_fused": (1, 2, 3, 5, 6, 8, 9), "encoder": (6, 9)}
 BN_EPS_DEFAULT = 1e-5
 
 
