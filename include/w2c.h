@@ -151,6 +151,36 @@ typedef struct w2c_enc_head_args {
 
 int w2c_enc_head_fwd(const w2c_enc_head_args* args, w2c_stream_t stream);
 
+/*
+ * Train-mode BatchNorm2d on a conv output, in place.  Replaces nn.BatchNorm2d in training mode inside
+ * conv2DBatchNormRelu / deconv2DBatchNormRelu (ptsemseg/models/utils.py:110-114,152-164) as Trainer_*.train() runs
+ * them after model.train() (trainer.py:659-669), plus the ReLU (and the BasicBlock residual add) that follows.
+ *   z        the raw conv output (w2c_conv_bnrelu_fwd with scale = 1, shift = conv bias, relu = 0), NHWC in `act`,
+ *            n_px pixels (N*H*W), channels [coffset, coffset + c) of cstride; overwritten with
+ *            act(gamma * (z - mean) / sqrt(var + eps) + beta (+ residual)), mean / var = batch statistics (var biased)
+ *   running_mean, running_var, num_batches_tracked: the module's own buffers, updated in place exactly like
+ *            nn.BatchNorm2d (momentum, UNBIASED variance, counter + 1); NULL = track_running_stats off
+ *   sums_ws  fp64 [2*c], ZEROED by the caller once (the call leaves it zeroed again); scale_ws / shift_ws fp32 [c].
+ * c must be a multiple of 8 with c / 8 dividing 256.  Three launches: statistics, finalize, apply.
+ */
+int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
+                     int32_t act, int32_t relu, const float* gamma, const float* beta, float eps, float momentum,
+                     float* running_mean, float* running_var, int64_t* num_batches_tracked, double* sums_ws,
+                     float* scale_ws, float* shift_ws, w2c_stream_t stream);
+/* The same on an fp32 NCHW map [n][c][hw] (the logits layer: deconv12 is conv + BatchNorm + ReLU, backbone.py:124). */
+int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw, int32_t relu, const float* gamma,
+                          const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                          int64_t* num_batches_tracked, double* sums_ws, float* scale_ws, float* shift_ws,
+                          w2c_stream_t stream);
+/* First layers without the ReLU (the raw conv output train-mode BatchNorm starts from); arguments as
+ * w2c_stem_conv3x3_fwd / w2c_stem_conv7x7s2_fwd. */
+int w2c_stem_conv3x3_raw_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
+                             int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout,
+                             int32_t act, int32_t n_split, w2c_stream_t stream);
+int w2c_stem_conv7x7s2_raw_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
+                               int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
+                               int32_t cout, int32_t act, int32_t n_split, w2c_stream_t stream);
+
 /* cout rounded up to the row padding the packed weight layout uses. */
 int32_t w2c_cout_pad(int32_t cout);
 /* Bytes of the packed weight buffer for a conv of the given geometry. */

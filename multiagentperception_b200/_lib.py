@@ -75,6 +75,12 @@ _SIGNATURES = {
     "w2c_launch_count": (ctypes.c_uint64, []),
     "w2c_conv_bnrelu_fwd": (ctypes.c_int, [ctypes.POINTER(ConvArgs), c_vp]),
     "w2c_enc_head_fwd": (ctypes.c_int, [ctypes.POINTER(EncHeadArgs), c_vp]),
+    "w2c_bn_train_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32,
+                                        c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "w2c_bn_train_nchw_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_f32, c_vp,
+                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "w2c_stem_conv3x3_raw_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
+    "w2c_stem_conv7x7s2_raw_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_cout_pad": (c_i32, [c_i32]),
     "w2c_packed_weight_bytes": (ctypes.c_size_t, [c_i32, c_i32, c_i32, c_i32]),
     "w2c_pack_conv_weight": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

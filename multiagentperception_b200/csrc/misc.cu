@@ -643,6 +643,31 @@ int w2c_stem_conv7x7s2_fwd(const float* x, const float* w, const float* scale, c
                             0, static_cast<cudaStream_t>(stream));
 }
 
+// The two first layers WITHOUT the ReLU (and normally with scale = 1, shift = conv bias): the raw conv output the
+// train-mode BatchNorm (csrc/bn_train.cu) takes its batch statistics from.
+int w2c_stem_conv3x3_raw_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
+                             int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout,
+                             int32_t act, int32_t n_split, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && w && scale && shift && y, "stem3x3_raw: null pointer");
+  W2C_CHECK_ARG(act_valid(act), "stem3x3_raw: bad act %d", act);
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0, "stem3x3_raw: bad extent");
+  W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem3x3_raw: channel window outside the input");
+  W2C_CHECK_ARG(cout == 64 || cout == 128, "stem3x3_raw: cout=%d (64 or 128)", cout);
+  return stem3x3_tc_forward(x, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act | 0x100, n_split,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int w2c_stem_conv7x7s2_raw_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y,
+                               int32_t b, int32_t n_agents, int32_t c_total, int32_t c_first, int32_t h, int32_t w_px,
+                               int32_t cout, int32_t act, int32_t n_split, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && w && scale && shift && y, "stem7x7_raw: null pointer");
+  W2C_CHECK_ARG(act_valid(act), "stem7x7_raw: bad act %d", act);
+  W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem7x7_raw: channel window outside the input");
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0, "stem7x7_raw: bad extent");
+  return stem7x7_tc_forward(x, nullptr, w, scale, shift, y, b, n_agents, c_total, c_first, h, w_px, cout, act | 0x100,
+                            n_split, 0, static_cast<cudaStream_t>(stream));
+}
+
 int w2c_stem_conv7x7s2_u8_fwd(const uint8_t* frames, const float* lut, const float* w, const float* scale,
                               const float* shift, void* y, int32_t b, int32_t n_agents, int32_t agents_total,
                               int32_t agent_first, int32_t h, int32_t w_px, int32_t cout, int32_t act, int32_t n_split,

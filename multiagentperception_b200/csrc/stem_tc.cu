@@ -30,6 +30,7 @@ namespace {
 constexpr int kTile = 128;      // pixels per tile = UMMA M
 constexpr int kRowBytes = 128;  // one swizzle row; only the first 64 B (K = 32 bf16) of an operand row are used
 constexpr int kStagingBytes = kTile * 64 * 2;
+constexpr int kStemNoRelu = 0x100;  // flag OR-ed into the kernels' `act` argument: no ReLU in the epilogue
 
 template <int COUT, int kNumStaging>
 struct StemSmem {
@@ -148,6 +149,8 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
       gather_taps(x, p, total, b_sz, c_total, c_first, h, wpx, dst);
   };
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool relu = (act & kStemNoRelu) == 0;   // (train-mode BatchNorm wants the raw conv output, csrc/bn_train.cu)
+  act &= 0xff;
   const bool x3 = act_planes(act) == 2;
   const bool f16 = act_is_f16(act);
 
@@ -257,16 +260,16 @@ __global__ void __launch_bounds__(kTile, 4) stem3x3_tc_kernel(const __grid_const
           for (int c4 = 0; c4 < 4; ++c4) {
             uint4 pk;
             if (!x3) {
-              pk.x = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 0]), __uint_as_float(r[c4 * 8 + 1]), true, f16);
-              pk.y = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 2]), __uint_as_float(r[c4 * 8 + 3]), true, f16);
-              pk.z = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 4]), __uint_as_float(r[c4 * 8 + 5]), true, f16);
-              pk.w = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 6]), __uint_as_float(r[c4 * 8 + 7]), true, f16);
+              pk.x = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 0]), __uint_as_float(r[c4 * 8 + 1]), relu, f16);
+              pk.y = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 2]), __uint_as_float(r[c4 * 8 + 3]), relu, f16);
+              pk.z = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 4]), __uint_as_float(r[c4 * 8 + 5]), relu, f16);
+              pk.w = ptx::pack_act2(__uint_as_float(r[c4 * 8 + 6]), __uint_as_float(r[c4 * 8 + 7]), relu, f16);
             } else {
               uint32_t* pw = reinterpret_cast<uint32_t*>(&pk);
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
-                const float a = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j]), 0.f);
-                const float b = fmaxf(__uint_as_float(r[c4 * 8 + 2 * j + 1]), 0.f);
+                float a = __uint_as_float(r[c4 * 8 + 2 * j]), b = __uint_as_float(r[c4 * 8 + 2 * j + 1]);
+                if (relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
                 uint32_t hi, lo;
                 split_act2(a, b, f16, hi, lo);
                 pw[j] = pln == 0 ? hi : lo;
@@ -327,7 +330,7 @@ int launch_stem_ns(const void* x, const float* lut, const float* w, const float*
     return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * h * wpx;
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
-  const int planes = act_planes(act);
+  const int planes = act_planes(act & 0xff);
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
   y_maps.direct = 0;
@@ -404,6 +407,8 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + L::kTmemPtr);
   float* s_lut = reinterpret_cast<float*>(smem + L::kLut);
   const int tid = threadIdx.x, warp = tid >> 5;
+  const bool relu = (act & kStemNoRelu) == 0;   // (train-mode BatchNorm wants the raw conv output, csrc/bn_train.cu)
+  act &= 0xff;
   const bool x3 = act_planes(act) == 2;
   const bool f16 = act_is_f16(act);
   const int ho = h / 2, wo = wpx / 2;
@@ -550,9 +555,9 @@ __global__ void __launch_bounds__(kTile, 2) stem7x7_tc_kernel(const __grid_const
             for (int j = 0; j < 4; ++j) {
               const float a = __uint_as_float(r[c4 * 8 + 2 * j]), b = __uint_as_float(r[c4 * 8 + 2 * j + 1]);
               if (!x3) {
-                pw[j] = ptx::pack_act2(a, b, true, f16);
+                pw[j] = ptx::pack_act2(a, b, relu, f16);
               } else {
-                const float ar = fmaxf(a, 0.f), br = fmaxf(b, 0.f);
+                const float ar = relu ? fmaxf(a, 0.f) : a, br = relu ? fmaxf(b, 0.f) : b;
                 uint32_t hi, lo;
                 split_act2(ar, br, f16, hi, lo);
                 pw[j] = pln == 0 ? hi : lo;
@@ -594,7 +599,7 @@ int launch_stem7(const void* x, const float* lut, const float* w, const float* s
     return rc;
   const size_t total = static_cast<size_t>(b) * n_agents * (h / 2) * (wpx / 2);
   const int num_tiles = static_cast<int>((total + kTile - 1) / kTile);
-  const int planes = act_planes(act);
+  const int planes = act_planes(act & 0xff);
   StemMaps y_maps;
   y_maps.cs = COUT / n_split;
   y_maps.direct = 0;

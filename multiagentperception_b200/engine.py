@@ -139,6 +139,20 @@ class WeightCache:
         return ops.fold_bn(conv.bias, None, None, None, None, BN_EPS_DEFAULT, conv.out_channels, self.device)
 
     # 3-input-channel stem: fp32 [cout][k] weight + scale/shift
+    def conv_raw(self, conv):
+        """The conv alone (scale = 1, shift = bias, no ReLU): what train-mode BatchNorm takes its statistics from."""
+        return self.conv(conv, None, False, key=("raw", id(conv)))
+
+    def stem_raw(self, conv):
+        key = ("stem_raw", id(conv))
+        st = self._misc.get(key)
+        if st is None:
+            w = conv.weight.detach().to(self.device, torch.float32).reshape(conv.out_channels, -1).contiguous()
+            scale, shift = self._fold(conv, None)
+            st = (w, scale, shift)
+            self._misc[key] = st
+        return st
+
     def stem(self, conv, bn):
         key = ("stem", id(conv))
         st = self._misc.get(key)
@@ -210,6 +224,7 @@ class Program:
         self.want_logits = True
         self.labels_out = None
         self.pass_plan = None   # {"stack": (layer numbers)} that run ONE MMA pass (two-plane formats; see PRECISIONS)
+        self.train = False      # train-mode forward: BatchNorm from batch statistics + running-stat update (bn_train.cu)
 
     # ---- buffers
     def act_buf(self, n, h, w, c):
@@ -315,11 +330,79 @@ class Program:
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret
 
+    # ---- conv + BatchNorm (+ residual) (+ ReLU) as the model sees it: folded in eval mode, batch statistics in train mode
+    def conv_bn(self, x, conv, bn, relu, out=None, residual=None, nchw_out=None, labels=None, passes=0):
+        if not self.train or bn is None:
+            return self.conv(x, self.weights.conv(conv, bn, relu), out=out, residual=residual, nchw_out=nchw_out,
+                             labels=labels, passes=passes)
+        if labels is not None or isinstance(nchw_out, str):
+            raise ValueError("train mode produces logits, not label maps")
+        pc = self.weights.conv_raw(conv)
+        if nchw_out is not None:
+            z = self.conv(x, pc, nchw_out=nchw_out)
+            self._bn_train_nchw(z, bn, relu)
+            return z
+        z = self.conv(x, pc, out=out)
+        self._bn_train(z, bn, relu, residual)
+        return z
+
+    def _bn_ws(self, c):
+        return (self.f32_buf(2 * c, dtype=torch.float64, zero=True), self.f32_buf(c), self.f32_buf(c))
+
+    @staticmethod
+    def _bn_ptrs(bn, device):
+        for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked):
+            if t is not None and (t.device != device or not t.is_contiguous()):
+                raise RuntimeError("train mode updates the BatchNorm buffers in place: the module must live on %s" % device)
+        p = lambda t: t.data_ptr() if t is not None else None
+        return (p(bn.weight), p(bn.bias), p(bn.running_mean), p(bn.running_var), p(bn.num_batches_tracked),
+                float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
+
+    def _bn_train(self, z, bn, relu, residual=None):
+        """z: ActMap holding the raw conv output -> normalised in place with batch statistics (+residual) (+ReLU)."""
+        gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
+        sums, scale, shift = self._bn_ws(z.c)
+        self._record(self._lib.w2c_bn_train_fwd, z.buf.data_ptr(), residual.buf.data_ptr() if residual is not None else None,
+                     z.n * z.h * z.w, z.c, z.cstride, z.coffset, self.act, int(bool(relu)), gamma, beta, eps, mom, rm, rv,
+                     nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr())
+
+    def _bn_train_nchw(self, z, bn, relu):
+        gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
+        n, c, h, w = z.shape
+        sums, scale, shift = self._bn_ws(c)
+        self._record(self._lib.w2c_bn_train_nchw_fwd, z.data_ptr(), n, c, h * w, int(bool(relu)), gamma, beta, eps, mom, rm,
+                     rv, nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr())
+
+    def stem_bn(self, x_in, conv, bn, b, n_agents, h, w, c_first=0):
+        """First layer (3x3 s1 of n_segnet_encoder or 7x7 s2 of resnet18) + BatchNorm + ReLU."""
+        k7 = tuple(conv.kernel_size) == (7, 7)
+        if not self.train:
+            st = self.weights.stem(conv, bn)
+            return (self.stem7x7 if k7 else self.stem3x3)(x_in, st, b, n_agents, h, w, c_first)
+        z = (self.stem7x7 if k7 else self.stem3x3)(x_in, self.weights.stem_raw(conv), b, n_agents, h, w, c_first, raw=True)
+        self._bn_train(z, bn, True)
+        return z
+
+    def stem_pair_bn(self, x_in, conv_a, bn_a, conv_b, bn_b, b, n_agents, h, w):
+        """Two encoders' first layers as one 3 -> 128 stem writing two dense 64-channel maps (+ BatchNorm + ReLU)."""
+        k7 = tuple(conv_a.kernel_size) == (7, 7)
+        fn = self.stem7x7 if k7 else self.stem3x3
+        if not self.train:
+            return fn(x_in, self.weights.stem_pair(conv_a, bn_a, conv_b, bn_b), b, n_agents, h, w, split=True)
+        wa, sa, ha = self.weights.stem_raw(conv_a)
+        wb, sb, hb = self.weights.stem_raw(conv_b)
+        st = (torch.cat((wa, wb), 0).contiguous(), torch.cat((sa, sb)).contiguous(), torch.cat((ha, hb)).contiguous())
+        self.keep.append(st)
+        za, zb = fn(x_in, st, b, n_agents, h, w, split=True, raw=True)
+        self._bn_train(za, bn_a, True)
+        self._bn_train(zb, bn_b, True)
+        return za, zb
+
     def can_fuse_head(self, stack):
         """True when conv1 + conv2 of an n_segnet encoder in `stack` may run as the fused head kernel: always in the
         one-plane formats; in a two-plane format only where the precision plan runs BOTH layers in one pass (the
         conv1 map inside the kernel is a single plane)."""
-        if not FUSE_ENCODER_HEAD:
+        if not FUSE_ENCODER_HEAD or self.train:
             return False
         if self.planes == 1:
             return True
@@ -341,8 +424,9 @@ class Program:
         self._record(self._lib.w2c_enc_head_fwd, ctypes.byref(a))
         return out
 
-    def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False):
-        """split=True (a fused pair of 64-channel first layers): returns TWO dense 64-channel maps."""
+    def stem3x3(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False, raw=False):
+        """split=True (a fused pair of 64-channel first layers): returns TWO dense 64-channel maps. raw=True: no ReLU
+        (the conv output train-mode BatchNorm starts from)."""
         wt, scale, shift = st
         cout = wt.shape[0]
         n_split = 2 if split else 1
@@ -361,11 +445,12 @@ class Program:
                          scale.data_ptr(), shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first // 3, h, w,
                          cout, self.act, n_split)
             return out
-        self._record(self._lib.w2c_stem_conv3x3_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
+        fn = self._lib.w2c_stem_conv3x3_raw_fwd if raw else self._lib.w2c_stem_conv3x3_fwd
+        self._record(fn, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
                      shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act, n_split)
         return out
 
-    def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False):
+    def stem7x7(self, x_nchw, st, b, n_agents, h, w, c_first=0, split=False, raw=False):
         """resnet18 first layer (7x7 s2). split=True (a fused pair of 64-channel first layers): two dense maps."""
         wt, scale, shift = st
         cout = wt.shape[0]
@@ -386,7 +471,8 @@ class Program:
                          scale.data_ptr(), shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first // 3, h, w,
                          cout, self.act, n_split)
             return out
-        self._record(self._lib.w2c_stem_conv7x7s2_fwd, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
+        fn = self._lib.w2c_stem_conv7x7s2_raw_fwd if raw else self._lib.w2c_stem_conv7x7s2_fwd
+        self._record(fn, x_nchw.data_ptr(), wt.data_ptr(), scale.data_ptr(),
                      shift.data_ptr(), y_ptr, b, n_agents, x_nchw.shape[1], c_first, h, w, cout, self.act, n_split)
         return out
 

@@ -138,54 +138,54 @@ def _build_encoder(prog, enc, key, x_nchw, b, n_agents, h, w, c_first=0, out=Non
                               b, n_agents, h, w, c_first)
             first = 2
         else:
-            a = prog.stem3x3(x_nchw, wc.stem(units[0].conv, units[0].bn), b, n_agents, h, w, c_first)
+            a = prog.stem_bn(x_nchw, units[0].conv, units[0].bn, b, n_agents, h, w, c_first)
         for i, u in enumerate(units[first:], first + 1):
-            a = prog.conv(a, wc.conv(u.conv, u.bn, True), passes=prog.passes_for(stack, i))
+            a = prog.conv_bn(a, u.conv, u.bn, True, passes=prog.passes_for(stack, i))
     elif isinstance(bb, resnet_encoder):
         if h % 32 or w % 32:
             raise ValueError("resnet_encoder needs H and W divisible by 32 (got %dx%d)" % (h, w))
         fb = bb.feature_backbone
-        a = stem if stem is not None else prog.stem7x7(x_nchw, wc.stem(fb.conv1, fb.bn1), b, n_agents, h, w, c_first)
+        a = stem if stem is not None else prog.stem_bn(x_nchw, fb.conv1, fb.bn1, b, n_agents, h, w, c_first)
         a = prog.maxpool(a)
         for li in range(1, 5):
             for blk in getattr(fb, "layer%d" % li):
                 idt = a
                 if blk.downsample is not None:
-                    idt = prog.conv(a, wc.conv(blk.downsample[0], blk.downsample[1], False))
-                y = prog.conv(a, wc.conv(blk.conv1, blk.bn1, True))
-                a = prog.conv(y, wc.conv(blk.conv2, blk.bn2, True), residual=idt)
+                    idt = prog.conv_bn(a, blk.downsample[0], blk.downsample[1], False)
+                y = prog.conv_bn(a, blk.conv1, blk.bn1, True)
+                a = prog.conv_bn(y, blk.conv2, blk.bn2, True, residual=idt)
     else:
         raise ValueError("unknown encoder backbone %r" % type(bb).__name__)
-    return prog.conv(a, wc.conv(enc.squeezer.conv, enc.squeezer.bn, True), out=out)
+    return prog.conv_bn(a, enc.squeezer.conv, enc.squeezer.bn, True, out=out)
 
 
 def _build_decoder(prog, dec, a):
     """img_decoder.forward (agent.py:80-89) -> fp32 NCHW logits tensor."""
     wc = prog.weights
     if dec.feat_squeezer == 2:
-        a = prog.conv(a, wc.conv(dec.desqueezer.conv, dec.desqueezer.bn, True))
+        a = prog.conv_bn(a, dec.desqueezer.conv, dec.desqueezer.bn, True)
     elif dec.feat_squeezer == 4:
-        a = prog.conv(a, wc.conv(dec.desqueezer1.conv, dec.desqueezer1.bn, True))
-        a = prog.conv(a, wc.conv(dec.desqueezer2.conv, dec.desqueezer2.bn, True))
+        a = prog.conv_bn(a, dec.desqueezer1.conv, dec.desqueezer1.bn, True)
+        a = prog.conv_bn(a, dec.desqueezer2.conv, dec.desqueezer2.bn, True)
     od = dec.output_decoder
     if isinstance(od, n_segnet_decoder):
         units = od.units()
         for u in units[:-1]:
-            a = prog.conv(a, wc.conv(u.conv, u.bn, True))
+            a = prog.conv_bn(a, u.conv, u.bn, True)
         last = units[-1]
         labels = prog.f32_buf(a.n, a.h, a.w, dtype=torch.uint8) if prog.want_labels else None
         prog.labels_out = labels
         if labels is not None and not prog.want_logits:
             # label map only: the arg-max is taken on the accumulators, the fp32 logits never reach HBM
-            return prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out="none", labels=labels)
+            return prog.conv_bn(a, last.conv, last.bn, True, nchw_out="none", labels=labels)
         logits = prog.f32_buf(a.n, last.conv.out_channels, a.h, a.w)
-        prog.conv(a, wc.conv(last.conv, last.bn, True), nchw_out=logits,  # logits pass BN+ReLU too, backbone.py:124
+        prog.conv_bn(a, last.conv, last.bn, True, nchw_out=logits,  # logits pass BN+ReLU too, backbone.py:124
                   labels=labels)
         return logits
     if isinstance(od, simple_decoder):
-        y = prog.conv(a, wc.conv(od.pred[0], None, True))
+        y = prog.conv_bn(a, od.pred[0], None, True)
         small = prog.f32_buf(a.n, od.pred[2].out_channels, a.h, a.w)
-        prog.conv(y, wc.conv(od.pred[2], None, False), nchw_out=small)
+        prog.conv_bn(y, od.pred[2], None, False, nchw_out=small)
         prog.labels_out = None
         if prog.want_labels and not prog.want_logits:
             # label map only: up-sample and take the arg-max per output pixel in one kernel, nothing else is written
@@ -206,14 +206,13 @@ def _fused_stems(prog, enc_a, enc_b, x_nchw, b, n_agents, h, w):
     ba, bb = enc_a.feature_backbone, enc_b.feature_backbone
     if isinstance(ba, resnet_encoder) and isinstance(bb, resnet_encoder):
         fa, fb = ba.feature_backbone, bb.feature_backbone
-        return prog.stem7x7(x_nchw, prog.weights.stem_pair(fa.conv1, fa.bn1, fb.conv1, fb.bn1), b, n_agents, h, w,
-                            split=True)
+        return prog.stem_pair_bn(x_nchw, fa.conv1, fa.bn1, fb.conv1, fb.bn1, b, n_agents, h, w)
     if not (isinstance(ba, n_segnet_encoder) and isinstance(bb, n_segnet_encoder)):
         return None, None
     ua, ub = ba.units()[0], bb.units()[0]
     # two dense 64-channel maps (not one interleaved 128-channel map: each encoder's stride-2 conv would read half of
     # every 256-byte pixel)
-    return prog.stem3x3(x_nchw, prog.weights.stem_pair(ua.conv, ua.bn, ub.conv, ub.bn), b, n_agents, h, w, split=True)
+    return prog.stem_pair_bn(x_nchw, ua.conv, ua.bn, ub.conv, ub.bn, b, n_agents, h, w)
 
 
 def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
@@ -223,7 +222,7 @@ def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
         raise ValueError("policy_net4 needs the %dx%d feature map divisible by 4" % (a.h, a.w))
     for i in range(1, 6):
         u = getattr(pol, "conv%d" % i)
-        a = prog.conv(a, prog.weights.conv(u.conv, u.bn, True))
+        a = prog.conv_bn(a, u.conv, u.bn, True)
     return a
 
 
@@ -307,11 +306,13 @@ class _W2CModel(nn.Module):
 
     # ---- compile / run
     def _compiled(self, inputs, tag, builder, pre_run=None):
-        if self.training:
-            raise RuntimeError(
-                "%s: the B200 path implements the eval-mode forward only (BatchNorm folded from running statistics, "
-                "no autograd). Call model.eval() first; training stays on the reference implementation."
-                % type(self).__name__)
+        # self.training (model.train(), trainer.py:659): the TRAIN-MODE FORWARD - every BatchNorm2d uses batch statistics
+        # and updates its running statistics in place (csrc/bn_train.cu). It is a forward only: the outputs carry no
+        # autograd graph, so loss.backward() on them raises; the backward pass is not part of this path.
+        train = bool(self.training)
+        if train and (self._w2c["io"]["u8"] or self._w2c["io"]["labels"]):
+            raise RuntimeError("train mode takes the fp32 views and returns logits (set_input_format / "
+                               "set_label_output are evaluation-path options)")
         if not (torch.is_tensor(inputs) and inputs.is_cuda):
             raise RuntimeError("%s.forward needs a CUDA tensor: there is no CPU fallback" % type(self).__name__)
         io = self._w2c["io"]
@@ -324,7 +325,7 @@ class _W2CModel(nn.Module):
         dev = inputs.device
         precision = self._w2c["precision"]
         act = engine.PRECISIONS[precision]
-        key = (dev, precision, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"])
+        key = (dev, precision, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"], train)
         c = self._w2c["programs"].get(key)
         if c is None:
             wkey = (dev, act)
@@ -334,7 +335,8 @@ class _W2CModel(nn.Module):
                 self._w2c["weights"][wkey] = wc
             with torch.cuda.device(dev), torch.no_grad():
                 prog = engine.Program(wc, dev, act)
-                prog.pass_plan = engine.MIXED_ONE_PASS if precision == "mixed" else None
+                prog.pass_plan = engine.MIXED_ONE_PASS if (precision == "mixed" and not train) else None
+                prog.train = train
                 prog.want_labels, prog.want_logits = io["labels"], io["logits"]
                 if io["u8"]:
                     prog.input_u8 = True

@@ -22,9 +22,23 @@ BN_EPS = 1e-5  # nn.BatchNorm2d default, utils.py:112
 
 
 # --------------------------------------------------------------------------------------------- blocks
+# Train-mode BatchNorm (model.train(), trainer.py:659): forward(..., train_stats={}) switches every BatchNorm2d to batch
+# statistics (biased variance for the normalisation, utils.py:110-114 -> nn.BatchNorm2d) and collects the buffers the
+# module would hold afterwards - running_mean / running_var updated with momentum 0.1 and the UNBIASED variance,
+# num_batches_tracked + 1 - under their state_dict keys.
+_TRAIN_STATS = None
+
+
 def _bn(x, sd, p):
-    return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
-                        False, 0.1, BN_EPS)
+    if _TRAIN_STATS is None:
+        return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],
+                            False, 0.1, BN_EPS)
+    rm = _TRAIN_STATS.get(p + ".running_mean", sd[p + ".running_mean"]).clone()
+    rv = _TRAIN_STATS.get(p + ".running_var", sd[p + ".running_var"]).clone()
+    y = F.batch_norm(x, rm, rv, sd[p + ".weight"], sd[p + ".bias"], True, 0.1, BN_EPS)
+    _TRAIN_STATS[p + ".running_mean"], _TRAIN_STATS[p + ".running_var"] = rm, rv
+    _TRAIN_STATS[p + ".num_batches_tracked"] = _TRAIN_STATS.get(p + ".num_batches_tracked", 0) + 1
+    return y
 
 
 def cbr(x, sd, p, stride=1):
@@ -364,11 +378,21 @@ def all_agents_forward(sd, cfg, x):
     return img_decoder(torch.cat(feats, 1), sd, "decoder", dec, m["feat_squeezer"])
 
 
-def forward(sd, cfg, x, **kw):
-    """Dispatch on cfg['model']['arch'] like ptsemseg.models.get_model (models/__init__.py:8-101)."""
+def forward(sd, cfg, x, train_stats=None, **kw):
+    """Dispatch on cfg['model']['arch'] like ptsemseg.models.get_model (models/__init__.py:8-101). train_stats: a dict
+    -> the model.train() forward (batch-statistics BatchNorm); it receives the updated BatchNorm buffers."""
+    global _TRAIN_STATS
     arch = cfg["model"]["arch"]
     sd = {k: v.detach().to(torch.float32).cpu() for k, v in sd.items() if torch.is_floating_point(v)}
     x = x.detach().to(torch.float32).cpu()
+    _TRAIN_STATS = train_stats
+    try:
+        return _dispatch(arch, sd, cfg, x, kw)
+    finally:
+        _TRAIN_STATS = None
+
+
+def _dispatch(arch, sd, cfg, x, kw):
     with torch.no_grad():
         if arch == "Single_agent":
             return single_agent_forward(sd, cfg, x)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from multiagentperception_b200 import synth
+from multiagentperception_b200 import configs, synth
 from multiagentperception_b200.models import get_model
 from oracle import ref_harness
 from oracle import when2com_oracle as orc
@@ -91,3 +91,35 @@ def test_miou_metric():
     got[0, :, 0, 0] = torch.tensor([0.0, 2.0, 0.0])  # one pixel of class 0 predicted as class 1
     m = orc.miou_between(ref, got, n_class=3)
     assert abs(m - (0.5 + 2.0 / 3.0) / 2) < 1e-12
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("arch,bb,over,kw,n", [
+    ("MIMOcom", "n_segnet", dict(agent_num=3), dict(training=True, MO_flag=True), 3),
+    ("MIMOcom", "resnet", dict(agent_num=2), dict(training=True, MO_flag=True), 2),
+    ("Single_agent", "n_segnet", dict(feat_squeezer=2), {}, 1),
+    ("LearnWhen2Com", "resnet", dict(query_size=8), dict(training=True), 5),
+])
+def test_train_mode_oracle_equals_the_reference_in_train_mode(arch, bb, over, kw, n):
+    """model.train() forward (trainer.py:659-669): batch-statistics BatchNorm and the running-stat update of the
+    oracle's train_stats path against the UNMODIFIED reference modules in train() mode, buffers included."""
+    import torch
+    cfg = configs.make_config(arch, img_size=128, backbones=bb, **over)
+    ref = ref_harness.build_reference_model(cfg)
+    synth.randomize_(ref, 1337)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    x = synth.synthetic_views(2, n, 128, 128, seed=7)
+    ref.train()
+    out = ref_harness.reference_forward(ref, x, **kw)
+    stats = {}
+    mine = orc.forward(sd0, cfg, x, train_stats=stats, **kw)
+    a = out[0] if isinstance(out, tuple) else out
+    b = mine[0] if isinstance(mine, tuple) else mine
+    assert float((a - b).abs().max()) <= 2e-5 * float(a.abs().max())
+    after = ref.state_dict()
+    assert stats, "no BatchNorm layer reported statistics"
+    for k, v in stats.items():
+        if torch.is_tensor(v):
+            assert float((after[k] - v).abs().max()) <= 1e-6 * max(1.0, float(v.abs().max())), k
+        else:
+            assert int(after[k]) == v, k

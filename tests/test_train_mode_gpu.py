@@ -1,0 +1,86 @@
+"""GPU: the train-mode FORWARD - model.train(); model(x, training=True, ...) as
+Trainer_*.train() calls it (ptsemseg/trainer.py:659-669): every BatchNorm2d normalises with batch statistics over the
+folded agent-batch and updates running_mean / running_var / num_batches_tracked in place (csrc/bn_train.cu).
+
+Checked against the oracle's train-mode restatement, which tests/test_oracle.py pins to the UNMODIFIED reference in
+train() mode: logits within the 1e-3 bound in the parity precisions, BatchNorm buffers after one and after two steps.
+The path is a forward only: outputs carry no autograd graph (the backward pass is not built)."""
+import pytest
+import torch
+
+from multiagentperception_b200 import configs, synth
+from multiagentperception_b200.models import get_model
+from oracle import when2com_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "mimocom_segnet": ("MIMOcom", "n_segnet", dict(agent_num=3), dict(training=True, MO_flag=True), 3),
+    "mimocom_resnet": ("MIMOcom", "resnet", dict(agent_num=3), dict(training=True, MO_flag=True), 3),
+    "single_segnet": ("Single_agent", "n_segnet", {}, {}, 1),
+    "single_segnet_squeeze2": ("Single_agent", "n_segnet", dict(feat_squeezer=2), {}, 1),
+    "when2com_resnet": ("LearnWhen2Com", "resnet", dict(query_size=8), dict(training=True), 5),
+}
+
+
+@pytest.mark.parametrize("precision", ["fp16x3", "bf16x3"])
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_train_mode_forward_matches_the_reference_semantics(name, precision, cuda_device):
+    arch, bb, over, kw, n = CASES[name]
+    cfg = configs.make_config(arch, img_size=128, backbones=bb, **over)
+    model = get_model(cfg, 11)
+    synth.randomize_(model, 1337)
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+    x = synth.synthetic_views(2, n, 128, 128, seed=7)
+    x2 = synth.synthetic_views(2, n, 128, 128, seed=8)
+    stats1 = {}
+    ref1 = orc.forward(sd0, cfg, x, train_stats=stats1, **kw)
+    sd1 = dict(sd0)
+    sd1.update({k: v for k, v in stats1.items() if torch.is_tensor(v)})
+    stats2 = {}
+    ref2 = orc.forward(sd1, cfg, x2, train_stats=stats2, **kw)
+    as_t = lambda o: o if isinstance(o, tuple) else (o,)
+
+    model = model.to(cuda_device).set_precision(precision)
+    model.train()
+    out1 = as_t(model(x.to(cuda_device), **kw))
+    assert not out1[0].requires_grad            # forward only: no autograd graph behind the outputs
+    rel = float((out1[0].cpu() - as_t(ref1)[0]).abs().max()) / float(as_t(ref1)[0].abs().max())
+    assert rel <= 1e-3, rel
+    if len(out1) > 1:
+        assert float((out1[1].cpu() - as_t(ref1)[1]).abs().max()) <= 1e-3
+    got = model.state_dict()
+    for k, v in stats1.items():
+        if torch.is_tensor(v):
+            assert float((got[k].cpu() - v).abs().max()) <= 2e-4 * max(1.0, float(v.abs().max())), k
+        else:
+            assert int(got[k]) == v, k
+    # second step: statistics accumulate on top of the first step's (and the captured CUDA graph replays correctly)
+    out2 = as_t(model(x2.to(cuda_device), **kw))
+    rel2 = float((out2[0].cpu() - as_t(ref2)[0]).abs().max()) / float(as_t(ref2)[0].abs().max())
+    assert rel2 <= 1e-3, rel2
+    got = model.state_dict()
+    for k, v in stats2.items():
+        if torch.is_tensor(v):
+            assert float((got[k].cpu() - v).abs().max()) <= 3e-4 * max(1.0, float(v.abs().max())), k
+        else:
+            assert int(got[k]) == 2, k
+    # back to eval: the folded BatchNorm now uses the UPDATED running statistics
+    model.eval()
+    sd2 = dict(sd1)
+    sd2.update({k: v for k, v in stats2.items() if torch.is_tensor(v)})
+    ekw = dict(kw)
+    if "training" in ekw:
+        ekw.update(training=False, inference="softmax")
+    ref_e = as_t(orc.forward(sd2, cfg, x, **ekw))
+    out_e = as_t(model(x.to(cuda_device), **ekw))
+    assert float((out_e[0].cpu() - ref_e[0]).abs().max()) / float(ref_e[0].abs().max()) <= 1e-3
+
+
+def test_train_mode_rejects_the_evaluation_only_options(cuda_device):
+    cfg = configs.make_config("Single_agent", img_size=128)
+    model = get_model(cfg, 11).to(cuda_device)
+    model.train()
+    model.set_label_output(True, logits=False)
+    with pytest.raises(RuntimeError):
+        model(synth.synthetic_views(1, 1, 128, 128).to(cuda_device))
