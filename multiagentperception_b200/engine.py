@@ -57,6 +57,13 @@ TWO_STREAMS = None if _TS is None else _TS == "1"
 FUSE_ENCODER_HEAD = os.environ.get("W2C_FUSE_ENDS", "1") != "0"
 
 
+# The one collective of a sharded forward (sharding.all_gather_slots) is captured INSIDE the step's CUDA graph: NCCL
+# collectives are graph-capturable once the communicator exists (the eager first run creates it), so the step stays
+# one graph launch and the host-side gap of splitting the program into two graphs around the collective disappears
+# (round 1, 8 GPUs: 0.5-0.7 ms of an 13.9 ms step). W2C_GRAPH_COLLECTIVE=0 restores the split.
+CAPTURE_COLLECTIVES = os.environ.get("W2C_GRAPH_COLLECTIVE", "1") != "0"
+
+
 def use_graphs_default():
     return os.environ.get("W2C_CUDA_GRAPH", "1") != "0"
 
@@ -550,11 +557,18 @@ class Program:
         self.keep.append(a)
         self._record(self._lib.w2c_attn_fuse_fwd, ctypes.byref(a))
 
-    def host_op(self, fn):
-        """A step that must run outside CUDA-graph capture (a torch.distributed collective): splits the program
-        into separately captured segments around it. fn() is called on the current stream at run time."""
+    def host_op(self, fn, capturable=False):
+        """A torch-side step between kernel launches (the torch.distributed collective of a sharded forward); fn() is
+        called on the current stream. capturable (and engine.CAPTURE_COLLECTIVES): it is recorded like a launch and
+        ends up inside the CUDA graph; otherwise it splits the program into separately captured segments."""
         if self._sid:
             raise RuntimeError("host ops cannot be recorded on the side stream")
+        if capturable and CAPTURE_COLLECTIVES:
+            def run(_stream):
+                fn()
+                return 0
+            self.calls.append((run, None, 0))
+            return
         self.calls.append((None, fn, 0))
 
     def gather_images(self, src, dst, b, n_groups, sel=None):

@@ -657,7 +657,7 @@ class MIMOcom(_AttentionModel):
             prog.keep.append(exchange)
             k_loc, q_loc, v_loc = lay.views(exchange)
             self._keys_queries(prog, x, b, apr, h, w, dst=(k_loc, q_loc, v_loc))
-            prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group))   # the one collective
+            prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group), capturable=True)   # the one collective
             k0, q0, v0 = lay.views(exchange, 0)
             val = engine.ActMap(v0, apr * b, fh, fw, fc)
             wq, bq, temp = self._attn_weights(prog)

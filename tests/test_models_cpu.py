@@ -59,7 +59,8 @@ def test_unknown_arch_and_backbones_raise_value_error():
 def test_no_silent_fallbacks():
     m = get_model(configs.make_config("MIMOcom", agent_num=2, img_size=128), 11)
     x = synth.synthetic_views(1, 2, 128, 128)
-    with pytest.raises(RuntimeError, match="eval-mode forward only"):
+    # train mode is a CUDA path too (batch-statistics BatchNorm, csrc/bn_train.cu): on a CPU tensor it fails loudly
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         m(x, training=True, MO_flag=True)
     m.eval()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
