@@ -9,6 +9,7 @@ PyTorch supplies device memory, streams and graphs only.
 """
 import ctypes
 import os
+import threading
 
 import torch
 
@@ -57,11 +58,17 @@ TWO_STREAMS = None if _TS is None else _TS == "1"
 FUSE_ENCODER_HEAD = os.environ.get("W2C_FUSE_ENDS", "1") != "0"
 
 
-# The one collective of a sharded forward (sharding.all_gather_slots) is captured INSIDE the step's CUDA graph: NCCL
-# collectives are graph-capturable once the communicator exists (the eager first run creates it), so the step stays
-# one graph launch and the host-side gap of splitting the program into two graphs around the collective disappears
-# (round 1, 8 GPUs: 0.5-0.7 ms of an 13.9 ms step). W2C_GRAPH_COLLECTIVE=0 restores the split.
-CAPTURE_COLLECTIVES = os.environ.get("W2C_GRAPH_COLLECTIVE", "1") != "0"
+# Experiment, off by default (W2C_GRAPH_COLLECTIVE=1): capture the one collective of a sharded forward
+# (sharding.all_gather_slots) INSIDE the step's CUDA graph instead of splitting the program into two graphs around it.
+# Measured on 2 x B200: the same throughput as the split (7123 vs 7129 agent-frames/s - the host gap is hidden by the
+# asynchronous launch queue) and destroy_process_group() then hangs at exit, so the split stays.
+CAPTURE_COLLECTIVES = os.environ.get("W2C_GRAPH_COLLECTIVE", "0") == "1"
+
+
+# CUDA-graph capture is serialised across host threads (one model per device per thread is the nn.DataParallel shape,
+# train.py:177) and runs in thread-local error mode: another thread's allocations or synchronisations would otherwise
+# invalidate a capture in flight (seen on 2 GPUs: "The CUDA Graph is empty", stale outputs on replay).
+_CAPTURE_LOCK = threading.Lock()
 
 
 def use_graphs_default():
@@ -668,7 +675,7 @@ class Program:
                 g = None
                 if calls:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with _CAPTURE_LOCK, torch.cuda.graph(g, capture_error_mode="thread_local"):
                         self._run_calls(calls)
                 graphs.append((g, host))
             self.graph = graphs
