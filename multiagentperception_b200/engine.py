@@ -224,6 +224,7 @@ class Program:
         self.calls = []      # (fn, args tuple, stream id) with the stream appended at run time; see side_stream()
         self._sid = 0        # stream id new calls are recorded on (0 = the caller's stream, 1 = the side stream)
         self._side = None    # torch.cuda.Stream of the side chain, created on first use
+        self._capture_stream = None
         self.keep = []       # keeps ctypes structs / tensors alive
         self.graph = None
         self.n_launches = 0  # kernel launches per run (counted from the library's counter)
@@ -675,7 +676,12 @@ class Program:
                 g = None
                 if calls:
                     g = torch.cuda.CUDAGraph()
-                    with _CAPTURE_LOCK, torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    # an explicit capture stream on THIS program's device: torch.cuda.graph's default capture stream
+                    # is created once per process, on whichever device captured first
+                    if self._capture_stream is None:
+                        self._capture_stream = torch.cuda.Stream(self.device)
+                    with _CAPTURE_LOCK, torch.cuda.graph(g, stream=self._capture_stream,
+                                                         capture_error_mode="thread_local"):
                         self._run_calls(calls)
                 graphs.append((g, host))
             self.graph = graphs
