@@ -275,6 +275,7 @@ class Program:
                 if enabled:
                     prog.calls.append((Program._FORK, None, 0))
                     prog._sid = 1
+                return enabled
 
             def __exit__(self, *exc):
                 prog._sid = 0

@@ -487,9 +487,12 @@ class _AttentionModel(_W2CModel):
             prog.weights._misc[key] = u
         return u
 
-    def _keys_queries(self, prog, x, b, n, h, w, dst=None):
+    def _keys_queries(self, prog, x, b, n, h, w, dst=None, after_values=None):
         """u_encoder features, key and query vectors for the n agents in x (agent.py:1111-1148). dst = (keys,
-        queries, val) tensors to write into (the rank's slot of the exchange buffer when agents are sharded)."""
+        queries, val) tensors to write into (the rank's slot of the exchange buffer when agents are sharded).
+        after_values(): recorded right after the feature encoder when that chain is NOT forked onto the side stream
+        (the sharded forward starts its feature-map all-gather there); returns True if it did."""
+        prog.values_hook_ran = False
         val_out = None
         if dst is not None:
             val_out = engine.ActMap(dst[2], n * b, dst[2].shape[1], dst[2].shape[2], dst[2].shape[3] // prog.planes)
@@ -505,9 +508,12 @@ class _AttentionModel(_W2CModel):
             # the feature encoder runs beside the policy net + heads (independent chains); worth it for the resnet
             # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
             small_kernels = isinstance(self.u_encoder.feature_backbone, resnet_encoder)
-            with prog.side_stream(auto=small_kernels):
+            with prog.side_stream(auto=small_kernels) as forked:
                 val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u,
                                      stack=self._value_stack)
+            if after_values is not None and not forked:
+                after_values()
+                prog.values_hook_ran = True
         else:
             # separate encoders per agent group (agent.py:579-594,823-838), each writing its agents' images of the
             # agent-major feature buffer
@@ -656,8 +662,23 @@ class MIMOcom(_AttentionModel):
             exchange = lay.allocate(prog.device)
             prog.keep.append(exchange)
             k_loc, q_loc, v_loc = lay.views(exchange)
-            self._keys_queries(prog, x, b, apr, h, w, dst=(k_loc, q_loc, v_loc))
-            prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group), capturable=True)   # the one collective
+            # The exchange: the feature maps (99 % of the bytes) are gathered asynchronously right after the feature
+            # encoder and travel over NVLink while the policy net runs; only the key / query gather sits before the
+            # attention. (Chains forked onto two streams - the resnet pair - keep the single gather at the end.)
+            pending = {}
+
+            def start_values():
+                prog.host_op(lambda: pending.__setitem__(
+                    "work", sharding.all_gather_values(exchange, lay, group, async_op=True)))
+
+            self._keys_queries(prog, x, b, apr, h, w, dst=(k_loc, q_loc, v_loc), after_values=start_values)
+            if prog.values_hook_ran:
+                def finish():
+                    sharding.all_gather_keys_queries(exchange, lay, group)
+                    pending.pop("work").wait()
+                prog.host_op(finish)
+            else:
+                prog.host_op(lambda: sharding.all_gather_slots(exchange, lay, group), capturable=True)
             k0, q0, v0 = lay.views(exchange, 0)
             val = engine.ActMap(v0, apr * b, fh, fw, fc)
             wq, bq, temp = self._attn_weights(prog)

@@ -1,14 +1,17 @@
-"""Agent sharding across GPUs: one process per GPU, agents split evenly over the ranks, ONE all-gather per forward.
+"""Agent sharding across GPUs: one process per GPU, agents split evenly over the ranks.
 
 Everything before the attention (encoder, policy net, key/query heads) and after it (decoder) is per-agent
 independent; the attention needs every agent's key, query and feature map. Each rank writes
-those three things for its local agents straight into its own slot of a packed exchange buffer
+those three things for its local agents straight into its own slots of a packed exchange buffer
 
-    slot(rank) = [ keys  f32 [apr*B][k_dim] | queries f32 [apr*B][q_dim] | feature maps bf16 [apr*B][h][w][P*C] ]
+    [ feature-map region: world x slot_v ]   slot_v(rank)  = bf16 [apr*B][h][w][P*C]
+    [ key/query region:   world x slot_kq ]  slot_kq(rank) = keys f32 [apr*B][k_dim] | queries f32 [apr*B][q_dim]
 
-(apr = agents per rank, sub-regions padded to 256 B) and a single in-place all_gather_into_tensor over NCCL /
-NVLink fills the other slots. The attention kernel then reads the gathered buffer directly through the per-rank
-strides of w2c_attn_args; there is no pack or unpack copy.
+(apr = agents per rank, slots padded to 256 B) and in-place all_gather_into_tensor calls over NCCL / NVLink fill the
+other ranks' slots. The exchange is ONE logical step split in two so that it hides: the feature maps (99 % of the bytes)
+are gathered asynchronously as soon as the feature encoder has written them and travel while the policy net runs; only
+the key/query gather (a few KB per scene) sits on the critical path before the attention. The attention kernel reads
+the gathered buffer directly through the per-rank strides of w2c_attn_args; there is no pack or unpack copy.
 """
 import torch
 
@@ -31,40 +34,50 @@ class AgentShardLayout:
         self.keys_bytes = rows * k_dim * 4
         self.queries_bytes = rows * q_dim * 4
         self.val_bytes = rows * h * w * planes * c * 2
-        self.keys_off = 0
-        self.queries_off = _pad(self.keys_bytes)
-        self.val_off = self.queries_off + _pad(self.queries_bytes)
-        self.slot_bytes = self.val_off + _pad(self.val_bytes)
+        # per-rank slots
+        self.val_slot_bytes = _pad(self.val_bytes)
+        self.queries_off = _pad(self.keys_bytes)                 # inside a key/query slot
+        self.kq_slot_bytes = self.queries_off + _pad(self.queries_bytes)
+        # regions of the exchange buffer
+        self.val_region_off = 0
+        self.kq_region_off = world * self.val_slot_bytes
+        self.total_bytes = self.kq_region_off + world * self.kq_slot_bytes
 
     # strides between rank slots, in elements of each sub-array's dtype (what w2c_attn_args wants)
     @property
     def keys_rank_stride(self):
-        return self.slot_bytes // 4
+        return self.kq_slot_bytes // 4
 
     @property
     def queries_rank_stride(self):
-        return self.slot_bytes // 4
+        return self.kq_slot_bytes // 4
 
     @property
     def val_rank_stride(self):
-        return self.slot_bytes // 2
+        return self.val_slot_bytes // 2
 
     @property
     def first_agent(self):
         return self.rank * self.apr
 
     def allocate(self, device):
-        return torch.zeros((self.world, self.slot_bytes), dtype=torch.uint8, device=device)
+        return torch.zeros(self.total_bytes, dtype=torch.uint8, device=device)
+
+    def val_region(self, exchange):
+        return exchange[self.val_region_off:self.val_region_off + self.world * self.val_slot_bytes]
+
+    def kq_region(self, exchange):
+        return exchange[self.kq_region_off:self.kq_region_off + self.world * self.kq_slot_bytes]
 
     def views(self, exchange, rank=None):
-        """Typed views (keys, queries, val) of one rank's slot of the exchange buffer."""
+        """Typed views (keys, queries, val) of one rank's slots of the exchange buffer."""
         r = self.rank if rank is None else rank
         rows = self.apr * self.batch
-        slot = exchange[r]
-        keys = slot[self.keys_off:self.keys_off + self.keys_bytes].view(torch.float32).view(rows, self.k_dim)
-        queries = slot[self.queries_off:self.queries_off + self.queries_bytes].view(torch.float32).view(rows, self.q_dim)
-        val = slot[self.val_off:self.val_off + self.val_bytes].view(torch.bfloat16).view(
-            rows, self.h, self.w, self.planes * self.c)
+        kq = self.kq_region(exchange)[r * self.kq_slot_bytes:(r + 1) * self.kq_slot_bytes]
+        keys = kq[:self.keys_bytes].view(torch.float32).view(rows, self.k_dim)
+        queries = kq[self.queries_off:self.queries_off + self.queries_bytes].view(torch.float32).view(rows, self.q_dim)
+        vs = self.val_region(exchange)[r * self.val_slot_bytes:r * self.val_slot_bytes + self.val_bytes]
+        val = vs.view(torch.bfloat16).view(rows, self.h, self.w, self.planes * self.c)
         return keys, queries, val
 
     def dense(self, exchange):
@@ -73,11 +86,26 @@ class AgentShardLayout:
         return tuple(torch.cat([p[i] for p in parts], 0) for i in range(3))
 
 
-def all_gather_slots(exchange, layout, group=None):
-    """The one collective of the forward: every rank contributes its slot, in place."""
+def _gather_region(region, slot_bytes, rank, group, async_op=False):
     import torch.distributed as dist
-    flat = exchange.view(-1)
-    mine = exchange[layout.rank]
+    mine = region[rank * slot_bytes:(rank + 1) * slot_bytes]
     if dist.get_backend(group) == "gloo":
         mine = mine.clone()  # gloo does not document in-place all-gather; the CPU tests take the copy
-    dist.all_gather_into_tensor(flat, mine, group=group)
+    return dist.all_gather_into_tensor(region, mine, group=group, async_op=async_op)
+
+
+def all_gather_values(exchange, layout, group=None, async_op=False):
+    """Feature maps of every rank -> every rank. async_op=True returns the work handle: the transfer then runs on
+    NCCL's own stream behind whatever the current stream has queued so far, concurrently with what is queued next."""
+    return _gather_region(layout.val_region(exchange), layout.val_slot_bytes, layout.rank, group, async_op)
+
+
+def all_gather_keys_queries(exchange, layout, group=None):
+    """Key and query vectors of every rank -> every rank (small; on the critical path before the attention)."""
+    return _gather_region(layout.kq_region(exchange), layout.kq_slot_bytes, layout.rank, group)
+
+
+def all_gather_slots(exchange, layout, group=None):
+    """The whole exchange in one go (both regions, synchronously ordered on the current stream)."""
+    all_gather_values(exchange, layout, group)
+    all_gather_keys_queries(exchange, layout, group)

@@ -37,21 +37,24 @@ def _worker(rank, world, port, planes, ret):
         k.copy_(keys[rows])
         q.copy_(queries[rows])
         v.copy_(val[rows])
-        sharding.all_gather_slots(ex, lay)
+        work = sharding.all_gather_values(ex, lay, async_op=True)   # the two-step exchange of the sharded forward
+        sharding.all_gather_keys_queries(ex, lay)
+        work.wait()
         dk, dq, dv = lay.dense(ex)
         ok = torch.equal(dk, keys) and torch.equal(dq, queries) and torch.equal(dv, val)
         # strides the kernel will use address the same data: agent i, scene b
-        flat32 = ex.view(-1).view(torch.float32)
-        flat16 = ex.view(-1).view(torch.bfloat16)
+        # (base pointers = rank 0's arrays, as models/agents.py passes them; strides in elements of each dtype)
+        flat32 = lay.kq_region(ex).view(torch.float32)
+        flat16 = lay.val_region(ex).view(torch.bfloat16)
         for i in range(AGENTS):
             r, l = divmod(i, lay.apr)
             for b in range(BATCH):
-                base = r * lay.keys_rank_stride + lay.keys_off // 4 + (l * BATCH + b) * KD
+                base = r * lay.keys_rank_stride + (l * BATCH + b) * KD
                 ok &= torch.equal(flat32[base:base + KD], keys[i * BATCH + b])
                 base = r * lay.queries_rank_stride + lay.queries_off // 4 + (l * BATCH + b) * QD
                 ok &= torch.equal(flat32[base:base + QD], queries[i * BATCH + b])
                 per_img = H * W * planes * C
-                base = r * lay.val_rank_stride + lay.val_off // 2 + (l * BATCH + b) * per_img
+                base = r * lay.val_rank_stride + (l * BATCH + b) * per_img
                 ok &= torch.equal(flat16[base:base + per_img], val[i * BATCH + b].reshape(-1))
         # attention over the gathered arrays == attention over the unsharded ones
         sd = {"a.linear.weight": torch.randn(KD, QD, generator=torch.Generator().manual_seed(1)),

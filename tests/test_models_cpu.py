@@ -123,12 +123,14 @@ def test_shard_layout_geometry():
                                     planes=1)
     assert lay.apr == 2 and lay.first_agent == 4
     assert lay.keys_bytes == 2 * 3 * 1024 * 4 and lay.val_bytes == 2 * 3 * 256 * 512 * 2
-    assert lay.queries_off % 256 == 0 and lay.val_off % 256 == 0 and lay.slot_bytes % 256 == 0
+    assert lay.queries_off % 256 == 0 and lay.val_slot_bytes % 256 == 0 and lay.kq_slot_bytes % 256 == 0
+    assert lay.kq_region_off % 256 == 0 and lay.total_bytes == 4 * (lay.val_slot_bytes + lay.kq_slot_bytes)
     ex = lay.allocate("cpu")
     k, q, v = lay.views(ex)
     assert k.shape == (6, 1024) and q.shape == (6, 32) and v.shape == (6, 16, 16, 512)
     k.fill_(1.5)
-    assert float(ex[2, :lay.keys_bytes].view(torch.float32).sum()) == 1.5 * 6 * 1024
-    assert float(ex[1].sum()) == 0
+    mine = lay.kq_region(ex)[2 * lay.kq_slot_bytes:3 * lay.kq_slot_bytes]
+    assert float(mine[:lay.keys_bytes].view(torch.float32).sum()) == 1.5 * 6 * 1024
+    assert float(ex.sum()) == float(mine.sum())
     with pytest.raises(ValueError):
         sharding.AgentShardLayout(5, 2, 0, 1, 8, 8, 4, 4, 8, 1)
