@@ -334,7 +334,9 @@ typedef struct w2c_attn_args {
    * queries [q_first, q_first + q_count) are fused and written, as images 0..q_count*b_sz of `fused`
    * (q_count = 0: all n_q).  keys / queries / val may point into an all-gathered buffer in which every rank
    * contributed agents_per_rank agents: agent i is row-block (i % agents_per_rank) of rank segment
-   * (i / agents_per_rank), segments *_rank_stride ELEMENTS apart (agents_per_rank = 0: dense agent-major). */
+   * (i / agents_per_rank), segments *_rank_stride ELEMENTS apart (agents_per_rank = 0: dense agent-major).  * Alignment: val and fused must be 16-byte aligned (bulk copies / 16-byte stores), wq 16-byte aligned when
+ * q_dim is a multiple of 4 (vector loads of the projection rows); checked, W2C_ERR_INVALID otherwise.
+ */
   int32_t q_first, q_count;
   int32_t agents_per_rank;
   int64_t keys_rank_stride, queries_rank_stride, val_rank_stride;

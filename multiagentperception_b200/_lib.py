@@ -123,8 +123,15 @@ def load():
         if _lib is not None:
             return _lib
         path = os.environ.get("W2C_LIB") or _build.LIB_PATH   # W2C_LIB: an alternative build, for A/B runs
-        if path == _build.LIB_PATH and (not os.path.exists(path) or os.environ.get("W2C_REBUILD") == "1"):
-            path = _build.build()
+        if path == _build.LIB_PATH:
+            # build() is a no-op when lib/libw2c.stamp equals the fingerprint of the sources + flags, and recompiles
+            # otherwise: an edited .cu / .cuh / w2c.h can never run against a stale binary. Where the sources are
+            # there but nvcc is not (it always is in this image), a stale library is an error, not a warning.
+            try:
+                path = _build.build(force=os.environ.get("W2C_REBUILD") == "1")
+            except RuntimeError as e:
+                if not os.path.exists(path) or not _build.is_current():
+                    raise W2CError("libw2c.so is missing or older than its sources and cannot be rebuilt: %s" % e)
         lib = ctypes.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError = the .so is stale / incomplete: fail loudly

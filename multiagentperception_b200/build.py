@@ -41,6 +41,14 @@ def _fingerprint(extra_flags):
     return h.hexdigest()
 
 
+def is_current(extra_flags=()):
+    """True when lib/libw2c.so exists and its stamp equals the fingerprint of the present sources and flags."""
+    if not (os.path.exists(LIB_PATH) and os.path.exists(STAMP)):
+        return False
+    with open(STAMP) as f:
+        return f.read().strip() == _fingerprint(extra_flags)
+
+
 def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile every CUDA source for sm_100a into lib/libw2c.so (or `out`: a variant build, e.g. the instrumented one
     tools/time_enc_head.py makes with -DW2C_HEAD_TIMING; variants are never stamped). Returns the library path."""

@@ -276,6 +276,13 @@ extern "C" int w2c_attn_fuse_fwd(const w2c_attn_args* args, w2c_stream_t stream)
   W2C_CHECK_ARG(a.hw > 0 && a.c > 0 && a.c % 8 == 0, "attn: c=%d must be a multiple of 8", a.c);
   W2C_CHECK_ARG(a.mode >= W2C_FUSE_SOFTMAX && a.mode <= W2C_FUSE_ARGMAX, "attn: bad mode %d", a.mode);
   W2C_CHECK_ARG(a.temperature != 0.f, "attn: temperature must be non-zero");
+  // 16-byte vector loads of the projection rows and bulk copies / 16-byte stores of the feature maps
+  W2C_CHECK_ARG(!a.wq || a.q_dim % 4 != 0 || reinterpret_cast<uintptr_t>(a.wq) % 16 == 0,
+                "attn: wq must be 16-byte aligned when q_dim is a multiple of 4");
+  W2C_CHECK_ARG(reinterpret_cast<uintptr_t>(a.val) % 16 == 0 && reinterpret_cast<uintptr_t>(a.fused) % 16 == 0,
+                "attn: val and fused must be 16-byte aligned");
+  W2C_CHECK_ARG(a.agents_per_rank == 0 || (a.val_rank_stride * 2) % 16 == 0,
+                "attn: val_rank_stride must keep every rank's feature maps 16-byte aligned");
   W2C_CHECK_ARG(!a.mask_self || a.n_k > 1, "attn: mask_self needs at least two supporting agents");
   W2C_CHECK_ARG(a.q_first >= 0 && a.q_count >= 0 && a.q_first + a.q_count <= a.n_q, "attn: fused query window "
                 "[%d, %d) outside n_q=%d", a.q_first, a.q_first + a.q_count, a.n_q);

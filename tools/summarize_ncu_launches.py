@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """Turn the ncu launch list of one bench step (the `--metrics gpu__time_duration.sum,dram__bytes_read.sum,
-dram__bytes_write.sum,...` pass of tools/profile_step.sh) into a markdown table + profiles/r1_traffic.json, which
+dram__bytes_write.sum,...` pass, see the command in the written file) into a markdown table + profiles/r2_traffic.json, which
 bench.py reads for roofline.traffic.
 
-    python tools/summarize_ncu_launches.py gpurun_out/launches.csv profiles/r1_ncu_launches_vN.md
+    python tools/summarize_ncu_launches.py gpurun_out/launches.csv profiles/r2_ncu_launches_vN.md
 """
 import csv
 import json
@@ -22,7 +22,7 @@ def main(src, dst):
         name = r[4].replace("void w2c::<unnamed>::", "").replace("w2c::<unnamed>::", "").split("(")[0]
         launches.setdefault(key, {"name": name, "grid": r[8], "block": r[7]})[r[-3]] = float(r[-1].replace(",", ""))
     total = sum(v["gpu__time_duration.sum"] for v in launches.values())
-    conv = [v for v in launches.values() if v["name"].startswith("conv_")]
+    conv = [v for v in launches.values() if v["name"].startswith("conv_") or v["name"].startswith("enc_head")]
     conv_bytes = sum(v.get("dram__bytes_read.sum", 0) + v.get("dram__bytes_write.sum", 0) for v in conv)
     conv_ns = sum(v["gpu__time_duration.sum"] for v in conv)
     with open(dst, "w") as f:
@@ -42,9 +42,13 @@ def main(src, dst):
                 "DRAM traffic %.1f MB per step = %.1f MB per launch\n" % (
                     total / 1e3, len(launches), len(conv), conv_ns / 1e3, 100 * conv_ns / total, conv_bytes / 1e6,
                     conv_bytes / 1e6 / max(1, len(conv))))
-    with open(os.path.join(ROOT, "profiles", "r1_traffic.json"), "w") as f:
+    sys.path.insert(0, ROOT)
+    from multiagentperception_b200 import build as _b
+    with open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w") as f:
+        # csrc_fingerprint: bench.py reports this traffic only while the kernel sources are the ones it was measured on
         json.dump({"conv_launches": len(conv), "conv_dram_bytes_per_step": conv_bytes,
-                   "conv_share_of_step_ncu": conv_ns / total, "source": os.path.basename(dst)}, f, indent=1)
+                   "conv_share_of_step_ncu": conv_ns / total, "source": os.path.basename(dst),
+                   "csrc_fingerprint": _b._fingerprint(())[:16]}, f, indent=1)
     print("wrote", dst)
 
 
