@@ -52,6 +52,8 @@ def default_precision():
 # (3399 / 3386 vs 3419 agent-frames/s serial - that step runs at the 1 kW power cap, where overlapping kernels cannot
 # add throughput) but +7 % for the resnet18 pair, whose 55 launches of 20-90 us each leave SMs idle (12310 -> 13208
 # agent-frames/s, two runs each): the models switch it on for resnet backbones.
+# n_segnet steps of at most this many input pixels per rank also fork (measured: see profiles/r2_bench.md, B = 1 rows)
+TWO_STREAM_MAX_PIXELS = int(os.environ.get("W2C_TWO_STREAM_MAX_PIXELS", str(8 * 512 * 512)))
 _TS = os.environ.get("W2C_TWO_STREAMS")
 TWO_STREAMS = None if _TS is None else _TS == "1"
 

@@ -507,7 +507,10 @@ class _AttentionModel(_W2CModel):
                 stem_u, stem_p = _fused_stems(prog, self.u_encoder, self.query_key_net.img_encoder, x, b, n, h, w)
             # the feature encoder runs beside the policy net + heads (independent chains); worth it for the resnet
             # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
-            small_kernels = isinstance(self.u_encoder.feature_backbone, resnet_encoder)
+            # ... and for small steps (latency points: at <= 8 agent-frames the <= 64x64 layers of either chain give
+            # a 148-SM part 2-32 tiles each, so the two chains fill each other's idle SMs)
+            small_kernels = (isinstance(self.u_encoder.feature_backbone, resnet_encoder)
+                             or n * b * h * w <= engine.TWO_STREAM_MAX_PIXELS)
             with prog.side_stream(auto=small_kernels) as forked:
                 val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u,
                                      stack=self._value_stack)
