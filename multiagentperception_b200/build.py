@@ -49,29 +49,73 @@ def is_current(extra_flags=()):
         return f.read().strip() == _fingerprint(extra_flags)
 
 
+def _compile_flags():
+    return [f for f in NVCC_FLAGS if f != "-shared"]
+
+
+def _object_for(name, extra_flags, obj_dir):
+    """Object file of one source, named by the hash of that source, every header and the flags: editing one .cu
+    recompiles one object (the link takes a second), editing a header recompiles all."""
+    h = hashlib.sha256()
+    for dep in [name] + HEADERS:
+        with open(os.path.join(CSRC, dep), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(_compile_flags() + list(extra_flags)).encode())
+    return os.path.join(obj_dir, "%s.%s.o" % (os.path.splitext(name)[0], h.hexdigest()[:16]))
+
+
+def _compile_and_link(extra_flags, out, verbose=False):
+    """Compile the sources as parallel nvcc processes (one object each, cached under lib/obj) and link them."""
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    nvcc = _nvcc()
+    objs, procs = [], []
+    for name in SOURCES:
+        obj = _object_for(name, extra_flags, obj_dir)
+        objs.append(obj)
+        if not os.path.exists(obj):
+            tmp = obj + ".tmp%d" % os.getpid()
+            cmd = [nvcc] + _compile_flags() + list(extra_flags) + ["-c", os.path.join(CSRC, name), "-o", tmp]
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+            procs.append((name, obj, tmp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    errors = []
+    for name, obj, tmp, pr in procs:
+        log, _ = pr.communicate()
+        if pr.returncode != 0:
+            errors.append("%s:\n%s" % (name, log))
+        else:
+            os.replace(tmp, obj)
+            if verbose and log:
+                print(log, file=sys.stderr)
+    if errors:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(errors))
+    # drop objects of older source versions
+    keep = {os.path.basename(o) for o in objs}
+    for f in os.listdir(obj_dir):
+        if f.endswith(".o") and f not in keep:
+            os.remove(os.path.join(obj_dir, f))
+    cmd = [nvcc] + NVCC_FLAGS + objs + ["-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + "\n" + res.stderr)
+    return out
+
+
 def build(force=False, verbose=False, extra_flags=(), out=None):
     """Compile every CUDA source for sm_100a into lib/libw2c.so (or `out`: a variant build, e.g. the instrumented one
     tools/time_enc_head.py makes with -DW2C_HEAD_TIMING; variants are never stamped). Returns the library path."""
     os.makedirs(LIB_DIR, exist_ok=True)
     if out is not None:
-        cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", out]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise RuntimeError("nvcc failed:\n" + res.stdout + "\n" + res.stderr)
-        return out
+        return _compile_and_link(extra_flags, out, verbose)
     fp = _fingerprint(extra_flags)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(STAMP):
         with open(STAMP) as f:
             if f.read().strip() == fp:
                 return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + list(extra_flags) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    if verbose:
-        print(" ".join(cmd), file=sys.stderr)
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + "\n" + res.stderr)
-    if verbose and (res.stdout or res.stderr):
-        print(res.stdout + res.stderr, file=sys.stderr)
+    if force:
+        shutil.rmtree(os.path.join(LIB_DIR, "obj"), ignore_errors=True)
+    _compile_and_link(extra_flags, LIB_PATH, verbose)
     with open(STAMP, "w") as f:
         f.write(fp)
     return LIB_PATH
