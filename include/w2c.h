@@ -162,16 +162,21 @@ int w2c_enc_head_fwd(const w2c_enc_head_args* args, w2c_stream_t stream);
  *            nn.BatchNorm2d (momentum, UNBIASED variance, counter + 1); NULL = track_running_stats off
  *   sums_ws  fp64 [2*c], ZEROED by the caller once (the call leaves it zeroed again); scale_ws / shift_ws fp32 [c].
  * c must be a multiple of 8 with c / 8 dividing 256.  Three launches: statistics, finalize, apply.
+ *   y_out    NULL: normalise z in place.  Otherwise the result goes to y_out (NHWC in `act`, channels [y_coffset,
+ *            y_coffset + c) of y_cstride; a residual is then laid out like y_out) and z keeps the raw conv output -
+ *            what the backward pass (w2c_bn_train_bwd) needs.
+ *   stats_out  NULL, or fp32 [2*c] receiving mean | 1/sqrt(var + eps) of this batch for the backward pass.
  */
 int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
                      int32_t act, int32_t relu, const float* gamma, const float* beta, float eps, float momentum,
                      float* running_mean, float* running_var, int64_t* num_batches_tracked, double* sums_ws,
-                     float* scale_ws, float* shift_ws, w2c_stream_t stream);
+                     float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride, int32_t y_coffset,
+                     float* stats_out, w2c_stream_t stream);
 /* The same on an fp32 NCHW map [n][c][hw] (the logits layer: deconv12 is conv + BatchNorm + ReLU, backbone.py:124). */
 int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw, int32_t relu, const float* gamma,
                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,
                           int64_t* num_batches_tracked, double* sums_ws, float* scale_ws, float* shift_ws,
-                          w2c_stream_t stream);
+                          float* y_out, float* stats_out, w2c_stream_t stream);
 /* First layers without the ReLU (the raw conv output train-mode BatchNorm starts from); arguments as
  * w2c_stem_conv3x3_fwd / w2c_stem_conv7x7s2_fwd. */
 int w2c_stem_conv3x3_raw_fwd(const float* x, const float* w, const float* scale, const float* shift, void* y, int32_t b,
@@ -377,6 +382,161 @@ int w2c_gather_images_fwd(const void* src, void* dst, const int32_t* sel, int32_
  * label-map output of a simple_decoder model; equals w2c_bilinear_up_fwd + w2c_argmax_labels_fwd bit for bit). */
 int w2c_bilinear_argmax_fwd(const float* x, uint8_t* labels, int32_t n, int32_t c, int32_t h, int32_t w_px,
                             int32_t factor, w2c_stream_t stream);
+
+/* ---- backward pass (second half): loss.backward() of Trainer_*.train(), ptsemseg/trainer.py:668-670 ---
+ * Gradient maps are NHWC like the activations, in their own storage `act_g` (bf16 / bf16 hi|lo planes: gradients need
+ * the fp32 exponent range); `act_f` is the storage of the forward maps they are combined with.  Parameter gradients
+ * are fp32 and ACCUMULATED (+=) like autograd's .grad. */
+
+/*
+ * Weight gradient of a conv / transposed conv on the tensor cores (csrc/wgrad.cu).  Replaces the weight-gradient half of
+ * autograd's conv backward for the Conv2d / ConvTranspose2d of conv2DBatchNormRelu / deconv2DBatchNormRelu
+ * (ptsemseg/models/utils.py:87-120,148-168).
+ *   x    the layer's forward INPUT map, n x h_in x w_in pixels, channels [x_coffset, x_coffset + cin) of x_cstride
+ *   dy   gradient w.r.t. the conv's raw OUTPUT (h_out x w_out as the kind implies), channels [dy_coffset, + cout)
+ *   dw   fp32, +=:  Conv2d kinds [cout][ntaps][cin];  W2C_DECONV3X3_S2 [cin][ntaps][cout]   (tap = kh*3 + kw; both are
+ *        the parameter's [d0][d1][kh][kw] layout with the last three axes permuted: .view(d0,3,3,d1).permute(0,3,1,2))
+ * cin and cout as the MAPS hold them: multiples of 64 (an 11-class logits gradient lives in a 64-channel padded map),
+ * and 64 or a multiple of 128 on the small-grid operand (dy for convs, x for the transposed conv).
+ * act_x and act_dy must agree in plane count and element type (a mixed f16 x bf16 MMA faults on B200); passes as in
+ * w2c_conv_args.
+ */
+typedef struct w2c_wgrad_args {
+  const void* x;
+  const void* dy;
+  float* dw;
+  int32_t n, h_in, w_in;
+  int32_t cin, cout;
+  int32_t x_cstride, x_coffset;
+  int32_t dy_cstride, dy_coffset;
+  int32_t kind;
+  int32_t act_x, act_dy;
+  int32_t passes;
+} w2c_wgrad_args;
+int w2c_conv_wgrad(const w2c_wgrad_args* args, w2c_stream_t stream);
+
+/* w2c_pack_conv_weight with an optional tap flip (tap -> ntaps-1-tap): the operand of the DATA-gradient convs, which run
+ * on w2c_conv_bnrelu_fwd (scale = 1, shift = 0) over dL/dy:
+ *   Conv2d k3 s1 [co][ci][k]      -> W2C_CONV3X3_S1,   pack(w, cout=ci, cin=co, transposed=1, flip=1)
+ *   Conv2d k3 s2                  -> W2C_DECONV3X3_S2, pack(w, cout=ci, cin=co, transposed=1, flip=0)
+ *   ConvTranspose2d k3 s2 [ci][co][k] -> W2C_CONV3X3_S2, pack(w, cout=ci, cin=co, transposed=0, flip=0)
+ *   Conv2d k1 (s1, or s2 followed by w2c_upsample_zero2) -> W2C_CONV1X1_S1, pack(w, cout=ci, cin=co, transposed=1) */
+int w2c_pack_conv_weight_ex(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
+                            int32_t transposed, int32_t flip, int32_t act, void* packed, w2c_stream_t stream);
+
+/*
+ * Backward of train-mode BatchNorm2d (+ residual) (+ ReLU) between the gradient of the unit's output and the gradient
+ * of the raw conv output (nn.BatchNorm2d + nn.ReLU of cbr_unit / dcbr_unit, utils.py:110-114,152-164; BasicBlock tail).
+ *   du = dy * [y > 0] (relu);  dres = du;  dbeta += sum du;  dgamma += sum du * xhat;
+ *   dz = gamma * invstd * (du - mean(du) - xhat * mean(du * xhat)),  xhat = (z - mean) * invstd
+ * stats = the fp32 [2c] mean | invstd the train forward saved; stats == NULL: no BatchNorm (dz = du, dbeta = conv-bias
+ * gradient).  y is only read when relu != 0, z only with stats.  sums_ws fp64 [2c] zeroed by the caller once (left zeroed),
+ * coef_ws fp32 [3c].  dres may be NULL.  Channel strides 0 = c.
+ */
+typedef struct w2c_bn_bwd_args {
+  const void* dy;
+  const void* y;
+  const void* z;
+  void* dz;
+  void* dres;
+  int64_t n_px;
+  int32_t c;
+  int32_t dy_cstride, dy_coffset;
+  int32_t y_cstride, y_coffset;
+  int32_t z_cstride, z_coffset;
+  int32_t dz_cstride, dz_coffset;
+  int32_t dres_cstride, dres_coffset;
+  int32_t act_f, act_g, relu;
+  const float* gamma;
+  const float* stats;
+  float* dgamma;
+  float* dbeta;
+  double* sums_ws;
+  float* coef_ws;
+} w2c_bn_bwd_args;
+int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream);
+/* The same for the fp32 NCHW logits layer: dy / y / z fp32 [n][c][hw]; dz is written as an NHWC gradient map of c_pad
+ * channels (c .. c_pad-1 zero) at [dz_coffset, dz_coffset + c_pad) of dz_cstride - the input of the data- and
+ * weight-gradient convs of that layer. */
+int w2c_bn_train_nchw_bwd(const float* dy, const float* y, const float* z, void* dz, int32_t n, int32_t c, int64_t hw,
+                          int32_t c_pad, int32_t dz_cstride, int32_t dz_coffset, int32_t act_g, int32_t relu,
+                          const float* gamma, const float* stats, float* dgamma, float* dbeta, double* sums_ws,
+                          float* coef_ws, w2c_stream_t stream);
+
+/*
+ * Backward of w2c_attn_fuse_fwd in its differentiable mode (W2C_FUSE_SOFTMAX, what forward(training=True) runs,
+ * agent.py:1170-1179): autograd through MIMOGeneralDotProductAttention.forward (agent.py:252-286) and the
+ * single-request attentions (agent.py:194-213,345-368).  prob = the UN-biased probabilities the forward fused with
+ * (its coef_out).  Outputs: dval (NHWC act_g, dense, n_k*b_sz images; dval_accumulate != 0 adds to what is there),
+ * dkeys fp32 [n_k*b_sz][k_dim], dqueries fp32 [n_q*b_sz][q_dim] (may be NULL), dwq / dbq fp32 += (NULL without a
+ * projection).  dp_ws: fp32 [b_sz][n_k][n_q] zeroed by the caller once (left zeroed).  Dense agent-major inputs only.
+ */
+typedef struct w2c_attn_bwd_args {
+  const float* keys;
+  const float* queries;
+  const float* wq;
+  const float* bq;
+  const void* val;
+  const void* dfused;
+  const float* prob;
+  void* dval;
+  float* dkeys;
+  float* dqueries;
+  float* dwq;
+  float* dbq;
+  float* dp_ws;
+  int32_t b_sz, n_k, n_q;
+  int32_t k_dim, q_dim;
+  int32_t hw, c;
+  int32_t dfused_cstride, dfused_coffset;
+  int32_t act_f, act_g;
+  int32_t sparse;
+  int32_t dval_accumulate;
+  float temperature;
+} w2c_attn_bwd_args;
+int w2c_attn_fuse_bwd(const w2c_attn_bwd_args* args, w2c_stream_t stream);
+
+/*
+ * Backward of w2c_kq_mlp_heads_fwd (km_generator / linear, agent.py:145-178).  heads = the forward's weights (out
+ * unused), ws_fwd = the forward's scratch (the first hidden layer per head).  Per head: dout fp32 [m][out_dim] in,
+ * parameter gradients += (dw0 in the NHWC flatten order of w0).  dfeat: NHWC act_g gradient of the policy map, the sum
+ * over the heads.  ws: fp32 scratch of n_heads*m*512 + 256 floats.
+ */
+typedef struct w2c_mlp_head_grad {
+  const float* dout;
+  float* dw0;
+  float* db0;
+  float* dw1;
+  float* db1;
+  float* dw2;
+  float* db2;
+} w2c_mlp_head_grad;
+int w2c_kq_mlp_heads_bwd(const void* feat, int32_t act_f, int32_t m, int32_t n_feat, const w2c_mlp_head* heads,
+                         const w2c_mlp_head_grad* grads, int32_t n_heads, const float* ws_fwd, void* dfeat,
+                         int32_t act_g, float* ws, w2c_stream_t stream);
+
+/* Weight gradient of the 3-channel first layers from the fp32 NCHW views: ksize 3 = Conv2d(3, cout, 3, 1, 1)
+ * (n_segnet_encoder.conv1), 7 = Conv2d(3, cout, 7, 2, 3) (resnet18 conv1).  dz: NHWC act_g gradient of the raw conv
+ * output, channels [dz_coffset, + cout) of dz_cstride; dw fp32 [cout][3][k][k] +=; cout <= 64; other arguments as
+ * w2c_stem_conv3x3_fwd. */
+int w2c_stem_conv_wgrad(const float* x, const void* dz, float* dw, int32_t ksize, int32_t b, int32_t n_agents,
+                        int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout, int32_t dz_cstride,
+                        int32_t dz_coffset, int32_t act_g, w2c_stream_t stream);
+
+/* MaxPool2d(3, 2, 1) backward (the gradient goes to the first maximum of each window, like torch). */
+int w2c_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w_px, int32_t c,
+                         int32_t act_f, int32_t act_g, w2c_stream_t stream);
+/* Adjoint of w2c_bilinear_up_fwd: dy fp32 [n][c][h*factor][w*factor] -> dx fp32 [n][c][h][w]. */
+int w2c_bilinear_up_bwd(const float* dy, float* dx, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
+                        w2c_stream_t stream);
+/* dst[n][2i][2j] = src[n][i][j], zero elsewhere (+ add, same layout as dst, may be NULL or dst): completes the data
+ * gradient of a stride-2 1x1 conv.  h, w_px: extent of dst.  Dense NHWC maps in `act`. */
+int w2c_upsample_zero2(const void* src, const void* add, void* dst, int32_t n, int32_t h, int32_t w_px, int32_t c,
+                       int32_t act, w2c_stream_t stream);
+/* dst slice = a slice (+ b slice) over n_px pixels of c channels: gradient accumulation / concat-slice extraction. */
+int w2c_grad_add(const void* a, int32_t a_cstride, int32_t a_coffset, const void* b, int32_t b_cstride,
+                 int32_t b_coffset, void* dst, int32_t d_cstride, int32_t d_coffset, int64_t n_px, int32_t c,
+                 int32_t act, w2c_stream_t stream);
 
 /* ---- layout helpers --------------------------------------------------------------------------------- */
 /* NHWC activation (act storage) -> fp32 NCHW, and back.  Used at module boundaries and by the tests. */

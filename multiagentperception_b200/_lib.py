@@ -68,6 +68,38 @@ class MlpHead(ctypes.Structure):
                 ("out_dim", c_i32)]
 
 
+class WgradArgs(ctypes.Structure):
+    """struct w2c_wgrad_args (include/w2c.h)."""
+    _fields_ = [("x", c_vp), ("dy", c_vp), ("dw", c_vp), ("n", c_i32), ("h_in", c_i32), ("w_in", c_i32),
+                ("cin", c_i32), ("cout", c_i32), ("x_cstride", c_i32), ("x_coffset", c_i32), ("dy_cstride", c_i32),
+                ("dy_coffset", c_i32), ("kind", c_i32), ("act_x", c_i32), ("act_dy", c_i32), ("passes", c_i32)]
+
+
+class BnBwdArgs(ctypes.Structure):
+    """struct w2c_bn_bwd_args (include/w2c.h)."""
+    _fields_ = [("dy", c_vp), ("y", c_vp), ("z", c_vp), ("dz", c_vp), ("dres", c_vp), ("n_px", ctypes.c_int64),
+                ("c", c_i32), ("dy_cstride", c_i32), ("dy_coffset", c_i32), ("y_cstride", c_i32), ("y_coffset", c_i32),
+                ("z_cstride", c_i32), ("z_coffset", c_i32), ("dz_cstride", c_i32), ("dz_coffset", c_i32),
+                ("dres_cstride", c_i32), ("dres_coffset", c_i32), ("act_f", c_i32), ("act_g", c_i32), ("relu", c_i32),
+                ("gamma", c_vp), ("stats", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("sums_ws", c_vp),
+                ("coef_ws", c_vp)]
+
+
+class AttnBwdArgs(ctypes.Structure):
+    """struct w2c_attn_bwd_args (include/w2c.h)."""
+    _fields_ = [("keys", c_vp), ("queries", c_vp), ("wq", c_vp), ("bq", c_vp), ("val", c_vp), ("dfused", c_vp),
+                ("prob", c_vp), ("dval", c_vp), ("dkeys", c_vp), ("dqueries", c_vp), ("dwq", c_vp), ("dbq", c_vp),
+                ("dp_ws", c_vp), ("b_sz", c_i32), ("n_k", c_i32), ("n_q", c_i32), ("k_dim", c_i32), ("q_dim", c_i32),
+                ("hw", c_i32), ("c", c_i32), ("dfused_cstride", c_i32), ("dfused_coffset", c_i32), ("act_f", c_i32),
+                ("act_g", c_i32), ("sparse", c_i32), ("dval_accumulate", c_i32), ("temperature", c_f32)]
+
+
+class MlpHeadGrad(ctypes.Structure):
+    """struct w2c_mlp_head_grad (include/w2c.h)."""
+    _fields_ = [("dout", c_vp), ("dw0", c_vp), ("db0", c_vp), ("dw1", c_vp), ("db1", c_vp), ("dw2", c_vp),
+                ("db2", c_vp)]
+
+
 # symbol -> (restype, argtypes); every symbol include/w2c.h declares must be listed here (tests check both ways)
 _SIGNATURES = {
     "w2c_version": (ctypes.c_int, []),
@@ -76,9 +108,23 @@ _SIGNATURES = {
     "w2c_conv_bnrelu_fwd": (ctypes.c_int, [ctypes.POINTER(ConvArgs), c_vp]),
     "w2c_enc_head_fwd": (ctypes.c_int, [ctypes.POINTER(EncHeadArgs), c_vp]),
     "w2c_bn_train_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32,
-                                        c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                        c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
     "w2c_bn_train_nchw_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_f32, c_vp,
-                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "w2c_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradArgs), c_vp]),
+    "w2c_pack_conv_weight_ex": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "w2c_bn_train_bwd": (ctypes.c_int, [ctypes.POINTER(BnBwdArgs), c_vp]),
+    "w2c_bn_train_nchw_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, c_i32, c_i32, c_i32,
+                                             c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "w2c_attn_fuse_bwd": (ctypes.c_int, [ctypes.POINTER(AttnBwdArgs), c_vp]),
+    "w2c_kq_mlp_heads_bwd": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, ctypes.POINTER(MlpHead),
+                                            ctypes.POINTER(MlpHeadGrad), c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "w2c_stem_conv_wgrad": (ctypes.c_int, [c_vp, c_vp, c_vp] + [c_i32] * 11 + [c_vp]),
+    "w2c_maxpool3x3s2_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_bilinear_up_bwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_upsample_zero2": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_grad_add": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, ctypes.c_int64, c_i32,
+                                    c_i32, c_vp]),
     "w2c_stem_conv3x3_raw_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_stem_conv7x7s2_raw_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),
     "w2c_cout_pad": (c_i32, [c_i32]),

@@ -14,7 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libw2c.so")
 STAMP = os.path.join(LIB_DIR, "libw2c.stamp")
-SOURCES = ["conv_tc.cu", "conv_pers_v1.cu", "enc_head.cu", "bn_train.cu", "stem_tc.cu", "misc.cu", "attn.cu", "mlp.cu"]
+SOURCES = ["conv_tc.cu", "conv_pers_v1.cu", "enc_head.cu", "bn_train.cu", "stem_tc.cu", "misc.cu", "attn.cu", "mlp.cu", "wgrad.cu", "bn_bwd.cu",
+           "attn_bwd.cu", "bwd_misc.cu"]
 HEADERS = ["ptx.cuh", "common.cuh", "conv_plan.cuh", os.path.join("..", "..", "include", "w2c.h")]
 
 NVCC_FLAGS = [

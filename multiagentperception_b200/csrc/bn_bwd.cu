@@ -1,0 +1,310 @@
+// Backward of the train-mode conv -> BatchNorm2d (-> + residual) (-> ReLU) unit (conv2DBatchNormRelu /
+// deconv2DBatchNormRelu, ptsemseg/models/utils.py:87-120,148-168; the BasicBlock tail of the resnet18 trunk,
+// backbone.py:63-96) between the gradient of the layer OUTPUT and the gradient of the raw conv output z: what
+// autograd runs for nn.ReLU + nn.BatchNorm2d in training mode under loss.backward() (ptsemseg/trainer.py:668-670).
+//
+//   du     = dy * [y > 0]                                  (ReLU; y is the stored forward output)     -> dres = du
+//   dbeta  = sum du,  dgamma = sum du * xhat,              xhat = (z - mean) * invstd   (batch statistics of the forward)
+//   dz     = gamma * invstd * (du - dbeta / M - xhat * dgamma / M)
+// Without BatchNorm (simple_decoder.pred, backbone.py:150-154): dz = du, dbias = sum du.
+// Three launches like the forward: per-channel sums (fp32 per thread, fp64 across threads), finalize, apply - all
+// HBM-bound passes (algorithmic bytes: dy + y + z read twice, dz written once).
+#include "common.cuh"
+
+namespace w2c {
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* q, int cstride, int planes, bool f16, float (&v)[8]) {
+  const uint4 hv = __ldg(reinterpret_cast<const uint4*>(q));
+  const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_act2(hb[e], f16);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+  if (planes == 2) {
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(q + cstride));
+    const uint32_t* lb = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_act2(lb[e], f16);
+      v[2 * e] += f.x, v[2 * e + 1] += f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* q, int cstride, int planes, bool f16, const float (&v)[8]) {
+  uint4 hv, lv;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_act2(v[2 * e], v[2 * e + 1], f16, hw[e], lw[e]);
+  *reinterpret_cast<uint4*>(q) = hv;
+  if (planes == 2) *reinterpret_cast<uint4*>(q + cstride) = lv;
+}
+
+struct BwdMaps {
+  const __nv_bfloat16* dy;
+  const __nv_bfloat16* y;
+  const __nv_bfloat16* z;
+  __nv_bfloat16* dz;
+  __nv_bfloat16* dres;
+  int dy_cs, dy_co, y_cs, y_co, z_cs, z_co, dz_cs, dz_co, dres_cs, dres_co;
+  int act_f, act_g, relu;
+  size_t n_px;
+  int c;
+};
+
+// sums[ch] += sum du, sums[c + ch] += sum du * xhat
+__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
+                                                                 double* __restrict__ sums) {
+  extern __shared__ double s_red[];
+  const int groups = m.c / 8;
+  const int lanes = kThreads / groups;
+  const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
+  const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
+  const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
+  float mean[8], inv[8], s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    mean[e] = stats ? stats[g * 8 + e] : 0.f;
+    inv[e] = stats ? stats[m.c + g * 8 + e] : 0.f;
+    s1[e] = s2[e] = 0.f;
+  }
+  if (lane < lanes) {
+    for (size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane; px < m.n_px; px += static_cast<size_t>(gridDim.x) * lanes) {
+      float du[8];
+      load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
+      if (m.relu) {
+        float yv[8];
+        load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1[e] += du[e];
+      if (stats) {
+        float zv[8];
+        load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
+      }
+    }
+  }
+  double* mine = s_red + static_cast<size_t>(threadIdx.x) * 16;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) mine[e] = s1[e], mine[8 + e] = s2[e];
+  __syncthreads();
+  if (lane == 0) {
+    double t[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) t[e] = 0.0;
+    for (int l = 0; l < lanes; ++l) {
+      const double* o = s_red + static_cast<size_t>(l * groups + g) * 16;
+#pragma unroll
+      for (int e = 0; e < 16; ++e) t[e] += o[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      atomicAdd(&sums[g * 8 + e], t[e]);
+      atomicAdd(&sums[m.c + g * 8 + e], t[8 + e]);
+    }
+  }
+}
+
+// parameter gradients (accumulated, like autograd's .grad) + the per-channel coefficients of the apply pass
+__global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                       const float* __restrict__ stats, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef, int c) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double sb = sums[ch], sg = sums[c + ch];
+  if (dbeta) dbeta[ch] += static_cast<float>(sb);
+  if (dgamma && stats) dgamma[ch] += static_cast<float>(sg);
+  // dz = k * (du - a - xhat * b)
+  coef[ch] = static_cast<float>(sb / count);
+  coef[c + ch] = static_cast<float>(sg / count);
+  coef[2 * c + ch] = stats ? (gamma ? gamma[ch] : 1.f) * stats[c + ch] : 1.f;
+  sums[ch] = 0.0, sums[c + ch] = 0.0;
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdMaps m, const float* __restrict__ stats,
+                                                           const float* __restrict__ coef) {
+  const int groups = m.c / 8;
+  const size_t total = m.n_px * groups;
+  const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
+  const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    const size_t px = idx / groups;
+    float du[8];
+    load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
+    if (m.relu) {
+      float yv[8];
+      load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
+    }
+    if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
+    if (stats) {
+      float zv[8];
+      load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const int ch = g * 8 + e;
+        const float xhat = (zv[e] - stats[ch]) * stats[m.c + ch];
+        du[e] = coef[2 * m.c + ch] * (du[e] - coef[ch] - xhat * coef[m.c + ch]);
+      }
+    }
+    store8(m.dz + px * (static_cast<size_t>(m.dz_cs) * pg) + m.dz_co + g * 8, m.dz_cs, pg, f16g, du);
+  }
+}
+
+// ---- the logits layer: fp32 NCHW maps in (dy, y, z), NHWC gradient map out (channels c .. c_pad-1 zero-filled)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_nchw_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                 const float* __restrict__ z, int n, int c, size_t hw,
+                                                                 int chunks, int relu, const float* __restrict__ stats,
+                                                                 double* __restrict__ sums) {
+  __shared__ double s1[256], s2[256];
+  const int ch = blockIdx.x / chunks, part = blockIdx.x % chunks;
+  const float mean = stats ? stats[ch] : 0.f, inv = stats ? stats[c + ch] : 0.f;
+  float a = 0.f, b = 0.f;
+  for (int img = 0; img < n; ++img) {
+    const size_t base = (static_cast<size_t>(img) * c + ch) * hw;
+    for (size_t i = static_cast<size_t>(part) * 256 + threadIdx.x; i < hw; i += static_cast<size_t>(chunks) * 256) {
+      float du = dy[base + i];
+      if (relu && !(y[base + i] > 0.f)) du = 0.f;
+      a += du;
+      if (stats) b = fmaf(du, (z[base + i] - mean) * inv, b);
+    }
+  }
+  s1[threadIdx.x] = a, s2[threadIdx.x] = b;
+  __syncthreads();
+  for (int st = 128; st > 0; st >>= 1) {
+    if (threadIdx.x < st) s1[threadIdx.x] += s1[threadIdx.x + st], s2[threadIdx.x] += s2[threadIdx.x + st];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(&sums[ch], s1[0]), atomicAdd(&sums[c + ch], s2[0]);
+}
+
+// one thread per (pixel, 8-channel group of the padded NHWC output)
+__global__ void __launch_bounds__(256) bn_bwd_apply_nchw_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                                const float* __restrict__ z, __nv_bfloat16* __restrict__ dz,
+                                                                int n, int c, size_t hw, int c_pad, int dz_cs, int dz_co,
+                                                                int act_g, int relu, const float* __restrict__ stats,
+                                                                const float* __restrict__ coef) {
+  const int groups = c_pad / 8;
+  const size_t total = static_cast<size_t>(n) * hw * groups;
+  const bool f16g = act_is_f16(act_g);
+  const int pg = act_planes(act_g);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    // pixel fastest within a group so that the NCHW reads of a warp are contiguous
+    const size_t px_all = idx % (static_cast<size_t>(n) * hw);
+    const int g = static_cast<int>(idx / (static_cast<size_t>(n) * hw));
+    const int img = static_cast<int>(px_all / hw);
+    const size_t i = px_all % hw;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int ch = g * 8 + e;
+      float du = 0.f;
+      if (ch < c) {
+        const size_t off = (static_cast<size_t>(img) * c + ch) * hw + i;
+        du = dy[off];
+        if (relu && !(y[off] > 0.f)) du = 0.f;
+        if (stats) {
+          const float xhat = (z[off] - stats[ch]) * stats[c + ch];
+          du = coef[2 * c + ch] * (du - coef[ch] - xhat * coef[c + ch]);
+        }
+      }
+      v[e] = du;
+    }
+    store8(dz + px_all * (static_cast<size_t>(dz_cs) * pg) + dz_co + g * 8, dz_cs, pg, f16g, v);
+  }
+}
+
+}  // namespace
+}  // namespace w2c
+
+using namespace w2c;
+
+extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream) {
+  if (!args) return set_error(W2C_ERR_INVALID, "bn_bwd: args is NULL");
+  const w2c_bn_bwd_args& a = *args;
+  W2C_CHECK_ARG(a.dy && a.dz && a.sums_ws && a.coef_ws, "bn_bwd: null pointer argument");
+  W2C_CHECK_ARG(!a.relu || a.y, "bn_bwd: the ReLU mask needs the forward output y");
+  W2C_CHECK_ARG(!a.stats || a.z, "bn_bwd: BatchNorm needs the raw conv output z");
+  W2C_CHECK_ARG(act_valid(a.act_f) && act_valid(a.act_g), "bn_bwd: bad act");
+  W2C_CHECK_ARG(a.n_px > 0 && a.c > 0 && a.c % 8 == 0 && 256 % (a.c / 8) == 0 && a.c <= 2048,
+                "bn_bwd: n_px=%lld c=%d (c / 8 must divide 256)", static_cast<long long>(a.n_px), a.c);
+  BwdMaps m{};
+  m.dy = static_cast<const __nv_bfloat16*>(a.dy), m.y = static_cast<const __nv_bfloat16*>(a.y);
+  m.z = static_cast<const __nv_bfloat16*>(a.z), m.dz = static_cast<__nv_bfloat16*>(a.dz);
+  m.dres = static_cast<__nv_bfloat16*>(a.dres);
+  auto cs = [&](int v) { return v > 0 ? v : a.c; };
+  m.dy_cs = cs(a.dy_cstride), m.dy_co = a.dy_coffset, m.y_cs = cs(a.y_cstride), m.y_co = a.y_coffset;
+  m.z_cs = cs(a.z_cstride), m.z_co = a.z_coffset, m.dz_cs = cs(a.dz_cstride), m.dz_co = a.dz_coffset;
+  m.dres_cs = cs(a.dres_cstride), m.dres_co = a.dres_coffset;
+  m.act_f = a.act_f, m.act_g = a.act_g, m.relu = a.relu, m.n_px = static_cast<size_t>(a.n_px), m.c = a.c;
+  const int strides[5] = {m.dy_cs, m.y_cs, m.z_cs, m.dz_cs, m.dres_cs}, offs[5] = {m.dy_co, m.y_co, m.z_co, m.dz_co, m.dres_co};
+  for (int i = 0; i < 5; ++i)
+    W2C_CHECK_ARG(offs[i] >= 0 && offs[i] + a.c <= strides[i] && strides[i] % 8 == 0 && offs[i] % 8 == 0,
+                  "bn_bwd: channel slice %d out of range", i);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int groups = a.c / 8, lanes = kThreads / groups;
+  long long want = (a.n_px + lanes - 1) / lanes;
+  const int cap = device_sm_count() * 8;
+  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
+  static DeviceOnce attr;
+  const size_t smem = static_cast<size_t>(kThreads) * 16 * sizeof(double);
+  if (int rc = attr.ensure([=] {
+        return cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      }, "bn_bwd_reduce_kernel"))
+    return rc;
+  bn_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(m, a.stats, a.sums_ws);
+  W2C_CHECK_LAUNCH("bn_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(a.c + 127) / 128, 128, 0, s>>>(a.sums_ws, static_cast<double>(a.n_px), a.gamma, a.stats,
+                                                           a.dgamma, a.dbeta, a.coef_ws, a.c);
+  W2C_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  const size_t total = static_cast<size_t>(a.n_px) * groups;
+  const size_t blocks = (total + 255) / 256;
+  const int grid2 = static_cast<int>(blocks < static_cast<size_t>(cap) * 4 ? blocks : static_cast<size_t>(cap) * 4);
+  bn_bwd_apply_kernel<<<grid2, 256, 0, s>>>(m, a.stats, a.coef_ws);
+  W2C_CHECK_LAUNCH("bn_bwd_apply_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_bn_train_nchw_bwd(const float* dy, const float* y, const float* z, void* dz, int32_t n, int32_t c,
+                                     int64_t hw, int32_t c_pad, int32_t dz_cstride, int32_t dz_coffset, int32_t act_g,
+                                     int32_t relu, const float* gamma, const float* stats, float* dgamma, float* dbeta,
+                                     double* sums_ws, float* coef_ws, w2c_stream_t stream) {
+  W2C_CHECK_ARG(dy && dz && sums_ws && coef_ws && n > 0 && c > 0 && hw > 0, "bn_bwd_nchw: bad arguments");
+  W2C_CHECK_ARG(!relu || y, "bn_bwd_nchw: the ReLU mask needs the forward output y");
+  W2C_CHECK_ARG(!stats || z, "bn_bwd_nchw: BatchNorm needs the raw conv output z");
+  W2C_CHECK_ARG(act_valid(act_g) && c_pad >= c && c_pad % 8 == 0, "bn_bwd_nchw: act_g=%d c_pad=%d", act_g, c_pad);
+  const int cs = dz_cstride > 0 ? dz_cstride : c_pad;
+  W2C_CHECK_ARG(dz_coffset >= 0 && dz_coffset + c_pad <= cs && cs % 8 == 0 && dz_coffset % 8 == 0,
+                "bn_bwd_nchw: output channel slice out of range");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int chunks = static_cast<int>((hw + 256 * 16 - 1) / (256 * 16));
+  const int cap = (device_sm_count() * 8 + c - 1) / c;
+  if (chunks > cap) chunks = cap;
+  if (chunks < 1) chunks = 1;
+  bn_bwd_reduce_nchw_kernel<<<c * chunks, 256, 0, s>>>(dy, y, z, n, c, static_cast<size_t>(hw), chunks, relu, stats, sums_ws);
+  W2C_CHECK_LAUNCH("bn_bwd_reduce_nchw_kernel");
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums_ws, static_cast<double>(n) * static_cast<double>(hw), gamma,
+                                                         stats, dgamma, dbeta, coef_ws, c);
+  W2C_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  const size_t total = static_cast<size_t>(n) * static_cast<size_t>(hw) * (c_pad / 8);
+  const size_t blocks = (total + 255) / 256;
+  const size_t capb = static_cast<size_t>(device_sm_count()) * 32;
+  bn_bwd_apply_nchw_kernel<<<static_cast<int>(blocks < capb ? blocks : capb), 256, 0, s>>>(
+      dy, y, z, static_cast<__nv_bfloat16*>(dz), n, c, static_cast<size_t>(hw), c_pad, cs, dz_coffset, act_g, relu, stats,
+      coef_ws);
+  W2C_CHECK_LAUNCH("bn_bwd_apply_nchw_kernel");
+  return W2C_OK;
+}

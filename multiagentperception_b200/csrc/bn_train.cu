@@ -84,7 +84,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
                                    const float* __restrict__ beta, float eps, float momentum,
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    long long* __restrict__ num_batches_tracked, float* __restrict__ scale,
-                                   float* __restrict__ shift, int c) {
+                                   float* __restrict__ shift, float* __restrict__ stats, int c) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch < c) {
     const double mean = sums[ch] / count;
@@ -93,6 +93,10 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
     const float sc = (gamma ? gamma[ch] : 1.f) * static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
     scale[ch] = sc;
     shift[ch] = (beta ? beta[ch] : 0.f) - static_cast<float>(mean) * sc;
+    if (stats) {   // what the backward pass normalises with: xhat = (z - mean) * invstd
+      stats[ch] = static_cast<float>(mean);
+      stats[c + ch] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
     if (running_mean) {
       // nn.BatchNorm2d: running = (1 - momentum) * running + momentum * batch, the variance UNBIASED (n / (n - 1))
       const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
@@ -104,21 +108,25 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
   if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
-// z <- act(z * scale + shift (+ residual)) in place; one thread per (pixel, 8-channel group)
-__global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict__ z, const __nv_bfloat16* __restrict__ res,
+// y <- act(z * scale + shift (+ residual)) (y may be z: in place); one thread per (pixel, 8-channel group)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* z, __nv_bfloat16* y,
+                                                       const __nv_bfloat16* __restrict__ res,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                       size_t n_px, int c, int cstride, int coffset, int act, int relu) {
+                                                       size_t n_px, int c, int cstride, int coffset, int y_cstride,
+                                                       int y_coffset, int act, int relu) {
   const int groups = c / 8;
   const size_t total = n_px * groups;
   const bool f16 = act_is_f16(act);
   const int planes = act_planes(act);
   const size_t pix_elems = static_cast<size_t>(cstride) * planes;
+  const size_t y_pix_elems = static_cast<size_t>(y_cstride) * planes;
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int g = idx % groups;
     const size_t px = idx / groups;
-    __nv_bfloat16* p = z + px * pix_elems + coffset + g * 8;
-    auto load8 = [&](const __nv_bfloat16* q, float (&v)[8]) {
+    const __nv_bfloat16* p = z + px * pix_elems + coffset + g * 8;
+    __nv_bfloat16* q_out = y + px * y_pix_elems + y_coffset + g * 8;
+    auto load8 = [&](const __nv_bfloat16* q, float (&v)[8], int cstride) {
       const uint4 hv = *reinterpret_cast<const uint4*>(q);
       const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
 #pragma unroll
@@ -137,7 +145,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
       }
     };
     float v[8];
-    load8(p, v);
+    load8(p, v, cstride);
     const float4 sa = *reinterpret_cast<const float4*>(scale + g * 8), sb = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
     const float4 ha = *reinterpret_cast<const float4*>(shift + g * 8), hb4 = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
     const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
@@ -146,7 +154,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
     for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
     if (res) {
       float r[8];
-      load8(res + px * pix_elems + coffset + g * 8, r);
+      load8(res + px * y_pix_elems + y_coffset + g * 8, r, y_cstride);   // the residual is laid out like the output
 #pragma unroll
       for (int e = 0; e < 8; ++e) v[e] += r[e];
     }
@@ -159,8 +167,8 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(__nv_bfloat16* __restrict
     uint32_t* lw = reinterpret_cast<uint32_t*>(&lv);
 #pragma unroll
     for (int e = 0; e < 4; ++e) split_act2(v[2 * e], v[2 * e + 1], f16, hw[e], lw[e]);
-    *reinterpret_cast<uint4*>(p) = hv;
-    if (planes == 2) *reinterpret_cast<uint4*>(p + cstride) = lv;
+    *reinterpret_cast<uint4*>(q_out) = hv;
+    if (planes == 2) *reinterpret_cast<uint4*>(q_out + y_cstride) = lv;
   }
 }
 
@@ -187,14 +195,14 @@ __global__ void __launch_bounds__(256) bn_stats_nchw_kernel(const float* __restr
   if (threadIdx.x == 0) atomicAdd(&sums[ch], s1[0]), atomicAdd(&sums[c + ch], s2[0]);
 }
 
-__global__ void __launch_bounds__(256) bn_apply_nchw_kernel(float* __restrict__ z, const float* __restrict__ scale,
+__global__ void __launch_bounds__(256) bn_apply_nchw_kernel(const float* z, float* y, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, int c, size_t hw,
                                                             size_t total, int relu) {
   for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int ch = static_cast<int>((i / hw) % c);
     float v = fmaf(z[i], scale[ch], shift[ch]);
-    z[i] = relu ? fmaxf(v, 0.f) : v;
+    y[i] = relu ? fmaxf(v, 0.f) : v;
   }
 }
 
@@ -206,7 +214,7 @@ using namespace w2c;
 extern "C" int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw, int32_t relu, const float* gamma,
                                      const float* beta, float eps, float momentum, float* running_mean,
                                      float* running_var, int64_t* num_batches_tracked, double* sums_ws, float* scale_ws,
-                                     float* shift_ws, w2c_stream_t stream) {
+                                     float* shift_ws, float* y_out, float* stats_out, w2c_stream_t stream) {
   W2C_CHECK_ARG(z && sums_ws && scale_ws && shift_ws && n > 0 && c > 0 && hw > 0, "bn_train_nchw: bad arguments");
   W2C_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_train_nchw: running_mean and running_var go together");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -218,12 +226,13 @@ extern "C" int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw,
   W2C_CHECK_LAUNCH("bn_stats_nchw_kernel");
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums_ws, static_cast<double>(n) * static_cast<double>(hw), gamma, beta,
                                                      eps, momentum, running_mean, running_var,
-                                                     reinterpret_cast<long long*>(num_batches_tracked), scale_ws, shift_ws, c);
+                                                     reinterpret_cast<long long*>(num_batches_tracked), scale_ws, shift_ws,
+                                                     stats_out, c);
   W2C_CHECK_LAUNCH("bn_finalize_kernel");
   const size_t total = static_cast<size_t>(n) * c * static_cast<size_t>(hw);
   const size_t blocks = (total + 255) / 256;
   const size_t capb = static_cast<size_t>(device_sm_count()) * 32;
-  bn_apply_nchw_kernel<<<static_cast<int>(blocks < capb ? blocks : capb), 256, 0, s>>>(z, scale_ws, shift_ws, c,
+  bn_apply_nchw_kernel<<<static_cast<int>(blocks < capb ? blocks : capb), 256, 0, s>>>(z, y_out ? y_out : z, scale_ws, shift_ws, c,
                                                                                        static_cast<size_t>(hw), total, relu);
   W2C_CHECK_LAUNCH("bn_apply_nchw_kernel");
   return W2C_OK;
@@ -232,7 +241,8 @@ extern "C" int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw,
 extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
                                 int32_t act, int32_t relu, const float* gamma, const float* beta, float eps,
                                 float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                                double* sums_ws, float* scale_ws, float* shift_ws, w2c_stream_t stream) {
+                                double* sums_ws, float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride,
+                                int32_t y_coffset, float* stats_out, w2c_stream_t stream) {
   W2C_CHECK_ARG(z && sums_ws && scale_ws && shift_ws, "bn_train: null pointer argument");
   W2C_CHECK_ARG(act_valid(act), "bn_train: bad act %d", act);
   W2C_CHECK_ARG(n_px > 0 && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && c <= 2048,
@@ -240,6 +250,9 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   const int cs = cstride > 0 ? cstride : c;
   W2C_CHECK_ARG(coffset >= 0 && coffset + c <= cs && cs % 8 == 0 && coffset % 8 == 0, "bn_train: channel slice out of range");
   W2C_CHECK_ARG((running_mean == nullptr) == (running_var == nullptr), "bn_train: running_mean and running_var go together");
+  const int ycs = y_cstride > 0 ? y_cstride : c;
+  W2C_CHECK_ARG(!y_out || (y_coffset >= 0 && y_coffset + c <= ycs && ycs % 8 == 0 && y_coffset % 8 == 0),
+                "bn_train: output channel slice out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = c / 8, lanes = kStatThreads / groups;
   long long want = (n_px + lanes - 1) / lanes;
@@ -257,13 +270,16 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums_ws, static_cast<double>(n_px), gamma, beta, eps, momentum,
                                                      running_mean, running_var,
                                                      reinterpret_cast<long long*>(num_batches_tracked), scale_ws,
-                                                     shift_ws, c);
+                                                     shift_ws, stats_out, c);
   W2C_CHECK_LAUNCH("bn_finalize_kernel");
   const size_t total = static_cast<size_t>(n_px) * groups;
   const size_t blocks = (total + 255) / 256;
   const int grid2 = static_cast<int>(blocks < static_cast<size_t>(cap) * 4 ? blocks : static_cast<size_t>(cap) * 4);
-  bn_apply_kernel<<<grid2, 256, 0, s>>>(static_cast<__nv_bfloat16*>(z), static_cast<const __nv_bfloat16*>(residual),
-                                        scale_ws, shift_ws, static_cast<size_t>(n_px), c, cs, coffset, act, relu);
+  bn_apply_kernel<<<grid2, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(z),
+                                        static_cast<__nv_bfloat16*>(y_out ? y_out : z),
+                                        static_cast<const __nv_bfloat16*>(residual),
+                                        scale_ws, shift_ws, static_cast<size_t>(n_px), c, cs, coffset,
+                                        y_out ? ycs : cs, y_out ? y_coffset : coffset, act, relu);
   W2C_CHECK_LAUNCH("bn_apply_kernel");
   return W2C_OK;
 }

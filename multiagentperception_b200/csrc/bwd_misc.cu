@@ -1,0 +1,578 @@
+// Backward of the small stages of the path (loss.backward() of ptsemseg/trainer.py:668-670):
+//   * the key / query heads (km_generator / linear, ptsemseg/models/agent.py:145-178): three Linear layers with ReLU
+//   * the weight gradient of the 3-channel first layers (n_segnet_encoder.conv1 3x3 s1, backbone.py:19,42; the resnet18
+//     stem 7x7 s2, backbone.py:63-69), which read the caller's fp32 NCHW views directly
+//   * the operand packing of the data-gradient convs (a conv's data gradient is a conv / transposed conv of dL/dy with
+//     the SAME weight tensor re-indexed, so it runs on the forward tensor-core kernels)
+//   * MaxPool2d(3, 2, 1) and the x32 bilinear up-sampling of the resnet18 + simple_decoder pair (backbone.py:72-96,
+//     156-164), the stride-2 1x1 shortcut's zero-interleave, gradient accumulation
+// Everything here is CUDA-core work: tens of rows (M = agents x scenes) against weight matrices, or HBM-bound passes.
+#include "common.cuh"
+
+namespace w2c {
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* q, int cstride, int planes, bool f16, float (&v)[8]) {
+  const uint4 hv = __ldg(reinterpret_cast<const uint4*>(q));
+  const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_act2(hb[e], f16);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+  if (planes == 2) {
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(q + cstride));
+    const uint32_t* lb = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = unpack_act2(lb[e], f16);
+      v[2 * e] += f.x, v[2 * e + 1] += f.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store8(__nv_bfloat16* q, int cstride, int planes, bool f16, const float (&v)[8]) {
+  uint4 hv, lv;
+  uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+  uint32_t* lw = reinterpret_cast<uint32_t*>(&lv);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) split_act2(v[2 * e], v[2 * e + 1], f16, hw[e], lw[e]);
+  *reinterpret_cast<uint4*>(q) = hv;
+  if (planes == 2) *reinterpret_cast<uint4*>(q + cstride) = lv;
+}
+
+int grid_for(size_t total, int threads, int per_sm = 16) {
+  const size_t want = (total + threads - 1) / threads;
+  const size_t cap = static_cast<size_t>(device_sm_count()) * per_sm;
+  return static_cast<int>(want < cap ? (want ? want : 1) : cap);
+}
+
+// ------------------------------------------------------------------------------------------------ key / query heads
+struct HeadsBwd {
+  w2c_mlp_head h[2];
+  w2c_mlp_head_grad g[2];
+  int n_heads;
+};
+
+// One CTA per (row, head): recompute h1 = relu(W1 h0 + b1), then dh1 = (dout W2) * [h1 > 0], dh0 = (dh1 W1) * [h0 > 0].
+// ws per head: [h1: m*128][dh1: m*128][dh0: m*256]
+__global__ void __launch_bounds__(256) mlp_bwd_hidden_kernel(const HeadsBwd hd, const float* __restrict__ ws_fwd,
+                                                             float* __restrict__ ws, int m) {
+  __shared__ float s_h0[256], s_h1[128], s_dh1[128];
+  __shared__ float s_dout[1024];
+  const int row = blockIdx.x, head = blockIdx.y;
+  const w2c_mlp_head& h = hd.h[head];
+  const float* __restrict__ dout = hd.g[head].dout + static_cast<size_t>(row) * h.out_dim;
+  const float* __restrict__ h0 = ws_fwd + (static_cast<size_t>(head) * m + row) * 256;
+  float* w_h1 = ws + static_cast<size_t>(head) * m * 512 + static_cast<size_t>(row) * 128;
+  float* w_dh1 = ws + static_cast<size_t>(head) * m * 512 + static_cast<size_t>(m) * 128 + static_cast<size_t>(row) * 128;
+  float* w_dh0 = ws + static_cast<size_t>(head) * m * 512 + static_cast<size_t>(m) * 256 + static_cast<size_t>(row) * 256;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  s_h0[tid] = h0[tid];
+  __syncthreads();
+  for (int j = warp; j < 128; j += 8) {
+    const float* wr = h.w1 + j * 256;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = lane; k < 256; k += 32) acc = fmaf(__ldg(wr + k), s_h0[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) s_h1[j] = fmaxf(acc + h.b1[j], 0.f);
+  }
+  // dh1[k] = sum_o dout[o] W2[o][k], out_dim staged through shared memory 1024 at a time
+  float acc1 = 0.f;
+  for (int o0 = 0; o0 < h.out_dim; o0 += 1024) {
+    __syncthreads();
+    for (int o = tid; o < 1024 && o0 + o < h.out_dim; o += 256) s_dout[o] = dout[o0 + o];
+    __syncthreads();
+    if (tid < 128) {
+      const int n = min(1024, h.out_dim - o0);
+      for (int o = 0; o < n; ++o) acc1 = fmaf(s_dout[o], __ldg(h.w2 + static_cast<size_t>(o0 + o) * 128 + tid), acc1);
+    }
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const float d = s_h1[tid] > 0.f ? acc1 : 0.f;
+    s_dh1[tid] = d;
+    w_h1[tid] = s_h1[tid];
+    w_dh1[tid] = d;
+  }
+  __syncthreads();
+  float acc0 = 0.f;
+#pragma unroll 4
+  for (int j = 0; j < 128; ++j) acc0 = fmaf(s_dh1[j], __ldg(h.w1 + j * 256 + tid), acc0);
+  w_dh0[tid] = s_h0[tid] > 0.f ? acc0 : 0.f;
+}
+
+// dW[o][k] += sum_r A[r][o] * B[r][k];  db[o] += sum_r A[r][o]   (A: [m][no], B: [m][nk], both fp32)
+__global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict__ A, const float* __restrict__ B, int m,
+                                                        int no, int nk, float* __restrict__ dW, float* __restrict__ db) {
+  const size_t total = static_cast<size_t>(no) * nk;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx / nk), k = static_cast<int>(idx % nk);
+    float acc = 0.f, bs = 0.f;
+    for (int r = 0; r < m; ++r) {
+      const float av = __ldg(A + static_cast<size_t>(r) * no + o);
+      acc = fmaf(av, __ldg(B + static_cast<size_t>(r) * nk + k), acc);
+      bs += av;
+    }
+    dW[idx] += acc;
+    if (db && k == 0) db[o] += bs;
+  }
+}
+
+// fc0: dW0[j][k] += sum_r dh0[r][j] x[r][k] (x = the NHWC policy map, k in NHWC flatten order) and
+//      dx[r][k] = sum_heads sum_j dh0[r][j] W0[j][k].  One thread per 8 consecutive k; the dh0 rows sit in shared
+//      memory 8 rows at a time.
+__global__ void __launch_bounds__(256) mlp_bwd_fc0_kernel(const HeadsBwd hd, const __nv_bfloat16* __restrict__ feat,
+                                                          int act_f, const float* __restrict__ ws, int m, int n_feat,
+                                                          __nv_bfloat16* __restrict__ dfeat, int act_g) {
+  __shared__ float s_dh0[2][8][256];
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  const bool active = k0 < n_feat;
+  const int pf = act_planes(act_f), pg = act_planes(act_g);
+  const size_t off_f = static_cast<size_t>(k0 >> 8) * (256 * pf) + (k0 & 255);
+  const size_t off_g = static_cast<size_t>(k0 >> 8) * (256 * pg) + (k0 & 255);
+  for (int r0 = 0; r0 < m; r0 += 8) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < hd.n_heads * 8 * 256; i += blockDim.x) {
+      const int hh = i / (8 * 256), r = (i / 256) % 8, j = i % 256;
+      s_dh0[hh][r][j] = r0 + r < m ? ws[static_cast<size_t>(hh) * m * 512 + static_cast<size_t>(m) * 256 +
+                                        static_cast<size_t>(r0 + r) * 256 + j]
+                                   : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float x[8][8], dx[8][8];
+    const int rows = min(8, m - r0);
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) dx[r][e] = 0.f, x[r][e] = 0.f;
+      if (r < rows) load8(feat + static_cast<size_t>(r0 + r) * (static_cast<size_t>(n_feat) * pf) + off_f, 256, pf, act_is_f16(act_f), x[r]);
+    }
+    for (int hh = 0; hh < hd.n_heads; ++hh) {
+      const float* __restrict__ W0 = hd.h[hh].w0;
+      float* __restrict__ dW0 = hd.g[hh].dw0;
+      for (int j = 0; j < 256; ++j) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0 + 4));
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+        float gw[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) gw[e] = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const float d = s_dh0[hh][r][j];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            dx[r][e] = fmaf(d, wv[e], dx[r][e]);
+            gw[e] = fmaf(d, x[r][e], gw[e]);
+          }
+        }
+        float4* gp = reinterpret_cast<float4*>(dW0 + static_cast<size_t>(j) * n_feat + k0);
+        float4 ga = gp[0], gb = gp[1];
+        ga.x += gw[0], ga.y += gw[1], ga.z += gw[2], ga.w += gw[3];
+        gb.x += gw[4], gb.y += gw[5], gb.z += gw[6], gb.w += gw[7];
+        gp[0] = ga, gp[1] = gb;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+      if (r < rows)
+        store8(dfeat + static_cast<size_t>(r0 + r) * (static_cast<size_t>(n_feat) * pg) + off_g, 256, pg, act_is_f16(act_g), dx[r]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ first-layer wgrad
+// dW[co][ci][kh][kw] += sum over pixels dz[pix][co] * x[ci][pix*stride + k - pad].  Persistent CTAs walk tiles of
+// TP x TP output pixels of one image: the dz tile (TP*TP x 64) and the input patch are staged in shared memory, thread t
+// owns the (co, k) pairs t, t + 256, ... in registers across ALL its tiles; one atomicAdd per pair and CTA at the end.
+template <int KS, int STRIDE>
+__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+                                                         float* __restrict__ dw, int b, int n_agents, int c_total,
+                                                         int c_first, int h, int w, int cout, int dz_cs, int dz_co,
+                                                         int act_g, int tiles_w, int tiles_h, int n_tiles) {
+  constexpr int TP = 8;                                   // output pixels per tile edge
+  constexpr int PAD = KS / 2;
+  constexpr int PW = (TP - 1) * STRIDE + KS;              // input patch edge
+  constexpr int KK = 3 * KS * KS;
+  constexpr int PAIRS = (64 * KK + 255) / 256;            // (co, k) pairs per thread, cout <= 64
+  extern __shared__ float s_mem[];
+  float* s_patch = s_mem;                                 // [3][PW][PW]
+  float* s_dz = s_mem + 3 * PW * PW;                      // [TP*TP][cout + 1]
+  const int ho = h / STRIDE, wo = w / STRIDE;
+  const bool f16g = act_is_f16(act_g);
+  const int pg = act_planes(act_g);
+  const int cs1 = cout + 1;
+  const int n_pairs = cout * KK;
+  float acc[PAIRS];
+#pragma unroll
+  for (int i = 0; i < PAIRS; ++i) acc[i] = 0.f;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int t = tile;
+    const int tx = t % tiles_w;
+    t /= tiles_w;
+    const int ty = t % tiles_h;
+    const int img = t / tiles_h;                          // agent-major image: agent * b + scene
+    const int agent = img / b, scene = img % b;
+    const int ox0 = tx * TP, oy0 = ty * TP;
+    const int ix0 = ox0 * STRIDE - PAD, iy0 = oy0 * STRIDE - PAD;
+    const float* xin = x + (static_cast<size_t>(scene) * c_total + c_first + 3 * agent) * h * w;
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * PW * PW; i += blockDim.x) {
+      const int ci = i / (PW * PW), py = (i / PW) % PW, px = i % PW;
+      const int iy = iy0 + py, ix = ix0 + px;
+      s_patch[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xin + (static_cast<size_t>(ci) * h + iy) * w + ix) : 0.f;
+    }
+    for (int i = threadIdx.x; i < TP * TP * (cout / 8); i += blockDim.x) {
+      const int p = i / (cout / 8), g = i % (cout / 8);
+      const int oy = oy0 + p / TP, ox = ox0 + p % TP;
+      float v[8];
+      if (oy < ho && ox < wo)
+        load8(dz + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(dz_cs) * pg) + dz_co + g * 8, dz_cs, pg, f16g, v);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_dz[p * cs1 + g * 8 + e] = v[e];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < PAIRS; ++i) {
+      const int pair = threadIdx.x + i * 256;
+      if (pair < n_pairs) {
+        const int co = pair / KK, k = pair % KK;
+        const int ci = k / (KS * KS), kh = (k / KS) % KS, kw = k % KS;
+        float a = acc[i];
+#pragma unroll 4
+        for (int p = 0; p < TP * TP; ++p) {
+          const int py = (p / TP) * STRIDE + kh, px = (p % TP) * STRIDE + kw;
+          a = fmaf(s_dz[p * cs1 + co], s_patch[(ci * PW + py) * PW + px], a);
+        }
+        acc[i] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < PAIRS; ++i) {
+    const int pair = threadIdx.x + i * 256;
+    if (pair < n_pairs) atomicAdd(dw + pair, acc[i]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ packing for dgrad
+__global__ void pack_weight_ex_kernel(const float* __restrict__ w, int cout, int cin_real, int cin, int ntaps,
+                                      int transposed, int flip, int planes, int cout_pad, __nv_bfloat16* __restrict__ out,
+                                      bool f16) {
+  const size_t ktot = static_cast<size_t>(ntaps) * cin;
+  const size_t total = static_cast<size_t>(cout_pad) * ktot;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int co = idx / ktot;
+    const int k = idx % ktot;
+    const int tap = k / cin, ci = k % cin;
+    const int st = flip ? ntaps - 1 - tap : tap;
+    float v = 0.f;
+    if (co < cout && ci < cin_real)
+      v = transposed ? w[(static_cast<size_t>(ci) * cout + co) * ntaps + st] : w[(static_cast<size_t>(co) * cin_real + ci) * ntaps + st];
+    const __nv_bfloat16 hi = float_to_elem(v, f16);
+    out[idx] = hi;
+    if (planes == 2) out[total + idx] = float_to_elem(v - elem_to_float(hi, f16), f16);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resnet / simple_decoder
+// MaxPool2d(3, 2, 1) backward: every input pixel collects the gradient of the output windows whose FIRST maximum (scan
+// order kh, kw: the element torch's max_pool2d_with_indices records) it is. One thread per (input pixel, 8 channels).
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+                                                          __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c,
+                                                          int act_f, int act_g) {
+  const int groups = c / 8, ho = h / 2, wo = w / 2;
+  const size_t total = static_cast<size_t>(n) * h * w * groups;
+  const bool f16f = act_is_f16(act_f), f16g = act_is_f16(act_g);
+  const int pf = act_planes(act_f), pg = act_planes(act_g);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t t = idx;
+    const int g = t % groups;
+    t /= groups;
+    const int ix = t % w;
+    t /= w;
+    const int iy = t % h;
+    const int img = static_cast<int>(t / h);
+    float out[8], mine[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = 0.f;
+    load8(x + ((static_cast<size_t>(img) * h + iy) * w + ix) * (static_cast<size_t>(c) * pf) + g * 8, c, pf, f16f, mine);
+    // output windows containing (iy, ix): oy with 2*oy - 1 <= iy <= 2*oy + 1
+    for (int oy = (iy) / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy >= ho) continue;
+      for (int ox = (ix) / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox >= wo) continue;
+        // is (iy, ix) the first maximum of window (oy, ox)?
+        bool first[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) first[e] = true;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int yy = 2 * oy - 1 + kh, xx = 2 * ox - 1 + kw;
+            if (yy < 0 || yy >= h || xx < 0 || xx >= w || (yy == iy && xx == ix)) continue;
+            float o[8];
+            load8(x + ((static_cast<size_t>(img) * h + yy) * w + xx) * (static_cast<size_t>(c) * pf) + g * 8, c, pf, f16f, o);
+            const bool before = yy < iy || (yy == iy && xx < ix);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) first[e] = first[e] && (before ? o[e] < mine[e] : o[e] <= mine[e]);
+          }
+        float d[8];
+        load8(dy + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(c) * pg) + g * 8, c, pg, f16g, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[e] += first[e] ? d[e] : 0.f;
+      }
+    }
+    store8(dx + ((static_cast<size_t>(img) * h + iy) * w + ix) * (static_cast<size_t>(c) * pg) + g * 8, c, pg, f16g, out);
+  }
+}
+
+// Adjoint of F.interpolate(bilinear, align_corners=False) by an integer factor: dx[n][c][iy][ix] = sum of dy over the
+// output pixels that read input (iy, ix), with the forward weights. One thread per input element.
+__global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int nc,
+                                                           int h, int w, int f) {
+  const size_t total = static_cast<size_t>(nc) * h * w;
+  const int ho = h * f, wo = w * f;
+  const float inv = 1.f / static_cast<float>(f);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ix = idx % w, iy = (idx / w) % h;
+    const size_t plane = idx / (static_cast<size_t>(w) * h);
+    const float* src = dy + plane * ho * wo;
+    // output rows whose source coordinate sy = max((oy + 0.5) / f - 0.5, 0) has floor iy - 1 or iy
+    const int oy_lo = max(0, (iy - 1) * f), oy_hi = min(ho - 1, (iy + 1) * f + f);
+    const int ox_lo = max(0, (ix - 1) * f), ox_hi = min(wo - 1, (ix + 1) * f + f);
+    float acc = 0.f;
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+      const float sy = fmaxf((oy + 0.5f) * inv - 0.5f, 0.f);
+      const int y0 = static_cast<int>(sy);
+      const int y1 = min(y0 + 1, h - 1);
+      const float ly = sy - y0;
+      float wy = 0.f;
+      if (y0 == iy) wy += 1.f - ly;
+      if (y1 == iy) wy += ly;
+      if (wy == 0.f) continue;
+      for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+        const float sx = fmaxf((ox + 0.5f) * inv - 0.5f, 0.f);
+        const int x0 = static_cast<int>(sx);
+        const int x1 = min(x0 + 1, w - 1);
+        const float lx = sx - x0;
+        float wx = 0.f;
+        if (x0 == ix) wx += 1.f - lx;
+        if (x1 == ix) wx += lx;
+        if (wx != 0.f) acc = fmaf(wy * wx, src[static_cast<size_t>(oy) * wo + ox], acc);
+      }
+    }
+    dx[idx] = acc;
+  }
+}
+
+// dst[n][2i][2j] = src[n][i][j], zeros elsewhere (+ optional accumulate of `add`): the data gradient of a stride-2 1x1
+// conv after the 1x1 stride-1 conv with the transposed weight ran on the small grid. One thread per (dst pixel, 8 ch).
+__global__ void __launch_bounds__(256) upsample_zero_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16* add,
+                                                            __nv_bfloat16* dst, int n, int h, int w, int c, int act) {
+  const int groups = c / 8;
+  const size_t total = static_cast<size_t>(n) * h * w * groups;
+  const bool f16 = act_is_f16(act);
+  const int pl = act_planes(act);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    size_t t = idx;
+    const int g = t % groups;
+    t /= groups;
+    const int x = t % w;
+    t /= w;
+    const int y = t % h;
+    const int img = static_cast<int>(t / h);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (!(x & 1) && !(y & 1))
+      load8(src + ((static_cast<size_t>(img) * (h / 2) + y / 2) * (w / 2) + x / 2) * (static_cast<size_t>(c) * pl) + g * 8, c, pl, f16, v);
+    const size_t off = ((static_cast<size_t>(img) * h + y) * w + x) * (static_cast<size_t>(c) * pl) + g * 8;
+    if (add) {
+      float o[8];
+      load8(add + off, c, pl, f16, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += o[e];
+    }
+    store8(dst + off, c, pl, f16, v);
+  }
+}
+
+// dst (channel slice) = a (+ b): gradient accumulation / concat-slice extraction on NHWC maps
+__global__ void __launch_bounds__(256) grad_add_kernel(const __nv_bfloat16* __restrict__ a, int a_cs, int a_co,
+                                                       const __nv_bfloat16* b, int b_cs, int b_co, __nv_bfloat16* dst,
+                                                       int d_cs, int d_co, size_t n_px, int c, int act) {
+  const int groups = c / 8;
+  const size_t total = n_px * groups;
+  const bool f16 = act_is_f16(act);
+  const int pl = act_planes(act);
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int g = idx % groups;
+    const size_t px = idx / groups;
+    float v[8];
+    load8(a + px * (static_cast<size_t>(a_cs) * pl) + a_co + g * 8, a_cs, pl, f16, v);
+    if (b) {
+      float o[8];
+      load8(b + px * (static_cast<size_t>(b_cs) * pl) + b_co + g * 8, b_cs, pl, f16, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += o[e];
+    }
+    store8(dst + px * (static_cast<size_t>(d_cs) * pl) + d_co + g * 8, d_cs, pl, f16, v);
+  }
+}
+
+}  // namespace
+}  // namespace w2c
+
+using namespace w2c;
+
+extern "C" int w2c_kq_mlp_heads_bwd(const void* feat, int32_t act_f, int32_t m, int32_t n_feat, const w2c_mlp_head* heads,
+                                    const w2c_mlp_head_grad* grads, int32_t n_heads, const float* ws_fwd, void* dfeat,
+                                    int32_t act_g, float* ws, w2c_stream_t stream) {
+  W2C_CHECK_ARG(feat && heads && grads && ws_fwd && dfeat && ws, "kq_mlp_bwd: null pointer");
+  W2C_CHECK_ARG(n_heads == 1 || n_heads == 2, "kq_mlp_bwd: n_heads=%d (1 or 2)", n_heads);
+  W2C_CHECK_ARG(m > 0 && n_feat > 0 && n_feat % 256 == 0, "kq_mlp_bwd: bad sizes m=%d n_feat=%d", m, n_feat);
+  W2C_CHECK_ARG(act_valid(act_f) && act_valid(act_g), "kq_mlp_bwd: bad act");
+  HeadsBwd hd{};
+  hd.n_heads = n_heads;
+  for (int i = 0; i < n_heads; ++i) {
+    const w2c_mlp_head& h = heads[i];
+    const w2c_mlp_head_grad& g = grads[i];
+    W2C_CHECK_ARG(h.w0 && h.b0 && h.w1 && h.b1 && h.w2 && h.b2 && h.out_dim > 0, "kq_mlp_bwd: head %d weights", i);
+    W2C_CHECK_ARG(g.dout && g.dw0 && g.db0 && g.dw1 && g.db1 && g.dw2 && g.db2, "kq_mlp_bwd: head %d gradients", i);
+    hd.h[i] = h, hd.g[i] = g;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  mlp_bwd_hidden_kernel<<<dim3(m, n_heads), 256, 0, s>>>(hd, ws_fwd, ws, m);
+  W2C_CHECK_LAUNCH("mlp_bwd_hidden_kernel");
+  for (int i = 0; i < n_heads; ++i) {
+    float* base = ws + static_cast<size_t>(i) * m * 512;
+    const float* h1 = base;
+    const float* dh1 = base + static_cast<size_t>(m) * 128;
+    const float* dh0 = base + static_cast<size_t>(m) * 256;
+    const float* h0 = ws_fwd + static_cast<size_t>(i) * m * 256;
+    outer_sum_kernel<<<grid_for(static_cast<size_t>(hd.h[i].out_dim) * 128, 256), 256, 0, s>>>(hd.g[i].dout, h1, m, hd.h[i].out_dim,
+                                                                                            128, hd.g[i].dw2, hd.g[i].db2);
+    W2C_CHECK_LAUNCH("outer_sum_kernel");
+    outer_sum_kernel<<<grid_for(128 * 256, 256), 256, 0, s>>>(dh1, h0, m, 128, 256, hd.g[i].dw1, hd.g[i].db1);
+    W2C_CHECK_LAUNCH("outer_sum_kernel");
+    outer_sum_kernel<<<1, 256, 0, s>>>(dh0, dh0, m, 256, 1, ws + static_cast<size_t>(n_heads) * m * 512, hd.g[i].db0);
+    W2C_CHECK_LAUNCH("outer_sum_kernel");
+  }
+  mlp_bwd_fc0_kernel<<<ceil_div(n_feat / 8, 128), 128, 0, s>>>(hd, static_cast<const __nv_bfloat16*>(feat), act_f, ws, m, n_feat,
+                                                              static_cast<__nv_bfloat16*>(dfeat), act_g);
+  W2C_CHECK_LAUNCH("mlp_bwd_fc0_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_stem_conv_wgrad(const float* x, const void* dz, float* dw, int32_t ksize, int32_t b, int32_t n_agents,
+                                   int32_t c_total, int32_t c_first, int32_t h, int32_t w_px, int32_t cout,
+                                   int32_t dz_cstride, int32_t dz_coffset, int32_t act_g, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && dz && dw, "stem_wgrad: null pointer");
+  W2C_CHECK_ARG(ksize == 3 || ksize == 7, "stem_wgrad: ksize=%d (3: 3x3 s1, 7: 7x7 s2)", ksize);
+  W2C_CHECK_ARG(b > 0 && n_agents > 0 && h > 0 && w_px > 0 && cout > 0 && cout % 8 == 0 && cout <= 64, "stem_wgrad: bad sizes (cout <= 64)");
+  W2C_CHECK_ARG(c_first >= 0 && c_first + 3 * n_agents <= c_total, "stem_wgrad: channel range");
+  W2C_CHECK_ARG(act_valid(act_g), "stem_wgrad: bad act");
+  const int cs = dz_cstride > 0 ? dz_cstride : cout;
+  W2C_CHECK_ARG(dz_coffset >= 0 && dz_coffset + cout <= cs && cs % 8 == 0 && dz_coffset % 8 == 0, "stem_wgrad: dz slice");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int stride = ksize == 7 ? 2 : 1;
+  W2C_CHECK_ARG(h % stride == 0 && w_px % stride == 0, "stem_wgrad: H, W must be even for the 7x7 s2 stem");
+  const int ho = h / stride, wo = w_px / stride;
+  const int tiles_w = ceil_div(wo, 8), tiles_h = ceil_div(ho, 8);
+  const int pw = 7 * stride + ksize;
+  const size_t smem = (static_cast<size_t>(3) * pw * pw + 64 * (cout + 1)) * sizeof(float);
+  const long long tiles = static_cast<long long>(tiles_w) * tiles_h * b * n_agents;
+  W2C_CHECK_ARG(tiles < (1ll << 31), "stem_wgrad: too many tiles");
+  const int cap = device_sm_count() * 4;
+  const int blocks = static_cast<int>(tiles < cap ? tiles : cap);
+  if (ksize == 3)
+    stem_wgrad_kernel<3, 1><<<blocks, 256, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dz), dw, b, n_agents, c_total, c_first, h,
+                                                      w_px, cout, cs, dz_coffset, act_g, tiles_w, tiles_h, static_cast<int>(tiles));
+  else
+    stem_wgrad_kernel<7, 2><<<blocks, 256, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dz), dw, b, n_agents, c_total, c_first, h,
+                                                      w_px, cout, cs, dz_coffset, act_g, tiles_w, tiles_h, static_cast<int>(tiles));
+  W2C_CHECK_LAUNCH("stem_wgrad_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_pack_conv_weight_ex(const float* w, int32_t cout, int32_t cin_real, int32_t cin, int32_t ntaps,
+                                       int32_t transposed, int32_t flip, int32_t act, void* packed, w2c_stream_t stream) {
+  W2C_CHECK_ARG(w && packed, "pack_conv_weight_ex: null pointer");
+  W2C_CHECK_ARG(cout > 0 && cin_real > 0 && cin >= cin_real && cin % 64 == 0 && (ntaps == 9 || ntaps == 1),
+                "pack_conv_weight_ex: cout=%d cin_real=%d cin=%d ntaps=%d", cout, cin_real, cin, ntaps);
+  W2C_CHECK_ARG(act_valid(act), "pack_conv_weight_ex: bad act %d", act);
+  const int cout_pad = w2c_cout_pad(cout);
+  const size_t total = static_cast<size_t>(cout_pad) * ntaps * cin;
+  pack_weight_ex_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      w, cout, cin_real, cin, ntaps, transposed, flip, act_planes(act), cout_pad, static_cast<__nv_bfloat16*>(packed),
+      act_is_f16(act));
+  W2C_CHECK_LAUNCH("pack_weight_ex_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int32_t n, int32_t h, int32_t w_px, int32_t c,
+                                    int32_t act_f, int32_t act_g, w2c_stream_t stream) {
+  W2C_CHECK_ARG(x && dy && dx && n > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0 && c % 8 == 0, "maxpool_bwd: bad arguments");
+  W2C_CHECK_ARG(act_valid(act_f) && act_valid(act_g), "maxpool_bwd: bad act");
+  const size_t total = static_cast<size_t>(n) * h * w_px * (c / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), n, h, w_px, c,
+      act_f, act_g);
+  W2C_CHECK_LAUNCH("maxpool_bwd_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_bilinear_up_bwd(const float* dy, float* dx, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
+                                   w2c_stream_t stream) {
+  W2C_CHECK_ARG(dy && dx && n > 0 && c > 0 && h > 0 && w_px > 0 && factor >= 1, "bilinear_bwd: bad arguments");
+  const size_t total = static_cast<size_t>(n) * c * h * w_px;
+  bilinear_bwd_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dx, n * c, h, w_px, factor);
+  W2C_CHECK_LAUNCH("bilinear_bwd_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_upsample_zero2(const void* src, const void* add, void* dst, int32_t n, int32_t h, int32_t w_px, int32_t c,
+                                  int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(src && dst && n > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0 && c % 8 == 0 && act_valid(act),
+                "upsample_zero2: bad arguments");
+  const size_t total = static_cast<size_t>(n) * h * w_px * (c / 8);
+  upsample_zero_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(src), static_cast<const __nv_bfloat16*>(add), static_cast<__nv_bfloat16*>(dst), n, h, w_px, c,
+      act);
+  W2C_CHECK_LAUNCH("upsample_zero_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_grad_add(const void* a, int32_t a_cstride, int32_t a_coffset, const void* b, int32_t b_cstride,
+                            int32_t b_coffset, void* dst, int32_t d_cstride, int32_t d_coffset, int64_t n_px, int32_t c,
+                            int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(a && dst && n_px > 0 && c > 0 && c % 8 == 0 && act_valid(act), "grad_add: bad arguments");
+  const int acs = a_cstride > 0 ? a_cstride : c, bcs = b_cstride > 0 ? b_cstride : c, dcs = d_cstride > 0 ? d_cstride : c;
+  W2C_CHECK_ARG(a_coffset + c <= acs && d_coffset + c <= dcs && (!b || b_coffset + c <= bcs), "grad_add: channel slices");
+  W2C_CHECK_ARG(acs % 8 == 0 && bcs % 8 == 0 && dcs % 8 == 0 && a_coffset % 8 == 0 && b_coffset % 8 == 0 && d_coffset % 8 == 0,
+                "grad_add: strides / offsets must be multiples of 8");
+  const size_t total = static_cast<size_t>(n_px) * (c / 8);
+  grad_add_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(a), acs, a_coffset, static_cast<const __nv_bfloat16*>(b), bcs, b_coffset,
+      static_cast<__nv_bfloat16*>(dst), dcs, d_coffset, static_cast<size_t>(n_px), c, act);
+  W2C_CHECK_LAUNCH("grad_add_kernel");
+  return W2C_OK;
+}

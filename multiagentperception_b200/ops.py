@@ -282,3 +282,38 @@ def act_to_nchw(x_act, c, act, cstride=0, coffset=0):
     _lib.check(lib.w2c_nhwc_to_nchw_f32(_ptr(x_act), _ptr(out), n, h, w, c, cs, coffset, act, _stream()),
                "w2c_nhwc_to_nchw_f32")
     return out
+
+
+# ------------------------------------------------------------------------------------------------ backward ops
+def pack_conv_weight_ex(w, cout, cin_real, cin_pad, ntaps, transposed, flip, act, out=None):
+    """w2c_pack_conv_weight with explicit geometry and an optional tap flip (the data-gradient operands, w2c.h)."""
+    lib = _lib.load()
+    nbytes = lib.w2c_packed_weight_bytes(cout, cin_pad, ntaps, act)
+    if out is None:
+        out = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=w.device)
+    _lib.check(lib.w2c_pack_conv_weight_ex(_ptr(w), cout, cin_real, cin_pad, ntaps, int(bool(transposed)),
+                                           int(bool(flip)), act, _ptr(out), _stream()), "w2c_pack_conv_weight_ex")
+    return out
+
+
+def conv_wgrad(x, dy, dw, *, n, h_in, w_in, cin, cout, kind, act_x, act_dy, x_cstride=0, x_coffset=0, dy_cstride=0,
+               dy_coffset=0, passes=0):
+    """dw (fp32, accumulated): [cout][ntaps][cin] for Conv2d kinds, [cin][ntaps][cout] for DECONV3X3_S2."""
+    lib = _lib.load()
+    a = _lib.WgradArgs(x=_ptr(x), dy=_ptr(dy), dw=_ptr(dw), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout,
+                       x_cstride=x_cstride, x_coffset=x_coffset, dy_cstride=dy_cstride, dy_coffset=dy_coffset, kind=kind,
+                       act_x=act_x, act_dy=act_dy, passes=passes)
+    _lib.check(lib.w2c_conv_wgrad(ctypes.byref(a), _stream()), "w2c_conv_wgrad")
+    return dw
+
+
+def bn_train_bwd(dy, y, z, dz, *, n_px, c, act_f, act_g, relu, gamma, stats, dgamma, dbeta, sums_ws, coef_ws, dres=None,
+                 dy_cs=0, dy_co=0, y_cs=0, y_co=0, z_cs=0, z_co=0, dz_cs=0, dz_co=0, dres_cs=0, dres_co=0):
+    lib = _lib.load()
+    a = _lib.BnBwdArgs(dy=_ptr(dy), y=_ptr(y), z=_ptr(z), dz=_ptr(dz), dres=_ptr(dres), n_px=n_px, c=c, dy_cstride=dy_cs,
+                       dy_coffset=dy_co, y_cstride=y_cs, y_coffset=y_co, z_cstride=z_cs, z_coffset=z_co, dz_cstride=dz_cs,
+                       dz_coffset=dz_co, dres_cstride=dres_cs, dres_coffset=dres_co, act_f=act_f, act_g=act_g,
+                       relu=int(bool(relu)), gamma=_ptr(gamma), stats=_ptr(stats), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta),
+                       sums_ws=_ptr(sums_ws), coef_ws=_ptr(coef_ws))
+    _lib.check(lib.w2c_bn_train_bwd(ctypes.byref(a), _stream()), "w2c_bn_train_bwd")
+    return dz
