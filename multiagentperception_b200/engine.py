@@ -111,13 +111,44 @@ def _stride2_view(pc):
 
 
 class WeightCache:
-    """Device-side packed operands for one (model, device, precision). Rebuilt when the model invalidates it."""
+    """Device-side packed operands for one (model, device, precision). Rebuilt when the model invalidates it.
 
-    def __init__(self, device, act):
+    live=prog (train mode): the operands are re-derived from the module's parameters INSIDE the program, every run -
+    the pack / fold launches are recorded into `prog` ahead of the first launch that reads them - because an optimizer
+    step changes the parameters in place between two forwards (trainer.py:668-670). The parameters must then live on
+    the program's device as contiguous fp32 tensors (their storage is read by the recorded launches)."""
+
+    def __init__(self, device, act, live=None):
         self.device = device
         self.act = act
+        self.live = live
         self._convs = {}
         self._misc = {}
+
+    def _param(self, t):
+        """fp32 device tensor of a parameter: a copy at setup time, the parameter's own storage in live mode."""
+        if t is None:
+            return None
+        if self.live is None:
+            return t.detach().to(self.device, torch.float32).contiguous()
+        d = t.detach()
+        if d.device != self.device or d.dtype != torch.float32 or not d.is_contiguous():
+            raise RuntimeError("train mode reads the parameters in place: they must be contiguous fp32 tensors on %s"
+                               % self.device)
+        return d
+
+    def _emit(self, fn, *args):
+        """Run a setup launch now (eval) or record it into the live program (train)."""
+        if self.live is None:
+            _lib.check(fn(*args, ops._stream()), getattr(fn, "__name__", "setup launch"))
+        else:
+            self.live._record(fn, *args)
+
+    def _emit_torch(self, fn):
+        if self.live is None:
+            fn()
+        else:
+            self.live.calls.append((lambda _s, fn=fn: fn() or 0, None, self.live._sid))
 
     # conv / transposed conv (+ optional BatchNorm) -> packed bf16 weight + fp32 scale/shift
     def conv(self, conv, bn, relu, key=None):
@@ -126,7 +157,7 @@ class WeightCache:
         if pc is not None:
             return pc
         transposed = isinstance(conv, torch.nn.ConvTranspose2d)
-        w = conv.weight.detach().to(self.device, torch.float32)
+        w = self._param(conv.weight)
         cin_real = conv.in_channels
         cin = (cin_real + 63) // 64 * 64
         kh, kw = conv.kernel_size
@@ -144,7 +175,14 @@ class WeightCache:
         if kind is None:
             raise NotImplementedError("no sm_100a kernel for conv k=%s stride=%s" % ((kh, kw), stride))
         pc = PackedConv()
-        pc.w = ops.pack_conv_weight(w, cin, transposed, self.act)
+        lib = _lib.load()
+        ntaps = kh * kw
+        pc.w = torch.empty(lib.w2c_packed_weight_bytes(conv.out_channels, cin, ntaps, self.act) // 2,
+                           dtype=torch.bfloat16, device=self.device)
+        self.keep = getattr(self, "keep", [])
+        self.keep.append(w)
+        self._emit(lib.w2c_pack_conv_weight, w.data_ptr(), conv.out_channels, cin_real, cin, ntaps, int(transposed),
+                   self.act, pc.w.data_ptr())
         pc.cin, pc.cout, pc.kind, pc.relu = cin, conv.out_channels, kind, bool(relu)
         pc.subsample = 2 if (not transposed and stride == 4) else 1
         pc.scale, pc.shift = self._fold(conv, bn)
@@ -152,10 +190,63 @@ class WeightCache:
         return pc
 
     def _fold(self, conv, bn):
+        cout = conv.out_channels
+        scale = torch.empty(cout, dtype=torch.float32, device=self.device)
+        shift = torch.empty(cout, dtype=torch.float32, device=self.device)
+        ts = [self._param(conv.bias)]
+        eps = BN_EPS_DEFAULT
         if bn is not None:
-            return ops.fold_bn(conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                               conv.out_channels, self.device)
-        return ops.fold_bn(conv.bias, None, None, None, None, BN_EPS_DEFAULT, conv.out_channels, self.device)
+            ts += [self._param(t) for t in (bn.weight, bn.bias, bn.running_mean, bn.running_var)]
+            eps = bn.eps
+        else:
+            ts += [None] * 4
+        self.keep = getattr(self, "keep", [])
+        self.keep.append(ts)
+        p = lambda t: t.data_ptr() if t is not None else None
+        self._emit(_lib.load().w2c_fold_bn, p(ts[0]), p(ts[1]), p(ts[2]), p(ts[3]), p(ts[4]), float(eps), cout,
+                   scale.data_ptr(), shift.data_ptr())
+        return scale, shift
+
+    def dgrad(self, conv):
+        """Operand of the DATA-gradient conv of `conv` (include/w2c.h, w2c_pack_conv_weight_ex): the same weight tensor
+        re-indexed so that the forward tensor-core kernels compute dL/dx from dL/dy. Returns a PackedConv whose cin /
+        cout are the gradient conv's (cin = the forward layer's padded cout)."""
+        key = ("dgrad", id(conv))
+        pc = self._convs.get(key)
+        if pc is not None:
+            return pc
+        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        w = self._param(conv.weight)
+        kh, kw = conv.kernel_size
+        ntaps = kh * kw
+        stride = conv.stride[0]
+        fin, fout = conv.in_channels, conv.out_channels      # forward channel counts
+        fout_pad = (fout + 63) // 64 * 64
+        if fin % 64:
+            raise NotImplementedError("data gradient of a conv with %d input channels" % fin)
+        if transposed:
+            kind, tr, flip = ops.CONV3X3_S2, 0, 0
+        elif (kh, kw) == (3, 3) and stride == 1:
+            kind, tr, flip = ops.CONV3X3_S1, 1, 1
+        elif (kh, kw) == (3, 3) and stride == 2:
+            kind, tr, flip = ops.DECONV3X3_S2, 1, 0
+        elif (kh, kw) == (1, 1) and stride in (1, 2):
+            kind, tr, flip = ops.CONV1X1_S1, 1, 0               # (stride 2: followed by the zero interleave)
+        else:
+            raise NotImplementedError("no data-gradient kernel for conv k=%s stride=%s" % ((kh, kw), stride))
+        lib = _lib.load()
+        pc = PackedConv()
+        pc.w = torch.empty(lib.w2c_packed_weight_bytes(fin, fout_pad, ntaps, self.act) // 2, dtype=torch.bfloat16,
+                           device=self.device)
+        self.keep = getattr(self, "keep", [])
+        self.keep.append(w)
+        self._emit(lib.w2c_pack_conv_weight_ex, w.data_ptr(), fin, fout, fout_pad, ntaps, tr, flip, self.act,
+                   pc.w.data_ptr())
+        pc.cin, pc.cout, pc.kind, pc.relu, pc.subsample = fout_pad, fin, kind, False, 1
+        pc.scale = torch.ones(fin, dtype=torch.float32, device=self.device)
+        pc.shift = torch.zeros(fin, dtype=torch.float32, device=self.device)
+        self._convs[key] = pc
+        return pc
 
     # 3-input-channel stem: fp32 [cout][k] weight + scale/shift
     def conv_raw(self, conv):
@@ -166,9 +257,27 @@ class WeightCache:
         key = ("stem_raw", id(conv))
         st = self._misc.get(key)
         if st is None:
-            w = conv.weight.detach().to(self.device, torch.float32).reshape(conv.out_channels, -1).contiguous()
+            w = self._param(conv.weight).reshape(conv.out_channels, -1)   # (a view: the parameter is contiguous)
             scale, shift = self._fold(conv, None)
             st = (w, scale, shift)
+            self._misc[key] = st
+        return st
+
+    def stem_raw_pair(self, conv_a, conv_b):
+        """Two raw first layers concatenated on the output-channel axis; refreshed per run in live mode."""
+        key = ("stem_raw_pair", id(conv_a), id(conv_b))
+        st = self._misc.get(key)
+        if st is None:
+            parts = [self.stem_raw(conv_a), self.stem_raw(conv_b)]
+            st = tuple(torch.cat((parts[0][i], parts[1][i]), 0).contiguous() for i in range(3))
+
+            def refresh(parts=parts, st=st):
+                for i in range(3):
+                    n0 = parts[0][i].shape[0]
+                    st[i][:n0].copy_(parts[0][i])
+                    st[i][n0:].copy_(parts[1][i])
+            if self.live is not None:
+                self._emit_torch(refresh)
             self._misc[key] = st
         return st
 
@@ -176,7 +285,7 @@ class WeightCache:
         key = ("stem", id(conv))
         st = self._misc.get(key)
         if st is None:
-            w = conv.weight.detach().to(self.device, torch.float32).reshape(conv.out_channels, -1).contiguous()
+            w = self._param(conv.weight).reshape(conv.out_channels, -1).contiguous()
             scale, shift = self._fold(conv, bn)
             st = (w, scale, shift)
             self._misc[key] = st
@@ -199,13 +308,17 @@ class WeightCache:
         key = ("mlp", id(fc))
         m = self._misc.get(key)
         if m is None:
-            f32 = lambda t: t.detach().to(self.device, torch.float32).contiguous()
-            w0 = fc[0].weight.detach().to(self.device, torch.float32)
-            n_feat = w0.shape[1]
+            f32 = self._param
+            w0_src = self._param(fc[0].weight)
+            n_feat = w0_src.shape[1]
             if n_feat != 256 * spatial * spatial:
                 raise ValueError("key/query head expects %d input features, the policy map provides %d"
                                  % (n_feat, 256 * spatial * spatial))
-            w0 = w0.view(256, 256, spatial, spatial).permute(0, 2, 3, 1).reshape(256, n_feat).contiguous()
+            w0 = torch.empty((256, n_feat), dtype=torch.float32, device=self.device)
+
+            def refresh(w0=w0, w0_src=w0_src):
+                w0.view(256, spatial, spatial, 256).copy_(w0_src.view(256, 256, spatial, spatial).permute(0, 2, 3, 1))
+            self._emit_torch(refresh)
             m = (w0, f32(fc[0].bias), f32(fc[2].weight), f32(fc[2].bias), f32(fc[4].weight), f32(fc[4].bias))
             self._misc[key] = m
         return m
@@ -213,7 +326,7 @@ class WeightCache:
     def tensor(self, t, key):
         v = self._misc.get(key)
         if v is None:
-            v = t.detach().to(self.device, torch.float32).contiguous()
+            v = self._param(t)
             self._misc[key] = v
         return v
 
@@ -245,6 +358,19 @@ class Program:
         self.labels_out = None
         self.pass_plan = None   # {"stack": (layer numbers)} that run ONE MMA pass (two-plane formats; see PRECISIONS)
         self.train = False      # train-mode forward: BatchNorm from batch statistics + running-stat update (bn_train.cu)
+        # grad: the train-mode forward also records its backward pass: every op appends a closure to
+        # `tape`; finish_backward() replays the tape in reverse into `bprog`, a second Program of launches that turns
+        # the gradient of the logits (copied into `dlogits` by the autograd bridge, models/agents.py) into parameter
+        # gradients. Gradient maps mirror the forward buffers one to one (same shape, same views; see grad_map).
+        self.grad = False
+        self.tape = []
+        self.bprog = None
+        self.dlogits = None
+        self.param_grads = []   # [(parameter, fn() -> gradient tensor in the parameter's layout)]
+        self._grad_roots = {}
+        self._f32_grads = {}
+        self._grad_claimed = set()
+        self._zero_list = []
 
     # ---- buffers
     def act_buf(self, n, h, w, c):
@@ -353,19 +479,42 @@ class Program:
 
     # ---- conv + BatchNorm (+ residual) (+ ReLU) as the model sees it: folded in eval mode, batch statistics in train mode
     def conv_bn(self, x, conv, bn, relu, out=None, residual=None, nchw_out=None, labels=None, passes=0):
-        if not self.train or bn is None:
+        if not self.train:
             return self.conv(x, self.weights.conv(conv, bn, relu), out=out, residual=residual, nchw_out=nchw_out,
                              labels=labels, passes=passes)
         if labels is not None or isinstance(nchw_out, str):
             raise ValueError("train mode produces logits, not label maps")
+        if bn is None:
+            # plain Conv2d (+ReLU) of simple_decoder.pred: bias and ReLU stay in the conv epilogue
+            y = self.conv(x, self.weights.conv(conv, None, relu), out=out, residual=residual, nchw_out=nchw_out)
+            if self.grad:
+                if residual is not None:
+                    raise NotImplementedError("backward of a residual conv without BatchNorm")
+                self.tape.append(lambda: self._bwd_conv_unit(x, conv, None, relu, y, None, None, nchw=nchw_out is not None))
+            return y
         pc = self.weights.conv_raw(conv)
         if nchw_out is not None:
-            z = self.conv(x, pc, nchw_out=nchw_out)
-            self._bn_train_nchw(z, bn, relu)
+            if not self.grad:
+                z = self.conv(x, pc, nchw_out=nchw_out)
+                self._bn_train_nchw(z, z, bn, relu, None)
+                return z
+            z = self.conv(x, pc, nchw_out=self.f32_buf(*nchw_out.shape))
+            stats = self.f32_buf(2 * z.shape[1])
+            self._bn_train_nchw(z, nchw_out, bn, relu, stats)
+            self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, nchw_out, z, stats, nchw=True))
+            return nchw_out
+        if not self.grad:
+            z = self.conv(x, pc, out=out)
+            self._bn_train(z, z, bn, relu, residual, None)
             return z
-        z = self.conv(x, pc, out=out)
-        self._bn_train(z, bn, relu, residual)
-        return z
+        z = self.conv(x, pc)            # the raw conv output is kept: the backward pass normalises it again
+        y = out if out is not None else self.act_buf(z.n, z.h, z.w, z.c)
+        if (y.n, y.h, y.w, y.c) != (z.n, z.h, z.w, z.c):
+            raise ValueError("conv: the caller's output map does not match the layer's output")
+        stats = self.f32_buf(2 * z.c)
+        self._bn_train(z, y, bn, relu, residual, stats)
+        self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, y, z, stats, residual=residual))
+        return y
 
     def _bn_ws(self, c):
         return (self.f32_buf(2 * c, dtype=torch.float64, zero=True), self.f32_buf(c), self.f32_buf(c))
@@ -379,20 +528,154 @@ class Program:
         return (p(bn.weight), p(bn.bias), p(bn.running_mean), p(bn.running_var), p(bn.num_batches_tracked),
                 float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
 
-    def _bn_train(self, z, bn, relu, residual=None):
-        """z: ActMap holding the raw conv output -> normalised in place with batch statistics (+residual) (+ReLU)."""
+    def _bn_train(self, z, y, bn, relu, residual=None, stats=None):
+        """z: ActMap holding the raw conv output -> y (may be z: in place) = normalised with batch statistics
+        (+residual) (+ReLU). stats: fp32 [2c] tensor receiving mean | invstd for the backward pass."""
         gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
         sums, scale, shift = self._bn_ws(z.c)
+        inplace = y is z
         self._record(self._lib.w2c_bn_train_fwd, z.buf.data_ptr(), residual.buf.data_ptr() if residual is not None else None,
                      z.n * z.h * z.w, z.c, z.cstride, z.coffset, self.act, int(bool(relu)), gamma, beta, eps, mom, rm, rv,
-                     nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr())
+                     nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr(), None if inplace else y.buf.data_ptr(),
+                     0 if inplace else y.cstride, 0 if inplace else y.coffset,
+                     stats.data_ptr() if stats is not None else None)
+        if residual is not None and not inplace and (residual.cstride, residual.coffset) != (y.cstride, y.coffset):
+            raise ValueError("bn_train: the residual must be laid out like the output")
 
-    def _bn_train_nchw(self, z, bn, relu):
+    def _bn_train_nchw(self, z, y, bn, relu, stats=None):
         gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
         n, c, h, w = z.shape
         sums, scale, shift = self._bn_ws(c)
         self._record(self._lib.w2c_bn_train_nchw_fwd, z.data_ptr(), n, c, h * w, int(bool(relu)), gamma, beta, eps, mom, rm,
-                     rv, nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr())
+                     rv, nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr(), None if y is z else y.data_ptr(),
+                     stats.data_ptr() if stats is not None else None)
+
+    # ---- backward-pass recording (grad mode) ---------------------------------------------------------------------
+    def grad_map(self, a):
+        """The gradient map of forward map `a`: the same view (shape, strides, channel slice) of a zero-initialised
+        mirror of a's underlying buffer, so that slices / image ranges of one forward buffer are slices of one
+        gradient buffer. Gradients use the program's own storage format (train mode runs bf16 / bf16x3)."""
+        st = a.buf.untyped_storage()
+        root = self._grad_roots.get(st.data_ptr())
+        if root is None:
+            root = torch.zeros(st.nbytes() // 2, dtype=torch.bfloat16, device=self.device)
+            self._grad_roots[st.data_ptr()] = root
+        gv = torch.as_strided(root, a.buf.shape, a.buf.stride(), a.buf.storage_offset())
+        return ActMap(gv, a.n, a.h, a.w, a.c, a.cstride, a.coffset)
+
+    def f32_grad(self, t):
+        """Gradient buffer of an fp32 NCHW tensor of the forward program (the logits; simple_decoder's small map)."""
+        st = t.untyped_storage()
+        root = self._f32_grads.get(st.data_ptr())
+        if root is None:
+            root = torch.zeros(st.nbytes() // 4, dtype=torch.float32, device=self.device)
+            self._f32_grads[st.data_ptr()] = root
+        return torch.as_strided(root, t.shape, t.stride(), t.storage_offset())
+
+    def _claim(self, g):
+        """True for the first writer of gradient map g (later writers must accumulate)."""
+        key = (g.buf.data_ptr(), g.n, g.coffset, g.c)
+        first = key not in self._grad_claimed
+        self._grad_claimed.add(key)
+        return first
+
+    def _pgrad(self, *shape):
+        t = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        self._zero_list.append(t)
+        return t
+
+    def _bwd_conv_unit(self, x, conv, bn, relu, y, z, stats, residual=None, nchw=False, stem=None):
+        """Backward of one conv (+BatchNorm) (+residual) (+ReLU) unit, recorded into self.bprog: gradient of y ->
+        gradient of the raw conv output (BatchNorm / ReLU backward, csrc/bn_bwd.cu) -> weight gradient (csrc/wgrad.cu)
+        and data gradient (the forward conv kernels on the re-indexed weight). x: input ActMap, or None for a first
+        layer (`stem` = (x_nchw, b, n_agents, h, w, c_first, ksize): its weight gradient reads the fp32 views)."""
+        bp = self.bprog
+        lib = self._lib
+        transposed = isinstance(conv, torch.nn.ConvTranspose2d)
+        cout = conv.out_channels
+        cpad = (cout + 63) // 64 * 64
+        g_act = self.act
+        p = lambda t: t.data_ptr() if t is not None else None
+        # ---- 1. gradient of the raw conv output
+        dgamma = self._pgrad(cout) if bn is not None else None
+        dbeta = self._pgrad(cout)          # BatchNorm bias, or the conv bias when there is no BatchNorm
+        sums = bp.f32_buf(2 * cout, dtype=torch.float64, zero=True)
+        coef = bp.f32_buf(3 * cout)
+        gamma_t = bn.weight if bn is not None else None
+        if nchw:
+            n, _, hh, ww = y.shape
+            dy_t = self.f32_grad(y)
+            dz = bp.act_buf(n, hh, ww, cpad)
+            bp._record(lib.w2c_bn_train_nchw_bwd, dy_t.data_ptr(), y.data_ptr(), p(z), dz.buf.data_ptr(), n, cout, hh * ww,
+                       cpad, dz.cstride, 0, g_act, int(bool(relu)), p(gamma_t), p(stats), p(dgamma), dbeta.data_ptr(),
+                       sums.data_ptr(), coef.data_ptr())
+        else:
+            gy = self.grad_map(y)
+            if z is None:
+                dz = bp.act_buf(y.n, y.h, y.w, y.c)
+            else:
+                dz = self.grad_map(z)
+            dres = None
+            if residual is not None:
+                dres = self.grad_map(residual)
+                if not self._claim(dres):
+                    raise NotImplementedError("residual gradient must be the first gradient of its map")
+            a = _lib.BnBwdArgs(dy=gy.buf.data_ptr(), y=y.buf.data_ptr(), z=z.buf.data_ptr() if z is not None else None,
+                               dz=dz.buf.data_ptr(), dres=dres.buf.data_ptr() if dres is not None else None,
+                               n_px=y.n * y.h * y.w, c=y.c, dy_cstride=gy.cstride, dy_coffset=gy.coffset,
+                               y_cstride=y.cstride, y_coffset=y.coffset, z_cstride=z.cstride if z is not None else 0,
+                               z_coffset=z.coffset if z is not None else 0, dz_cstride=dz.cstride, dz_coffset=dz.coffset,
+                               dres_cstride=dres.cstride if dres is not None else 0,
+                               dres_coffset=dres.coffset if dres is not None else 0, act_f=self.act, act_g=g_act,
+                               relu=int(bool(relu)), gamma=p(gamma_t), stats=p(stats), dgamma=p(dgamma),
+                               dbeta=dbeta.data_ptr(), sums_ws=sums.data_ptr(), coef_ws=coef.data_ptr())
+            bp.keep.append(a)
+            bp._record(lib.w2c_bn_train_bwd, ctypes.byref(a))
+        if bn is not None:
+            self.param_grads.append((bn.weight, lambda: dgamma))
+            self.param_grads.append((bn.bias, lambda: dbeta))
+            if conv.bias is not None:   # a bias in front of a train-mode BatchNorm has no gradient (the mean removes it)
+                zb = torch.zeros(cout, dtype=torch.float32, device=self.device)
+                self.param_grads.append((conv.bias, lambda: zb))
+        elif conv.bias is not None:
+            self.param_grads.append((conv.bias, lambda: dbeta))
+        # ---- 2. weight gradient
+        kh, kw = conv.kernel_size
+        if stem is not None:
+            x_nchw, b, n_agents, h, w, c_first, ksize = stem
+            dw = self._pgrad(cout, 3, ksize, ksize)
+            bp._record(lib.w2c_stem_conv_wgrad, x_nchw.data_ptr(), dz.buf.data_ptr(), dw.data_ptr(), ksize, b, n_agents,
+                       x_nchw.shape[1], c_first, h, w, cout, dz.cstride, dz.coffset, g_act)
+            self.param_grads.append((conv.weight, lambda: dw))
+            return
+        stride = conv.stride[0]
+        kind = self.weights.conv_raw(conv).kind if bn is not None else self.weights.conv(conv, None, relu).kind
+        if stride == 4:
+            raise NotImplementedError("backward of the stride-4 squeezer (feat_squeezer=4)")
+        d0, d1 = (x.c, cpad) if transposed else (cpad, x.c)
+        dwk = self._pgrad(d0, kh * kw, d1)
+        wa = _lib.WgradArgs(x=x.buf.data_ptr(), dy=dz.buf.data_ptr(), dw=dwk.data_ptr(), n=x.n, h_in=x.h, w_in=x.w,
+                            cin=x.c, cout=cpad, x_cstride=x.cstride, x_coffset=x.coffset, dy_cstride=dz.cstride,
+                            dy_coffset=dz.coffset, kind=kind, act_x=self.act, act_dy=g_act, passes=0)
+        bp.keep.append(wa)
+        bp._record(lib.w2c_conv_wgrad, ctypes.byref(wa))
+
+        def weight_grad(dwk=dwk, d0=d0, d1=d1):
+            gq = dwk.view(d0, kh, kw, d1).permute(0, 3, 1, 2)
+            return gq[:, :cout] if transposed else gq[:cout]
+        self.param_grads.append((conv.weight, weight_grad))
+        # ---- 3. data gradient (not for maps nothing upstream differentiates through)
+        gx = self.grad_map(x)
+        first = self._claim(gx)
+        pcd = bp.weights.dgrad(conv)
+        if (kh, kw) == (1, 1) and stride == 2:
+            small = bp.conv(dz, pcd)
+            bp._record(lib.w2c_upsample_zero2, small.buf.data_ptr(), None if first else gx.buf.data_ptr(), gx.buf.data_ptr(),
+                       x.n, x.h, x.w, x.c, g_act)
+            if gx.cstride != gx.c:
+                raise NotImplementedError("stride-2 1x1 data gradient into a channel slice")
+        else:
+            bp.conv(dz, pcd, out=gx, residual=None if first else gx)
 
     def stem_bn(self, x_in, conv, bn, b, n_agents, h, w, c_first=0):
         """First layer (3x3 s1 of n_segnet_encoder or 7x7 s2 of resnet18) + BatchNorm + ReLU."""
@@ -401,8 +684,18 @@ class Program:
             st = self.weights.stem(conv, bn)
             return (self.stem7x7 if k7 else self.stem3x3)(x_in, st, b, n_agents, h, w, c_first)
         z = (self.stem7x7 if k7 else self.stem3x3)(x_in, self.weights.stem_raw(conv), b, n_agents, h, w, c_first, raw=True)
-        self._bn_train(z, bn, True)
-        return z
+        return self._stem_bn_tail(x_in, conv, bn, z, b, n_agents, h, w, c_first, 7 if k7 else 3)
+
+    def _stem_bn_tail(self, x_in, conv, bn, z, b, n_agents, h, w, c_first, ksize):
+        if not self.grad:
+            self._bn_train(z, z, bn, True)
+            return z
+        y = self.act_buf(z.n, z.h, z.w, z.c)
+        stats = self.f32_buf(2 * z.c)
+        self._bn_train(z, y, bn, True, None, stats)
+        self.tape.append(lambda: self._bwd_conv_unit(None, conv, bn, True, y, z, stats,
+                                                     stem=(x_in, b, n_agents, h, w, c_first, ksize)))
+        return y
 
     def stem_pair_bn(self, x_in, conv_a, bn_a, conv_b, bn_b, b, n_agents, h, w):
         """Two encoders' first layers as one 3 -> 128 stem writing two dense 64-channel maps (+ BatchNorm + ReLU)."""
@@ -410,14 +703,11 @@ class Program:
         fn = self.stem7x7 if k7 else self.stem3x3
         if not self.train:
             return fn(x_in, self.weights.stem_pair(conv_a, bn_a, conv_b, bn_b), b, n_agents, h, w, split=True)
-        wa, sa, ha = self.weights.stem_raw(conv_a)
-        wb, sb, hb = self.weights.stem_raw(conv_b)
-        st = (torch.cat((wa, wb), 0).contiguous(), torch.cat((sa, sb)).contiguous(), torch.cat((ha, hb)).contiguous())
-        self.keep.append(st)
+        st = self.weights.stem_raw_pair(conv_a, conv_b)
         za, zb = fn(x_in, st, b, n_agents, h, w, split=True, raw=True)
-        self._bn_train(za, bn_a, True)
-        self._bn_train(zb, bn_b, True)
-        return za, zb
+        ks = 7 if k7 else 3
+        return (self._stem_bn_tail(x_in, conv_a, bn_a, za, b, n_agents, h, w, 0, ks),
+                self._stem_bn_tail(x_in, conv_b, bn_b, zb, b, n_agents, h, w, 0, ks))
 
     def can_fuse_head(self, stack):
         """True when conv1 + conv2 of an n_segnet encoder in `stack` may run as the fused head kernel: always in the
@@ -500,12 +790,25 @@ class Program:
     def maxpool(self, x):
         out = self.act_buf(x.n, x.h // 2, x.w // 2, x.c)
         self._record(self._lib.w2c_maxpool3x3s2_fwd, x.buf.data_ptr(), out.buf.data_ptr(), x.n, x.h, x.w, x.c, self.act)
+        if self.grad:
+            def bwd():
+                if x.cstride != x.c or x.coffset:
+                    raise NotImplementedError("max-pool backward on a channel slice")
+                gx, gy = self.grad_map(x), self.grad_map(out)
+                if not self._claim(gx):
+                    raise NotImplementedError("max-pool gradient must be the first gradient of its input")
+                self.bprog._record(self._lib.w2c_maxpool3x3s2_bwd, x.buf.data_ptr(), gy.buf.data_ptr(), gx.buf.data_ptr(),
+                                   x.n, x.h, x.w, x.c, self.act, self.act)
+            self.tape.append(bwd)
         return out
 
     def bilinear(self, x_nchw, factor):
         n, c, h, w = x_nchw.shape
         out = self.f32_buf(n, c, h * factor, w * factor)
         self._record(self._lib.w2c_bilinear_up_fwd, x_nchw.data_ptr(), out.data_ptr(), n, c, h, w, factor)
+        if self.grad:
+            self.tape.append(lambda: self.bprog._record(self._lib.w2c_bilinear_up_bwd, self.f32_grad(out).data_ptr(),
+                                                        self.f32_grad(x_nchw).data_ptr(), n, c, h, w, factor))
         return out
 
     def bilinear_argmax(self, x_nchw, factor, labels):
@@ -531,9 +834,10 @@ class Program:
                      w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), out_dim, out.data_ptr(), ws.data_ptr())
         return out
 
-    def kq_mlp_heads(self, feat, heads):
+    def kq_mlp_heads(self, feat, heads, fcs=None):
         """heads: [(mlp weights tuple, out_dim, out tensor or None), ...] (1 or 2) over the same feature map, run as
-        ONE fc0 + ONE fc12 launch. Returns the output tensors."""
+        ONE fc0 + ONE fc12 launch. Returns the output tensors. fcs: the nn.Sequential of each head (grad mode: where
+        the parameter gradients go)."""
         m = feat.n
         n_feat = feat.h * feat.w * feat.c
         arr = (_lib.MlpHead * len(heads))()
@@ -551,11 +855,42 @@ class Program:
         self.keep.append(arr)
         self._record(self._lib.w2c_kq_mlp_heads_fwd, feat.buf.data_ptr(), self.act, m, n_feat, arr, len(heads),
                      ws.data_ptr())
+        if self.grad:
+            self.tape.append(lambda: self._bwd_mlp_heads(feat, heads, fcs, arr, outs, ws, m, n_feat))
         return outs
+
+    def _bwd_mlp_heads(self, feat, heads, fcs, arr, outs, ws_fwd, m, n_feat):
+        if fcs is None:
+            raise NotImplementedError("kq_mlp_heads: the modules are needed to route the parameter gradients")
+        if feat.cstride != feat.c or feat.coffset or feat.c != 256:
+            raise NotImplementedError("MLP-head backward needs a dense 256-channel policy map")
+        bp = self.bprog
+        garr = (_lib.MlpHeadGrad * len(heads))()
+        side = feat.h
+        for i, ((mlp, out_dim, _), fc) in enumerate(zip(heads, fcs)):
+            dout = self.f32_grad(outs[i])
+            dw0, db0 = self._pgrad(256, n_feat), self._pgrad(256)
+            dw1, db1 = self._pgrad(128, 256), self._pgrad(128)
+            dw2, db2 = self._pgrad(out_dim, 128), self._pgrad(out_dim)
+            garr[i] = _lib.MlpHeadGrad(dout.data_ptr(), dw0.data_ptr(), db0.data_ptr(), dw1.data_ptr(), db1.data_ptr(),
+                                       dw2.data_ptr(), db2.data_ptr())
+            # fc.0.weight is stored NCHW-flattened, the kernel works in NHWC flatten order (WeightCache.mlp)
+            self.param_grads.append((fc[0].weight, lambda dw0=dw0: dw0.view(256, side, side, 256).permute(0, 3, 1, 2)
+                                     .reshape(256, n_feat)))
+            for prm, gt in ((fc[0].bias, db0), (fc[2].weight, dw1), (fc[2].bias, db1), (fc[4].weight, dw2),
+                            (fc[4].bias, db2)):
+                self.param_grads.append((prm, lambda gt=gt: gt))
+        gfeat = self.grad_map(feat)
+        if not self._claim(gfeat):
+            raise NotImplementedError("MLP-head gradient must be the first gradient of the policy map")
+        ws = bp.f32_buf(len(heads) * m * 512 + 256)
+        bp.keep.append(garr)
+        bp._record(self._lib.w2c_kq_mlp_heads_bwd, feat.buf.data_ptr(), self.act, m, n_feat, arr, garr, len(heads),
+                   ws_fwd.data_ptr(), gfeat.buf.data_ptr(), self.act, ws.data_ptr())
 
     def attn(self, keys, queries, wq, bq, val, fused, prob, coef, action, connect, *, b_sz, n_k, n_q, k_dim, q_dim,
              mode, sparse=False, mask_self=False, temperature=1.0, diag_bias=0.0, thresh=0.2, q_first=0, q_count=0,
-             agents_per_rank=0, keys_rank_stride=0, queries_rank_stride=0, val_rank_stride=0):
+             agents_per_rank=0, keys_rank_stride=0, queries_rank_stride=0, val_rank_stride=0, attn_module=None):
         p = lambda t: t.data_ptr() if t is not None else None
         a = _lib.AttnArgs(keys=p(keys), queries=p(queries), wq=p(wq), bq=p(bq), val=val.buf.data_ptr(),
                           fused=fused.buf.data_ptr(), prob_out=p(prob), coef_out=p(coef), action=p(action),
@@ -570,6 +905,36 @@ class Program:
             raise ValueError("attention values must be a dense NHWC map")
         self.keep.append(a)
         self._record(self._lib.w2c_attn_fuse_fwd, ctypes.byref(a))
+        if self.grad:
+            if mode != ops.FUSE_SOFTMAX or agents_per_rank or coef is None:
+                raise NotImplementedError("attention backward: dense agent-major softmax mode with coef_out only")
+            self.tape.append(lambda: self._bwd_attn(keys, queries, wq, bq, val, fused, coef, b_sz, n_k, n_q, k_dim, q_dim,
+                                                    sparse, temperature, attn_module))
+
+    def _bwd_attn(self, keys, queries, wq, bq, val, fused, coef, b_sz, n_k, n_q, k_dim, q_dim, sparse, temperature,
+                  attn_module):
+        bp = self.bprog
+        p = lambda t: t.data_ptr() if t is not None else None
+        gval = self.grad_map(val)
+        first = self._claim(gval)
+        gfused = self.grad_map(fused)
+        dkeys, dqueries = self.f32_grad(keys), self.f32_grad(queries)
+        dwq = dbq = None
+        if wq is not None:
+            if attn_module is None:
+                raise NotImplementedError("attention backward needs the projection module for its parameter gradients")
+            dwq, dbq = self._pgrad(*wq.shape), self._pgrad(*bq.shape)
+            self.param_grads.append((attn_module.linear.weight, lambda: dwq))
+            self.param_grads.append((attn_module.linear.bias, lambda: dbq))
+        dp = bp.f32_buf(b_sz * n_k * n_q, zero=True)
+        a = _lib.AttnBwdArgs(keys=p(keys), queries=p(queries), wq=p(wq), bq=p(bq), val=val.buf.data_ptr(),
+                             dfused=gfused.buf.data_ptr(), prob=p(coef), dval=gval.buf.data_ptr(), dkeys=p(dkeys),
+                             dqueries=p(dqueries), dwq=p(dwq), dbq=p(dbq), dp_ws=p(dp), b_sz=b_sz, n_k=n_k, n_q=n_q,
+                             k_dim=k_dim, q_dim=q_dim, hw=val.h * val.w, c=val.c, dfused_cstride=gfused.cstride,
+                             dfused_coffset=gfused.coffset, act_f=self.act, act_g=self.act, sparse=int(bool(sparse)),
+                             dval_accumulate=0 if first else 1, temperature=float(temperature))
+        bp.keep.append(a)
+        bp._record(self._lib.w2c_attn_fuse_bwd, ctypes.byref(a))
 
     def host_op(self, fn, capturable=False):
         """A torch-side step between kernel launches (the torch.distributed collective of a sharded forward); fn() is
@@ -590,12 +955,23 @@ class Program:
         identity), channel slice of `src`."""
         if src.c != dst.c or (src.h, src.w) != (dst.h, dst.w):
             raise ValueError("gather_images: source and destination maps differ in shape")
+        if self.grad:
+            raise NotImplementedError("backward of the indexed image gather (selection / ComNet baselines)")
         self._record(self._lib.w2c_gather_images_fwd, src.buf.data_ptr(), dst.buf.data_ptr(),
                      sel.data_ptr() if sel is not None else None, n_groups, b, src.h, src.w, src.c, src.cstride,
                      src.coffset, dst.cstride, dst.coffset, self.act)
 
     def copy_channels(self, src, dst):
         """dst[..., slice] = src (device-to-device strided copy through torch; used for concat inputs only)."""
+        if self.grad:
+            def bwd():
+                gs, gd = self.grad_map(src), self.grad_map(dst)
+                first = self._claim(gs)
+                self.bprog._record(self._lib.w2c_grad_add, gd.buf.data_ptr(), gd.cstride, gd.coffset,
+                                   None if first else gs.buf.data_ptr(), gs.cstride, gs.coffset, gs.buf.data_ptr(),
+                                   gs.cstride, gs.coffset, src.n * src.h * src.w, src.c, self.act)
+            self.tape.append(bwd)
+
         def run(_stream):
             for pl in range(self.planes):
                 d = dst.buf[..., pl * dst.cstride + dst.coffset: pl * dst.cstride + dst.coffset + dst.c]
@@ -609,6 +985,43 @@ class Program:
             t.zero_()
             return 0
         self.calls.append((run, None, self._sid))
+
+    # ---- backward program
+    def begin_backward(self):
+        """Switch the program into grad mode (before any op is recorded): a second Program collects the backward
+        launches, with its own live operand cache (the data-gradient weights are re-packed every backward)."""
+        if self.act not in (ops.ACT_BF16, ops.ACT_BF16X2):
+            raise NotImplementedError(
+                "the backward pass runs in the 'bf16' / 'bf16x3' precisions (gradients need the fp32 exponent range, and "
+                "the tensor cores take one element type per MMA): model.set_precision('bf16x3') for training")
+        self.grad = True
+        self.bprog = Program(None, self.device, self.act)
+        self.bprog.weights = WeightCache(self.device, self.act, live=self.bprog)
+
+    def finish_backward(self, pred):
+        """Replay the tape in reverse into self.bprog. pred: the fp32 logits the loss is taken on."""
+        self.dlogits = self.f32_grad(pred)
+        bp = self.bprog
+        zl = self._zero_list
+
+        def zero(_s):
+            if zl:
+                torch._foreach_zero_(zl)
+            return 0
+        bp.calls.append((zero, None, 0))
+        for fn in reversed(self.tape):
+            fn()
+        self.tape = None
+        # the prologue was recorded before the list was complete; it reads zl at run time
+
+    def param_gradients(self):
+        """{parameter: fp32 gradient tensor in the parameter's layout} after a run of self.bprog (views of the static
+        gradient buffers: copy before the next backward)."""
+        out = {}
+        for prm, fn in self.param_grads:
+            g = fn()
+            out[prm] = g if prm not in out else out[prm] + g   # a module used twice in one forward
+        return out
 
     # ---- execution
     def _segments(self):

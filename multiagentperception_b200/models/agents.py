@@ -228,7 +228,37 @@ def _build_policy(prog, pol, x_nchw, b, n_agents, h, w, stem=None):
 
 class _Compiled:
     """One compiled forward: the program, its static input and its output buffers."""
-    __slots__ = ("prog", "x", "out")
+    __slots__ = ("prog", "x", "out", "generation")
+
+
+class _BackwardBridge(torch.autograd.Function):
+    """Hands the program's logits to autograd: `loss.backward()` (trainer.py:669) reaches backward() below with the
+    gradient of the logits, which is copied into the backward program's static input; the program's launches
+    (engine.Program.bprog: BatchNorm / ReLU backward, tensor-core weight and data gradients, attention and MLP-head
+    backward) then produce every parameter gradient, returned to autograd so that .grad accumulates as usual."""
+
+    @staticmethod
+    def forward(ctx, model, compiled, pred, *params):
+        ctx.model, ctx.compiled, ctx.generation = model, compiled, compiled.generation
+        ctx.params = params
+        return pred.view_as(pred)
+
+    @staticmethod
+    def backward(ctx, gpred):
+        c = ctx.compiled
+        if c.generation != ctx.generation:
+            raise RuntimeError("backward() after another forward of the same input shape: the program's buffers hold "
+                               "the newer step (call backward before the next forward)")
+        prog = c.prog
+        with torch.cuda.device(prog.device), torch.no_grad():
+            prog.dlogits.copy_(gpred)
+            prog.bprog.run(ctx.model._w2c["graphs"])
+            grads = prog.param_gradients()
+        out = []
+        for prm in ctx.params:
+            g = grads.get(prm)
+            out.append(None if g is None else g.to(prm.dtype).reshape(prm.shape).clone())
+        return (None, None, None) + tuple(out)
 
 
 # ------------------------------------------------------------------------------------------- model base
@@ -310,6 +340,8 @@ class _W2CModel(nn.Module):
         # and updates its running statistics in place (csrc/bn_train.cu). It is a forward only: the outputs carry no
         # autograd graph, so loss.backward() on them raises; the backward pass is not part of this path.
         train = bool(self.training)
+        # grad: also record the backward pass (the second half of SURVEY 8 f-1) when autograd is listening
+        grad = train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
         if train and (self._w2c["io"]["u8"] or self._w2c["io"]["labels"]):
             raise RuntimeError("train mode takes the fp32 views and returns logits (set_input_format / "
                                "set_label_output are evaluation-path options)")
@@ -325,16 +357,23 @@ class _W2CModel(nn.Module):
         dev = inputs.device
         precision = self._w2c["precision"]
         act = engine.PRECISIONS[precision]
-        key = (dev, precision, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"], train)
+        key = (dev, precision, tuple(inputs.shape), tag, io["u8"], io["mean"], io["norm"], io["labels"], io["logits"], train,
+               grad)
         c = self._w2c["programs"].get(key)
         if c is None:
             wkey = (dev, act)
             wc = self._w2c["weights"].get(wkey)
-            if wc is None:
+            if wc is None and not train:
                 wc = engine.WeightCache(dev, act)
                 self._w2c["weights"][wkey] = wc
             with torch.cuda.device(dev), torch.no_grad():
                 prog = engine.Program(wc, dev, act)
+                if train:
+                    # the optimizer changes the parameters between two forwards: a train-mode program re-derives its
+                    # packed operands from the live parameters on every run (engine.WeightCache, live mode)
+                    prog.weights = engine.WeightCache(dev, act, live=prog)
+                if grad:
+                    prog.begin_backward()
                 prog.pass_plan = engine.MIXED_ONE_PASS if (precision == "mixed" and not train) else None
                 prog.train = train
                 prog.want_labels, prog.want_logits = io["labels"], io["logits"]
@@ -345,17 +384,29 @@ class _W2CModel(nn.Module):
                 c.prog = prog
                 c.x = prog.f32_buf(*inputs.shape, dtype=torch.uint8 if io["u8"] else torch.float32)
                 c.out = builder(prog, c.x)
+                c.generation = 0
+                if grad:
+                    prog.finish_backward(c.out["pred"])
             self._w2c["programs"][key] = c
         with torch.cuda.device(dev), torch.no_grad():
             c.x.copy_(inputs)
             if pre_run is not None:
                 pre_run(c)  # per-call device state of a static program (e.g. the drawn selection indices)
             c.prog.run(self._w2c["graphs"])
+        c.generation += 1
         self._w2c["last"] = c
         return c
 
     def _ret(self, t):
         return t.clone() if self._w2c["clone_outputs"] else t
+
+    def _ret_pred(self, c):
+        """The logits of a compiled forward; in train mode with autograd listening they carry the backward program."""
+        pred = self._ret(c.out["pred"])
+        if c.prog.grad and torch.is_grad_enabled():
+            params = [p for p in self.parameters() if p.requires_grad]
+            pred = _BackwardBridge.apply(self, c, pred, *params)
+        return pred
 
 
 def _bhw(inputs):
@@ -392,7 +443,7 @@ class Single_agent(_W2CModel):
             feat = _build_encoder(prog, self.encoder, "encoder", x, b, 1, h, w)
             return {"pred": _build_decoder(prog, self.decoder, feat)}
 
-        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+        return self._ret_pred(self._compiled(inputs, "fwd", build))
 
 
 class _AttentionModel(_W2CModel):
@@ -478,12 +529,18 @@ class _AttentionModel(_W2CModel):
         """[rows, 128] fp32 buffer whose every row is u = linear_feat.weight^T linear_out.weight^T (see
         _AdditiveAttention): the stand-in query matrix of the additive attention."""
         a = self.attention_net
+        if prog.grad:
+            raise NotImplementedError("backward of the additive attention (its projections fold into one fixed query "
+                                      "vector here): train with attention='general' or under torch.no_grad()")
         key = ("additive_u", id(a), rows)
         u = prog.weights._misc.get(key)
         if u is None:
-            w = a.linear_out.weight.detach().to(prog.device, torch.float32) @ \
-                a.linear_feat.weight.detach().to(prog.device, torch.float32)          # [1, 128]
-            u = w.expand(rows, 128).contiguous()
+            u = torch.empty((rows, 128), dtype=torch.float32, device=prog.device)
+            w_out, w_feat = prog.weights._param(a.linear_out.weight), prog.weights._param(a.linear_feat.weight)
+
+            def refresh(u=u, w_out=w_out, w_feat=w_feat):
+                u.copy_((w_out @ w_feat).expand(rows, 128))
+            prog.weights._emit_torch(refresh)       # (train mode: re-derived from the live parameters every run)
             prog.weights._misc[key] = u
         return u
 
@@ -533,9 +590,9 @@ class _AttentionModel(_W2CModel):
         if self.has_query:
             heads.append((prog.weights.mlp(self.query_net.fc, qk.h), self.query_size,
                           None if dst is None else dst[1]))
-            keys, queries = prog.kq_mlp_heads(qk, heads)  # both heads in one pair of launches
+            keys, queries = prog.kq_mlp_heads(qk, heads, fcs=(self.key_net.fc, self.query_net.fc))  # one pair of launches
         else:
-            keys, = prog.kq_mlp_heads(qk, heads)
+            keys, = prog.kq_mlp_heads(qk, heads, fcs=(self.key_net.fc,))
             queries = prog.f32_buf(n * b, self.query_size) if dst is None else dst[1]
             queries.fill_(1.0)  # torch.ones(batch, 1, query_size), agent.py:1144
         prog.join()
@@ -589,6 +646,9 @@ class MIMOcom(_AttentionModel):
         if self.shared_img_encoder != "unified":
             raise ValueError("Incorrect encoder")  # agent.py:1116-1118,1335-1337: only the unified encoder exists
         if self._w2c.get("shard") is not None:
+            if self.training and torch.is_grad_enabled():
+                raise NotImplementedError("the backward pass is not sharded by agent: train on replicas "
+                                          "(DistributedDataParallel over scenes) or under torch.no_grad()")
             return self._forward_sharded(inputs, training, MO_flag, inference)
         n = self.agent_num
         _check_views(inputs, n)
@@ -620,7 +680,7 @@ class MIMOcom(_AttentionModel):
             prog.memset(connect)
             prog.attn(keys, queries, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=n,
                       k_dim=self.key_size, q_dim=self.query_size, mode=_MODES[mode], mask_self=self.who,
-                      temperature=temp, diag_bias=0.0 if self.who else 0.001)
+                      temperature=temp, diag_bias=0.0 if self.who else 0.001, attn_module=self.attention_net)
             return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob, "action": action,
                     "connect": connect}
 
@@ -635,7 +695,7 @@ class MIMOcom(_AttentionModel):
             num_connect = n - 1
         else:  # counted by the attention kernel; stays on the device until somebody reads it (lazy.DeviceScalar)
             num_connect = DeviceScalar.from_count(out["connect"], n * b)
-        return self._ret(out["pred"]), prob, action, num_connect
+        return self._ret_pred(c), prob, action, num_connect
 
 
     def _forward_sharded(self, inputs, training, MO_flag, inference):
@@ -760,12 +820,13 @@ class LearnWhen2Com(_AttentionModel):
             # one requester (agent 0: the first b rows of the agent-major query matrix), all five supporters
             prog.attn(keys, queries, wq, bq, val, fused, prob, coef, action, connect, b_sz=b, n_k=n, n_q=1,
                       k_dim=self.key_size, q_dim=q_dim, mode=_MODES[mode], sparse=self.sparse,
-                      temperature=temp, diag_bias=0.0)
+                      temperature=temp, diag_bias=0.0, attn_module=self.attention_net)
             return {"pred": _build_decoder(prog, self.decoder, fused), "prob": prob, "coef": coef,
                     "action": action, "connect": connect}
 
-        out = self._compiled(inputs, mode, build).out
-        pred = self._ret(out["pred"])
+        c = self._compiled(inputs, mode, build)
+        out = c.out
+        pred = self._ret_pred(c)
         prob = out["prob"].transpose(1, 2).clone()  # (B, 1, 5) like attn_orig.transpose(2, 1), agent.py:368
         action = torch.argmax(prob, dim=2)
         if training:
@@ -805,6 +866,7 @@ class LearnWho2Com(_AttentionModel):
             val, keys, queries = self._keys_queries(prog, x, b, n, h, w)
             wq, bq, temp = self._attn_weights(prog)
             prob = prog.f32_buf(b, n - 1, 1)
+            coef = prog.f32_buf(b, n - 1, 1)
             action = prog.f32_buf(b, 1, dtype=torch.int64)
             cat = prog.act_buf(b, val.h, val.w, 2 * val.c)  # cat(own, aux) on channels, agent.py:623
             prog.copy_channels(val.images(0, b), cat.slice(0, val.c))
@@ -812,14 +874,15 @@ class LearnWho2Com(_AttentionModel):
             q_dim = self.query_size
             if isinstance(self.attention_net, _AdditiveAttention):
                 queries, q_dim = self._additive_queries(prog, queries.shape[0]), 128
-            prog.attn(keys[b:], queries, wq, bq, val.images(b, (n - 1) * b), cat.slice(val.c, val.c), prob, None,
+            prog.attn(keys[b:], queries, wq, bq, val.images(b, (n - 1) * b), cat.slice(val.c, val.c), prob, coef,
                       action, None, b_sz=b, n_k=n - 1, n_q=1, k_dim=self.key_size, q_dim=q_dim,
-                      mode=_MODES[mode], sparse=self.sparse, temperature=temp, diag_bias=0.0)
+                      mode=_MODES[mode], sparse=self.sparse, temperature=temp, diag_bias=0.0,
+                      attn_module=self.attention_net)
             return {"pred": _build_decoder(prog, self.decoder, cat), "prob": prob}
 
-        out = self._compiled(inputs, mode, build).out
-        prob = out["prob"].transpose(1, 2).clone()
-        return self._ret(out["pred"]), prob, torch.argmax(prob, dim=2)
+        c = self._compiled(inputs, mode, build)
+        prob = c.out["prob"].transpose(1, 2).clone()
+        return self._ret_pred(c), prob, torch.argmax(prob, dim=2)
 
 
 class MIMO_All_agents(_W2CModel):
@@ -862,7 +925,7 @@ class MIMO_All_agents(_W2CModel):
                     prog.copy_channels(src, cat.images(i * b, b).slice(j * feat.c, feat.c))
             return {"pred": _build_decoder(prog, self.decoder, cat)}
 
-        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+        return self._ret_pred(self._compiled(inputs, "fwd", build))
 
     def _forward_selection(self, inputs, n, b, h, w):
         """Random-selection baseline, agent.py:934-947: agent i decodes cat(own map, map of a randomly drawn agent).
@@ -922,7 +985,7 @@ class All_agents(_W2CModel):
                                c_first=3 * i, out=cat.slice(i * fc, fc))
             return {"pred": _build_decoder(prog, self.decoder, cat)}
 
-        return self._ret(self._compiled(inputs, "fwd", build).out["pred"])
+        return self._ret_pred(self._compiled(inputs, "fwd", build))
 
     def _forward_selection(self, inputs, b, h, w, fc):
         """Random-selection baseline, agent.py:447-452,466-467: the requester decodes cat(own map, map of ONE randomly

@@ -164,3 +164,24 @@ def reference_forward(model, x, **kw):
     shims = cpu_cuda_shims() if on_cpu else contextlib.nullcontext()
     with torch.no_grad(), shims, contextlib.redirect_stdout(io.StringIO()):
         return model(x, **kw)
+
+
+def reference_train_step_grads(model, x, labels, **kw):
+    """model.train(); loss = cross_entropy2d(model(x, ...), labels); loss.backward() exactly as Trainer_*.train() does
+    (trainer.py:659-670), with the reference's own loss (ptsemseg/loss/loss.py:5-18). Returns (outputs, loss,
+    {state_dict key: gradient}). On CPU the forward runs behind the .cuda() shims."""
+    import io
+    loss_mod = import_reference_module("ptsemseg.loss.loss")
+    on_cpu = not x.is_cuda
+    shims = cpu_cuda_shims() if on_cpu else contextlib.nullcontext()
+    model.train()
+    model.zero_grad()
+    import warnings
+    with shims, contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = model(x, **kw)
+        pred = out[0] if isinstance(out, tuple) else out
+        loss = loss_mod.cross_entropy2d(input=pred, target=labels)
+        loss.backward()
+    grads = {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None}
+    return out, float(loss.detach()), grads

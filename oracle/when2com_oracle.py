@@ -392,8 +392,11 @@ def forward(sd, cfg, x, train_stats=None, **kw):
         _TRAIN_STATS = None
 
 
+_GRAD_MODE = False   # forward_with_grads() switches autograd on for one forward
+
+
 def _dispatch(arch, sd, cfg, x, kw):
-    with torch.no_grad():
+    with torch.set_grad_enabled(_GRAD_MODE):
         if arch == "Single_agent":
             return single_agent_forward(sd, cfg, x)
         if arch == "MIMOcom":
@@ -409,6 +412,43 @@ def _dispatch(arch, sd, cfg, x, kw):
         if arch == "All_agents":
             return all_agents_forward(sd, cfg, x)
     raise ValueError("Model {} not available".format(arch))
+
+
+def cross_entropy2d(logits, target):
+    """ptsemseg/loss/loss.py:5-18 for equal input / target sizes: mean cross-entropy over the pixels, ignore_index 250."""
+    n, c, h, w = logits.shape
+    flat = logits.permute(0, 2, 3, 1).reshape(-1, c)
+    return F.cross_entropy(flat, target.reshape(-1), ignore_index=250)
+
+
+def forward_with_grads(sd, cfg, x, labels, **kw):
+    """One training step's forward + backward as Trainer_*.train() runs it (trainer.py:659-670): model.train();
+    outputs = model(images, training=True, ...); loss = cross_entropy2d(outputs, labels); loss.backward().
+    Returns (outputs, loss, {state_dict key: gradient}) - the gradients autograd leaves on the reference's parameters
+    (keys the forward does not touch are absent). Test infrastructure like the rest of this file."""
+    global _TRAIN_STATS, _GRAD_MODE
+    arch = cfg["model"]["arch"]
+    leaves = {}
+    for k, v in sd.items():
+        if not torch.is_floating_point(v):
+            continue
+        t = v.detach().to(torch.float32).cpu().clone()
+        if not (k.endswith("running_mean") or k.endswith("running_var")):
+            t.requires_grad_(True)
+        leaves[k] = t
+    x = x.detach().to(torch.float32).cpu()
+    _TRAIN_STATS, _GRAD_MODE = {}, True
+    try:
+        out = _dispatch(arch, leaves, cfg, x, kw)
+    finally:
+        _TRAIN_STATS, _GRAD_MODE = None, False
+    pred = out[0] if isinstance(out, tuple) else out
+    loss = cross_entropy2d(pred, labels.cpu())
+    loss.backward()
+    grads = {k: t.grad for k, t in leaves.items() if t.requires_grad and t.grad is not None}
+    detach = lambda o: o.detach() if torch.is_tensor(o) else o
+    out = tuple(detach(o) for o in out) if isinstance(out, tuple) else out.detach()
+    return out, float(loss.detach()), grads
 
 
 # --------------------------------------------------------------------------------------------- loader / eval glue

@@ -123,3 +123,33 @@ def test_train_mode_oracle_equals_the_reference_in_train_mode(arch, bb, over, kw
             assert float((after[k] - v).abs().max()) <= 1e-6 * max(1.0, float(v.abs().max())), k
         else:
             assert int(after[k]) == v, k
+
+
+@pytest.mark.skipif(not ref_harness.available(), reason="reference tree not mounted (GPU box)")
+@pytest.mark.parametrize("arch,bb,over,kw,n", [
+    ("MIMOcom", "n_segnet", dict(agent_num=2), dict(training=True, MO_flag=True), 2),
+    ("MIMOcom", "resnet", dict(agent_num=2), dict(training=True, MO_flag=True), 2),
+    ("Single_agent", "n_segnet", {}, {}, 1),
+    ("LearnWhen2Com", "resnet", dict(query_size=8), dict(training=True), 5),
+])
+def test_oracle_gradients_equal_the_reference_autograd(arch, bb, over, kw, n):
+    """The backward pass (trainer.py:668-670): the oracle's forward_with_grads against loss.backward() through the
+    UNMODIFIED reference modules in train() mode with the reference's own cross_entropy2d - every parameter gradient."""
+    import torch
+    cfg = configs.make_config(arch, img_size=128, backbones=bb, **over)
+    ref = ref_harness.build_reference_model(cfg)
+    synth.randomize_(ref, 1337)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    x = synth.synthetic_views(2, n, 128, 128, seed=7)
+    n_img = 2 * (n if kw.get("MO_flag") else 1)
+    labels = torch.randint(0, 11, (n_img, 128, 128), generator=torch.Generator().manual_seed(3))
+    labels[0, :8] = 250     # an ignored region, like the loader's void label
+    _, loss_r, g_ref = ref_harness.reference_train_step_grads(ref, x, labels, **kw)
+    _, loss_o, g_orc = orc.forward_with_grads(sd0, cfg, x, labels, **kw)
+    assert abs(loss_r - loss_o) <= 1e-5 * abs(loss_r)
+    assert g_ref and set(g_ref) == set(g_orc)
+    for k, g in g_ref.items():
+        # (a conv bias in front of a train-mode BatchNorm has a mathematically zero gradient: both sides hold ~1e-7 of
+        # rounding noise there, hence the absolute floor)
+        scale = float(g.abs().max())
+        assert float((g - g_orc[k]).abs().max()) <= 1e-2 * scale + 2e-6, k   # fp32 vs fp32 in another summation order: ~6e-3 seen
