@@ -342,6 +342,14 @@ class _W2CModel(nn.Module):
         train = bool(self.training)
         # grad: also record the backward pass (the second half of SURVEY 8 f-1) when autograd is listening
         grad = train and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if train:
+            # train-mode programs read the live parameters; the packed operands of the EVAL programs go stale with the
+            # first optimizer step, so the next eval forward (the trainers' validation pass, trainer.py:687-700)
+            # re-packs them
+            self._w2c["stale_eval"] = True
+        elif self._w2c.get("stale_eval"):
+            self.invalidate()
+            self._w2c["stale_eval"] = False
         if train and (self._w2c["io"]["u8"] or self._w2c["io"]["labels"]):
             raise RuntimeError("train mode takes the fp32 views and returns logits (set_input_format / "
                                "set_label_output are evaluation-path options)")

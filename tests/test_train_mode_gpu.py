@@ -4,7 +4,8 @@ folded agent-batch and updates running_mean / running_var / num_batches_tracked 
 
 Checked against the oracle's train-mode restatement, which tests/test_oracle.py pins to the UNMODIFIED reference in
 train() mode: logits within the 1e-3 bound in the parity precisions, BatchNorm buffers after one and after two steps.
-The path is a forward only: outputs carry no autograd graph (the backward pass is not built)."""
+These cases run under torch.no_grad() (the forward alone, in every parity precision); with autograd listening the same
+forward also records its backward program: tests/test_backward_gpu.py."""
 import pytest
 import torch
 
@@ -50,8 +51,9 @@ def test_train_mode_forward_matches_the_reference_semantics(name, precision, cud
 
     model = model.to(cuda_device).set_precision(precision)
     model.train()
-    out1 = as_t(model(x.to(cuda_device), **kw))
-    assert not out1[0].requires_grad            # forward only: no autograd graph behind the outputs
+    with torch.no_grad():
+        out1 = as_t(model(x.to(cuda_device), **kw))
+    assert not out1[0].requires_grad
     rel = float((out1[0].cpu() - as_t(ref1)[0]).abs().max()) / float(as_t(ref1)[0].abs().max())
     assert rel <= tol, rel
     if len(out1) > 1:
@@ -63,7 +65,8 @@ def test_train_mode_forward_matches_the_reference_semantics(name, precision, cud
         else:
             assert int(got[k]) == v, k
     # second step: statistics accumulate on top of the first step's (and the captured CUDA graph replays correctly)
-    out2 = as_t(model(x2.to(cuda_device), **kw))
+    with torch.no_grad():
+        out2 = as_t(model(x2.to(cuda_device), **kw))
     rel2 = float((out2[0].cpu() - as_t(ref2)[0]).abs().max()) / float(as_t(ref2)[0].abs().max())
     assert rel2 <= tol, rel2
     got = model.state_dict()
@@ -89,5 +92,5 @@ def test_train_mode_rejects_the_evaluation_only_options(cuda_device):
     model = get_model(cfg, 11).to(cuda_device)
     model.train()
     model.set_label_output(True, logits=False)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError), torch.no_grad():
         model(synth.synthetic_views(1, 1, 128, 128).to(cuda_device))
