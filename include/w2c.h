@@ -453,6 +453,11 @@ typedef struct w2c_bn_bwd_args {
   float* dbeta;
   double* sums_ws;
   float* coef_ws;
+  /* Optional: the scale_ws / shift_ws the train forward left behind.  The ReLU mask is then taken from
+   * z * scale + shift > 0 (exactly what the forward evaluated) and y is not read at all: two of the seven map passes
+   * less.  Units without a residual only (a residual changes the sign test). */
+  const float* fwd_scale;
+  const float* fwd_shift;
 } w2c_bn_bwd_args;
 int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream);
 /* The same for the fp32 NCHW logits layer: dy / y / z fp32 [n][c][hw]; dz is written as an NHWC gradient map of c_pad
@@ -537,6 +542,14 @@ int w2c_upsample_zero2(const void* src, const void* add, void* dst, int32_t n, i
 int w2c_grad_add(const void* a, int32_t a_cstride, int32_t a_coffset, const void* b, int32_t b_cstride,
                  int32_t b_coffset, void* dst, int32_t d_cstride, int32_t d_coffset, int64_t n_px, int32_t c,
                  int32_t act, w2c_stream_t stream);
+
+/* The trainers' loss with its gradient in one pass: cross_entropy2d (ptsemseg/loss/loss.py:5-18; F.cross_entropy over
+ * the pixels of fp32 NCHW logits [n][c][hw], int64 target [n][hw], ignore_index 250, mean over the counted pixels).
+ * dlogits receives softmax - onehot per counted pixel (zero for ignored ones), UNSCALED; totals fp64 [2] += {sum of the
+ * per-pixel losses, number of counted pixels} (caller-zeroed): loss = totals[0] / totals[1], dL/dlogits = dlogits /
+ * totals[1].  c <= 32. */
+int w2c_cross_entropy2d(const float* logits, const int64_t* target, int32_t n, int32_t c, int64_t hw,
+                        int64_t ignore_index, float* dlogits, double* totals, w2c_stream_t stream);
 
 /* ---- layout helpers --------------------------------------------------------------------------------- */
 /* NHWC activation (act storage) -> fp32 NCHW, and back.  Used at module boundaries and by the tests. */

@@ -82,7 +82,7 @@ class BnBwdArgs(ctypes.Structure):
                 ("z_cstride", c_i32), ("z_coffset", c_i32), ("dz_cstride", c_i32), ("dz_coffset", c_i32),
                 ("dres_cstride", c_i32), ("dres_coffset", c_i32), ("act_f", c_i32), ("act_g", c_i32), ("relu", c_i32),
                 ("gamma", c_vp), ("stats", c_vp), ("dgamma", c_vp), ("dbeta", c_vp), ("sums_ws", c_vp),
-                ("coef_ws", c_vp)]
+                ("coef_ws", c_vp), ("fwd_scale", c_vp), ("fwd_shift", c_vp)]
 
 
 class AttnBwdArgs(ctypes.Structure):
@@ -123,6 +123,7 @@ _SIGNATURES = {
     "w2c_maxpool3x3s2_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_bilinear_up_bwd": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
     "w2c_upsample_zero2": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    "w2c_cross_entropy2d": (ctypes.c_int, [c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, ctypes.c_int64, c_vp, c_vp, c_vp]),
     "w2c_grad_add": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, c_vp, c_i32, c_i32, ctypes.c_int64, c_i32,
                                     c_i32, c_vp]),
     "w2c_stem_conv3x3_raw_fwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp] + [c_i32] * 9 + [c_vp]),

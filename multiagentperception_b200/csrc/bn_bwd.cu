@@ -55,7 +55,31 @@ struct BwdMaps {
   int act_f, act_g, relu;
   size_t n_px;
   int c;
+  // ReLU mask without reading y: y > 0  <=>  z * scale + shift > 0 with the forward's own scale / shift (the forward
+  // evaluates exactly this fmaf in fp32 and a positive fp32 never rounds to a zero bf16). NULL: read y (residual units).
+  const float* fwd_scale;
+  const float* fwd_shift;
 };
+
+// du = dy masked by the unit's ReLU; zv receives the raw conv output when it is needed (statistics or the mask)
+__device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bool need_z, float (&du)[8], float (&zv)[8]) {
+  const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
+  const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
+  load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
+  const bool mask_from_z = m.relu && m.fwd_scale != nullptr;
+  if (need_z || mask_from_z) load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
+  if (m.relu) {
+    if (mask_from_z) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], m.fwd_scale[g * 8 + e], m.fwd_shift[g * 8 + e]) > 0.f ? du[e] : 0.f;
+    } else {
+      float yv[8];
+      load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
+    }
+  }
+}
 
 // sums[ch] += sum du, sums[c + ch] += sum du * xhat
 __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
@@ -64,8 +88,6 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m
   const int groups = m.c / 8;
   const int lanes = kThreads / groups;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
-  const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
-  const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
   float mean[8], inv[8], s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -74,22 +96,29 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m
     s1[e] = s2[e] = 0.f;
   }
   if (lane < lanes) {
-    for (size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane; px < m.n_px; px += static_cast<size_t>(gridDim.x) * lanes) {
-      float du[8];
-      load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
-      if (m.relu) {
-        float yv[8];
-        load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
+    size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane;
+    const size_t stride = static_cast<size_t>(gridDim.x) * lanes;
+    const bool bn = stats != nullptr;
+    // two pixels per trip (independent loads in flight)
+    for (; px + stride < m.n_px; px += 2 * stride) {
+      float du[2][8], zv[2][8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
-      }
+      for (int u = 0; u < 2; ++u) masked_du(m, px + u * stride, g, bn, du[u], zv[u]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s1[e] += du[e];
-      if (stats) {
-        float zv[8];
-        load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
+        for (int e = 0; e < 8; ++e) {
+          s1[e] += du[u][e];
+          if (bn) s2[e] = fmaf(du[u][e], (zv[u][e] - mean[e]) * inv[e], s2[e]);
+        }
+    }
+    for (; px < m.n_px; px += stride) {
+      float du[8], zv[8];
+      masked_du(m, px, g, bn, du, zv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += du[e];
+        if (bn) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
       }
     }
   }
@@ -134,24 +163,16 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdMaps m, cons
                                                            const float* __restrict__ coef) {
   const int groups = m.c / 8;
   const size_t total = m.n_px * groups;
-  const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
-  const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
+  const bool f16g = act_is_f16(m.act_g);
+  const int pg = act_planes(m.act_g);
   for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
     const int g = idx % groups;
     const size_t px = idx / groups;
-    float du[8];
-    load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
-    if (m.relu) {
-      float yv[8];
-      load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
-    }
+    float du[8], zv[8];
+    masked_du(m, px, g, stats != nullptr, du, zv);
     if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
     if (stats) {
-      float zv[8];
-      load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ch = g * 8 + e;
@@ -236,7 +257,7 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
   if (!args) return set_error(W2C_ERR_INVALID, "bn_bwd: args is NULL");
   const w2c_bn_bwd_args& a = *args;
   W2C_CHECK_ARG(a.dy && a.dz && a.sums_ws && a.coef_ws, "bn_bwd: null pointer argument");
-  W2C_CHECK_ARG(!a.relu || a.y, "bn_bwd: the ReLU mask needs the forward output y");
+  W2C_CHECK_ARG(!a.relu || a.y || a.fwd_scale, "bn_bwd: the ReLU mask needs the forward output y (or fwd_scale / fwd_shift)");
   W2C_CHECK_ARG(!a.stats || a.z, "bn_bwd: BatchNorm needs the raw conv output z");
   W2C_CHECK_ARG(act_valid(a.act_f) && act_valid(a.act_g), "bn_bwd: bad act");
   W2C_CHECK_ARG(a.n_px > 0 && a.c > 0 && a.c % 8 == 0 && 256 % (a.c / 8) == 0 && a.c <= 2048,
@@ -250,6 +271,9 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
   m.z_cs = cs(a.z_cstride), m.z_co = a.z_coffset, m.dz_cs = cs(a.dz_cstride), m.dz_co = a.dz_coffset;
   m.dres_cs = cs(a.dres_cstride), m.dres_co = a.dres_coffset;
   m.act_f = a.act_f, m.act_g = a.act_g, m.relu = a.relu, m.n_px = static_cast<size_t>(a.n_px), m.c = a.c;
+  m.fwd_scale = a.fwd_scale, m.fwd_shift = a.fwd_shift;
+  W2C_CHECK_ARG((a.fwd_scale == nullptr) == (a.fwd_shift == nullptr), "bn_bwd: fwd_scale and fwd_shift go together");
+  W2C_CHECK_ARG(!a.fwd_scale || a.z, "bn_bwd: the mask from z needs z");
   const int strides[5] = {m.dy_cs, m.y_cs, m.z_cs, m.dz_cs, m.dres_cs}, offs[5] = {m.dy_co, m.y_co, m.z_co, m.dz_co, m.dres_co};
   for (int i = 0; i < 5; ++i)
     W2C_CHECK_ARG(offs[i] >= 0 && offs[i] + a.c <= strides[i] && strides[i] % 8 == 0 && offs[i] % 8 == 0,

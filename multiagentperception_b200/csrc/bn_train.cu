@@ -35,11 +35,10 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
   if (lane < lanes) {
-    for (size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane; px < n_px; px += static_cast<size_t>(gridDim.x) * lanes) {
+    auto load_px = [&](size_t px, float (&v)[8]) {
       const __nv_bfloat16* p = z + px * pix_elems + coffset + g * 8;
       const uint4 hv = __ldg(reinterpret_cast<const uint4*>(p));
       const uint32_t* hb = reinterpret_cast<const uint32_t*>(&hv);
-      float v[8];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float2 f = unpack_act2(hb[e], f16);
@@ -54,6 +53,23 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
           v[2 * e] += f.x, v[2 * e + 1] += f.y;
         }
       }
+    };
+    // four pixels per trip: four independent 16-byte loads in flight per thread (one per trip left the pass at a
+    // seventh of the HBM rate - ncu, profiles/r2_train_step.md)
+    size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane;
+    const size_t stride = static_cast<size_t>(gridDim.x) * lanes;
+    for (; px + 3 * stride < n_px; px += 4 * stride) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load_px(px + u * stride, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s1[e] += v[u][e], s2[e] = fmaf(v[u][e], v[u][e], s2[e]);
+    }
+    for (; px < n_px; px += stride) {
+      float v[8];
+      load_px(px, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) s1[e] += v[e], s2[e] = fmaf(v[e], v[e], s2[e]);
     }

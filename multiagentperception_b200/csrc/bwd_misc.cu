@@ -127,73 +127,81 @@ __global__ void __launch_bounds__(256) outer_sum_kernel(const float* __restrict_
   }
 }
 
-// fc0: dW0[j][k] += sum_r dh0[r][j] x[r][k] (x = the NHWC policy map, k in NHWC flatten order) and
-//      dx[r][k] = sum_heads sum_j dh0[r][j] W0[j][k].  One thread per 8 consecutive k; the dh0 rows sit in shared
-//      memory 8 rows at a time.
-__global__ void __launch_bounds__(256) mlp_bwd_fc0_kernel(const HeadsBwd hd, const __nv_bfloat16* __restrict__ feat,
-                                                          int act_f, const float* __restrict__ ws, int m, int n_feat,
-                                                          __nv_bfloat16* __restrict__ dfeat, int act_g) {
-  __shared__ float s_dh0[2][8][256];
+// fc0 weight gradient: dW0[j][k] += sum_r dh0[r][j] x[r][k] (x = the NHWC policy map, k in NHWC flatten order).
+// One thread per (8 consecutive k, 8 consecutive j), grid (k blocks, 32 j groups, heads): the 8 activations of each row
+// are loaded once and used for 8 rows of W0.
+__global__ void __launch_bounds__(128) mlp_bwd_fc0_wgrad_kernel(const HeadsBwd hd, const __nv_bfloat16* __restrict__ feat,
+                                                                int act_f, const float* __restrict__ ws, int m, int n_feat) {
   const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
-  const bool active = k0 < n_feat;
-  const int pf = act_planes(act_f), pg = act_planes(act_g);
+  if (k0 >= n_feat) return;
+  const int j0 = blockIdx.y * 8, hh = blockIdx.z;
+  const int pf = act_planes(act_f);
   const size_t off_f = static_cast<size_t>(k0 >> 8) * (256 * pf) + (k0 & 255);
-  const size_t off_g = static_cast<size_t>(k0 >> 8) * (256 * pg) + (k0 & 255);
-  for (int r0 = 0; r0 < m; r0 += 8) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < hd.n_heads * 8 * 256; i += blockDim.x) {
-      const int hh = i / (8 * 256), r = (i / 256) % 8, j = i % 256;
-      s_dh0[hh][r][j] = r0 + r < m ? ws[static_cast<size_t>(hh) * m * 512 + static_cast<size_t>(m) * 256 +
-                                        static_cast<size_t>(r0 + r) * 256 + j]
-                                   : 0.f;
-    }
-    __syncthreads();
-    if (!active) continue;
-    float x[8][8], dx[8][8];
-    const int rows = min(8, m - r0);
+  const float* dh0 = ws + static_cast<size_t>(hh) * m * 512 + static_cast<size_t>(m) * 256;
+  float gw[8][8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+  for (int j = 0; j < 8; ++j)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) dx[r][e] = 0.f, x[r][e] = 0.f;
-      if (r < rows) load8(feat + static_cast<size_t>(r0 + r) * (static_cast<size_t>(n_feat) * pf) + off_f, 256, pf, act_is_f16(act_f), x[r]);
-    }
-    for (int hh = 0; hh < hd.n_heads; ++hh) {
-      const float* __restrict__ W0 = hd.h[hh].w0;
-      float* __restrict__ dW0 = hd.g[hh].dw0;
-      for (int j = 0; j < 256; ++j) {
-        const float4 wa = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0));
-        const float4 wb = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0 + 4));
-        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
-        float gw[8];
+    for (int e = 0; e < 8; ++e) gw[j][e] = 0.f;
+  for (int r = 0; r < m; ++r) {
+    float x[8];
+    load8(feat + static_cast<size_t>(r) * (static_cast<size_t>(n_feat) * pf) + off_f, 256, pf, act_is_f16(act_f), x);
+    const float4 da = __ldg(reinterpret_cast<const float4*>(dh0 + static_cast<size_t>(r) * 256 + j0));
+    const float4 db = __ldg(reinterpret_cast<const float4*>(dh0 + static_cast<size_t>(r) * 256 + j0 + 4));
+    const float d[8] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w};
 #pragma unroll
-        for (int e = 0; e < 8; ++e) gw[e] = 0.f;
+    for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int r = 0; r < 8; ++r) {
-          const float d = s_dh0[hh][r][j];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            dx[r][e] = fmaf(d, wv[e], dx[r][e]);
-            gw[e] = fmaf(d, x[r][e], gw[e]);
-          }
-        }
-        float4* gp = reinterpret_cast<float4*>(dW0 + static_cast<size_t>(j) * n_feat + k0);
-        float4 ga = gp[0], gb = gp[1];
-        ga.x += gw[0], ga.y += gw[1], ga.z += gw[2], ga.w += gw[3];
-        gb.x += gw[4], gb.y += gw[5], gb.z += gw[6], gb.w += gw[7];
-        gp[0] = ga, gp[1] = gb;
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < 8; ++r)
-      if (r < rows)
-        store8(dfeat + static_cast<size_t>(r0 + r) * (static_cast<size_t>(n_feat) * pg) + off_g, 256, pg, act_is_f16(act_g), dx[r]);
+      for (int e = 0; e < 8; ++e) gw[j][e] = fmaf(d[j], x[e], gw[j][e]);
   }
+  float* dW0 = hd.g[hh].dw0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4* gp = reinterpret_cast<float4*>(dW0 + static_cast<size_t>(j0 + j) * n_feat + k0);
+    float4 ga = gp[0], gb = gp[1];
+    ga.x += gw[j][0], ga.y += gw[j][1], ga.z += gw[j][2], ga.w += gw[j][3];
+    gb.x += gw[j][4], gb.y += gw[j][5], gb.z += gw[j][6], gb.w += gw[j][7];
+    gp[0] = ga, gp[1] = gb;
+  }
+}
+
+// fc0 data gradient: dx[r][k] = sum_heads sum_j dh0[r][j] W0[j][k]. One thread per (row, 8 consecutive k); the row's
+// dh0 vectors sit in shared memory.
+__global__ void __launch_bounds__(128) mlp_bwd_fc0_dgrad_kernel(const HeadsBwd hd, const float* __restrict__ ws, int m,
+                                                                int n_feat, __nv_bfloat16* __restrict__ dfeat, int act_g) {
+  __shared__ float s_dh0[2][256];
+  const int r = blockIdx.y;
+  for (int i = threadIdx.x; i < hd.n_heads * 256; i += blockDim.x)
+    s_dh0[i / 256][i % 256] = ws[static_cast<size_t>(i / 256) * m * 512 + static_cast<size_t>(m) * 256 +
+                                 static_cast<size_t>(r) * 256 + (i % 256)];
+  __syncthreads();
+  const int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (k0 >= n_feat) return;
+  const int pg = act_planes(act_g);
+  float dx[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) dx[e] = 0.f;
+  for (int hh = 0; hh < hd.n_heads; ++hh) {
+    const float* __restrict__ W0 = hd.h[hh].w0;
+#pragma unroll 4
+    for (int j = 0; j < 256; ++j) {
+      const float4 wa = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0));
+      const float4 wb = __ldg(reinterpret_cast<const float4*>(W0 + static_cast<size_t>(j) * n_feat + k0 + 4));
+      const float d = s_dh0[hh][j];
+      dx[0] = fmaf(d, wa.x, dx[0]), dx[1] = fmaf(d, wa.y, dx[1]), dx[2] = fmaf(d, wa.z, dx[2]), dx[3] = fmaf(d, wa.w, dx[3]);
+      dx[4] = fmaf(d, wb.x, dx[4]), dx[5] = fmaf(d, wb.y, dx[5]), dx[6] = fmaf(d, wb.z, dx[6]), dx[7] = fmaf(d, wb.w, dx[7]);
+    }
+  }
+  const size_t off_g = static_cast<size_t>(k0 >> 8) * (256 * pg) + (k0 & 255);
+  store8(dfeat + static_cast<size_t>(r) * (static_cast<size_t>(n_feat) * pg) + off_g, 256, pg, act_is_f16(act_g), dx);
 }
 
 // ------------------------------------------------------------------------------------------------ first-layer wgrad
 // dW[co][ci][kh][kw] += sum over pixels dz[pix][co] * x[ci][pix*stride + k - pad].  Persistent CTAs walk tiles of
-// TP x TP output pixels of one image: the dz tile (TP*TP x 64) and the input patch are staged in shared memory, thread t
-// owns the (co, k) pairs t, t + 256, ... in registers across ALL its tiles; one atomicAdd per pair and CTA at the end.
+// TP x TP output pixels of one image: the dz tile (TP*TP x 64) and the input patch are staged in shared memory; thread t
+// owns the 8 output channels of group t / KK for tap k = t % KK in registers across ALL its tiles (one 16-byte pair of
+// shared loads of dz and one of the patch value per 8 FMAs: the one-FMA-per-two-loads version ran at the shared-memory
+// rate, 1.7 ms per 10 frames); one atomicAdd per (co, k) and CTA at the end.
 template <int KS, int STRIDE>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                                          float* __restrict__ dw, int b, int n_agents, int c_total,
@@ -203,18 +211,19 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   constexpr int PAD = KS / 2;
   constexpr int PW = (TP - 1) * STRIDE + KS;              // input patch edge
   constexpr int KK = 3 * KS * KS;
-  constexpr int PAIRS = (64 * KK + 255) / 256;            // (co, k) pairs per thread, cout <= 64
+  constexpr int ITEMS = (8 * KK + 255) / 256;             // (8-channel group, k) items per thread, cout <= 64
   extern __shared__ float s_mem[];
   float* s_patch = s_mem;                                 // [3][PW][PW]
-  float* s_dz = s_mem + 3 * PW * PW;                      // [TP*TP][cout + 1]
+  float* s_dz = s_mem + ((3 * PW * PW + 3) & ~3);         // [TP*TP][cout] (16-byte aligned rows)
   const int ho = h / STRIDE, wo = w / STRIDE;
   const bool f16g = act_is_f16(act_g);
   const int pg = act_planes(act_g);
-  const int cs1 = cout + 1;
-  const int n_pairs = cout * KK;
-  float acc[PAIRS];
+  const int n_items = (cout / 8) * KK;
+  float acc[ITEMS][8];
 #pragma unroll
-  for (int i = 0; i < PAIRS; ++i) acc[i] = 0.f;
+  for (int i = 0; i < ITEMS; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     int t = tile;
     const int tx = t % tiles_w;
@@ -241,30 +250,40 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_dz[p * cs1 + g * 8 + e] = v[e];
+      float4* d4 = reinterpret_cast<float4*>(s_dz + p * cout + g * 8);
+      d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+      d4[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < PAIRS; ++i) {
-      const int pair = threadIdx.x + i * 256;
-      if (pair < n_pairs) {
-        const int co = pair / KK, k = pair % KK;
+    for (int i = 0; i < ITEMS; ++i) {
+      const int item = threadIdx.x + i * 256;
+      if (item < n_items) {
+        const int g = item / KK, k = item % KK;
         const int ci = k / (KS * KS), kh = (k / KS) % KS, kw = k % KS;
-        float a = acc[i];
+        const float* pp = s_patch + (ci * PW + kh) * PW + kw;
+        const float* dp = s_dz + g * 8;
 #pragma unroll 4
         for (int p = 0; p < TP * TP; ++p) {
-          const int py = (p / TP) * STRIDE + kh, px = (p % TP) * STRIDE + kw;
-          a = fmaf(s_dz[p * cs1 + co], s_patch[(ci * PW + py) * PW + px], a);
+          const float xv = pp[((p / TP) * PW + (p % TP)) * STRIDE];
+          const float4 d0 = *reinterpret_cast<const float4*>(dp + p * cout);
+          const float4 d1 = *reinterpret_cast<const float4*>(dp + p * cout + 4);
+          acc[i][0] = fmaf(d0.x, xv, acc[i][0]), acc[i][1] = fmaf(d0.y, xv, acc[i][1]);
+          acc[i][2] = fmaf(d0.z, xv, acc[i][2]), acc[i][3] = fmaf(d0.w, xv, acc[i][3]);
+          acc[i][4] = fmaf(d1.x, xv, acc[i][4]), acc[i][5] = fmaf(d1.y, xv, acc[i][5]);
+          acc[i][6] = fmaf(d1.z, xv, acc[i][6]), acc[i][7] = fmaf(d1.w, xv, acc[i][7]);
         }
-        acc[i] = a;
       }
     }
   }
 #pragma unroll
-  for (int i = 0; i < PAIRS; ++i) {
-    const int pair = threadIdx.x + i * 256;
-    if (pair < n_pairs) atomicAdd(dw + pair, acc[i]);
+  for (int i = 0; i < ITEMS; ++i) {
+    const int item = threadIdx.x + i * 256;
+    if (item < n_items) {
+      const int g = item / KK, k = item % KK;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(dw + (g * 8 + e) * KK + k, acc[i][e]);
+    }
   }
 }
 
@@ -476,9 +495,12 @@ extern "C" int w2c_kq_mlp_heads_bwd(const void* feat, int32_t act_f, int32_t m, 
     outer_sum_kernel<<<1, 256, 0, s>>>(dh0, dh0, m, 256, 1, ws + static_cast<size_t>(n_heads) * m * 512, hd.g[i].db0);
     W2C_CHECK_LAUNCH("outer_sum_kernel");
   }
-  mlp_bwd_fc0_kernel<<<ceil_div(n_feat / 8, 128), 128, 0, s>>>(hd, static_cast<const __nv_bfloat16*>(feat), act_f, ws, m, n_feat,
-                                                              static_cast<__nv_bfloat16*>(dfeat), act_g);
-  W2C_CHECK_LAUNCH("mlp_bwd_fc0_kernel");
+  mlp_bwd_fc0_wgrad_kernel<<<dim3(ceil_div(n_feat / 8, 128), 32, n_heads), 128, 0, s>>>(
+      hd, static_cast<const __nv_bfloat16*>(feat), act_f, ws, m, n_feat);
+  W2C_CHECK_LAUNCH("mlp_bwd_fc0_wgrad_kernel");
+  mlp_bwd_fc0_dgrad_kernel<<<dim3(ceil_div(n_feat / 8, 128), m), 128, 0, s>>>(hd, ws, m, n_feat,
+                                                                             static_cast<__nv_bfloat16*>(dfeat), act_g);
+  W2C_CHECK_LAUNCH("mlp_bwd_fc0_dgrad_kernel");
   return W2C_OK;
 }
 
@@ -498,7 +520,7 @@ extern "C" int w2c_stem_conv_wgrad(const float* x, const void* dz, float* dw, in
   const int ho = h / stride, wo = w_px / stride;
   const int tiles_w = ceil_div(wo, 8), tiles_h = ceil_div(ho, 8);
   const int pw = 7 * stride + ksize;
-  const size_t smem = (static_cast<size_t>(3) * pw * pw + 64 * (cout + 1)) * sizeof(float);
+  const size_t smem = (((static_cast<size_t>(3) * pw * pw + 3) & ~static_cast<size_t>(3)) + 64 * cout) * sizeof(float);
   const long long tiles = static_cast<long long>(tiles_w) * tiles_h * b * n_agents;
   W2C_CHECK_ARG(tiles < (1ll << 31), "stem_wgrad: too many tiles");
   const int cap = device_sm_count() * 4;
@@ -574,5 +596,82 @@ extern "C" int w2c_grad_add(const void* a, int32_t a_cstride, int32_t a_coffset,
       static_cast<const __nv_bfloat16*>(a), acs, a_coffset, static_cast<const __nv_bfloat16*>(b), bcs, b_coffset,
       static_cast<__nv_bfloat16*>(dst), dcs, d_coffset, static_cast<size_t>(n_px), c, act);
   W2C_CHECK_LAUNCH("grad_add_kernel");
+  return W2C_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ loss
+// cross_entropy2d (ptsemseg/loss/loss.py:5-18: F.cross_entropy over the pixels of fp32 NCHW logits, ignore_index,
+// mean over the counted pixels) with its gradient in the same pass: one thread per pixel keeps the <= 32 logits in
+// registers, writes softmax - onehot (zero rows for ignored pixels) and adds its loss term and its count to fp64 totals.
+// torch's nll_loss 2-D kernels run this reduction in ONE block: 4.1 ms per 10 frames, 11 % of a training step.
+namespace w2c {
+namespace {
+constexpr int kMaxClasses = 32;
+
+__global__ void __launch_bounds__(256) xent2d_kernel(const float* __restrict__ logits, const long long* __restrict__ target,
+                                                     int n, int c, size_t hw, long long ignore_index,
+                                                     float* __restrict__ dlogits, double* __restrict__ totals) {
+  __shared__ double s_loss[8], s_cnt[8];
+  const size_t total = static_cast<size_t>(n) * hw;
+  double loss = 0.0, cnt = 0.0;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const size_t img = idx / hw, i = idx % hw;
+    const float* p = logits + img * c * hw + i;
+    float v[kMaxClasses];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < c) {
+        v[k] = p[static_cast<size_t>(k) * hw];
+        mx = fmaxf(mx, v[k]);
+      }
+    float se = 0.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < c) {
+        v[k] = __expf(v[k] - mx);
+        se += v[k];
+      }
+    const long long t = target[idx];
+    const bool counted = t != ignore_index && t >= 0 && t < c;
+    const float inv = counted ? 1.f / se : 0.f;
+    float* d = dlogits + img * c * hw + i;
+    float pt = 1.f;
+#pragma unroll
+    for (int k = 0; k < kMaxClasses; ++k)
+      if (k < c) {
+        const float sm = v[k] * inv;
+        if (k == t) pt = sm;
+        d[static_cast<size_t>(k) * hw] = counted ? sm - (k == t ? 1.f : 0.f) : 0.f;
+      }
+    if (counted) loss -= static_cast<double>(__logf(fmaxf(pt, 1e-38f))), cnt += 1.0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    loss += __shfl_xor_sync(0xffffffffu, loss, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_loss[warp] = loss, s_cnt[warp] = cnt;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < 8; ++w) a += s_loss[w], b += s_cnt[w];
+    atomicAdd(&totals[0], a);
+    atomicAdd(&totals[1], b);
+  }
+}
+}  // namespace
+}  // namespace w2c
+
+extern "C" int w2c_cross_entropy2d(const float* logits, const int64_t* target, int32_t n, int32_t c, int64_t hw,
+                                   int64_t ignore_index, float* dlogits, double* totals, w2c_stream_t stream) {
+  W2C_CHECK_ARG(logits && target && dlogits && totals && n > 0 && hw > 0, "cross_entropy2d: bad arguments");
+  W2C_CHECK_ARG(c > 0 && c <= kMaxClasses, "cross_entropy2d: %d classes (at most %d)", c, kMaxClasses);
+  const size_t total = static_cast<size_t>(n) * static_cast<size_t>(hw);
+  xent2d_kernel<<<grid_for(total, 256, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      logits, reinterpret_cast<const long long*>(target), n, c, static_cast<size_t>(hw), ignore_index, dlogits, totals);
+  W2C_CHECK_LAUNCH("xent2d_kernel");
   return W2C_OK;
 }

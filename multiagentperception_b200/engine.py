@@ -512,8 +512,8 @@ class Program:
         if (y.n, y.h, y.w, y.c) != (z.n, z.h, z.w, z.c):
             raise ValueError("conv: the caller's output map does not match the layer's output")
         stats = self.f32_buf(2 * z.c)
-        self._bn_train(z, y, bn, relu, residual, stats)
-        self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, y, z, stats, residual=residual))
+        ss = self._bn_train(z, y, bn, relu, residual, stats)
+        self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, y, z, stats, residual=residual, fwd_affine=ss))
         return y
 
     def _bn_ws(self, c):
@@ -541,6 +541,7 @@ class Program:
                      stats.data_ptr() if stats is not None else None)
         if residual is not None and not inplace and (residual.cstride, residual.coffset) != (y.cstride, y.coffset):
             raise ValueError("bn_train: the residual must be laid out like the output")
+        return scale, shift
 
     def _bn_train_nchw(self, z, y, bn, relu, stats=None):
         gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
@@ -584,7 +585,7 @@ class Program:
         self._zero_list.append(t)
         return t
 
-    def _bwd_conv_unit(self, x, conv, bn, relu, y, z, stats, residual=None, nchw=False, stem=None):
+    def _bwd_conv_unit(self, x, conv, bn, relu, y, z, stats, residual=None, nchw=False, stem=None, fwd_affine=None):
         """Backward of one conv (+BatchNorm) (+residual) (+ReLU) unit, recorded into self.bprog: gradient of y ->
         gradient of the raw conv output (BatchNorm / ReLU backward, csrc/bn_bwd.cu) -> weight gradient (csrc/wgrad.cu)
         and data gradient (the forward conv kernels on the re-indexed weight). x: input ActMap, or None for a first
@@ -629,6 +630,9 @@ class Program:
                                dres_coffset=dres.coffset if dres is not None else 0, act_f=self.act, act_g=g_act,
                                relu=int(bool(relu)), gamma=p(gamma_t), stats=p(stats), dgamma=p(dgamma),
                                dbeta=dbeta.data_ptr(), sums_ws=sums.data_ptr(), coef_ws=coef.data_ptr())
+            if fwd_affine is not None and residual is None and relu and z is not None:
+                # the ReLU mask from z * scale + shift (what the forward evaluated): y is not read (csrc/bn_bwd.cu)
+                a.fwd_scale, a.fwd_shift = fwd_affine[0].data_ptr(), fwd_affine[1].data_ptr()
             bp.keep.append(a)
             bp._record(lib.w2c_bn_train_bwd, ctypes.byref(a))
         if bn is not None:
@@ -692,8 +696,8 @@ class Program:
             return z
         y = self.act_buf(z.n, z.h, z.w, z.c)
         stats = self.f32_buf(2 * z.c)
-        self._bn_train(z, y, bn, True, None, stats)
-        self.tape.append(lambda: self._bwd_conv_unit(None, conv, bn, True, y, z, stats,
+        ss = self._bn_train(z, y, bn, True, None, stats)
+        self.tape.append(lambda: self._bwd_conv_unit(None, conv, bn, True, y, z, stats, fwd_affine=ss,
                                                      stem=(x_in, b, n_agents, h, w, c_first, ksize)))
         return y
 

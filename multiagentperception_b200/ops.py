@@ -308,12 +308,13 @@ def conv_wgrad(x, dy, dw, *, n, h_in, w_in, cin, cout, kind, act_x, act_dy, x_cs
 
 
 def bn_train_bwd(dy, y, z, dz, *, n_px, c, act_f, act_g, relu, gamma, stats, dgamma, dbeta, sums_ws, coef_ws, dres=None,
-                 dy_cs=0, dy_co=0, y_cs=0, y_co=0, z_cs=0, z_co=0, dz_cs=0, dz_co=0, dres_cs=0, dres_co=0):
+                 dy_cs=0, dy_co=0, y_cs=0, y_co=0, z_cs=0, z_co=0, dz_cs=0, dz_co=0, dres_cs=0, dres_co=0, fwd_scale=None,
+                 fwd_shift=None):
     lib = _lib.load()
     a = _lib.BnBwdArgs(dy=_ptr(dy), y=_ptr(y), z=_ptr(z), dz=_ptr(dz), dres=_ptr(dres), n_px=n_px, c=c, dy_cstride=dy_cs,
                        dy_coffset=dy_co, y_cstride=y_cs, y_coffset=y_co, z_cstride=z_cs, z_coffset=z_co, dz_cstride=dz_cs,
                        dz_coffset=dz_co, dres_cstride=dres_cs, dres_coffset=dres_co, act_f=act_f, act_g=act_g,
                        relu=int(bool(relu)), gamma=_ptr(gamma), stats=_ptr(stats), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta),
-                       sums_ws=_ptr(sums_ws), coef_ws=_ptr(coef_ws))
+                       sums_ws=_ptr(sums_ws), coef_ws=_ptr(coef_ws), fwd_scale=_ptr(fwd_scale), fwd_shift=_ptr(fwd_shift))
     _lib.check(lib.w2c_bn_train_bwd(ctypes.byref(a), _stream()), "w2c_bn_train_bwd")
     return dz

@@ -171,3 +171,95 @@ def test_num_connect_is_lazy_and_behaves_like_a_number(cuda_device):
     avg = total / 3.0                   # get_avg_bandW, metrics.py:110-111
     assert float(avg) == pytest.approx(ref[3], abs=1e-12)
     assert str(avg) == str(float(avg)) and avg == float(avg) and round(avg * 100, 2) == round(ref[3] * 100, 2)
+
+
+class _Writer:
+    """tensorboardX.SummaryWriter as the trainer uses it (add_scalar, file_writer.get_logdir)."""
+
+    def __init__(self, logdir):
+        self._dir = logdir
+        self.file_writer = self
+        self.scalars = []
+
+    def get_logdir(self):
+        return self._dir
+
+    def add_scalar(self, tag, value, step):
+        self.scalars.append((tag, float(value), step))
+
+
+@needs_ref
+def test_reference_trainer_trains_the_b200_model(tmp_path, cuda_device):
+    """The REFERENCE's Trainer_MIMOcom.train() (ptsemseg/trainer.py:610-768) - scheduler.step, model.train(), forward,
+    its own cross_entropy2d, loss.backward(), optimizer.step, the periodic validation pass and the best-model checkpoint
+    - runs unchanged on this repo's model, and moves the weights the way the same loop moves the reference model on
+    the CPU (same initial weights, same batches, plain SGD so that the parameter deltas are lr x gradient)."""
+    import logging
+    models, trainer_mod = _overlay_trainer_module()
+    try:
+        n, img, iters = 2, 256, 3
+        cfg = configs.make_config("MIMOcom", agent_num=n, img_size=img, backbones="resnet")
+        cfg["data"]["commun_label"] = "mimo"
+        cfg["data"]["dataset"] = "airsim"
+        cfg["model"]["precision"] = "bf16x3"
+        cfg["training"] = {"train_iters": iters, "print_interval": 1, "val_interval": 2, "batch_size": B, "resume": None}
+        loss_mod = ref_harness.import_reference_module("ptsemseg.loss.loss")
+        g = torch.Generator().manual_seed(5)
+        batches = []
+        for i in range(iters):
+            views = synth.synthetic_views(B, n, img, img, seed=20 + i)
+            images_list = [views[:, 3 * a:3 * a + 3].contiguous() for a in range(n)]
+            labels_list = [torch.randint(0, NCLS, (B, img, img), generator=g) for _ in range(n)]
+            commun = torch.stack((torch.randint(0, 2, (B, n), generator=g), torch.randint(0, n, (B, n), generator=g)), 1)
+            batches.append((images_list, labels_list, commun.to(torch.int64)))
+        donor = get_model(cfg, NCLS)
+        synth.randomize_(donor, 99)
+        sd0 = {k: v.clone() for k, v in donor.state_dict().items()}
+
+        def run(model, device, logdir):
+            model.load_state_dict(sd0, strict=False)
+            model = model.to(device)
+            opt = torch.optim.SGD(model.parameters(), lr=0.02)
+            sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1000)
+            writer = _Writer(str(logdir))
+            os.makedirs(str(logdir), exist_ok=True)
+            tr = trainer_mod.Trainer_MIMOcom(cfg, writer, logging.getLogger("w2c-test"), model, loss_mod.cross_entropy2d,
+                                             batches, batches[:1], opt, sched, device)
+            import contextlib
+            import io
+            import warnings
+            with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                path = tr.train()
+            return model, path, writer
+
+        ours, path, writer = run(models.get_model(cfg, NCLS), cuda_device, tmp_path / "b200")
+        assert type(ours).__module__.startswith("multiagentperception_b200")
+        assert os.path.isfile(path)                                # the best-model checkpoint of the validation pass
+        losses = [v for tag, v, _ in writer.scalars if tag == "loss/train_loss"]
+        assert len(losses) >= 2 and all(np.isfinite(losses))
+        # the checkpoint holds the trained weights and loads back into a fresh model
+        state = torch.load(path, weights_only=False)["model_state"]   # (the trainer stores a numpy best_iou next to the weights)
+        fresh = get_model(cfg, NCLS)
+        fresh.load_state_dict(state, strict=False)
+        # the same loop on the UNMODIFIED reference model, on the CPU
+        ref_model = ref_harness.build_reference_model(cfg)
+        with ref_harness.cpu_cuda_shims():
+            ref_model, _, ref_writer = run(ref_model, torch.device("cpu"), tmp_path / "ref")
+        ref_losses = [v for tag, v, _ in ref_writer.scalars if tag == "loss/train_loss"]
+        for a, b in zip(losses, ref_losses):
+            assert a == pytest.approx(b, rel=5e-3), (losses, ref_losses)
+        ours_sd, ref_sd = ours.state_dict(), ref_model.state_dict()
+        num = den = 0.0
+        for k, p0 in sd0.items():
+            if not torch.is_floating_point(p0) or "running_" in k or k not in ref_sd:
+                continue
+            d_ref = (ref_sd[k].cpu() - p0).double()
+            d_our = (ours_sd[k].cpu() - p0).double()
+            num += float(((d_our - d_ref) ** 2).sum())
+            den += float((d_ref ** 2).sum())
+        assert den > 0
+        assert (num / den) ** 0.5 <= 0.1, (num / den) ** 0.5   # three steps of lr x gradient: the gradient noise floor
+    finally:
+        for name in [n_ for n_ in sys.modules if n_ == "ptsemseg" or n_.startswith("ptsemseg.")]:
+            del sys.modules[name]

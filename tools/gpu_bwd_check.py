@@ -172,7 +172,7 @@ DGRAD_CASES = {
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm backward
-def case_bn_bwd(act_f=1, act_g=1, relu=True, residual=False, bn=True, c=64, seed=0):
+def case_bn_bwd(act_f=1, act_g=1, relu=True, residual=False, bn=True, c=64, seed=0, mask_from_z=False):
     torch, F, ops, _ = _imports()
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(seed)
@@ -218,9 +218,10 @@ def case_bn_bwd(act_f=1, act_g=1, relu=True, residual=False, bn=True, c=64, seed
     dres = torch.empty_like(dz) if residual else None
     dgamma, dbeta = torch.zeros(c, device=dev), torch.zeros(c, device=dev)
     coef = torch.empty(3 * c, device=dev)
-    ops.bn_train_bwd(dya, ya, za, dz, n_px=n_px, c=c, act_f=act_f, act_g=act_g, relu=relu, gamma=gd if bn else None,
-                     stats=stats if bn else None, dgamma=dgamma if bn else None, dbeta=dbeta, sums_ws=sums, coef_ws=coef,
-                     dres=dres)
+    ops.bn_train_bwd(dya, None if mask_from_z else ya, za, dz, n_px=n_px, c=c, act_f=act_f, act_g=act_g, relu=relu,
+                     gamma=gd if bn else None, stats=stats if bn else None, dgamma=dgamma if bn else None, dbeta=dbeta,
+                     sums_ws=sums, coef_ws=coef, dres=dres, fwd_scale=scale if mask_from_z else None,
+                     fwd_shift=shift if mask_from_z else None)
     torch.cuda.synchronize()
     tol = {0: 8e-3, 1: 1e-4, 3: 1e-4}[act_g]
     out = {"dz": _verdict(ops.act_to_nchw(dz, c, act_g), zq.grad, tol),
@@ -503,10 +504,36 @@ def case_wgrad_mixed_rejected():
     return {"ok": False}
 
 
+def case_cross_entropy2d():
+    torch, F, ops, _ = _imports()
+    from multiagentperception_b200.loss import cross_entropy2d
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(0)
+    n, c, h, w = 3, 11, 40, 56
+    x = (torch.randn(n, c, h, w, generator=g) * 3).clamp_min(0)      # ReLU'd logits like the n_segnet decoder's
+    t = torch.randint(0, c, (n, h, w), generator=g)
+    t[0, :5] = 250
+    t[2, 7, 9] = 250
+    xr = x.double().requires_grad_(True)
+    ref = F.cross_entropy(xr.permute(0, 2, 3, 1).reshape(-1, c), t.reshape(-1), ignore_index=250)
+    (ref * 1.7).backward()
+    xd = x.to(dev).requires_grad_(True)
+    loss = cross_entropy2d(input=xd, target=t.to(dev))
+    (loss * 1.7).backward()
+    torch.cuda.synchronize()
+    out = {"loss": _verdict(loss.detach().reshape(1), ref.detach().reshape(1), 2e-6),
+           "grad": _verdict(xd.grad, xr.grad, 1e-5)}
+    out["ok"] = all(v["ok"] for v in out.values())
+    return out
+
+
 OTHER_CASES = {
+    "cross_entropy2d": case_cross_entropy2d,
     "wgrad_mixed_rejected": case_wgrad_mixed_rejected,
     "bn_bwd": lambda: case_bn_bwd(),
     "bn_bwd_bf16": lambda: case_bn_bwd(act_f=0, act_g=0),
+    "bn_bwd_mask_from_z": lambda: case_bn_bwd(mask_from_z=True),
+    "bn_bwd_mask_from_z_bf16": lambda: case_bn_bwd(act_f=0, act_g=0, mask_from_z=True, c=128),
     "bn_bwd_f16": lambda: case_bn_bwd(act_f=3, act_g=3, c=128),
     "bn_bwd_res": lambda: case_bn_bwd(residual=True),
     "bn_bwd_norelu": lambda: case_bn_bwd(relu=False),
