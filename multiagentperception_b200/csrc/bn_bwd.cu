@@ -62,7 +62,8 @@ struct BwdMaps {
 };
 
 // du = dy masked by the unit's ReLU; zv receives the raw conv output when it is needed (statistics or the mask)
-__device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bool need_z, float (&du)[8], float (&zv)[8]) {
+__device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bool need_z, const float (&sc)[8],
+                                          const float (&sh)[8], float (&du)[8], float (&zv)[8]) {
   const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
   const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
   load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
@@ -71,7 +72,7 @@ __device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bo
   if (m.relu) {
     if (mask_from_z) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], m.fwd_scale[g * 8 + e], m.fwd_shift[g * 8 + e]) > 0.f ? du[e] : 0.f;
+      for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], sc[e], sh[e]) > 0.f ? du[e] : 0.f;
     } else {
       float yv[8];
       load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
@@ -88,11 +89,14 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m
   const int groups = m.c / 8;
   const int lanes = kThreads / groups;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
-  float mean[8], inv[8], s1[8], s2[8];
+  // (the group g of a thread never changes: its per-channel constants live in registers)
+  float mean[8], inv[8], sc[8], sh[8], s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
     mean[e] = stats ? stats[g * 8 + e] : 0.f;
     inv[e] = stats ? stats[m.c + g * 8 + e] : 0.f;
+    sc[e] = m.fwd_scale ? m.fwd_scale[g * 8 + e] : 0.f;
+    sh[e] = m.fwd_shift ? m.fwd_shift[g * 8 + e] : 0.f;
     s1[e] = s2[e] = 0.f;
   }
   if (lane < lanes) {
@@ -103,7 +107,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m
     for (; px + stride < m.n_px; px += 2 * stride) {
       float du[2][8], zv[2][8];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) masked_du(m, px + u * stride, g, bn, du[u], zv[u]);
+      for (int u = 0; u < 2; ++u) masked_du(m, px + u * stride, g, bn, sc, sh, du[u], zv[u]);
 #pragma unroll
       for (int u = 0; u < 2; ++u)
 #pragma unroll
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m
     }
     for (; px < m.n_px; px += stride) {
       float du[8], zv[8];
-      masked_du(m, px, g, bn, du, zv);
+      masked_du(m, px, g, bn, sc, sh, du, zv);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         s1[e] += du[e];
@@ -152,10 +156,13 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, double count, 
   const double sb = sums[ch], sg = sums[c + ch];
   if (dbeta) dbeta[ch] += static_cast<float>(sb);
   if (dgamma && stats) dgamma[ch] += static_cast<float>(sg);
-  // dz = k * (du - a - xhat * b)
-  coef[ch] = static_cast<float>(sb / count);
-  coef[c + ch] = static_cast<float>(sg / count);
-  coef[2 * c + ch] = stats ? (gamma ? gamma[ch] : 1.f) * stats[c + ch] : 1.f;
+  // dz = k * (du - a - xhat * b), xhat = (z - mean) * inv   ->   dz = A * du + B * z + C
+  const double a = sb / count, b = sg / count;
+  const double k = stats ? static_cast<double>(gamma ? gamma[ch] : 1.f) * stats[c + ch] : 1.0;
+  const double inv = stats ? stats[c + ch] : 0.0, mean = stats ? stats[ch] : 0.0;
+  coef[ch] = static_cast<float>(k);
+  coef[c + ch] = static_cast<float>(stats ? -k * b * inv : 0.0);
+  coef[2 * c + ch] = static_cast<float>(stats ? -k * a + k * b * inv * mean : 0.0);
   sums[ch] = 0.0, sums[c + ch] = 0.0;
 }
 
@@ -165,20 +172,25 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdMaps m, cons
   const size_t total = m.n_px * groups;
   const bool f16g = act_is_f16(m.act_g);
   const int pg = act_planes(m.act_g);
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
-    const int g = idx % groups;
+  const size_t first = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;   // a multiple of groups: g is fixed per thread
+  const int g = first % groups;
+  float sc[8], sh[8], ca[8], cb[8], cc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int ch = g * 8 + e;
+    sc[e] = m.fwd_scale ? m.fwd_scale[ch] : 0.f;
+    sh[e] = m.fwd_shift ? m.fwd_shift[ch] : 0.f;
+    ca[e] = coef[ch], cb[e] = coef[m.c + ch], cc[e] = coef[2 * m.c + ch];
+  }
+  for (size_t idx = first; idx < total; idx += stride) {
     const size_t px = idx / groups;
     float du[8], zv[8];
-    masked_du(m, px, g, stats != nullptr, du, zv);
+    masked_du(m, px, g, stats != nullptr, sc, sh, du, zv);
     if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
     if (stats) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const int ch = g * 8 + e;
-        const float xhat = (zv[e] - stats[ch]) * stats[m.c + ch];
-        du[e] = coef[2 * m.c + ch] * (du[e] - coef[ch] - xhat * coef[m.c + ch]);
-      }
+      for (int e = 0; e < 8; ++e) du[e] = fmaf(ca[e], du[e], fmaf(cb[e], zv[e], cc[e]));
     }
     store8(m.dz + px * (static_cast<size_t>(m.dz_cs) * pg) + m.dz_co + g * 8, m.dz_cs, pg, f16g, du);
   }
@@ -237,10 +249,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nchw_kernel(const float* __r
         const size_t off = (static_cast<size_t>(img) * c + ch) * hw + i;
         du = dy[off];
         if (relu && !(y[off] > 0.f)) du = 0.f;
-        if (stats) {
-          const float xhat = (z[off] - stats[ch]) * stats[c + ch];
-          du = coef[2 * c + ch] * (du - coef[ch] - xhat * coef[c + ch]);
-        }
+        if (stats) du = fmaf(coef[ch], du, fmaf(coef[c + ch], z[off], coef[2 * c + ch]));
       }
       v[e] = du;
     }
@@ -280,8 +289,10 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
                   "bn_bwd: channel slice %d out of range", i);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = a.c / 8, lanes = kThreads / groups;
-  long long want = (a.n_px + lanes - 1) / lanes;
-  const int cap = device_sm_count() * 8;
+  // at least 8 pixels per thread: every CTA ends in a shared-memory reduction and 2c fp64 atomics, which set a ~60 us
+  // floor per launch when 1184 CTAs each brought one pixel per thread (ncu, profiles/r2_train_step.md)
+  long long want = (a.n_px + lanes * 8 - 1) / (lanes * 8);
+  const int cap = device_sm_count() * 4;
   const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   static DeviceOnce attr;
   const size_t smem = static_cast<size_t>(kThreads) * 16 * sizeof(double);
@@ -296,7 +307,8 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
   W2C_CHECK_LAUNCH("bn_bwd_finalize_kernel");
   const size_t total = static_cast<size_t>(a.n_px) * groups;
   const size_t blocks = (total + 255) / 256;
-  const int grid2 = static_cast<int>(blocks < static_cast<size_t>(cap) * 4 ? blocks : static_cast<size_t>(cap) * 4);
+  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 16;
+  const int grid2 = static_cast<int>(blocks < cap2 ? blocks : cap2);
   bn_bwd_apply_kernel<<<grid2, 256, 0, s>>>(m, a.stats, a.coef_ws);
   W2C_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return W2C_OK;

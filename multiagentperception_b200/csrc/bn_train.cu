@@ -271,8 +271,10 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
                 "bn_train: output channel slice out of range");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = c / 8, lanes = kStatThreads / groups;
-  long long want = (n_px + lanes - 1) / lanes;
-  const int cap = device_sm_count() * 8;
+  // at least 8 pixels per thread (four loads in flight, two trips): every CTA ends in a shared-memory reduction and 2c
+  // fp64 atomics, a ~60 us floor per launch when 1184 CTAs each brought one pixel per thread
+  long long want = (n_px + lanes * 8 - 1) / (lanes * 8);
+  const int cap = device_sm_count() * 4;
   const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   static DeviceOnce attr;
   const size_t smem = static_cast<size_t>(kStatThreads) * 16 * sizeof(double);   // 32 KB
@@ -290,7 +292,8 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   W2C_CHECK_LAUNCH("bn_finalize_kernel");
   const size_t total = static_cast<size_t>(n_px) * groups;
   const size_t blocks = (total + 255) / 256;
-  const int grid2 = static_cast<int>(blocks < static_cast<size_t>(cap) * 4 ? blocks : static_cast<size_t>(cap) * 4);
+  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 32;
+  const int grid2 = static_cast<int>(blocks < cap2 ? blocks : cap2);
   bn_apply_kernel<<<grid2, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(z),
                                         static_cast<__nv_bfloat16*>(y_out ? y_out : z),
                                         static_cast<const __nv_bfloat16*>(residual),
