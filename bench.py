@@ -711,6 +711,15 @@ def run_b200(args):
                     torch.cuda.empty_cache()
                 except Exception as e:
                     extra[name] = {"error": str(e)[:300]}
+            # one training step (train-mode forward + loss + backward + SGD) next to the same step of the
+            # unmodified reference through stock torch autograd / cuDNN on this GPU (tools/gpu_train_bench.py)
+            try:
+                from tools.gpu_train_bench import train_step_rates
+                extra["train_step"] = train_step_rates(dev, scenes=2, agents=5, img=IMG, steps=max(3, args.steps // 4),
+                                                       library=not args.no_library_baseline)
+            except Exception as e:
+                extra["train_step"] = {"error": str(e)[:300]}
+            torch.cuda.empty_cache()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -8,8 +8,10 @@ libw2c launches over preallocated NHWC buffers; the engine
 PyTorch supplies device memory, streams and graphs only.
 """
 import ctypes
+import gc
 import os
 import threading
+import weakref
 
 import torch
 
@@ -121,7 +123,10 @@ class WeightCache:
     def __init__(self, device, act, live=None):
         self.device = device
         self.act = act
-        self.live = live
+        # (a weak reference: program -> cache -> program would make every train-mode program cyclic garbage, freed
+        # only when the collector happens to run - e.g. in the middle of a later CUDA-graph capture, which the
+        # destruction of the old program's graphs then invalidates)
+        self.live = weakref.proxy(live) if live is not None else None
         self._convs = {}
         self._misc = {}
 
@@ -1103,9 +1108,18 @@ class Program:
                     # is created once per process, on whichever device captured first
                     if self._capture_stream is None:
                         self._capture_stream = torch.cuda.Stream(self.device)
-                    with _CAPTURE_LOCK, torch.cuda.graph(g, stream=self._capture_stream,
-                                                         capture_error_mode="thread_local"):
-                        self._run_calls(calls)
+                    # no garbage collection while a capture is open: freeing an older program (its CUDA graphs, its
+                    # private memory pool) from inside the capturing thread invalidates the capture
+                    gc_was_on = gc.isenabled()
+                    gc.collect()
+                    gc.disable()
+                    try:
+                        with _CAPTURE_LOCK, torch.cuda.graph(g, stream=self._capture_stream,
+                                                             capture_error_mode="thread_local"):
+                            self._run_calls(calls)
+                    finally:
+                        if gc_was_on:
+                            gc.enable()
                 graphs.append((g, host))
             self.graph = graphs
             return  # results of the eager pass are already in the buffers
