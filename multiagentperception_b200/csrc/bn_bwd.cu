@@ -62,8 +62,8 @@ struct BwdMaps {
 };
 
 // du = dy masked by the unit's ReLU; zv receives the raw conv output when it is needed (statistics or the mask)
-__device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bool need_z, const float (&sc)[8],
-                                          const float (&sh)[8], float (&du)[8], float (&zv)[8]) {
+__device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bool need_z, const float* __restrict__ sc,
+                                          const float* __restrict__ sh, float (&du)[8], float (&zv)[8]) {
   const bool f16f = act_is_f16(m.act_f), f16g = act_is_f16(m.act_g);
   const int pf = act_planes(m.act_f), pg = act_planes(m.act_g);
   load8(m.dy + px * (static_cast<size_t>(m.dy_cs) * pg) + m.dy_co + g * 8, m.dy_cs, pg, f16g, du);
@@ -71,8 +71,13 @@ __device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bo
   if (need_z || mask_from_z) load8(m.z + px * (static_cast<size_t>(m.z_cs) * pf) + m.z_co + g * 8, m.z_cs, pf, f16f, zv);
   if (m.relu) {
     if (mask_from_z) {
+      // sc / sh: this group's 8 forward scale / shift values in shared memory (two 16-byte loads each)
+      const float4 a0 = *reinterpret_cast<const float4*>(sc), a1 = *reinterpret_cast<const float4*>(sc + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(sh), b1 = *reinterpret_cast<const float4*>(sh + 4);
+      const float s8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float h8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], sc[e], sh[e]) > 0.f ? du[e] : 0.f;
+      for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], s8[e], h8[e]) > 0.f ? du[e] : 0.f;
     } else {
       float yv[8];
       load8(m.y + px * (static_cast<size_t>(m.y_cs) * pf) + m.y_co + g * 8, m.y_cs, pf, f16f, yv);
@@ -83,47 +88,54 @@ __device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bo
 }
 
 // sums[ch] += sum du, sums[c + ch] += sum du * xhat
-__global__ void __launch_bounds__(kThreads) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
-                                                                 double* __restrict__ sums) {
+// dynamic shared memory: [reduction scratch: kThreads * 16 doubles][per-channel constants: mean, inv, scale, shift: 4c floats]
+__global__ void __launch_bounds__(kThreads, 3) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
+                                                                    double* __restrict__ sums) {
   extern __shared__ double s_red[];
+  float* s_c = reinterpret_cast<float*>(s_red + static_cast<size_t>(kThreads) * 16);
   const int groups = m.c / 8;
   const int lanes = kThreads / groups;
   const int g = threadIdx.x % groups, lane = threadIdx.x / groups;
-  // (the group g of a thread never changes: its per-channel constants live in registers)
-  float mean[8], inv[8], sc[8], sh[8], s1[8], s2[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    mean[e] = stats ? stats[g * 8 + e] : 0.f;
-    inv[e] = stats ? stats[m.c + g * 8 + e] : 0.f;
-    sc[e] = m.fwd_scale ? m.fwd_scale[g * 8 + e] : 0.f;
-    sh[e] = m.fwd_shift ? m.fwd_shift[g * 8 + e] : 0.f;
-    s1[e] = s2[e] = 0.f;
+  for (int i = threadIdx.x; i < m.c; i += kThreads) {
+    s_c[i] = stats ? stats[i] : 0.f;
+    s_c[m.c + i] = stats ? stats[m.c + i] : 0.f;
+    s_c[2 * m.c + i] = m.fwd_scale ? m.fwd_scale[i] : 0.f;
+    s_c[3 * m.c + i] = m.fwd_shift ? m.fwd_shift[i] : 0.f;
   }
+  __syncthreads();
+  const float* sc = s_c + 2 * m.c + g * 8;
+  const float* sh = s_c + 3 * m.c + g * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = s2[e] = 0.f;
   if (lane < lanes) {
     size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane;
     const size_t stride = static_cast<size_t>(gridDim.x) * lanes;
     const bool bn = stats != nullptr;
+    auto accumulate = [&](const float (&du)[8], const float (&zv)[8]) {
+      const float4 m0 = *reinterpret_cast<const float4*>(s_c + g * 8), m1 = *reinterpret_cast<const float4*>(s_c + g * 8 + 4);
+      const float4 i0 = *reinterpret_cast<const float4*>(s_c + m.c + g * 8);
+      const float4 i1 = *reinterpret_cast<const float4*>(s_c + m.c + g * 8 + 4);
+      const float mean[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+      const float inv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += du[e];
+        if (bn) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
+      }
+    };
     // two pixels per trip (independent loads in flight)
     for (; px + stride < m.n_px; px += 2 * stride) {
       float du[2][8], zv[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) masked_du(m, px + u * stride, g, bn, sc, sh, du[u], zv[u]);
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          s1[e] += du[u][e];
-          if (bn) s2[e] = fmaf(du[u][e], (zv[u][e] - mean[e]) * inv[e], s2[e]);
-        }
+      for (int u = 0; u < 2; ++u) accumulate(du[u], zv[u]);
     }
     for (; px < m.n_px; px += stride) {
       float du[8], zv[8];
       masked_du(m, px, g, bn, sc, sh, du, zv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s1[e] += du[e];
-        if (bn) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
-      }
+      accumulate(du, zv);
     }
   }
   double* mine = s_red + static_cast<size_t>(threadIdx.x) * 16;
@@ -166,8 +178,16 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, double count, 
   sums[ch] = 0.0, sums[c + ch] = 0.0;
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdMaps m, const float* __restrict__ stats,
-                                                           const float* __restrict__ coef) {
+// dynamic shared memory: per-channel constants scale, shift, A, B, C: 5c floats
+__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const BwdMaps m, const float* __restrict__ stats,
+                                                              const float* __restrict__ coef) {
+  extern __shared__ float s_k[];
+  for (int i = threadIdx.x; i < m.c; i += blockDim.x) {
+    s_k[i] = m.fwd_scale ? m.fwd_scale[i] : 0.f;
+    s_k[m.c + i] = m.fwd_shift ? m.fwd_shift[i] : 0.f;
+    s_k[2 * m.c + i] = coef[i], s_k[3 * m.c + i] = coef[m.c + i], s_k[4 * m.c + i] = coef[2 * m.c + i];
+  }
+  __syncthreads();
   const int groups = m.c / 8;
   const size_t total = m.n_px * groups;
   const bool f16g = act_is_f16(m.act_g);
@@ -175,22 +195,23 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BwdMaps m, cons
   const size_t first = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;   // a multiple of groups: g is fixed per thread
   const int g = first % groups;
-  float sc[8], sh[8], ca[8], cb[8], cc[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int ch = g * 8 + e;
-    sc[e] = m.fwd_scale ? m.fwd_scale[ch] : 0.f;
-    sh[e] = m.fwd_shift ? m.fwd_shift[ch] : 0.f;
-    ca[e] = coef[ch], cb[e] = coef[m.c + ch], cc[e] = coef[2 * m.c + ch];
-  }
+  const float* kc = s_k + g * 8;
   for (size_t idx = first; idx < total; idx += stride) {
     const size_t px = idx / groups;
     float du[8], zv[8];
-    masked_du(m, px, g, stats != nullptr, sc, sh, du, zv);
+    masked_du(m, px, g, stats != nullptr, kc, kc + m.c, du, zv);
     if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
     if (stats) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) du[e] = fmaf(ca[e], du[e], fmaf(cb[e], zv[e], cc[e]));
+      for (int h = 0; h < 2; ++h) {
+        const float4 a = *reinterpret_cast<const float4*>(kc + 2 * m.c + 4 * h);
+        const float4 b = *reinterpret_cast<const float4*>(kc + 3 * m.c + 4 * h);
+        const float4 c = *reinterpret_cast<const float4*>(kc + 4 * m.c + 4 * h);
+        du[4 * h + 0] = fmaf(a.x, du[4 * h + 0], fmaf(b.x, zv[4 * h + 0], c.x));
+        du[4 * h + 1] = fmaf(a.y, du[4 * h + 1], fmaf(b.y, zv[4 * h + 1], c.y));
+        du[4 * h + 2] = fmaf(a.z, du[4 * h + 2], fmaf(b.z, zv[4 * h + 2], c.z));
+        du[4 * h + 3] = fmaf(a.w, du[4 * h + 3], fmaf(b.w, zv[4 * h + 3], c.w));
+      }
     }
     store8(m.dz + px * (static_cast<size_t>(m.dz_cs) * pg) + m.dz_co + g * 8, m.dz_cs, pg, f16g, du);
   }
@@ -289,27 +310,34 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
                   "bn_bwd: channel slice %d out of range", i);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int groups = a.c / 8, lanes = kThreads / groups;
-  // at least 8 pixels per thread: every CTA ends in a shared-memory reduction and 2c fp64 atomics, which set a ~60 us
-  // floor per launch when 1184 CTAs each brought one pixel per thread (ncu, profiles/r2_train_step.md)
-  long long want = (a.n_px + lanes * 8 - 1) / (lanes * 8);
-  const int cap = device_sm_count() * 4;
-  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   static DeviceOnce attr;
-  const size_t smem = static_cast<size_t>(kThreads) * 16 * sizeof(double);
+  const size_t smem = static_cast<size_t>(kThreads) * 16 * sizeof(double) + static_cast<size_t>(4) * a.c * sizeof(float);
+  const size_t smem_max = static_cast<size_t>(kThreads) * 16 * sizeof(double) + static_cast<size_t>(4) * 2048 * sizeof(float);
   if (int rc = attr.ensure([=] {
-        return cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        return cudaFuncSetAttribute(bn_bwd_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_max));
       }, "bn_bwd_reduce_kernel"))
     return rc;
+  // at least 8 pixels per thread: every CTA ends in a shared-memory reduction and 2c fp64 atomics (a ~60 us floor per
+  // launch when 1184 CTAs each brought one pixel per thread); at most ONE wave of resident CTAs (no tail)
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_bwd_reduce_kernel, kThreads, smem);
+  long long want = (a.n_px + lanes * 8 - 1) / (lanes * 8);
+  const int cap = device_sm_count() * (occ > 0 ? occ : 1);
+  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   bn_bwd_reduce_kernel<<<grid, kThreads, smem, s>>>(m, a.stats, a.sums_ws);
   W2C_CHECK_LAUNCH("bn_bwd_reduce_kernel");
   bn_bwd_finalize_kernel<<<(a.c + 127) / 128, 128, 0, s>>>(a.sums_ws, static_cast<double>(a.n_px), a.gamma, a.stats,
                                                            a.dgamma, a.dbeta, a.coef_ws, a.c);
   W2C_CHECK_LAUNCH("bn_bwd_finalize_kernel");
+  // >= 4 items per thread (the per-CTA constant table is amortised), one wave of resident CTAs at most
   const size_t total = static_cast<size_t>(a.n_px) * groups;
-  const size_t blocks = (total + 255) / 256;
-  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 16;
-  const int grid2 = static_cast<int>(blocks < cap2 ? blocks : cap2);
-  bn_bwd_apply_kernel<<<grid2, 256, 0, s>>>(m, a.stats, a.coef_ws);
+  const size_t blocks = (total + 256 * 4 - 1) / (256 * 4);
+  const size_t smem2 = static_cast<size_t>(5) * a.c * sizeof(float);
+  int occ2 = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, bn_bwd_apply_kernel, 256, smem2);
+  const size_t cap2 = static_cast<size_t>(device_sm_count()) * (occ2 > 0 ? occ2 : 1);
+  const int grid2 = static_cast<int>(blocks < cap2 ? (blocks ? blocks : 1) : cap2);
+  bn_bwd_apply_kernel<<<grid2, 256, smem2, s>>>(m, a.stats, a.coef_ws);
   W2C_CHECK_LAUNCH("bn_bwd_apply_kernel");
   return W2C_OK;
 }

@@ -274,14 +274,16 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   // at least 8 pixels per thread (four loads in flight, two trips): every CTA ends in a shared-memory reduction and 2c
   // fp64 atomics, a ~60 us floor per launch when 1184 CTAs each brought one pixel per thread
   long long want = (n_px + lanes * 8 - 1) / (lanes * 8);
-  const int cap = device_sm_count() * 4;
-  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   static DeviceOnce attr;
   const size_t smem = static_cast<size_t>(kStatThreads) * 16 * sizeof(double);   // 32 KB
   if (int rc = attr.ensure([=] {
         return cudaFuncSetAttribute(bn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
       }, "bn_stats_kernel"))
     return rc;
+  int occ = 1;   // one wave of resident CTAs at most: a partial second wave doubled the time of the largest maps
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_stats_kernel, kStatThreads, smem);
+  const int cap = device_sm_count() * (occ > 0 ? occ : 1);
+  const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
   bn_stats_kernel<<<grid, kStatThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(z), static_cast<size_t>(n_px), c, cs,
                                                    coffset, act, sums_ws);
   W2C_CHECK_LAUNCH("bn_stats_kernel");
@@ -292,7 +294,7 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   W2C_CHECK_LAUNCH("bn_finalize_kernel");
   const size_t total = static_cast<size_t>(n_px) * groups;
   const size_t blocks = (total + 255) / 256;
-  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 32;
+  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 8;   // 31 registers: eight CTAs of 256 threads per SM
   const int grid2 = static_cast<int>(blocks < cap2 ? blocks : cap2);
   bn_apply_kernel<<<grid2, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(z),
                                         static_cast<__nv_bfloat16*>(y_out ? y_out : z),
