@@ -14,8 +14,10 @@
 // as MN-major operands (instruction-descriptor bits 15 / 16, leading-byte-offset = distance between 64-channel
 // groups, stride-byte-offset = distance between 8-pixel K atoms). One CTA owns an output tile
 //   M = 128 P-channels  x  N = (3 taps of one filter row) x 64 Q-channels = 192 fp32 TMEM columns
-// and a contiguous range of pixel blocks (split-K); the three taps of a filter row are three 64-wide N groups of ONE
-// MMA (LBO walks from tap tile to tap tile). Partial sums are added to G with fp32 atomics.
+// (two such M halves - 256 P-channels, 384 columns - when the layer has them: the kernel is bound by the L2 -> SM
+// traffic of its operand tiles, ncu: 35 % tensor-pipe active at 8.1 TB/s of tile loads with one half, and the second
+// half re-uses the Q tiles) and a contiguous range of pixel blocks (split-K); the three taps of a filter row are three
+// 64-wide N groups of ONE MMA (LBO walks from tap tile to tap tile). Partial sums are added to G with fp32 atomics.
 //   warp 0 (one lane)  TMA producer: per pixel block the P tile (1-2 channel groups x planes) and the 3 shifted Q tiles
 //   warp 1 (one lane)  tcgen05.mma M128 x N192 x K16, 4 per block and plane pair (lo*hi, hi*lo, hi*hi)
 //   warps 2..5         epilogue: tcgen05.ld, red.global.add.f32
@@ -34,7 +36,6 @@ namespace {
 constexpr int kPixBlock = 64;                  // K per stage: 64 pixels
 constexpr int kTileBytes = kPixBlock * 128;    // one [64 px][64 ch] box: 8 KB
 constexpr int kThreads = 192;
-constexpr int kTmemCols = 256;
 
 struct WgradParams {
   CUtensorMap p_map;
@@ -53,11 +54,13 @@ struct WgradParams {
   int m_groups;          // 64-channel groups of P a tile really holds (1 when cp == 64)
 };
 
-template <int PLANES>
+// MH: M halves per CTA (1: 128 P-channels, 2: 256)
+template <int PLANES, int MH>
 struct WgSmem {
-  static constexpr int kStages = PLANES == 1 ? 4 : 2;
-  static constexpr int kPBytes = PLANES * 2 * kTileBytes;
+  static constexpr int kStages = PLANES == 1 ? (MH == 1 ? 5 : 4) : 2;
+  static constexpr int kPBytes = PLANES * 2 * MH * kTileBytes;
   static constexpr int kQBytes = PLANES * 3 * kTileBytes;
+  static constexpr int kTmemCols = MH == 1 ? 256 : 512;
   static constexpr int kStageBytes = kPBytes + kQBytes;
   static constexpr int kBarOff = kStages * kStageBytes;
   static constexpr int kTmemPtrOff = kBarOff + (2 * kStages + 1) * 8;
@@ -83,9 +86,10 @@ __device__ __forceinline__ uint32_t make_idesc_mn(uint32_t m, uint32_t n, bool f
          ((m >> 4) << 24);
 }
 
-template <int PLANES>
+template <int PLANES, int MH>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
-  using L = WgSmem<PLANES>;
+  using L = WgSmem<PLANES, MH>;
+  constexpr int kTmemCols = L::kTmemCols;
   constexpr int STAGES = L::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
   const int split = blockIdx.y;
   const int kb0 = static_cast<int>(static_cast<long long>(p.kblocks) * split / p.splits);
   const int kb1 = static_cast<int>(static_cast<long long>(p.kblocks) * (split + 1) / p.splits);
-  const int cp0 = m_tile * 128, cq0 = q_chunk * 64, tap0 = tap_group * p.tpg;
+  const int cp0 = m_tile * (128 * MH), cq0 = q_chunk * 64, tap0 = tap_group * p.tpg;
   const int n_cols = p.tpg * 64;
 
   if (warp == 0 && lane == 0) {
@@ -145,7 +149,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
 #pragma unroll
         for (int pl = 0; pl < PLANES; ++pl) {
           for (int g = 0; g < p.m_groups; ++g)
-            ptx::tma_load_4d(&p.p_map, &full_bar[stage], st + (pl * 2 + g) * kTileBytes,
+            ptx::tma_load_4d(&p.p_map, &full_bar[stage], st + (pl * 2 * MH + g) * kTileBytes,
                              p.p_c0 + pl * p.p_lo + cp0 + g * 64, w0, h0, i0);
           for (int tp = 0; tp < p.tpg; ++tp) {
             const int tap = tap0 + tp;
@@ -172,13 +176,16 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
           // corrections first (lo*hi, hi*lo), then hi*hi: the order of the forward kernels
           const int pl_p = (p.npass == 3 && pass == 0) ? 1 : 0;
           const int pl_q = (p.npass == 3 && pass == 1) ? 1 : 0;
-          const uint32_t a0 = st + pl_p * 2 * kTileBytes;
+          const uint32_t a0 = st + pl_p * 2 * MH * kTileBytes;
           const uint32_t b0 = st + L::kPBytes + pl_q * 3 * kTileBytes;
 #pragma unroll
           for (int ks = 0; ks < kPixBlock / 16; ++ks) {
             // 16 pixels = two 8-row atoms = 2048 B further along K
-            ptx::umma_bf16(tmem_base, make_sw128_mnmajor_desc(a0 + ks * 2048, kTileBytes),
-                           make_sw128_mnmajor_desc(b0 + ks * 2048, kTileBytes), idesc, accumulate);
+            const uint64_t b_desc = make_sw128_mnmajor_desc(b0 + ks * 2048, kTileBytes);
+#pragma unroll
+            for (int mh = 0; mh < MH; ++mh)   // the M halves share the Q tiles; each has its own 192 TMEM columns
+              ptx::umma_bf16(tmem_base + mh * 192, make_sw128_mnmajor_desc(a0 + mh * 2 * kTileBytes + ks * 2048, kTileBytes),
+                             b_desc, idesc, accumulate);
             accumulate = 1;
           }
         }
@@ -193,17 +200,21 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
     const int row = q * 32 + lane;
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tc_fence_after();
-    const bool row_ok = cp0 + row < p.cp;
-    float* grow = p.g + (static_cast<size_t>(cp0 + row) * p.ntaps + tap0) * p.cq + cq0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < n_cols; c0 += 32) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, r);
-      ptx::tmem_ld_wait();
-      if (row_ok) {
-        float* dst = grow + static_cast<size_t>(c0 >> 6) * p.cq + (c0 & 63);
+    for (int mh = 0; mh < MH; ++mh) {
+      const int ch = cp0 + mh * 128 + row;
+      const bool row_ok = ch < p.cp;
+      float* grow = p.g + (static_cast<size_t>(ch) * p.ntaps + tap0) * p.cq + cq0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mh * 192 + c0, r);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float* dst = grow + static_cast<size_t>(c0 >> 6) * p.cq + (c0 & 63);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -223,16 +234,17 @@ int pow2_ceil(int v) {
   return p;
 }
 
-template <int PLANES>
+template <int PLANES, int MH>
 int launch(const WgradParams& p, cudaStream_t stream) {
-  using L = WgSmem<PLANES>;
+  using L = WgSmem<PLANES, MH>;
+  static_assert(L::kDynamicBytes <= 227 * 1024, "wgrad stages exceed the shared memory of an SM");
   static DeviceOnce attr_set;
   if (int rc = attr_set.ensure([] {
-        return cudaFuncSetAttribute(wgrad_kernel<PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+        return cudaFuncSetAttribute(wgrad_kernel<PLANES, MH>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
       }, "wgrad_kernel"))
     return rc;
   dim3 grid(p.m_tiles * p.q_chunks * p.tap_groups, p.splits, 1);
-  wgrad_kernel<PLANES><<<grid, kThreads, L::kDynamicBytes, stream>>>(p);
+  wgrad_kernel<PLANES, MH><<<grid, kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("wgrad_kernel");
   return W2C_OK;
 }
@@ -317,9 +329,18 @@ extern "C" int w2c_conv_wgrad(const w2c_wgrad_args* args, w2c_stream_t stream) {
   const long long kblocks = static_cast<long long>(p.tiles_w) * p.tiles_h * tiles_img;
   W2C_CHECK_ARG(kblocks < (1ll << 30), "wgrad: too many pixel blocks");
   p.kblocks = static_cast<int>(kblocks);
-  p.m_tiles = ceil_div(p.cp, 128), p.q_chunks = p.cq / 64;
-  p.m_groups = p.cp >= 128 ? 2 : 1;
   W2C_CHECK_ARG(p.cp % 128 == 0 || p.cp == 64, "wgrad: %d channels on the dense operand (64 or a multiple of 128)", p.cp);
+  // two M halves per CTA where the layer has 256 P-channels to give AND every CTA still gets a long pixel loop (the
+  // epilogue adds 2 x 24.5 k atomics per CTA: measured on B200, 512 -> 512 at 64x64 gains 19 %, at 16x16 it loses 50 %)
+  int mh = 1;
+  if (p.cp % 256 == 0) {
+    const int tiles2 = (p.cp / 256) * (p.cq / 64) * p.tap_groups;
+    int splits2 = ceil_div(2 * device_sm_count(), tiles2);
+    if (splits2 > p.kblocks) splits2 = p.kblocks;
+    if (p.kblocks / splits2 >= 16) mh = 2;
+  }
+  p.m_tiles = ceil_div(p.cp, 128 * mh), p.q_chunks = p.cq / 64;
+  p.m_groups = p.cp >= 128 ? 2 * mh : 1;
   const int out_tiles = p.m_tiles * p.q_chunks * p.tap_groups;
   int splits = ceil_div(2 * device_sm_count(), out_tiles);
   if (splits > p.kblocks) splits = p.kblocks;
@@ -353,5 +374,6 @@ extern "C" int w2c_conv_wgrad(const w2c_wgrad_args* args, w2c_stream_t stream) {
     }
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  return planes == 2 ? launch<2>(p, st) : launch<1>(p, st);
+  if (mh == 2) return planes == 2 ? launch<2, 2>(p, st) : launch<1, 2>(p, st);
+  return planes == 2 ? launch<2, 1>(p, st) : launch<1, 1>(p, st);
 }

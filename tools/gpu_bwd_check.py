@@ -98,6 +98,11 @@ WGRAD_CASES = {
     "wg_small_2x2": (0, 6, 2, 2, 256, 256, 1, {}),
     "wg_small_s2_2x2": (1, 6, 2, 2, 256, 256, 0, {}),
     "wg_big_k": (0, 4, 64, 64, 64, 64, 0, {}),
+    # 256 channels on the dense operand and enough pixel blocks: two M halves per CTA
+    "wg_mh2": (0, 4, 64, 64, 64, 256, 0, {}),
+    "wg_mh2_x2": (0, 2, 64, 64, 128, 512, 1, {}),
+    "wg_mh2_deconv": (2, 8, 32, 32, 256, 64, 0, {}),
+    "wg_mh2_s2": (1, 4, 64, 64, 64, 256, 1, {}),
 }
 
 
