@@ -394,7 +394,7 @@ int w2c_bilinear_argmax_fwd(const float* x, uint8_t* labels, int32_t n, int32_t 
  * (ptsemseg/models/utils.py:87-120,148-168).
  *   x    the layer's forward INPUT map, n x h_in x w_in pixels, channels [x_coffset, x_coffset + cin) of x_cstride
  *   dy   gradient w.r.t. the conv's raw OUTPUT (h_out x w_out as the kind implies), channels [dy_coffset, + cout)
- *   dw   fp32, +=:  Conv2d kinds [cout][ntaps][cin];  W2C_DECONV3X3_S2 [cin][ntaps][cout]   (tap = kh*3 + kw; both are
+ *   dw   fp32, +=, 16-byte aligned:  Conv2d kinds [cout][ntaps][cin];  W2C_DECONV3X3_S2 [cin][ntaps][cout]   (tap = kh*3 + kw; both are
  *        the parameter's [d0][d1][kh][kw] layout with the last three axes permuted: .view(d0,3,3,d1).permute(0,3,1,2))
  * cin and cout as the MAPS hold them: multiples of 64 (an 11-class logits gradient lives in a 64-channel padded map),
  * and 64 or a multiple of 128 on the small-grid operand (dy for convs, x for the transposed conv).

@@ -198,33 +198,45 @@ __global__ void __launch_bounds__(128) mlp_bwd_fc0_dgrad_kernel(const HeadsBwd h
 
 // ------------------------------------------------------------------------------------------------ first-layer wgrad
 // dW[co][ci][kh][kw] += sum over pixels dz[pix][co] * x[ci][pix*stride + k - pad].  Persistent CTAs walk tiles of
-// TP x TP output pixels of one image: the dz tile (TP*TP x 64) and the input patch are staged in shared memory; thread t
-// owns the 8 output channels of group t / KK for tap k = t % KK in registers across ALL its tiles (one 16-byte pair of
-// shared loads of dz and one of the patch value per 8 FMAs: the one-FMA-per-two-loads version ran at the shared-memory
-// rate, 1.7 ms per 10 frames); one atomicAdd per (co, k) and CTA at the end.
+// TP x TP output pixels of one image: the dz tile (TP*TP x 64) and the input patch are staged in shared memory. A thread
+// owns one (8-channel group, input channel, filter row) and keeps the KS taps of that row x 8 channels in registers
+// across ALL its tiles: per pixel two 16-byte loads of dz and KS patch words feed 8 * KS FMAs (7x7: 56 FMAs per 9
+// loads; the one-tap-per-thread version did 8 per 3 and ran at the shared-memory rate, 0.67 ms per 10 frames). With
+// fewer items than compute threads (3x3: 72) the tile's pixels are dealt over `parts` partitions. The last warp(s) of
+// the CTA do no arithmetic: they stage the NEXT tile into the other half of a double buffer while the others compute
+// (staging and arithmetic took about the same time per tile and two 126-register CTAs per SM did not overlap them).
+// One atomicAdd per (co, k) and thread at the end.
+template <int KS, int STRIDE>
+struct StemWgradGeom {
+  static constexpr int TP = 8;                             // output pixels per tile edge
+  static constexpr int PAD = KS / 2;
+  static constexpr int PW = (TP - 1) * STRIDE + KS;        // input patch edge
+  static constexpr int KK = 3 * KS * KS;
+  static constexpr int kPatchWords = (3 * PW * PW + 3) & ~3;
+  static size_t smem_bytes(int cout) { return 2 * (static_cast<size_t>(kPatchWords) + TP * TP * cout) * sizeof(float); }
+};
+
 template <int KS, int STRIDE>
 __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                                          float* __restrict__ dw, int b, int n_agents, int c_total,
                                                          int c_first, int h, int w, int cout, int dz_cs, int dz_co,
                                                          int act_g, int tiles_w, int tiles_h, int n_tiles) {
-  constexpr int TP = 8;                                   // output pixels per tile edge
-  constexpr int PAD = KS / 2;
-  constexpr int PW = (TP - 1) * STRIDE + KS;              // input patch edge
-  constexpr int KK = 3 * KS * KS;
-  constexpr int ITEMS = (8 * KK + 255) / 256;             // (8-channel group, k) items per thread, cout <= 64
+  using G = StemWgradGeom<KS, STRIDE>;
+  constexpr int TP = G::TP, PAD = G::PAD, PW = G::PW, KK = G::KK;
   extern __shared__ float s_mem[];
-  float* s_patch = s_mem;                                 // [3][PW][PW]
-  float* s_dz = s_mem + ((3 * PW * PW + 3) & ~3);         // [TP*TP][cout] (16-byte aligned rows)
+  const int buf_words = G::kPatchWords + TP * TP * cout;  // one buffer: patch [3][PW][PW], then dz [TP*TP][cout]
   const int ho = h / STRIDE, wo = w / STRIDE;
   const bool f16g = act_is_f16(act_g);
   const int pg = act_planes(act_g);
-  const int n_items = (cout / 8) * KK;
-  float acc[ITEMS][8];
-#pragma unroll
-  for (int i = 0; i < ITEMS; ++i)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int n_items = (cout / 8) * 3 * KS;                // (group, ci, kh), kh fastest; cout <= 64: <= 168
+  const int parts = (256 - 32) / n_items;                 // pixel partitions (>= 1); at least one warp left to stage
+  const int first_loader = (parts * n_items + 31) & ~31;
+  const int n_loaders = 256 - first_loader;
+  const int item = threadIdx.x % n_items, part = threadIdx.x / n_items;
+  const bool active = part < parts;
+  const int g = item / (3 * KS), ci = (item / KS) % 3, kh = item % KS;
+
+  auto stage = [&](int tile, float* buf, int t0, int nt) {
     int t = tile;
     const int tx = t % tiles_w;
     t /= tiles_w;
@@ -234,56 +246,67 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     const int ox0 = tx * TP, oy0 = ty * TP;
     const int ix0 = ox0 * STRIDE - PAD, iy0 = oy0 * STRIDE - PAD;
     const float* xin = x + (static_cast<size_t>(scene) * c_total + c_first + 3 * agent) * h * w;
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * PW * PW; i += blockDim.x) {
-      const int ci = i / (PW * PW), py = (i / PW) % PW, px = i % PW;
+    float* s_patch = buf;
+    float* s_dz = buf + G::kPatchWords;
+    for (int i = t0; i < 3 * PW * PW; i += nt) {
+      const int cc = i / (PW * PW), py = (i / PW) % PW, px = i % PW;
       const int iy = iy0 + py, ix = ix0 + px;
-      s_patch[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xin + (static_cast<size_t>(ci) * h + iy) * w + ix) : 0.f;
+      s_patch[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xin + (static_cast<size_t>(cc) * h + iy) * w + ix) : 0.f;
     }
-    for (int i = threadIdx.x; i < TP * TP * (cout / 8); i += blockDim.x) {
-      const int p = i / (cout / 8), g = i % (cout / 8);
+    for (int i = t0; i < TP * TP * (cout / 8); i += nt) {
+      const int p = i / (cout / 8), gg = i % (cout / 8);
       const int oy = oy0 + p / TP, ox = ox0 + p % TP;
       float v[8];
       if (oy < ho && ox < wo)
-        load8(dz + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(dz_cs) * pg) + dz_co + g * 8, dz_cs, pg, f16g, v);
+        load8(dz + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(dz_cs) * pg) + dz_co + gg * 8, dz_cs, pg, f16g, v);
       else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = 0.f;
       }
-      float4* d4 = reinterpret_cast<float4*>(s_dz + p * cout + g * 8);
+      float4* d4 = reinterpret_cast<float4*>(s_dz + p * cout + gg * 8);
       d4[0] = make_float4(v[0], v[1], v[2], v[3]);
       d4[1] = make_float4(v[4], v[5], v[6], v[7]);
     }
-    __syncthreads();
+  };
+
+  float acc[KS][8];
 #pragma unroll
-    for (int i = 0; i < ITEMS; ++i) {
-      const int item = threadIdx.x + i * 256;
-      if (item < n_items) {
-        const int g = item / KK, k = item % KK;
-        const int ci = k / (KS * KS), kh = (k / KS) % KS, kw = k % KS;
-        const float* pp = s_patch + (ci * PW + kh) * PW + kw;
-        const float* dp = s_dz + g * 8;
-#pragma unroll 4
-        for (int p = 0; p < TP * TP; ++p) {
-          const float xv = pp[((p / TP) * PW + (p % TP)) * STRIDE];
-          const float4 d0 = *reinterpret_cast<const float4*>(dp + p * cout);
-          const float4 d1 = *reinterpret_cast<const float4*>(dp + p * cout + 4);
-          acc[i][0] = fmaf(d0.x, xv, acc[i][0]), acc[i][1] = fmaf(d0.y, xv, acc[i][1]);
-          acc[i][2] = fmaf(d0.z, xv, acc[i][2]), acc[i][3] = fmaf(d0.w, xv, acc[i][3]);
-          acc[i][4] = fmaf(d1.x, xv, acc[i][4]), acc[i][5] = fmaf(d1.y, xv, acc[i][5]);
-          acc[i][6] = fmaf(d1.z, xv, acc[i][6]), acc[i][7] = fmaf(d1.w, xv, acc[i][7]);
+  for (int k = 0; k < KS; ++k)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
+  if (static_cast<int>(blockIdx.x) < n_tiles) stage(blockIdx.x, s_mem, threadIdx.x, 256);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    // buffer it & 1 is staged, and everybody is done with the other one
+    __syncthreads();
+    float* cur = s_mem + (it & 1) * buf_words;
+    if (static_cast<int>(threadIdx.x) >= first_loader) {
+      const int next = tile + gridDim.x;
+      if (next < n_tiles) stage(next, s_mem + ((it + 1) & 1) * buf_words, threadIdx.x - first_loader, n_loaders);
+    } else if (active) {
+      const float* pp = cur + (ci * PW + kh) * PW;
+      const float* dp = cur + G::kPatchWords + g * 8;
+#pragma unroll 2
+      for (int p = part; p < TP * TP; p += parts) {
+        const float* px = pp + ((p / TP) * PW + (p % TP)) * STRIDE;
+        const float4 d0 = *reinterpret_cast<const float4*>(dp + p * cout);
+        const float4 d1 = *reinterpret_cast<const float4*>(dp + p * cout + 4);
+#pragma unroll
+        for (int k = 0; k < KS; ++k) {
+          const float xv = px[k];
+          acc[k][0] = fmaf(d0.x, xv, acc[k][0]), acc[k][1] = fmaf(d0.y, xv, acc[k][1]);
+          acc[k][2] = fmaf(d0.z, xv, acc[k][2]), acc[k][3] = fmaf(d0.w, xv, acc[k][3]);
+          acc[k][4] = fmaf(d1.x, xv, acc[k][4]), acc[k][5] = fmaf(d1.y, xv, acc[k][5]);
+          acc[k][6] = fmaf(d1.z, xv, acc[k][6]), acc[k][7] = fmaf(d1.w, xv, acc[k][7]);
         }
       }
     }
   }
+  if (active) {
 #pragma unroll
-  for (int i = 0; i < ITEMS; ++i) {
-    const int item = threadIdx.x + i * 256;
-    if (item < n_items) {
-      const int g = item / KK, k = item % KK;
+    for (int k = 0; k < KS; ++k)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) atomicAdd(dw + (g * 8 + e) * KK + k, acc[i][e]);
-    }
+      for (int e = 0; e < 8; ++e) atomicAdd(dw + (g * 8 + e) * KK + (ci * KS + kh) * KS + k, acc[k][e]);
   }
 }
 
@@ -360,6 +383,92 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// Tiled version for c % 64 == 0 (the resnet18 trunk: 64 channels). The per-pixel kernel above issues up to 33
+// dependent 16-byte loads per thread (0.85 ms per 10 frames @256x256x64, ncu: 0.18 TB/s). Here a CTA owns 8x8 input
+// pixels x 64 channels: (1) the 11x11 pixel window (one-pixel halo above / left, two below / right) goes to shared
+// memory as fp32 with independent coalesced loads, out-of-image pixels as -inf; (2) every one of the 5x5 pooling
+// windows that touch the tile finds the scan-order index of its FIRST maximum once per channel (4 bits each, eight
+// channels per word); (3) an input pixel sums dy over the <= 4 windows whose index points at it, in the (oy, ox) order
+// of the kernel above, so both produce the same bits.
+constexpr int kMpT = 4;                       // pooling windows per tile edge -> 2 * kMpT input pixels
+constexpr int kMpIn = 2 * kMpT + 3;           // staged pixels per edge
+constexpr int kMpWin = kMpT + 1;              // windows per edge that touch the tile
+__global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const __nv_bfloat16* __restrict__ x,
+                                                                const __nv_bfloat16* __restrict__ dy,
+                                                                __nv_bfloat16* __restrict__ dx, int h, int w, int c,
+                                                                int act_f, int act_g, int tiles_w, int tiles_h) {
+  __shared__ __align__(16) float s_x[kMpIn * kMpIn][64];
+  __shared__ uint32_t s_idx[kMpWin * kMpWin][8];
+  const int ho = h / 2, wo = w / 2;
+  const bool f16f = act_is_f16(act_f), f16g = act_is_f16(act_g);
+  const int pf = act_planes(act_f), pg = act_planes(act_g);
+  int t = blockIdx.x;
+  const int tx = t % tiles_w;
+  t /= tiles_w;
+  const int ty = t % tiles_h;
+  const int img = t / tiles_h;
+  const int c0 = blockIdx.y * 64;
+  const int oy0 = ty * kMpT, ox0 = tx * kMpT;          // first window of the tile
+  const int iy0 = 2 * oy0 - 1, ix0 = 2 * ox0 - 1;      // first staged pixel
+  const float ninf = __int_as_float(0xff800000);
+  for (int i = threadIdx.x; i < kMpIn * kMpIn * 8; i += blockDim.x) {
+    const int g = i & 7, p = i >> 3;
+    const int iy = iy0 + p / kMpIn, ix = ix0 + p % kMpIn;
+    float v[8];
+    if (iy >= 0 && iy < h && ix >= 0 && ix < w)
+      load8(x + ((static_cast<size_t>(img) * h + iy) * w + ix) * (static_cast<size_t>(c) * pf) + c0 + g * 8, c, pf, f16f, v);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = ninf;
+    }
+    float4* d4 = reinterpret_cast<float4*>(&s_x[p][g * 8]);
+    d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+    d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kMpWin * kMpWin * 8; i += blockDim.x) {
+    const int g = i & 7, wi = i >> 3;
+    const int wy = wi / kMpWin, wx = wi % kMpWin;
+    float best[8];
+    uint32_t arg = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = ninf;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      const float4* s4 = reinterpret_cast<const float4*>(&s_x[(2 * wy + k / 3) * kMpIn + 2 * wx + k % 3][g * 8]);
+      const float4 a = s4[0], b = s4[1];
+      const float o[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (k == 0 || o[e] > best[e]) best[e] = o[e], arg = (arg & ~(15u << (4 * e))) | (static_cast<uint32_t>(k) << (4 * e));
+    }
+    s_idx[wi][g] = arg;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * kMpT * kMpT * 8; i += blockDim.x) {
+    const int g = i & 7, p = i >> 3;
+    const int ly = p / (2 * kMpT), lx = p % (2 * kMpT);
+    const int iy = 2 * oy0 + ly, ix = 2 * ox0 + lx;
+    if (iy >= h || ix >= w) continue;
+    float out[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) out[e] = 0.f;
+    for (int oy = iy / 2; oy <= (iy + 1) / 2; ++oy) {
+      if (oy >= ho) continue;
+      for (int ox = ix / 2; ox <= (ix + 1) / 2; ++ox) {
+        if (ox >= wo) continue;
+        const uint32_t k = static_cast<uint32_t>((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
+        const uint32_t arg = s_idx[(oy - oy0) * kMpWin + (ox - ox0)][g];
+        float d[8];
+        load8(dy + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(c) * pg) + c0 + g * 8, c, pg, f16g, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) out[e] += ((arg >> (4 * e)) & 15u) == k ? d[e] : 0.f;
+      }
+    }
+    store8(dx + ((static_cast<size_t>(img) * h + iy) * w + ix) * (static_cast<size_t>(c) * pg) + c0 + g * 8, c, pg, f16g, out);
+  }
+}
+
 // Adjoint of F.interpolate(bilinear, align_corners=False) by an integer factor: dx[n][c][iy][ix] = sum of dy over the
 // output pixels that read input (iy, ix), with the forward weights. One thread per input element.
 __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int nc,
@@ -397,6 +506,46 @@ __global__ void __launch_bounds__(256) bilinear_bwd_kernel(const float* __restri
       }
     }
     dx[idx] = acc;
+  }
+}
+
+// Row version for the x32 up-sampling of simple_decoder (backbone.py:160): one thread per INPUT element leaves 28 k
+// threads walking ~64 x 97 output pixels each (0.78 ms per 10 frames, ncu: 0.27 TB/s). The adjoint is separable: one CTA
+// per (plane, input row) first folds the ~2f output rows that read the row into one weighted row in shared memory
+// (coalesced, independent loads), then one warp per input column folds the ~2f columns of that row.
+__device__ __forceinline__ float bilinear_w(int o, int i, int n_in, float inv) {
+  const float s = fmaxf((o + 0.5f) * inv - 0.5f, 0.f);
+  const int i0 = static_cast<int>(s);
+  const int i1 = min(i0 + 1, n_in - 1);
+  const float l = s - i0;
+  float wgt = 0.f;
+  if (i0 == i) wgt += 1.f - l;
+  if (i1 == i) wgt += l;
+  return wgt;
+}
+__global__ void __launch_bounds__(256) bilinear_bwd_rows_kernel(const float* __restrict__ dy, float* __restrict__ dx, int h,
+                                                                int w, int f) {
+  extern __shared__ float s_row[];            // [wo]
+  const int ho = h * f, wo = w * f;
+  const float inv = 1.f / static_cast<float>(f);
+  const int iy = blockIdx.x % h;
+  const size_t plane = blockIdx.x / h;
+  const float* src = dy + plane * ho * wo;
+  const int oy_lo = max(0, (iy - 1) * f), oy_hi = min(ho - 1, (iy + 1) * f + f);
+  for (int ox = threadIdx.x; ox < wo; ox += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int oy = oy_lo; oy <= oy_hi; ++oy) acc = fmaf(bilinear_w(oy, iy, h, inv), __ldg(src + static_cast<size_t>(oy) * wo + ox), acc);
+    s_row[ox] = acc;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int ix = warp; ix < w; ix += blockDim.x >> 5) {
+    const int ox_lo = max(0, (ix - 1) * f), ox_hi = min(wo - 1, (ix + 1) * f + f);
+    float acc = 0.f;
+    for (int ox = ox_lo + lane; ox <= ox_hi; ox += 32) acc = fmaf(bilinear_w(ox, ix, w, inv), s_row[ox], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) dx[(plane * h + iy) * w + ix] = acc;
   }
 }
 
@@ -519,11 +668,10 @@ extern "C" int w2c_stem_conv_wgrad(const float* x, const void* dz, float* dw, in
   W2C_CHECK_ARG(h % stride == 0 && w_px % stride == 0, "stem_wgrad: H, W must be even for the 7x7 s2 stem");
   const int ho = h / stride, wo = w_px / stride;
   const int tiles_w = ceil_div(wo, 8), tiles_h = ceil_div(ho, 8);
-  const int pw = 7 * stride + ksize;
-  const size_t smem = (((static_cast<size_t>(3) * pw * pw + 3) & ~static_cast<size_t>(3)) + 64 * cout) * sizeof(float);
+  const size_t smem = ksize == 3 ? StemWgradGeom<3, 1>::smem_bytes(cout) : StemWgradGeom<7, 2>::smem_bytes(cout);
   const long long tiles = static_cast<long long>(tiles_w) * tiles_h * b * n_agents;
   W2C_CHECK_ARG(tiles < (1ll << 31), "stem_wgrad: too many tiles");
-  const int cap = device_sm_count() * 4;
+  const int cap = device_sm_count() * 2;   // two resident CTAs per SM (registers / 43 KB of shared memory each)
   const int blocks = static_cast<int>(tiles < cap ? tiles : cap);
   if (ksize == 3)
     stem_wgrad_kernel<3, 1><<<blocks, 256, smem, s>>>(x, static_cast<const __nv_bfloat16*>(dz), dw, b, n_agents, c_total, c_first, h,
@@ -554,6 +702,16 @@ extern "C" int w2c_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int
                                     int32_t act_f, int32_t act_g, w2c_stream_t stream) {
   W2C_CHECK_ARG(x && dy && dx && n > 0 && h > 0 && w_px > 0 && h % 2 == 0 && w_px % 2 == 0 && c % 8 == 0, "maxpool_bwd: bad arguments");
   W2C_CHECK_ARG(act_valid(act_f) && act_valid(act_g), "maxpool_bwd: bad act");
+  if (c % 64 == 0) {
+    const int tiles_w = ceil_div(w_px / 2, kMpT), tiles_h = ceil_div(h / 2, kMpT);
+    const long long tiles = static_cast<long long>(tiles_w) * tiles_h * n;
+    W2C_CHECK_ARG(tiles < (1ll << 31) && c / 64 < 65536, "maxpool_bwd: too many tiles");
+    maxpool_bwd_tiled_kernel<<<dim3(static_cast<unsigned>(tiles), c / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), h, w_px, c,
+        act_f, act_g, tiles_w, tiles_h);
+    W2C_CHECK_LAUNCH("maxpool_bwd_tiled_kernel");
+    return W2C_OK;
+  }
   const size_t total = static_cast<size_t>(n) * h * w_px * (c / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(dy), static_cast<__nv_bfloat16*>(dx), n, h, w_px, c,
@@ -565,6 +723,13 @@ extern "C" int w2c_maxpool3x3s2_bwd(const void* x, const void* dy, void* dx, int
 extern "C" int w2c_bilinear_up_bwd(const float* dy, float* dx, int32_t n, int32_t c, int32_t h, int32_t w_px, int32_t factor,
                                    w2c_stream_t stream) {
   W2C_CHECK_ARG(dy && dx && n > 0 && c > 0 && h > 0 && w_px > 0 && factor >= 1, "bilinear_bwd: bad arguments");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t row_bytes = static_cast<size_t>(w_px) * factor * sizeof(float);
+  if (factor >= 4 && row_bytes <= 40 * 1024 && static_cast<long long>(n) * c * h < (1ll << 31)) {
+    bilinear_bwd_rows_kernel<<<n * c * h, 256, row_bytes, s>>>(dy, dx, h, w_px, factor);
+    W2C_CHECK_LAUNCH("bilinear_bwd_rows_kernel");
+    return W2C_OK;
+  }
   const size_t total = static_cast<size_t>(n) * c * h * w_px;
   bilinear_bwd_kernel<<<grid_for(total, 256, 32), 256, 0, static_cast<cudaStream_t>(stream)>>>(dy, dx, n * c, h, w_px, factor);
   W2C_CHECK_LAUNCH("bilinear_bwd_kernel");

@@ -198,6 +198,11 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t* r) 
       : "r"(taddr)
       : "memory");
 }
+// Four fp32 additions to consecutive, 16-byte aligned global words in ONE reduction (sm_90+): a quarter of the L2 atomic
+// operations of four scalar red.global.add.f32.
+__device__ __forceinline__ void red_add_v4_f32(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- epilogue packing

@@ -20,7 +20,8 @@
 // 64-wide N groups of ONE MMA (LBO walks from tap tile to tap tile). Partial sums are added to G with fp32 atomics.
 //   warp 0 (one lane)  TMA producer: per pixel block the P tile (1-2 channel groups x planes) and the 3 shifted Q tiles
 //   warp 1 (one lane)  tcgen05.mma M128 x N192 x K16, 4 per block and plane pair (lo*hi, hi*lo, hi*hi)
-//   warps 2..5         epilogue: tcgen05.ld, red.global.add.f32
+//   warps 2..5         epilogue: tcgen05.ld, red.global.add.v4.f32 (16-byte reductions: the scalar form issued 24.5 k
+//                      L2 atomics per CTA, a fixed ~60 us per launch whatever the layer - ncu launch lists of the step)
 // Two-plane storages (value = hi + lo) run the three-pass product of the forward kernels. P and Q must share the element
 // type: the instruction descriptor has a format field per operand, but f16 x bf16 faults on B200 (tested).
 #include "common.cuh"
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_kernel(const __grid_constan
         if (row_ok) {
           float* dst = grow + static_cast<size_t>(c0 >> 6) * p.cq + (c0 & 63);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            ptx::red_add_v4_f32(dst + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                                __uint_as_float(r[j + 3]));
         }
       }
     }
@@ -258,6 +261,7 @@ extern "C" int w2c_conv_wgrad(const w2c_wgrad_args* args, w2c_stream_t stream) {
   if (!args) return set_error(W2C_ERR_INVALID, "wgrad: args is NULL");
   const w2c_wgrad_args& a = *args;
   W2C_CHECK_ARG(a.x && a.dy && a.dw, "wgrad: null pointer argument");
+  W2C_CHECK_ARG(reinterpret_cast<uintptr_t>(a.dw) % 16 == 0, "wgrad: dw must be 16-byte aligned (vector reductions)");
   W2C_CHECK_ARG(a.n > 0 && a.h_in > 0 && a.w_in > 0, "wgrad: bad image extent %dx%dx%d", a.n, a.h_in, a.w_in);
   W2C_CHECK_ARG(a.cin > 0 && a.cin % 64 == 0 && a.cout > 0 && a.cout % 64 == 0,
                 "wgrad: cin=%d and cout=%d must be multiples of 64 (pad the maps)", a.cin, a.cout);
