@@ -720,6 +720,14 @@ def run_b200(args):
             except Exception as e:
                 extra["train_step"] = {"error": str(e)[:300]}
             torch.cuda.empty_cache()
+            # the same step with the resnet18 + simple_decoder pair every shipped YAML trains
+            try:
+                extra["train_step_resnet18_pair"] = train_step_rates(
+                    dev, scenes=2, agents=5, img=IMG, backbones="resnet", steps=max(3, args.steps // 4),
+                    precisions=("bf16",), library=not args.no_library_baseline)
+            except Exception as e:
+                extra["train_step_resnet18_pair"] = {"error": str(e)[:300]}
+            torch.cuda.empty_cache()
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",

@@ -110,9 +110,16 @@ typedef struct w2c_conv_args {
   /* MMA passes over the operand planes of a two-plane act: 0 = the format's default (3: hi*hi + hi*lo + lo*hi),
    * 1 = hi*hi only.  Ignored (1) for one-plane formats.  The output is written in `act` either way. */
   int32_t passes;
+  /* Train-mode BatchNorm statistics from the conv epilogue (NULL = off): fp64 [2 * cout], += the per-channel sum and
+   * sum of squares of the output AS STORED (the raw conv output z of w2c_bn_train_fwd), so the separate statistics pass
+   * over z is not needed (w2c_bn_train_from_sums_fwd).  Only where w2c_conv_fuses_bn_sums() says so. */
+  double* bn_sums;
 } w2c_conv_args;
 
 int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream);
+/* 1 when w2c_conv_bnrelu_fwd would accumulate args->bn_sums for this launch (persistent kernel, NHWC output through the
+ * TMA-store epilogue: cout % 64 == 0, a one-plane act), 0 when it would refuse it; < 0 on invalid arguments. */
+int w2c_conv_fuses_bn_sums(const w2c_conv_args* args);
 
 /*
  * Fused head of n_segnet_encoder: conv1 (3 -> 64, k3 s1) + BN + ReLU followed by conv2 (64 -> 64, k3 s2) + BN + ReLU
@@ -172,6 +179,13 @@ int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int
                      float* running_mean, float* running_var, int64_t* num_batches_tracked, double* sums_ws,
                      float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride, int32_t y_coffset,
                      float* stats_out, w2c_stream_t stream);
+/* The same without the statistics pass: sums_ws already holds sum(z) | sum(z^2) of this batch, accumulated by the conv
+ * that wrote z (w2c_conv_args.bn_sums).  Two launches: finalize, apply. */
+int w2c_bn_train_from_sums_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
+                               int32_t act, int32_t relu, const float* gamma, const float* beta, float eps,
+                               float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                               double* sums_ws, float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride,
+                               int32_t y_coffset, float* stats_out, w2c_stream_t stream);
 /* The same on an fp32 NCHW map [n][c][hw] (the logits layer: deconv12 is conv + BatchNorm + ReLU, backbone.py:124). */
 int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw, int32_t relu, const float* gamma,
                           const float* beta, float eps, float momentum, float* running_mean, float* running_var,

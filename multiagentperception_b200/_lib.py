@@ -32,6 +32,7 @@ class ConvArgs(ctypes.Structure):
         ("kind", c_i32), ("relu", c_i32), ("act", c_i32), ("out_fmt", c_i32), ("impl", c_i32), ("block_n", c_i32),
         ("labels", c_vp),
         ("passes", c_i32),
+        ("bn_sums", c_vp),
     ]
 
 
@@ -109,6 +110,10 @@ _SIGNATURES = {
     "w2c_enc_head_fwd": (ctypes.c_int, [ctypes.POINTER(EncHeadArgs), c_vp]),
     "w2c_bn_train_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_f32,
                                         c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "w2c_bn_train_from_sums_fwd": (ctypes.c_int, [c_vp, c_vp, ctypes.c_int64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp,
+                                                  c_f32, c_f32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp,
+                                                  c_vp]),
+    "w2c_conv_fuses_bn_sums": (ctypes.c_int, [ctypes.POINTER(ConvArgs)]),
     "w2c_bn_train_nchw_fwd": (ctypes.c_int, [c_vp, c_i32, c_i32, ctypes.c_int64, c_i32, c_vp, c_vp, c_f32, c_f32, c_vp,
                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "w2c_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradArgs), c_vp]),

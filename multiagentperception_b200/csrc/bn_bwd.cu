@@ -87,9 +87,58 @@ __device__ __forceinline__ void masked_du(const BwdMaps& m, size_t px, int g, bo
   }
 }
 
+// ---- one-plane storages: the 16-byte loads of U pixels are issued back to back and kept RAW (4 registers each) until
+// they are consumed one pixel at a time. With two pixels per trip unpacked on arrival the passes ran at 2.6 (reduce) and
+// 3.5 TB/s (apply) of the 6.5 the part delivers (ncu launch list of the step, profiles/r2_train_step_launches_v4.md):
+// 48 KB / 32 KB of loads in flight per SM; now 128 KB (two CTAs x 256 threads x 16 loads). NEED_Y: the ReLU mask comes from the stored output (residual units), else from z.
+constexpr int kRawU = 8;    // pixels in flight per thread (dy + z: 64 registers of raw loads; two 256-thread CTAs per SM)
+constexpr int kRawUY = 5;   // with y as well (60 registers)
+constexpr int kRawUA = 5;   // apply pass: 40 registers of per-channel constants next to the raw loads
+template <bool NEED_Y>
+struct RawPx {
+  uint4 dy, z, y;
+};
+template <bool NEED_Y>
+__device__ __forceinline__ void issue_px(const BwdMaps& m, size_t px, int g, bool ld_z, RawPx<NEED_Y>& r) {
+  r.dy = __ldg(reinterpret_cast<const uint4*>(m.dy + px * static_cast<size_t>(m.dy_cs) + m.dy_co + g * 8));
+  if (ld_z) r.z = __ldg(reinterpret_cast<const uint4*>(m.z + px * static_cast<size_t>(m.z_cs) + m.z_co + g * 8));
+  if (NEED_Y) r.y = __ldg(reinterpret_cast<const uint4*>(m.y + px * static_cast<size_t>(m.y_cs) + m.y_co + g * 8));
+}
+__device__ __forceinline__ void unpack8(const uint4& q, bool f16, float (&v)[8]) {
+  const uint32_t* b = reinterpret_cast<const uint32_t*>(&q);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 f = unpack_act2(b[e], f16);
+    v[2 * e] = f.x, v[2 * e + 1] = f.y;
+  }
+}
+// du = dy masked by the unit's ReLU, zv = z (when loaded): masked_du() on the raw loads
+// s8 / h8: this thread's eight forward scale / shift values IN REGISTERS (ncu on the shared-memory version: the
+// short-scoreboard stall - the per-pixel constant loads - was the top stall reason, 4.9-5.9 warps per issue, at 16
+// resident warps per SM)
+template <bool NEED_Y>
+__device__ __forceinline__ void consume_px(const BwdMaps& m, const RawPx<NEED_Y>& r, bool ld_z, const float (&s8)[8],
+                                           const float (&h8)[8], float (&du)[8], float (&zv)[8]) {
+  unpack8(r.dy, act_is_f16(m.act_g), du);
+  if (ld_z) unpack8(r.z, act_is_f16(m.act_f), zv);
+  if (NEED_Y) {
+    float yv[8];
+    unpack8(r.y, act_is_f16(m.act_f), yv);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) du[e] = yv[e] > 0.f ? du[e] : 0.f;
+  } else if (m.relu) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) du[e] = fmaf(zv[e], s8[e], h8[e]) > 0.f ? du[e] : 0.f;
+  }
+}
+__device__ __forceinline__ void load_const8(const float* __restrict__ p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x, v[1] = a.y, v[2] = a.z, v[3] = a.w, v[4] = b.x, v[5] = b.y, v[6] = b.z, v[7] = b.w;
+}
+
 // sums[ch] += sum du, sums[c + ch] += sum du * xhat
 // dynamic shared memory: [reduction scratch: kThreads * 16 doubles][per-channel constants: mean, inv, scale, shift: 4c floats]
-__global__ void __launch_bounds__(kThreads, 3) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
+__global__ void __launch_bounds__(kThreads, 2) bn_bwd_reduce_kernel(const BwdMaps m, const float* __restrict__ stats,
                                                                     double* __restrict__ sums) {
   extern __shared__ double s_red[];
   float* s_c = reinterpret_cast<float*>(s_red + static_cast<size_t>(kThreads) * 16);
@@ -112,19 +161,47 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_reduce_kernel(const BwdMap
     size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane;
     const size_t stride = static_cast<size_t>(gridDim.x) * lanes;
     const bool bn = stats != nullptr;
+    // s2 collects sum du * z; sum du * xhat = inv * (sum du * z - mean * sum du) follows once per thread, in fp64,
+    // below - no per-channel constant in the loop
     auto accumulate = [&](const float (&du)[8], const float (&zv)[8]) {
-      const float4 m0 = *reinterpret_cast<const float4*>(s_c + g * 8), m1 = *reinterpret_cast<const float4*>(s_c + g * 8 + 4);
-      const float4 i0 = *reinterpret_cast<const float4*>(s_c + m.c + g * 8);
-      const float4 i1 = *reinterpret_cast<const float4*>(s_c + m.c + g * 8 + 4);
-      const float mean[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-      const float inv[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         s1[e] += du[e];
-        if (bn) s2[e] = fmaf(du[e], (zv[e] - mean[e]) * inv[e], s2[e]);
+        if (bn) s2[e] = fmaf(du[e], zv[e], s2[e]);
       }
     };
-    // two pixels per trip (independent loads in flight)
+    if (act_planes(m.act_f) == 1 && act_planes(m.act_g) == 1) {
+      const bool need_y = m.relu && m.fwd_scale == nullptr;
+      const bool ld_z = bn || (m.relu && !need_y);
+      float s8[8], h8[8];
+      load_const8(sc, s8), load_const8(sh, h8);
+      if (!need_y) {
+        for (; px + (kRawU - 1) * stride < m.n_px; px += kRawU * stride) {
+          RawPx<false> r[kRawU];
+#pragma unroll
+          for (int u = 0; u < kRawU; ++u) issue_px(m, px + u * stride, g, ld_z, r[u]);
+#pragma unroll
+          for (int u = 0; u < kRawU; ++u) {
+            float du[8], zv[8];
+            consume_px(m, r[u], ld_z, s8, h8, du, zv);
+            accumulate(du, zv);
+          }
+        }
+      } else {
+        for (; px + (kRawUY - 1) * stride < m.n_px; px += kRawUY * stride) {
+          RawPx<true> r[kRawUY];
+#pragma unroll
+          for (int u = 0; u < kRawUY; ++u) issue_px(m, px + u * stride, g, ld_z, r[u]);
+#pragma unroll
+          for (int u = 0; u < kRawUY; ++u) {
+            float du[8], zv[8];
+            consume_px(m, r[u], ld_z, s8, h8, du, zv);
+            accumulate(du, zv);
+          }
+        }
+      }
+    }
+    // two pixels per trip (independent loads in flight): the two-plane storages, and the tails of the loops above
     for (; px + stride < m.n_px; px += 2 * stride) {
       float du[2][8], zv[2][8];
 #pragma unroll
@@ -140,7 +217,11 @@ __global__ void __launch_bounds__(kThreads, 3) bn_bwd_reduce_kernel(const BwdMap
   }
   double* mine = s_red + static_cast<size_t>(threadIdx.x) * 16;
 #pragma unroll
-  for (int e = 0; e < 8; ++e) mine[e] = s1[e], mine[8 + e] = s2[e];
+  for (int e = 0; e < 8; ++e) {
+    const double mean = s_c[g * 8 + e], inv = s_c[m.c + g * 8 + e];
+    mine[e] = s1[e];
+    mine[8 + e] = inv * (static_cast<double>(s2[e]) - mean * static_cast<double>(s1[e]));
+  }
   __syncthreads();
   if (lane == 0) {
     double t[16];
@@ -179,7 +260,7 @@ __global__ void bn_bwd_finalize_kernel(double* __restrict__ sums, double count, 
 }
 
 // dynamic shared memory: per-channel constants scale, shift, A, B, C: 5c floats
-__global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const BwdMaps m, const float* __restrict__ stats,
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(const BwdMaps m, const float* __restrict__ stats,
                                                               const float* __restrict__ coef) {
   extern __shared__ float s_k[];
   for (int i = threadIdx.x; i < m.c; i += blockDim.x) {
@@ -196,8 +277,52 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_apply_kernel(const BwdMaps m, c
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;   // a multiple of groups: g is fixed per thread
   const int g = first % groups;
   const float* kc = s_k + g * 8;
-  for (size_t idx = first; idx < total; idx += stride) {
-    const size_t px = idx / groups;
+  float s8[8], h8[8], ka[8], kb[8], kk[8];   // this thread's channel group: forward scale / shift, A, B, C
+  load_const8(kc, s8), load_const8(kc + m.c, h8);
+  load_const8(kc + 2 * m.c, ka), load_const8(kc + 3 * m.c, kb), load_const8(kc + 4 * m.c, kk);
+  auto finish = [&](size_t px, float (&du)[8], const float (&zv)[8]) {
+    if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
+    if (stats) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) du[e] = fmaf(ka[e], du[e], fmaf(kb[e], zv[e], kk[e]));
+    }
+    store8(m.dz + px * (static_cast<size_t>(m.dz_cs) * pg) + m.dz_co + g * 8, m.dz_cs, pg, f16g, du);
+  };
+  // (the grid stride is a multiple of groups: a thread keeps its channel group and walks pixels - no 64-bit division
+  // per item, which cost more than the arithmetic of the pass)
+  size_t px = first / groups;
+  const size_t pstride = stride / groups;
+  if (act_planes(m.act_f) == 1 && pg == 1) {
+    // one-plane storages: the loads of kRawU (kRawUY with y) pixels in flight per thread, see RawPx
+    const bool need_y = m.relu && m.fwd_scale == nullptr;
+    const bool ld_z = stats != nullptr || (m.relu && !need_y);
+    if (!need_y) {
+      for (; px + (kRawUA - 1) * pstride < m.n_px; px += kRawUA * pstride) {
+        RawPx<false> r[kRawUA];
+#pragma unroll
+        for (int u = 0; u < kRawUA; ++u) issue_px(m, px + u * pstride, g, ld_z, r[u]);
+#pragma unroll
+        for (int u = 0; u < kRawUA; ++u) {
+          float du[8], zv[8];
+          consume_px(m, r[u], ld_z, s8, h8, du, zv);
+          finish(px + u * pstride, du, zv);
+        }
+      }
+    } else {
+      for (; px + (kRawUY - 1) * pstride < m.n_px; px += kRawUY * pstride) {
+        RawPx<true> r[kRawUY];
+#pragma unroll
+        for (int u = 0; u < kRawUY; ++u) issue_px(m, px + u * pstride, g, ld_z, r[u]);
+#pragma unroll
+        for (int u = 0; u < kRawUY; ++u) {
+          float du[8], zv[8];
+          consume_px(m, r[u], ld_z, s8, h8, du, zv);
+          finish(px + u * pstride, du, zv);
+        }
+      }
+    }
+  }
+  for (; px < m.n_px; px += pstride) {
     float du[8], zv[8];
     masked_du(m, px, g, stats != nullptr, kc, kc + m.c, du, zv);
     if (m.dres) store8(m.dres + px * (static_cast<size_t>(m.dres_cs) * pg) + m.dres_co + g * 8, m.dres_cs, pg, f16g, du);
@@ -329,9 +454,9 @@ extern "C" int w2c_bn_train_bwd(const w2c_bn_bwd_args* args, w2c_stream_t stream
   bn_bwd_finalize_kernel<<<(a.c + 127) / 128, 128, 0, s>>>(a.sums_ws, static_cast<double>(a.n_px), a.gamma, a.stats,
                                                            a.dgamma, a.dbeta, a.coef_ws, a.c);
   W2C_CHECK_LAUNCH("bn_bwd_finalize_kernel");
-  // >= 4 items per thread (the per-CTA constant table is amortised), one wave of resident CTAs at most
+  // >= kRawU items per thread (one full trip of the raw-load loop), one wave of resident CTAs at most
   const size_t total = static_cast<size_t>(a.n_px) * groups;
-  const size_t blocks = (total + 256 * 4 - 1) / (256 * 4);
+  const size_t blocks = (total + 256 * kRawU - 1) / (256 * kRawU);
   const size_t smem2 = static_cast<size_t>(5) * a.c * sizeof(float);
   int occ2 = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, bn_bwd_apply_kernel, 256, smem2);

@@ -124,8 +124,55 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, double count, cons
   if (ch == 0 && num_batches_tracked) *num_batches_tracked += 1;
 }
 
+// U items of one thread's grid-stride walk per trip (one-plane storages): all loads first, raw; returns the first
+// index it did not handle.
+template <int U, bool RES>
+__device__ __forceinline__ size_t bn_apply_span(const __nv_bfloat16* z, __nv_bfloat16* y, const __nv_bfloat16* __restrict__ res,
+                                                const float* __restrict__ scale, const float* __restrict__ shift, size_t idx,
+                                                size_t stride, size_t total, int groups, size_t pix_elems,
+                                                size_t y_pix_elems, int coffset, int y_coffset, bool f16, int relu) {
+  const int g = idx % groups;   // the stride is a multiple of groups: g is fixed per thread
+  const float4 sa = *reinterpret_cast<const float4*>(scale + g * 8), sb = *reinterpret_cast<const float4*>(scale + g * 8 + 4);
+  const float4 ha = *reinterpret_cast<const float4*>(shift + g * 8), hb4 = *reinterpret_cast<const float4*>(shift + g * 8 + 4);
+  const float sc[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+  const float sh[8] = {ha.x, ha.y, ha.z, ha.w, hb4.x, hb4.y, hb4.z, hb4.w};
+  const size_t pstride = stride / groups;   // (no 64-bit division per item)
+  size_t px0 = idx / groups;
+  for (; idx + (U - 1) * stride < total; idx += U * stride, px0 += U * pstride) {
+    uint4 zr[U], rr[RES ? U : 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t px = px0 + u * pstride;
+      zr[u] = *reinterpret_cast<const uint4*>(z + px * pix_elems + coffset + g * 8);
+      if (RES) rr[u] = *reinterpret_cast<const uint4*>(res + px * y_pix_elems + y_coffset + g * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t px = px0 + u * pstride;
+      const uint32_t* zb = reinterpret_cast<const uint32_t*>(&zr[u]);
+      const uint32_t* rb = reinterpret_cast<const uint32_t*>(&rr[RES ? u : 0]);
+      uint4 hv;
+      uint32_t* hw = reinterpret_cast<uint32_t*>(&hv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_act2(zb[e], f16);
+        float a = fmaf(f.x, sc[2 * e], sh[2 * e]), b = fmaf(f.y, sc[2 * e + 1], sh[2 * e + 1]);
+        if (RES) {
+          const float2 r = unpack_act2(rb[e], f16);
+          a += r.x, b += r.y;
+        }
+        if (relu) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
+        uint32_t lo;
+        split_act2(a, b, f16, hw[e], lo);
+      }
+      *reinterpret_cast<uint4*>(y + px * y_pix_elems + y_coffset + g * 8) = hv;
+    }
+  }
+  return idx;
+}
+
 // y <- act(z * scale + shift (+ residual)) (y may be z: in place); one thread per (pixel, 8-channel group)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* z, __nv_bfloat16* y,
+__global__ void __launch_bounds__(256, 3) bn_apply_kernel(const __nv_bfloat16* z, __nv_bfloat16* y,
                                                        const __nv_bfloat16* __restrict__ res,
                                                        const float* __restrict__ scale, const float* __restrict__ shift,
                                                        size_t n_px, int c, int cstride, int coffset, int y_cstride,
@@ -136,8 +183,19 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const __nv_bfloat16* z, _
   const int planes = act_planes(act);
   const size_t pix_elems = static_cast<size_t>(cstride) * planes;
   const size_t y_pix_elems = static_cast<size_t>(y_cstride) * planes;
-  for (size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<size_t>(gridDim.x) * blockDim.x) {
+  size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;   // a multiple of groups: g is fixed per thread
+  if (planes == 1) {
+    // one-plane storages: the 16-byte loads of eight pixels (four with a residual) are issued back to back and kept raw
+    // until they are consumed: one load per thread and trip left the pass at 4.3 of the 6.5 TB/s (ncu launch list)
+    if (res)
+      idx = bn_apply_span<4, true>(z, y, res, scale, shift, idx, stride, total, groups, pix_elems, y_pix_elems, coffset,
+                                   y_coffset, f16, relu);
+    else
+      idx = bn_apply_span<8, false>(z, y, res, scale, shift, idx, stride, total, groups, pix_elems, y_pix_elems, coffset,
+                                    y_coffset, f16, relu);
+  }
+  for (; idx < total; idx += stride) {
     const int g = idx % groups;
     const size_t px = idx / groups;
     const __nv_bfloat16* p = z + px * pix_elems + coffset + g * 8;
@@ -254,11 +312,11 @@ extern "C" int w2c_bn_train_nchw_fwd(float* z, int32_t n, int32_t c, int64_t hw,
   return W2C_OK;
 }
 
-extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
-                                int32_t act, int32_t relu, const float* gamma, const float* beta, float eps,
-                                float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
-                                double* sums_ws, float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride,
-                                int32_t y_coffset, float* stats_out, w2c_stream_t stream) {
+static int bn_train_impl(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
+                         int32_t act, int32_t relu, const float* gamma, const float* beta, float eps, float momentum,
+                         float* running_mean, float* running_var, int64_t* num_batches_tracked, double* sums_ws,
+                         float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride, int32_t y_coffset,
+                         float* stats_out, bool sums_ready, w2c_stream_t stream) {
   W2C_CHECK_ARG(z && sums_ws && scale_ws && shift_ws, "bn_train: null pointer argument");
   W2C_CHECK_ARG(act_valid(act), "bn_train: bad act %d", act);
   W2C_CHECK_ARG(n_px > 0 && c > 0 && c % 8 == 0 && 256 % (c / 8) == 0 && c <= 2048,
@@ -284,18 +342,22 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bn_stats_kernel, kStatThreads, smem);
   const int cap = device_sm_count() * (occ > 0 ? occ : 1);
   const int grid = static_cast<int>(want < cap ? (want > 0 ? want : 1) : cap);
-  bn_stats_kernel<<<grid, kStatThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(z), static_cast<size_t>(n_px), c, cs,
-                                                   coffset, act, sums_ws);
-  W2C_CHECK_LAUNCH("bn_stats_kernel");
+  if (!sums_ready) {   // (else the conv that wrote z already added its sums: w2c_conv_args.bn_sums)
+    bn_stats_kernel<<<grid, kStatThreads, smem, s>>>(static_cast<const __nv_bfloat16*>(z), static_cast<size_t>(n_px), c, cs,
+                                                     coffset, act, sums_ws);
+    W2C_CHECK_LAUNCH("bn_stats_kernel");
+  }
   bn_finalize_kernel<<<(c + 127) / 128, 128, 0, s>>>(sums_ws, static_cast<double>(n_px), gamma, beta, eps, momentum,
                                                      running_mean, running_var,
                                                      reinterpret_cast<long long*>(num_batches_tracked), scale_ws,
                                                      shift_ws, stats_out, c);
   W2C_CHECK_LAUNCH("bn_finalize_kernel");
   const size_t total = static_cast<size_t>(n_px) * groups;
-  const size_t blocks = (total + 255) / 256;
-  const size_t cap2 = static_cast<size_t>(device_sm_count()) * 8;   // 31 registers: eight CTAs of 256 threads per SM
-  const int grid2 = static_cast<int>(blocks < cap2 ? blocks : cap2);
+  const size_t blocks = (total + 256 * 8 - 1) / (256 * 8);   // eight items per thread: one trip of the raw-load loop
+  int occ2 = 1;   // one wave of resident CTAs (the grid stride must stay a multiple of groups: 256 is)
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, bn_apply_kernel, 256, 0);
+  const size_t cap2 = static_cast<size_t>(device_sm_count()) * (occ2 > 0 ? occ2 : 1);
+  const int grid2 = static_cast<int>(blocks < cap2 ? (blocks ? blocks : 1) : cap2);
   bn_apply_kernel<<<grid2, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(z),
                                         static_cast<__nv_bfloat16*>(y_out ? y_out : z),
                                         static_cast<const __nv_bfloat16*>(residual),
@@ -303,4 +365,23 @@ extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int
                                         y_out ? ycs : cs, y_out ? y_coffset : coffset, act, relu);
   W2C_CHECK_LAUNCH("bn_apply_kernel");
   return W2C_OK;
+}
+
+extern "C" int w2c_bn_train_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride, int32_t coffset,
+                                int32_t act, int32_t relu, const float* gamma, const float* beta, float eps,
+                                float momentum, float* running_mean, float* running_var, int64_t* num_batches_tracked,
+                                double* sums_ws, float* scale_ws, float* shift_ws, void* y_out, int32_t y_cstride,
+                                int32_t y_coffset, float* stats_out, w2c_stream_t stream) {
+  return bn_train_impl(z, residual, n_px, c, cstride, coffset, act, relu, gamma, beta, eps, momentum, running_mean, running_var,
+                       num_batches_tracked, sums_ws, scale_ws, shift_ws, y_out, y_cstride, y_coffset, stats_out, false, stream);
+}
+
+extern "C" int w2c_bn_train_from_sums_fwd(void* z, const void* residual, int64_t n_px, int32_t c, int32_t cstride,
+                                          int32_t coffset, int32_t act, int32_t relu, const float* gamma, const float* beta,
+                                          float eps, float momentum, float* running_mean, float* running_var,
+                                          int64_t* num_batches_tracked, double* sums_ws, float* scale_ws, float* shift_ws,
+                                          void* y_out, int32_t y_cstride, int32_t y_coffset, float* stats_out,
+                                          w2c_stream_t stream) {
+  return bn_train_impl(z, residual, n_px, c, cstride, coffset, act, relu, gamma, beta, eps, momentum, running_mean, running_var,
+                       num_batches_tracked, sums_ws, scale_ws, shift_ws, y_out, y_cstride, y_coffset, stats_out, true, stream);
 }

@@ -217,7 +217,7 @@ struct StemWgradGeom {
 };
 
 template <int KS, int STRIDE>
-__global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
+__global__ void __launch_bounds__(256, 2) stem_wgrad_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ dz,
                                                          float* __restrict__ dw, int b, int n_agents, int c_total,
                                                          int c_first, int h, int w, int cout, int dz_cs, int dz_co,
                                                          int act_g, int tiles_w, int tiles_h, int n_tiles) {
@@ -229,7 +229,9 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
   const bool f16g = act_is_f16(act_g);
   const int pg = act_planes(act_g);
   const int n_items = (cout / 8) * 3 * KS;                // (group, ci, kh), kh fastest; cout <= 64: <= 168
-  const int parts = (256 - 32) / n_items;                 // pixel partitions (>= 1); at least one warp left to stage
+  // pixel partitions: three warps (two when the items fill the rest) are left to stage - with ONE loader warp the
+  // 3x3 layer waited on it (16 dependent-latency trips per tile: 2.1 ms per launch instead of 0.66)
+  const int parts = 160 / n_items > 1 ? 160 / n_items : 1;
   const int first_loader = (parts * n_items + 31) & ~31;
   const int n_loaders = 256 - first_loader;
   const int item = threadIdx.x % n_items, part = threadIdx.x / n_items;
@@ -248,45 +250,105 @@ __global__ void __launch_bounds__(256) stem_wgrad_kernel(const float* __restrict
     const float* xin = x + (static_cast<size_t>(scene) * c_total + c_first + 3 * agent) * h * w;
     float* s_patch = buf;
     float* s_dz = buf + G::kPatchWords;
-    for (int i = t0; i < 3 * PW * PW; i += nt) {
-      const int cc = i / (PW * PW), py = (i / PW) % PW, px = i % PW;
-      const int iy = iy0 + py, ix = ix0 + px;
-      s_patch[i] = (iy >= 0 && iy < h && ix >= 0 && ix < w) ? __ldg(xin + (static_cast<size_t>(cc) * h + iy) * w + ix) : 0.f;
-    }
-    for (int i = t0; i < TP * TP * (cout / 8); i += nt) {
-      const int p = i / (cout / 8), gg = i % (cout / 8);
-      const int oy = oy0 + p / TP, ox = ox0 + p % TP;
-      float v[8];
-      if (oy < ho && ox < wo)
-        load8(dz + ((static_cast<size_t>(img) * ho + oy) * wo + ox) * (static_cast<size_t>(dz_cs) * pg) + dz_co + gg * 8, dz_cs, pg, f16g, v);
-      else {
+    // every load of this thread is issued before the first one is used (clamped addresses, no branches around the
+    // loads: behind `if (inside)` they waited for each other, 5 dependent latencies per tile on a loader thread)
+    constexpr int MAXP = (3 * PW * PW + 63) / 64, MAXD = (TP * TP * 8 + 63) / 64;   // nt >= 64, cout <= 64
+    constexpr int PR = 8;   // patch words per round (registers: the 7x7 patch is 21 words per loader thread)
+    auto patch_round = [&](int k0, float (&pv)[PR]) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      for (int k = 0; k < PR; ++k) {
+        const int i = t0 + (k0 + k) * nt;
+        const int cc = i / (PW * PW), py = (i / PW) % PW, px = i % PW;
+        const int iy = iy0 + py, ix = ix0 + px;
+        const bool ok = k0 + k < MAXP && i < 3 * PW * PW && iy >= 0 && iy < h && ix >= 0 && ix < w;
+        const float v = __ldg(xin + (static_cast<size_t>(ok ? cc : 0) * h + (ok ? iy : 0)) * w + (ok ? ix : 0));
+        pv[k] = ok ? v : 0.f;
       }
-      float4* d4 = reinterpret_cast<float4*>(s_dz + p * cout + gg * 8);
-      d4[0] = make_float4(v[0], v[1], v[2], v[3]);
-      d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+    };
+    auto patch_store = [&](int k0, const float (&pv)[PR]) {
+#pragma unroll
+      for (int k = 0; k < PR; ++k) {
+        const int i = t0 + (k0 + k) * nt;
+        if (k0 + k < MAXP && i < 3 * PW * PW) s_patch[i] = pv[k];
+      }
+    };
+    float pv[PR];
+    patch_round(0, pv);
+    const int n_dz = TP * TP * (cout / 8);
+    // dz: the hi plane of every item, then (two-plane storages) a second round adds the lo plane - the same thread
+    // owns the same items, and one round of raw loads in registers at a time keeps the kernel at two CTAs per SM
+    for (int pl = 0; pl < pg; ++pl) {
+      uint4 dr[MAXD];
+#pragma unroll
+      for (int k = 0; k < MAXD; ++k) {
+        const int i = t0 + k * nt;
+        const int p = i / (cout / 8), gg = i % (cout / 8);
+        const int oy = oy0 + p / TP, ox = ox0 + p % TP;
+        const bool ok = i < n_dz && oy < ho && ox < wo;
+        dr[k] = __ldg(reinterpret_cast<const uint4*>(
+            dz + ((static_cast<size_t>(img) * ho + (ok ? oy : 0)) * wo + (ok ? ox : 0)) * (static_cast<size_t>(dz_cs) * pg) +
+            pl * dz_cs + dz_co + (ok ? gg : 0) * 8));
+      }
+      if (pl == 0) patch_store(0, pv);
+#pragma unroll
+      for (int k = 0; k < MAXD; ++k) {
+        const int i = t0 + k * nt;
+        if (i >= n_dz) continue;
+        const int p = i / (cout / 8), gg = i % (cout / 8);
+        const int oy = oy0 + p / TP, ox = ox0 + p % TP;
+        const bool ok = oy < ho && ox < wo;
+        float v[8];
+        const uint32_t* hb = reinterpret_cast<const uint32_t*>(&dr[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = unpack_act2(hb[e], f16g);
+          v[2 * e] = ok ? f.x : 0.f, v[2 * e + 1] = ok ? f.y : 0.f;
+        }
+        float4* d4 = reinterpret_cast<float4*>(s_dz + p * cout + gg * 8);
+        if (pl == 0) {
+          d4[0] = make_float4(v[0], v[1], v[2], v[3]);
+          d4[1] = make_float4(v[4], v[5], v[6], v[7]);
+        } else {
+          const float4 a = d4[0], b = d4[1];
+          d4[0] = make_float4(a.x + v[0], a.y + v[1], a.z + v[2], a.w + v[3]);
+          d4[1] = make_float4(b.x + v[4], b.y + v[5], b.z + v[6], b.w + v[7]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k0 = PR; k0 < MAXP; k0 += PR) {   // the rest of a large patch
+      patch_round(k0, pv);
+      patch_store(k0, pv);
     }
   };
 
+  // One named barrier per tile, hit from both role branches (256 arrivals): buffer it & 1 is staged and everybody is
+  // done with the other one. The roles are separate loops so that the loaders do not carry the accumulators (and the
+  // others not the raw loads) in their registers.
+  auto tile_barrier = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };
+  if (static_cast<int>(blockIdx.x) < n_tiles) stage(blockIdx.x, s_mem, threadIdx.x, 256);
+  if (static_cast<int>(threadIdx.x) >= first_loader) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      tile_barrier();
+      const int next = tile + gridDim.x;
+      if (next < n_tiles) stage(next, s_mem + ((it + 1) & 1) * buf_words, threadIdx.x - first_loader, n_loaders);
+    }
+    return;
+  }
   float acc[KS][8];
 #pragma unroll
   for (int k = 0; k < KS; ++k)
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[k][e] = 0.f;
-  if (static_cast<int>(blockIdx.x) < n_tiles) stage(blockIdx.x, s_mem, threadIdx.x, 256);
   int it = 0;
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-    // buffer it & 1 is staged, and everybody is done with the other one
-    __syncthreads();
-    float* cur = s_mem + (it & 1) * buf_words;
-    if (static_cast<int>(threadIdx.x) >= first_loader) {
-      const int next = tile + gridDim.x;
-      if (next < n_tiles) stage(next, s_mem + ((it + 1) & 1) * buf_words, threadIdx.x - first_loader, n_loaders);
-    } else if (active) {
+    tile_barrier();
+    const float* cur = s_mem + (it & 1) * buf_words;
+    if (active) {
       const float* pp = cur + (ci * PW + kh) * PW;
       const float* dp = cur + G::kPatchWords + g * 8;
-#pragma unroll 2
+#pragma unroll(KS == 7 ? 1 : 2)
       for (int p = part; p < TP * TP; p += parts) {
         const float* px = pp + ((p / TP) * PW + (p % TP)) * STRIDE;
         const float4 d0 = *reinterpret_cast<const float4*>(dp + p * cout);

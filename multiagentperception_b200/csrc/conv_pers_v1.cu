@@ -108,7 +108,10 @@ __device__ __forceinline__ bool tile_at(const PersParams& p, int it, int block_n
   return true;
 }
 
-template <int BLOCK_N, int STAGES, int GROUP, int EG, int RES>
+// STATS: the epilogue also sums the stored output per channel (train-mode BatchNorm, ConvPlan::bn_sums). A separate
+// instantiation, so that the eval-mode kernels carry none of its registers (the two-warpgroup variants sit at their
+// 168-register ceiling).
+template <int BLOCK_N, int STAGES, int GROUP, int EG, int RES, bool STATS>
 __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(const __grid_constant__ PersParams p) {
   using L = PersSmem<BLOCK_N, STAGES, GROUP, EG, RES>;
   constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
@@ -290,6 +293,11 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
     const int planes = act_planes(pl.act);
     const bool f16 = act_is_f16(pl.act);
     int unit = 0;  // staging-buffer rotation counter (EG == 1)
+    // train-mode BatchNorm statistics (pl.bn_sums): this thread's sum(z), sum(z^2) of channel 64 * k + (row & 63) over
+    // rows [64 * (row >> 6), + 64) of all its tiles; fp32 over <= a few hundred 64-term partial sums, fp64 from there on
+    float st1[STATS ? kMaxCout / 64 : 1], st2[STATS ? kMaxCout / 64 : 1];
+#pragma unroll
+    for (int k = 0; k < (STATS ? kMaxCout / 64 : 1); ++k) st1[k] = st2[k] = 0.f;
     TileCoord tc;
     for (int it = eg; tile_at(p, it, BLOCK_N, tc); it += EG) {
       const int acc = it & 1;  // == eg when EG == 2
@@ -347,6 +355,8 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
 #pragma unroll
                   for (int j = 0; j < 4; ++j)
                     pw[j] = ptx::pack_act2(v[c8 * 8 + 2 * j], v[c8 * 8 + 2 * j + 1], pl.relu != 0, f16);
+                  // statistics are summed from this tile: rows outside the image (clipped by the TMA store) count as 0
+                  if (STATS && !valid) pk = make_uint4(0u, 0u, 0u, 0u);
                 } else {
 #pragma unroll
                   for (int j = 0; j < 4; ++j) {
@@ -366,6 +376,25 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
                   ptx::tma_store_4d(&p.y_map[ocls], stg, och, tc.w0, tc.h0, tc.i0);
                   ptx::bulk_commit_group();
                 }
+              }
+              if constexpr (STATS) {
+                // train-mode BatchNorm statistics of the values AS STORED: thread (channel c, row half) walks a column of
+                // the staging tile (a warp reads 64 contiguous bytes per row: no bank conflicts) and keeps the two sums
+                // in registers (selected by predicates, so the arrays stay in registers); they go to the fp64 totals
+                // once, when the CTA retires. The tile is next written after a named barrier every thread only reaches
+                // behind these reads.
+                const int c = row & 63;
+                const uint8_t* col = stg + (row >> 6) * (64 * 128) + (c & 7) * 2;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+                for (int r = 0; r < 64; ++r) {
+                  const float zv = elem_to_float(*reinterpret_cast<const __nv_bfloat16*>(col + r * 128 + (((c >> 3) ^ (r & 7)) << 4)), f16);
+                  s1 += zv, s2 = fmaf(zv, zv, s2);
+                }
+                const int blk = cb >> 6;
+#pragma unroll
+                for (int k = 0; k < kMaxCout / 64; ++k)
+                  if (blk == k) st1[k] += s1, st2[k] += s2;
               }
             }
           }
@@ -486,6 +515,14 @@ __global__ void __launch_bounds__(64 + EG * kEpiThreads, 1) conv_persv1_kernel(c
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty_bar[acc]);
     }
+    if constexpr (STATS) {
+#pragma unroll
+      for (int k = 0; k < kMaxCout / 64; ++k)
+        if (k * 64 < pl.cout) {
+          atomicAdd(&pl.bn_sums[k * 64 + (row & 63)], static_cast<double>(st1[k]));
+          atomicAdd(&pl.bn_sums[pl.cout + k * 64 + (row & 63)], static_cast<double>(st2[k]));
+        }
+    }
     __syncwarp();
     if (lead_warp && ptx::elect_one_sync()) ptx::bulk_wait_group<0>();  // all TMA stores landed before the CTA retires
   }
@@ -510,16 +547,29 @@ int launch_persv1(const PersParams& p, cudaStream_t stream) {
   using L = PersSmem<BLOCK_N, STAGES, GROUP, EG, RES>;
   static_assert(L::kDynamicBytes <= 232448, "shared memory budget exceeded");
   // the opt-in is per DEVICE: one process may drive several (nn.DataParallel replicas, model.to('cuda:1'))
-  static DeviceOnce attr_set;
-  int rc = attr_set.ensure([] {
-    return cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
-  }, "conv_persv1_kernel");
-  if (rc) return rc;
   const int num_sms = device_sm_count();
   const int want = num_sms * (p.ctas_per_sm > 0 ? p.ctas_per_sm : 1);
   const int grid = p.groups < want ? p.groups : want;
-  conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
+  if constexpr (BLOCK_N >= 64) {
+    if (p.plan.bn_sums) {
+      static DeviceOnce attr_stats;
+      int rc = attr_stats.ensure([] {
+        return cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES, true>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+      }, "conv_persv1_kernel");
+      if (rc) return rc;
+      conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES, true><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
+      W2C_CHECK_LAUNCH("conv_persv1_kernel");
+      return W2C_OK;
+    }
+  }
+  static DeviceOnce attr_set;
+  int rc = attr_set.ensure([] {
+    return cudaFuncSetAttribute(conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES, false>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamicBytes);
+  }, "conv_persv1_kernel");
+  if (rc) return rc;
+  conv_persv1_kernel<BLOCK_N, STAGES, GROUP, EG, RES, false><<<grid, L::kThreads, L::kDynamicBytes, stream>>>(p);
   W2C_CHECK_LAUNCH("conv_persv1_kernel");
   return W2C_OK;
 }
@@ -527,6 +577,13 @@ int launch_persv1(const PersParams& p, cudaStream_t stream) {
 }  // namespace
 
 bool conv_persv1_supported(const ConvPlan& plan) { return plan.cout <= kMaxCout; }
+
+// The statistics live in the TMA-store epilogue: NHWC output in whole 64-channel groups, one storage plane. (With
+// block_n = 0 such a layer always gets BLOCK_N >= 64.)
+bool conv_persv1_fuses_bn_sums(const w2c_conv_args& a, const ConvPlan& plan) {
+  return conv_persv1_supported(plan) && plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && act_planes(plan.act) == 1 &&
+         (a.block_n == 0 || a.block_n >= 64);
+}
 
 int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream) {
   PersParams p;
@@ -573,6 +630,7 @@ int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream
   p.cls_shift = (plan.num_classes == 4 && p.m_tiles * p.n_tiles >= 8 * 148 && !((a.impl >> 8) & 128)) ? 2 : 0;
   p.groups = p.cls_shift ? p.m_tiles * p.n_tiles : p.total_tiles;
   p.tma_store = (plan.out_fmt == W2C_OUT_NHWC && plan.cout % 64 == 0 && bn >= 64) ? 1 : 0;
+  W2C_CHECK_ARG(!plan.bn_sums || (p.tma_store && planes == 1), "conv: bn_sums needs the TMA-store epilogue (w2c_conv_fuses_bn_sums)");
   // row-halo stages: 3x3 stride-1 convs on full 8x16 tiles, BLOCK_N <= 128 (at 256 three weight tiles do not fit)
   const bool row_halo = !((a.impl >> 8) & 1) && plan.num_classes == 1 && plan.in_s == 1 &&
                         plan.ntaps[0] == 9 && tn == 1 && tw == 16 && th == 8 && bn <= 128;

@@ -47,12 +47,14 @@ struct ConvPlan {
   // depend on which kernel / tile width the dispatch picks for a given batch (sharded == unsharded, scene i alone
   // == scene i inside a batch, bit for bit). Everything else runs (tap, chunk).
   int kw_major;
+  double* bn_sums;  // fp64 [2 * cout] += sum(z), sum(z^2) of the stored output (train-mode BatchNorm), or NULL
 };
 
 int conv_tc_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 int conv_persv1_forward(const w2c_conv_args& a, const ConvPlan& plan, cudaStream_t stream);
 bool conv_persistent_preferred(const ConvPlan& plan);
 bool conv_persv1_supported(const ConvPlan& plan);
+bool conv_persv1_fuses_bn_sums(const w2c_conv_args& a, const ConvPlan& plan);
 int conv_simt_forward(const ConvPlan& plan, cudaStream_t stream);
 
 inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
@@ -91,6 +93,7 @@ inline int build_conv_plan(const w2c_conv_args& a, ConvPlan& p) {
   p.npass = act_passes(a.act, a.passes);
   p.relu = a.relu;
   p.out_fmt = a.out_fmt;
+  p.bn_sums = a.bn_sums;
   W2C_CHECK_ARG(p.x_coffset >= 0 && p.x_coffset + p.cin <= p.x_cstride, "conv: input channel slice out of range");
   W2C_CHECK_ARG(p.x_cstride % 8 == 0 && p.x_coffset % 8 == 0, "conv: input channel stride/offset must be /8");
   if (a.out_fmt == W2C_OUT_NHWC) {

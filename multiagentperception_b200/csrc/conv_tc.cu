@@ -480,6 +480,16 @@ bool conv_persistent_preferred(const ConvPlan& plan) {
 }
 }  // namespace w2c
 
+extern "C" int w2c_conv_fuses_bn_sums(const w2c_conv_args* args) {
+  if (!args) return w2c::set_error(W2C_ERR_INVALID, "conv: args is NULL");
+  w2c::ConvPlan plan;
+  if (int rc = w2c::build_conv_plan(*args, plan)) return rc;
+  const int impl = args->impl & 0xff;
+  const bool pers = impl == W2C_IMPL_TC_PERSIST ||
+                    (impl == W2C_IMPL_TCGEN05 && w2c::conv_persv1_supported(plan) && w2c::conv_persistent_preferred(plan));
+  return pers && w2c::conv_persv1_fuses_bn_sums(*args, plan) ? 1 : 0;
+}
+
 extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t stream) {
   if (!args) return w2c::set_error(W2C_ERR_INVALID, "conv: args is NULL");
   w2c::ConvPlan plan;
@@ -487,6 +497,8 @@ extern "C" int w2c_conv_bnrelu_fwd(const w2c_conv_args* args, w2c_stream_t strea
   if (rc) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int impl = args->impl & 0xff;
+  if (plan.bn_sums && w2c_conv_fuses_bn_sums(args) != 1)
+    return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: this launch cannot accumulate bn_sums (ask w2c_conv_fuses_bn_sums)");
   if (plan.labels && impl != W2C_IMPL_TCGEN05 && impl != W2C_IMPL_TC_PERSIST)
     return w2c::set_error(W2C_ERR_UNSUPPORTED, "conv: impl %d has no label-map epilogue", impl);
   switch (impl) {

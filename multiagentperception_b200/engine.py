@@ -429,10 +429,13 @@ class Program:
             return 1
         return 0
 
-    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None, passes=0):
+    def conv(self, x, pc, out=None, residual=None, nchw_out=None, block_n=0, labels=None, passes=0, bn_sums=None):
         """x: ActMap -> ActMap (or the fp32 NCHW tensor when nchw_out is given). labels: uint8 [n, h, w] tensor that
         receives the arg-max class of the fp32 NCHW logits (nchw_out may then be the string 'none': labels only).
-        passes: MMA passes over the operand planes (0 = the format's default; 1 = hi*hi only)."""
+        passes: MMA passes over the operand planes (0 = the format's default; 1 = hi*hi only). bn_sums: fp64 [2 * cout]
+        tensor the conv epilogue adds sum(z) | sum(z^2) of its output to, where the launch can (w2c_conv_fuses_bn_sums);
+        self.conv_fused_sums says afterwards whether it does."""
+        self.conv_fused_sums = False
         if x.c != pc.cin:
             raise ValueError("conv expects %d input channels, got %d" % (pc.cin, x.c))
         if pc.subsample == 2:
@@ -478,6 +481,9 @@ class Program:
                           y_cstride=ycs, y_coffset=yco, kind=pc.kind, relu=int(pc.relu), act=self.act,
                           out_fmt=out_fmt, impl=ops.IMPL_TCGEN05, block_n=block_n,
                           labels=labels.data_ptr() if labels is not None else None, passes=passes)
+        if bn_sums is not None and self._lib.w2c_conv_fuses_bn_sums(ctypes.byref(a)) == 1:
+            a.bn_sums = bn_sums.data_ptr()
+            self.conv_fused_sums = True
         self.keep.append(a)
         self._record(self._lib.w2c_conv_bnrelu_fwd, ctypes.byref(a))
         return ret
@@ -508,16 +514,20 @@ class Program:
             self._bn_train_nchw(z, nchw_out, bn, relu, stats)
             self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, nchw_out, z, stats, nchw=True))
             return nchw_out
+        # the batch statistics come out of the conv epilogue where the launch can provide them (persistent kernel,
+        # whole 64-channel groups, one storage plane); otherwise _bn_train runs its own pass over z
+        ws = self._bn_ws(pc.cout)
         if not self.grad:
-            z = self.conv(x, pc, out=out)
-            self._bn_train(z, z, bn, relu, residual, None)
+            z = self.conv(x, pc, out=out, bn_sums=ws[0])
+            self._bn_train(z, z, bn, relu, residual, None, ws=ws, sums_ready=self.conv_fused_sums)
             return z
-        z = self.conv(x, pc)            # the raw conv output is kept: the backward pass normalises it again
+        z = self.conv(x, pc, bn_sums=ws[0])   # the raw conv output is kept: the backward pass normalises it again
+        fused = self.conv_fused_sums
         y = out if out is not None else self.act_buf(z.n, z.h, z.w, z.c)
         if (y.n, y.h, y.w, y.c) != (z.n, z.h, z.w, z.c):
             raise ValueError("conv: the caller's output map does not match the layer's output")
         stats = self.f32_buf(2 * z.c)
-        ss = self._bn_train(z, y, bn, relu, residual, stats)
+        ss = self._bn_train(z, y, bn, relu, residual, stats, ws=ws, sums_ready=fused)
         self.tape.append(lambda: self._bwd_conv_unit(x, conv, bn, relu, y, z, stats, residual=residual, fwd_affine=ss))
         return y
 
@@ -533,13 +543,15 @@ class Program:
         return (p(bn.weight), p(bn.bias), p(bn.running_mean), p(bn.running_var), p(bn.num_batches_tracked),
                 float(bn.eps), float(bn.momentum if bn.momentum is not None else 0.1))
 
-    def _bn_train(self, z, y, bn, relu, residual=None, stats=None):
+    def _bn_train(self, z, y, bn, relu, residual=None, stats=None, ws=None, sums_ready=False):
         """z: ActMap holding the raw conv output -> y (may be z: in place) = normalised with batch statistics
-        (+residual) (+ReLU). stats: fp32 [2c] tensor receiving mean | invstd for the backward pass."""
+        (+residual) (+ReLU). stats: fp32 [2c] tensor receiving mean | invstd for the backward pass. ws: the (sums,
+        scale, shift) work buffers; sums_ready: the conv that wrote z already added this batch's sums to ws[0]."""
         gamma, beta, rm, rv, nbt, eps, mom = self._bn_ptrs(bn, self.device)
-        sums, scale, shift = self._bn_ws(z.c)
+        sums, scale, shift = ws if ws is not None else self._bn_ws(z.c)
         inplace = y is z
-        self._record(self._lib.w2c_bn_train_fwd, z.buf.data_ptr(), residual.buf.data_ptr() if residual is not None else None,
+        fn = self._lib.w2c_bn_train_from_sums_fwd if sums_ready else self._lib.w2c_bn_train_fwd
+        self._record(fn, z.buf.data_ptr(), residual.buf.data_ptr() if residual is not None else None,
                      z.n * z.h * z.w, z.c, z.cstride, z.coffset, self.act, int(bool(relu)), gamma, beta, eps, mom, rm, rv,
                      nbt, sums.data_ptr(), scale.data_ptr(), shift.data_ptr(), None if inplace else y.buf.data_ptr(),
                      0 if inplace else y.cstride, 0 if inplace else y.coffset,

@@ -79,14 +79,15 @@ def pack_conv_weight(w, cin_pad, transposed, act):
 # ------------------------------------------------------------------------------------------------ hot-path ops
 def conv_bnrelu(x, w_packed, scale, shift, y, *, n, h_in, w_in, cin, cout, kind, relu, act, out_fmt=OUT_NHWC,
                 residual=None, x_cstride=0, x_coffset=0, y_cstride=0, y_coffset=0, impl=IMPL_TCGEN05, block_n=0,
-                labels=None, passes=0):
+                labels=None, passes=0, bn_sums=None):
     """labels: optional uint8 [n, h_out, w_out] tensor receiving argmax_co y (NCHW fp32 logits layout only); with
-    labels given, y may be None (label map only)."""
+    labels given, y may be None (label map only). bn_sums: optional fp64 [2 * cout] tensor, += sum | sum of squares
+    of the stored output per channel (only where w2c_conv_fuses_bn_sums says so; an error otherwise)."""
     lib = _lib.load()
     a = _lib.ConvArgs(x=_ptr(x), w=_ptr(w_packed), scale=_ptr(scale), shift=_ptr(shift), residual=_ptr(residual),
                       y=_ptr(y), labels=_ptr(labels), n=n, h_in=h_in, w_in=w_in, cin=cin, cout=cout, x_cstride=x_cstride,
                       x_coffset=x_coffset, y_cstride=y_cstride, y_coffset=y_coffset, kind=kind, relu=int(relu),
-                      act=act, out_fmt=out_fmt, impl=impl, block_n=block_n, passes=passes)
+                      act=act, out_fmt=out_fmt, impl=impl, block_n=block_n, passes=passes, bn_sums=_ptr(bn_sums))
     _lib.check(lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), _stream()), "w2c_conv_bnrelu_fwd")
     return y
 

@@ -46,7 +46,7 @@ def _quant(t, act):
 
 
 def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw_out=False, impl=0, block_n=0,
-               cin_real=None, seed=0, x_cs=0, x_co=0, y_cs=0, y_co=0, passes=0):
+               cin_real=None, seed=0, x_cs=0, x_co=0, y_cs=0, y_co=0, passes=0, bn_sums=False):
     torch, F, ops = _imports()
     dev = torch.device("cuda:0")
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -92,16 +92,28 @@ def _conv_case(kind, n, h, w, cin, cout, act, *, relu=True, residual=False, nchw
         y = torch.full((n, cout, ho, wo), float("nan"), dtype=torch.float32, device=dev)
     else:
         y = torch.zeros((n, ho, wo, ops.planes_of(act) * y_cs_eff), dtype=torch.bfloat16, device=dev)
+    # train-mode BatchNorm statistics from the epilogue: pre-loaded with a known offset (the kernel must ADD)
+    sums = torch.arange(2 * cout, dtype=torch.float64, device=dev) if bn_sums else None
     ops.conv_bnrelu(xa, wp, scale, shift, y, n=n, h_in=h, w_in=w, cin=cin, cout=cout, kind=kind, relu=relu, act=act,
                     out_fmt=ops.OUT_NCHW_F32 if nchw_out else ops.OUT_NHWC, residual=res_act, x_cstride=x_cs,
-                    x_coffset=x_co, y_cstride=y_cs, y_coffset=y_co, impl=impl, block_n=block_n, passes=passes)
+                    x_coffset=x_co, y_cstride=y_cs, y_coffset=y_co, impl=impl, block_n=block_n, passes=passes,
+                    bn_sums=sums)
     torch.cuda.synchronize()
     got = y.double() if nchw_out else ops.act_to_nchw(y, cout, act, cstride=y_cs_eff, coffset=y_co).double()
     err = (got - ref).abs().max().item()
     mag = ref.abs().max().item()
     # bf16 output rounding: 2^-9 relative per element (fp16: 2^-12); bf16x2 / fp32 outputs: ~1e-5
     tol = (6e-3 if (act == 0 and not nchw_out) else 8e-4 if (act == 2 and not nchw_out) else 2e-4) * max(mag, 1.0)
-    return {"max_err": err, "ref_max": mag, "tol": tol, "ok": bool(err <= tol) and bool(torch.isfinite(got).all())}
+    out = {"max_err": err, "ref_max": mag, "tol": tol, "ok": bool(err <= tol) and bool(torch.isfinite(got).all())}
+    if bn_sums:
+        # against the sums of the output AS STORED (fp32 partial sums in the kernel: 2e-5 of the absolute sums)
+        s = sums - torch.arange(2 * cout, dtype=torch.float64, device=dev)
+        r1, r2, ra = got.sum((0, 2, 3)), (got * got).sum((0, 2, 3)), got.abs().sum((0, 2, 3))
+        e1 = ((s[:cout] - r1).abs() / (ra + 1e-6)).max().item()
+        e2 = ((s[cout:] - r2).abs() / (r2 + 1e-6)).max().item()
+        out.update(sum_err=e1, sumsq_err=e2)
+        out["ok"] = out["ok"] and e1 <= 2e-5 and e2 <= 2e-5
+    return out
 
 
 def case_layout():
@@ -191,6 +203,17 @@ CONV_CASES = {
     "pers_ragged": (0, 3, 13, 21, 64, 72, 0, dict(impl=4)),
     "pers_ragged_c64": (0, 3, 13, 21, 64, 64, 0, dict(impl=4)),
     "pers_many_tiles": (0, 8, 64, 64, 64, 128, 0, dict(impl=4)),
+    # train-mode BatchNorm statistics out of the TMA-store epilogue (w2c_conv_args.bn_sums)
+    "pers_sums_rowhalo": (0, 3, 24, 40, 128, 128, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_ragged_c64": (0, 3, 13, 21, 64, 64, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_deconv": (2, 3, 40, 24, 64, 64, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_deconv_ragged": (2, 2, 12, 20, 128, 128, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_s2_f16": (1, 2, 32, 32, 64, 128, 2, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_bn256": (0, 2, 32, 32, 256, 512, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_many_tiles": (0, 8, 64, 64, 64, 128, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "pers_sums_slices": (0, 2, 16, 16, 64, 64, 0, dict(impl=4, relu=False, bn_sums=True, y_cs=192, y_co=64)),
+    "pers_sums_1x1s2": (4, 2, 32, 32, 64, 128, 0, dict(impl=4, relu=False, bn_sums=True)),
+    "auto_sums_dispatch": (0, 8, 64, 64, 64, 128, 0, dict(relu=False, bn_sums=True)),
 }
 
 
