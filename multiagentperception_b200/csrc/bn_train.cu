@@ -58,6 +58,24 @@ __global__ void __launch_bounds__(kStatThreads) bn_stats_kernel(const __nv_bfloa
     // seventh of the HBM rate - ncu, profiles/r2_train_step.md)
     size_t px = static_cast<size_t>(blockIdx.x) * lanes + lane;
     const size_t stride = static_cast<size_t>(gridDim.x) * lanes;
+    if (planes == 1) {
+      // one-plane storages: eight raw loads in flight, unpacked one pixel at a time (profiles/r2_bn_bwd_ncu.md)
+      for (; px + 7 * stride < n_px; px += 8 * stride) {
+        uint4 raw[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(z + (px + u * stride) * pix_elems + coffset + g * 8));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const uint32_t* hb = reinterpret_cast<const uint32_t*>(&raw[u]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 f = unpack_act2(hb[e], f16);
+            s1[2 * e] += f.x, s2[2 * e] = fmaf(f.x, f.x, s2[2 * e]);
+            s1[2 * e + 1] += f.y, s2[2 * e + 1] = fmaf(f.y, f.y, s2[2 * e + 1]);
+          }
+        }
+      }
+    }
     for (; px + 3 * stride < n_px; px += 4 * stride) {
       float v[4][8];
 #pragma unroll
