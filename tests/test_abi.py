@@ -88,3 +88,32 @@ def test_argument_validation_without_device():
     assert b"[1, 8]" in lib.w2c_last_error()
     with pytest.raises(_lib.W2CError):
         _lib.check(-1, "unit-test")
+
+
+def test_conv_fuses_bn_sums_is_host_logic():
+    """w2c_conv_fuses_bn_sums mirrors the dispatch of w2c_conv_bnrelu_fwd without touching a device: the statistics come
+    out of the persistent kernel's TMA-store epilogue only (NHWC, whole 64-channel groups, one storage plane, a tile
+    per SM), and a launch that cannot provide them refuses bn_sums instead of silently skipping them."""
+    lib = _lib.load()
+    dummy = ctypes.c_void_p(256)
+
+    def args(**kw):
+        base = dict(x=dummy, w=dummy, scale=dummy, shift=dummy, y=dummy, n=10, h_in=128, w_in=128, cin=128, cout=128,
+                    kind=_lib.CONV3X3_S1, act=_lib.ACT_BF16, out_fmt=_lib.OUT_NHWC, impl=_lib.IMPL_TCGEN05)
+        base.update(kw)
+        return _lib.ConvArgs(**base)
+
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args())) == 1
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(kind=_lib.DECONV3X3_S2))) == 1
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(act=_lib.ACT_FP16))) == 1
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(act=_lib.ACT_BF16X2))) == 0       # two planes
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(cout=72))) == 0                   # not whole 64-channel groups
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(cout=11, out_fmt=_lib.OUT_NCHW_F32))) == 0
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(n=1, h_in=8, w_in=8))) == 0       # sub-wave layer: one-tile kernel
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(block_n=32))) == 0
+    assert lib.w2c_conv_fuses_bn_sums(ctypes.byref(args(cin=48))) == -1                   # invalid arguments
+    assert lib.w2c_conv_fuses_bn_sums(None) == -1
+    # a launch that cannot accumulate the sums refuses them (before any device work)
+    a = args(n=1, h_in=8, w_in=8, bn_sums=dummy)
+    assert lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), None) == -2
+    assert b"bn_sums" in lib.w2c_last_error()

@@ -458,11 +458,11 @@ def case_stem_wgrad(ksize=3, act_g=1, seed=0):
     return _verdict(dw, w0.grad, 2e-4)
 
 
-def case_maxpool_bwd(act=1, seed=0):
+def case_maxpool_bwd(act=1, seed=0, c=64, h=12, w=20):
     torch, F, ops, _ = _imports()
     dev = torch.device("cuda:0")
     g = torch.Generator().manual_seed(seed)
-    n, c, h, w = 2, 64, 12, 20
+    n = 2
     x = torch.relu(torch.randn(n, c, h, w, generator=g))        # ReLU'd: plenty of ties at zero
     xq = _quant(x, act).requires_grad_(True)
     y = F.max_pool2d(xq, 3, 2, 1)
@@ -579,6 +579,8 @@ OTHER_CASES = {
     "stem_wgrad3": lambda: case_stem_wgrad(3),
     "stem_wgrad7": lambda: case_stem_wgrad(7),
     "maxpool_bwd": lambda: case_maxpool_bwd(),
+    "maxpool_bwd_c128_bf16": lambda: case_maxpool_bwd(act=0, c=128, h=18, w=34),   # two channel blocks, ragged tiles
+    "maxpool_bwd_c72": lambda: case_maxpool_bwd(c=72, h=8, w=12),                  # per-pixel kernel (c % 64 != 0)
     "bilinear_bwd": lambda: case_bilinear_bwd(),
     "bilinear_bwd_x2": lambda: case_bilinear_bwd(2),
     "grad_add": lambda: case_grad_add(),
