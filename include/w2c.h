@@ -439,6 +439,33 @@ int w2c_pack_conv_weight_ex(const float* w, int32_t cout, int32_t cin_real, int3
                             int32_t transposed, int32_t flip, int32_t act, void* packed, w2c_stream_t stream);
 
 /*
+ * Many w2c_pack_conv_weight_ex / w2c_fold_bn calls in ONE launch each: a training step re-derives every layer's packed
+ * operand and folded bias from the live parameters (an optimizer step changes them in place, trainer.py:668-670), 43-47
+ * layers x three tiny launches per step otherwise.  items: HOST array of n entries (copied into the kernel parameters,
+ * 48 per launch); every entry means exactly what the arguments of the single call mean; results are bit-identical.
+ */
+typedef struct w2c_pack_item {
+  const float* w;
+  void* packed;
+  int32_t cout, cin_real, cin, ntaps;
+  int32_t transposed, flip;
+} w2c_pack_item;
+int w2c_pack_conv_weights_batch(const w2c_pack_item* items, int32_t n, int32_t act, w2c_stream_t stream);
+
+typedef struct w2c_fold_item {
+  const float* conv_bias;
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* var;
+  float* scale;
+  float* shift;
+  float eps;
+  int32_t cout;
+} w2c_fold_item;
+int w2c_fold_bn_batch(const w2c_fold_item* items, int32_t n, w2c_stream_t stream);
+
+/*
  * Backward of train-mode BatchNorm2d (+ residual) (+ ReLU) between the gradient of the unit's output and the gradient
  * of the raw conv output (nn.BatchNorm2d + nn.ReLU of cbr_unit / dcbr_unit, utils.py:110-114,152-164; BasicBlock tail).
  *   du = dy * [y > 0] (relu);  dres = du;  dbeta += sum du;  dgamma += sum du * xhat;

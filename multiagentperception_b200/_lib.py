@@ -101,6 +101,18 @@ class MlpHeadGrad(ctypes.Structure):
                 ("db2", c_vp)]
 
 
+class PackItem(ctypes.Structure):
+    """struct w2c_pack_item (include/w2c.h)."""
+    _fields_ = [("w", c_vp), ("packed", c_vp), ("cout", c_i32), ("cin_real", c_i32), ("cin", c_i32), ("ntaps", c_i32),
+                ("transposed", c_i32), ("flip", c_i32)]
+
+
+class FoldItem(ctypes.Structure):
+    """struct w2c_fold_item (include/w2c.h)."""
+    _fields_ = [("conv_bias", c_vp), ("gamma", c_vp), ("beta", c_vp), ("mean", c_vp), ("var", c_vp), ("scale", c_vp),
+                ("shift", c_vp), ("eps", c_f32), ("cout", c_i32)]
+
+
 # symbol -> (restype, argtypes); every symbol include/w2c.h declares must be listed here (tests check both ways)
 _SIGNATURES = {
     "w2c_version": (ctypes.c_int, []),
@@ -118,6 +130,8 @@ _SIGNATURES = {
                                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "w2c_conv_wgrad": (ctypes.c_int, [ctypes.POINTER(WgradArgs), c_vp]),
     "w2c_pack_conv_weight_ex": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "w2c_pack_conv_weights_batch": (ctypes.c_int, [ctypes.POINTER(PackItem), c_i32, c_i32, c_vp]),
+    "w2c_fold_bn_batch": (ctypes.c_int, [ctypes.POINTER(FoldItem), c_i32, c_vp]),
     "w2c_bn_train_bwd": (ctypes.c_int, [ctypes.POINTER(BnBwdArgs), c_vp]),
     "w2c_bn_train_nchw_bwd": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, ctypes.c_int64, c_i32, c_i32, c_i32,
                                              c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),

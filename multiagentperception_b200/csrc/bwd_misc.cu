@@ -393,6 +393,60 @@ __global__ void pack_weight_ex_kernel(const float* __restrict__ w, int cout, int
   }
 }
 
+// ---- batched setup launches (w2c_pack_conv_weights_batch / w2c_fold_bn_batch): the items ride in the kernel parameters,
+// CTAs are dealt to items in proportion to their size (first_block: prefix sums), 8 elements per thread
+constexpr int kBatchItems = 48;
+constexpr int kPackPerBlock = 256 * 8;
+struct PackBatch {
+  w2c_pack_item it[kBatchItems];
+  int first_block[kBatchItems + 1];
+  int n;
+};
+__global__ void __launch_bounds__(256) pack_weight_batch_kernel(const __grid_constant__ PackBatch b, int planes, bool f16) {
+  int i = 0;
+  while (i + 1 < b.n && static_cast<int>(blockIdx.x) >= b.first_block[i + 1]) ++i;
+  const w2c_pack_item& p = b.it[i];
+  const int cout_pad = (p.cout + 15) / 16 * 16;   // w2c_cout_pad
+  const int ktot = p.ntaps * p.cin;
+  const int total = cout_pad * ktot;          // < 2^31, checked on the host
+  __nv_bfloat16* out = static_cast<__nv_bfloat16*>(p.packed);
+  const int base = (static_cast<int>(blockIdx.x) - b.first_block[i]) * kPackPerBlock;
+#pragma unroll 1
+  for (int j = 0; j < 8; ++j) {
+    const int idx = base + j * 256 + threadIdx.x;
+    if (idx >= total) break;
+    const int co = idx / ktot, k = idx - co * ktot;
+    const int tap = k / p.cin, ci = k - tap * p.cin;
+    const int st = p.flip ? p.ntaps - 1 - tap : tap;
+    float v = 0.f;
+    if (co < p.cout && ci < p.cin_real)
+      v = p.transposed ? p.w[(static_cast<size_t>(ci) * p.cout + co) * p.ntaps + st]
+                       : p.w[(static_cast<size_t>(co) * p.cin_real + ci) * p.ntaps + st];
+    const __nv_bfloat16 hi = float_to_elem(v, f16);
+    out[idx] = hi;
+    if (planes == 2) out[static_cast<size_t>(total) + idx] = float_to_elem(v - elem_to_float(hi, f16), f16);
+  }
+}
+
+struct FoldBatch {
+  w2c_fold_item it[kBatchItems];
+  int n;
+};
+__global__ void __launch_bounds__(128) fold_bn_batch_kernel(const __grid_constant__ FoldBatch b) {
+  const w2c_fold_item& p = b.it[blockIdx.y];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.cout) return;
+  const float bias = p.conv_bias ? p.conv_bias[c] : 0.f;
+  if (p.gamma) {   // the arithmetic of fold_bn_kernel (misc.cu), term for term
+    const float s = p.gamma[c] / sqrtf(p.var[c] + p.eps);
+    p.scale[c] = s;
+    p.shift[c] = p.beta[c] + (bias - p.mean[c]) * s;
+  } else {
+    p.scale[c] = 1.f;
+    p.shift[c] = bias;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ resnet / simple_decoder
 // MaxPool2d(3, 2, 1) backward: every input pixel collects the gradient of the output windows whose FIRST maximum (scan
 // order kh, kw: the element torch's max_pool2d_with_indices records) it is. One thread per (input pixel, 8 channels).
@@ -757,6 +811,51 @@ extern "C" int w2c_pack_conv_weight_ex(const float* w, int32_t cout, int32_t cin
       w, cout, cin_real, cin, ntaps, transposed, flip, act_planes(act), cout_pad, static_cast<__nv_bfloat16*>(packed),
       act_is_f16(act));
   W2C_CHECK_LAUNCH("pack_weight_ex_kernel");
+  return W2C_OK;
+}
+
+extern "C" int w2c_pack_conv_weights_batch(const w2c_pack_item* items, int32_t n, int32_t act, w2c_stream_t stream) {
+  W2C_CHECK_ARG(items && n > 0, "pack_conv_weights_batch: no items");
+  W2C_CHECK_ARG(act_valid(act), "pack_conv_weights_batch: bad act %d", act);
+  for (int i0 = 0; i0 < n; i0 += kBatchItems) {
+    PackBatch b{};
+    b.n = n - i0 < kBatchItems ? n - i0 : kBatchItems;
+    int blocks = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const w2c_pack_item& p = items[i0 + i];
+      W2C_CHECK_ARG(p.w && p.packed, "pack_conv_weights_batch: item %d: null pointer", i0 + i);
+      W2C_CHECK_ARG(p.cout > 0 && p.cin_real > 0 && p.cin >= p.cin_real && p.cin % 64 == 0 && (p.ntaps == 9 || p.ntaps == 1),
+                    "pack_conv_weights_batch: item %d: cout=%d cin_real=%d cin=%d ntaps=%d", i0 + i, p.cout, p.cin_real, p.cin, p.ntaps);
+      const long long total = static_cast<long long>(w2c_cout_pad(p.cout)) * p.ntaps * p.cin;
+      W2C_CHECK_ARG(total < (1ll << 31), "pack_conv_weights_batch: item %d too large", i0 + i);
+      b.it[i] = p;
+      b.first_block[i] = blocks;
+      blocks += static_cast<int>((total + kPackPerBlock - 1) / kPackPerBlock);
+    }
+    b.first_block[b.n] = blocks;
+    pack_weight_batch_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(b, act_planes(act), act_is_f16(act));
+    W2C_CHECK_LAUNCH("pack_weight_batch_kernel");
+  }
+  return W2C_OK;
+}
+
+extern "C" int w2c_fold_bn_batch(const w2c_fold_item* items, int32_t n, w2c_stream_t stream) {
+  W2C_CHECK_ARG(items && n > 0, "fold_bn_batch: no items");
+  for (int i0 = 0; i0 < n; i0 += kBatchItems) {
+    FoldBatch b{};
+    b.n = n - i0 < kBatchItems ? n - i0 : kBatchItems;
+    int cmax = 0;
+    for (int i = 0; i < b.n; ++i) {
+      const w2c_fold_item& p = items[i0 + i];
+      W2C_CHECK_ARG(p.scale && p.shift && p.cout > 0, "fold_bn_batch: item %d: bad arguments", i0 + i);
+      const bool any = p.gamma || p.beta || p.mean || p.var;
+      W2C_CHECK_ARG(!any || (p.gamma && p.beta && p.mean && p.var), "fold_bn_batch: item %d: BN tensors must be all present or all NULL", i0 + i);
+      b.it[i] = p;
+      cmax = p.cout > cmax ? p.cout : cmax;
+    }
+    fold_bn_batch_kernel<<<dim3(ceil_div(cmax, 128), b.n), 128, 0, static_cast<cudaStream_t>(stream)>>>(b);
+    W2C_CHECK_LAUNCH("fold_bn_batch_kernel");
+  }
   return W2C_OK;
 }
 

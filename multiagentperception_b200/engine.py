@@ -350,6 +350,7 @@ class Program:
         self._capture_stream = None
         self.keep = []       # keeps ctypes structs / tensors alive
         self.graph = None
+        self._batched = False   # _batch_setup_calls() ran
         self.n_launches = 0  # kernel launches per run (counted from the library's counter)
         self._lib = _lib.load()
         # program-level I/O options (models/agents.py sets them before building):
@@ -1090,6 +1091,45 @@ class Program:
         if forked:
             main.wait_stream(self._side)
 
+    def _batch_setup_calls(self):
+        """Live (train-mode) programs re-derive every layer's packed operand and folded bias from the parameters on
+        every run: 43-47 layers x (pack, fold) tiny launches in the forward program, as many data-gradient packs in
+        the backward one. They depend on the parameters only, so they are merged into ONE launch per kind at the head
+        of the program (w2c_pack_conv_weights_batch / w2c_fold_bn_batch: bit-identical results)."""
+        if self._batched:
+            return
+        self._batched = True
+        lib = self._lib
+        packs, folds, rest = [], [], []
+        for call in self.calls:
+            fn, args, _sid = call
+            if fn is lib.w2c_pack_conv_weight:
+                w, cout, cin_real, cin, ntaps, tr, act, packed = args
+                packs.append((act, _lib.PackItem(w=w, packed=packed, cout=cout, cin_real=cin_real, cin=cin, ntaps=ntaps,
+                                                 transposed=tr, flip=0)))
+            elif fn is lib.w2c_pack_conv_weight_ex:
+                w, cout, cin_real, cin, ntaps, tr, flip, act, packed = args
+                packs.append((act, _lib.PackItem(w=w, packed=packed, cout=cout, cin_real=cin_real, cin=cin, ntaps=ntaps,
+                                                 transposed=tr, flip=flip)))
+            elif fn is lib.w2c_fold_bn:
+                bias, gamma, beta, mean, var, eps, cout, scale, shift = args
+                folds.append(_lib.FoldItem(conv_bias=bias, gamma=gamma, beta=beta, mean=mean, var=var, scale=scale,
+                                           shift=shift, eps=eps, cout=cout))
+            else:
+                rest.append(call)
+        if len(packs) + len(folds) < 3 or len({a for a, _ in packs}) > 1:
+            return
+        head = []
+        if packs:
+            arr = (_lib.PackItem * len(packs))(*[it for _, it in packs])
+            self.keep.append(arr)
+            head.append((lib.w2c_pack_conv_weights_batch, (arr, len(packs), packs[0][0]), 0))
+        if folds:
+            arr = (_lib.FoldItem * len(folds))(*folds)
+            self.keep.append(arr)
+            head.append((lib.w2c_fold_bn_batch, (arr, len(folds)), 0))
+        self.calls = head + rest
+
     def _run_eager(self):
         for calls, host in self._segments():
             self._run_calls(calls)
@@ -1097,6 +1137,7 @@ class Program:
                 host()
 
     def run(self, use_graph):
+        self._batch_setup_calls()
         if not use_graph:
             if not self.n_launches:
                 before = ops.launch_count()

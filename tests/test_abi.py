@@ -56,6 +56,8 @@ def test_struct_layouts_match_header():
     assert fields("w2c_conv_args") == [f[0] for f in _lib.ConvArgs._fields_]
     assert fields("w2c_attn_args") == [f[0] for f in _lib.AttnArgs._fields_]
     assert fields("w2c_mlp_head") == [f[0] for f in _lib.MlpHead._fields_]
+    assert fields("w2c_pack_item") == [f[0] for f in _lib.PackItem._fields_]
+    assert fields("w2c_fold_item") == [f[0] for f in _lib.FoldItem._fields_]
 
 
 def test_tensor_core_and_tma_instructions_present():
@@ -117,3 +119,16 @@ def test_conv_fuses_bn_sums_is_host_logic():
     a = args(n=1, h_in=8, w_in=8, bn_sums=dummy)
     assert lib.w2c_conv_bnrelu_fwd(ctypes.byref(a), None) == -2
     assert b"bn_sums" in lib.w2c_last_error()
+
+
+def test_batched_setup_calls_validate_items_on_the_host():
+    lib = _lib.load()
+    dummy = ctypes.c_void_p(256)
+    items = (_lib.PackItem * 2)(_lib.PackItem(w=dummy, packed=dummy, cout=64, cin_real=64, cin=64, ntaps=9),
+                                _lib.PackItem(w=dummy, packed=dummy, cout=64, cin_real=64, cin=48, ntaps=9))
+    assert lib.w2c_pack_conv_weights_batch(items, 2, _lib.ACT_BF16, None) == -1
+    assert b"item 1" in lib.w2c_last_error()
+    assert lib.w2c_pack_conv_weights_batch(None, 0, _lib.ACT_BF16, None) == -1
+    folds = (_lib.FoldItem * 1)(_lib.FoldItem(gamma=dummy, scale=dummy, shift=dummy, cout=8))
+    assert lib.w2c_fold_bn_batch(folds, 1, None) == -1
+    assert b"all present or all NULL" in lib.w2c_last_error()

@@ -495,6 +495,56 @@ def case_bilinear_bwd(factor=32, seed=0):
     return _verdict(dx, x.grad, 1e-5)
 
 
+def case_setup_batch(act=1, seed=0):
+    """w2c_pack_conv_weights_batch / w2c_fold_bn_batch against the single calls they replace: identical bits."""
+    import ctypes
+    torch, F, ops, _ = _imports()
+    from multiagentperception_b200 import _lib as L
+    lib = _lib_load()
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(seed)
+    # (cout, cin_real, cin, ntaps, transposed, flip); 60 items: more than one launch of 48
+    geoms = [(64, 64, 64, 9, 0, 0), (11, 64, 64, 9, 0, 0), (128, 40, 64, 9, 1, 1), (512, 512, 512, 9, 0, 1),
+             (64, 128, 128, 1, 1, 0), (256, 192, 192, 9, 1, 0)] * 10
+    ws, singles, batched, items = [], [], [], []
+    for cout, cin_real, cin, ntaps, tr, flip in geoms:
+        shape = (cin_real, cout, ntaps) if tr else (cout, cin_real, ntaps)
+        w = torch.randn(shape, generator=g).to(dev)
+        n16 = lib.w2c_packed_weight_bytes(cout, cin, ntaps, act) // 2
+        a = torch.full((n16,), -1, dtype=torch.int16, device=dev)
+        b = torch.full((n16,), -2, dtype=torch.int16, device=dev)
+        rc = lib.w2c_pack_conv_weight_ex(_p(w), cout, cin_real, cin, ntaps, tr, flip, act, _p(a), ops._stream())
+        assert rc == 0, lib.w2c_last_error()
+        items.append(L.PackItem(w=_p(w), packed=_p(b), cout=cout, cin_real=cin_real, cin=cin, ntaps=ntaps, transposed=tr, flip=flip))
+        ws.append(w), singles.append(a), batched.append(b)
+    arr = (L.PackItem * len(items))(*items)
+    rc = lib.w2c_pack_conv_weights_batch(arr, len(items), act, ops._stream())
+    assert rc == 0, lib.w2c_last_error()
+    torch.cuda.synchronize()
+    out = {"pack": {"ok": all(bool(torch.equal(a, b)) for a, b in zip(singles, batched))}}
+    # fold: with and without BatchNorm, with and without a conv bias
+    fitems, pairs, keep = [], [], []
+    for i, cout in enumerate([64, 11, 512, 200] * 13):
+        t = [torch.randn(cout, generator=g).to(dev) for _ in range(4)] + [(torch.rand(cout, generator=g) + 0.1).to(dev)]
+        bias = t[0] if i % 3 else None
+        bn = i % 2 == 0
+        s1, h1, s2, h2 = (torch.empty(cout, device=dev) for _ in range(4))
+        rc = lib.w2c_fold_bn(_p(bias), _p(t[1]) if bn else None, _p(t[2]) if bn else None, _p(t[3]) if bn else None,
+                             _p(t[4]) if bn else None, 1e-5, cout, _p(s1), _p(h1), ops._stream())
+        assert rc == 0, lib.w2c_last_error()
+        fitems.append(L.FoldItem(conv_bias=_p(bias), gamma=_p(t[1]) if bn else None, beta=_p(t[2]) if bn else None,
+                                 mean=_p(t[3]) if bn else None, var=_p(t[4]) if bn else None, scale=_p(s2), shift=_p(h2),
+                                 eps=1e-5, cout=cout))
+        pairs.append((s1, h1, s2, h2)), keep.append(t)
+    farr = (L.FoldItem * len(fitems))(*fitems)
+    rc = lib.w2c_fold_bn_batch(farr, len(fitems), ops._stream())
+    assert rc == 0, lib.w2c_last_error()
+    torch.cuda.synchronize()
+    out["fold"] = {"ok": all(bool(torch.equal(s1, s2)) and bool(torch.equal(h1, h2)) for s1, h1, s2, h2 in pairs)}
+    out["ok"] = all(v["ok"] for v in out.values())
+    return out
+
+
 def case_grad_add(act=1):
     torch, F, ops, _ = _imports()
     dev = torch.device("cuda:0")
@@ -584,6 +634,8 @@ OTHER_CASES = {
     "bilinear_bwd": lambda: case_bilinear_bwd(),
     "bilinear_bwd_x2": lambda: case_bilinear_bwd(2),
     "grad_add": lambda: case_grad_add(),
+    "setup_batch_x2": lambda: case_setup_batch(1),
+    "setup_batch_bf16": lambda: case_setup_batch(0),
 }
 
 
