@@ -134,3 +134,43 @@ def test_shard_layout_geometry():
     assert float(ex.sum()) == float(mine.sum())
     with pytest.raises(ValueError):
         sharding.AgentShardLayout(5, 2, 0, 1, 8, 8, 4, 4, 8, 1)
+
+
+def test_live_program_batches_its_setup_launches():
+    """engine.Program._batch_setup_calls (host logic, no device): the per-layer pack / fold launches a train-mode program
+    records are merged into one batched call per kind at the head of the program; everything else keeps its order."""
+    import ctypes
+    from multiagentperception_b200 import _lib, engine
+    lib = _lib.load()
+    prog = engine.Program(None, torch.device("cpu"), _lib.ACT_BF16)
+    marker = object()
+    prog._record(lib.w2c_pack_conv_weight, 1000, 64, 3, 64, 9, 0, _lib.ACT_BF16, 2000)
+    prog._record(lib.w2c_fold_bn, None, 11, 12, 13, 14, 1e-5, 64, 3000, 3100)
+    prog.calls.append((marker, ("conv-1",), 0))
+    prog.calls.append((engine.Program._FORK, None, 0))
+    prog._sid = 1
+    prog._record(lib.w2c_pack_conv_weight_ex, 4000, 128, 64, 64, 9, 1, 1, _lib.ACT_BF16, 5000)
+    prog._record(lib.w2c_fold_bn, 21, None, None, None, None, 1e-5, 128, 6000, 6100)
+    prog.calls.append((marker, ("conv-2",), 1))
+    prog._sid = 0
+    prog.join()
+    prog._batch_setup_calls()
+    fns = [c[0] for c in prog.calls]
+    assert fns[:2] == [lib.w2c_pack_conv_weights_batch, lib.w2c_fold_bn_batch]
+    assert fns[2:] == [marker, engine.Program._FORK, marker, engine.Program._JOIN]
+    assert [c[2] for c in prog.calls] == [0, 0, 0, 0, 1, 0]          # the batched calls run on the main stream, first
+    items, n, act = prog.calls[0][1]
+    assert n == 2 and act == _lib.ACT_BF16
+    assert (items[0].w, items[0].packed, items[0].cout, items[0].cin_real, items[0].flip) == (1000, 2000, 64, 3, 0)
+    assert (items[1].w, items[1].packed, items[1].transposed, items[1].flip) == (4000, 5000, 1, 1)
+    folds, nf = prog.calls[1][1]
+    assert nf == 2 and folds[0].gamma == 11 and folds[0].conv_bias is None and folds[1].conv_bias == 21
+    assert folds[1].gamma is None and folds[1].cout == 128 and folds[1].scale == 6000
+    before = list(prog.calls)
+    prog._batch_setup_calls()                                          # idempotent
+    assert prog.calls == before
+    # an eval-mode program has no recorded setup launches: nothing to merge
+    ev = engine.Program(None, torch.device("cpu"), _lib.ACT_BF16)
+    ev.calls.append((marker, ("conv",), 0))
+    ev._batch_setup_calls()
+    assert [c[0] for c in ev.calls] == [marker]
