@@ -351,6 +351,7 @@ class Program:
         self.keep = []       # keeps ctypes structs / tensors alive
         self.graph = None
         self._batched = False   # _batch_setup_calls() ran
+        self._tape_side = False  # a side-stream region is on the tape and not joined yet
         self.n_launches = 0  # kernel launches per run (counted from the library's counter)
         self._lib = _lib.load()
         # program-level I/O options (models/agents.py sets them before building):
@@ -399,6 +400,7 @@ class Program:
     # chain's CTAs fill the other's tails: persistent kernels with 4.3 waves of tiles, ~5 us ramp-up per launch and
     # the sub-wave layers at 16x16 otherwise leave SMs idle at every kernel boundary.
     _FORK, _JOIN = "fork", "join"
+    _SIDE_BEGIN, _SIDE_END = "side-begin", "side-end"   # tape markers: the backward pass mirrors the two chains
 
     def side_stream(self, auto=False):
         """Context manager: calls recorded inside run on the side stream, which first waits for everything recorded
@@ -412,10 +414,15 @@ class Program:
                 if enabled:
                     prog.calls.append((Program._FORK, None, 0))
                     prog._sid = 1
+                    if prog.grad:
+                        prog.tape.append(Program._SIDE_BEGIN)
+                        prog._tape_side = True
                 return enabled
 
             def __exit__(self, *exc):
                 prog._sid = 0
+                if enabled and prog.grad:
+                    prog.tape.append(Program._SIDE_END)
                 return False
 
         return _Ctx()
@@ -423,6 +430,9 @@ class Program:
     def join(self):
         # (a join without a preceding fork is a no-op at run time)
         self.calls.append((Program._JOIN, None, 0))
+        if self.grad and self._tape_side:
+            self.tape.append(Program._JOIN)
+            self._tape_side = False
 
     def passes_for(self, stack, layer):
         """MMA passes of layer number `layer` of `stack` under this program's precision plan (0 = format default)."""
@@ -624,9 +634,14 @@ class Program:
         if nchw:
             n, _, hh, ww = y.shape
             dy_t = self.f32_grad(y)
+            # the NHWC gradient map is padded to the 64 channels the weight / data gradient kernels read; the kernel
+            # writes the 8-channel groups that hold real channels only (11 classes: 16 of 64), the rest is zeroed
+            # ONCE here and never written again (0.34 GB of scattered 16-byte stores per 10 frames otherwise)
             dz = bp.act_buf(n, hh, ww, cpad)
+            dz.buf.zero_()
+            c8 = (cout + 7) // 8 * 8
             bp._record(lib.w2c_bn_train_nchw_bwd, dy_t.data_ptr(), y.data_ptr(), p(z), dz.buf.data_ptr(), n, cout, hh * ww,
-                       cpad, dz.cstride, 0, g_act, int(bool(relu)), p(gamma_t), p(stats), p(dgamma), dbeta.data_ptr(),
+                       c8, dz.cstride, 0, g_act, int(bool(relu)), p(gamma_t), p(stats), p(dgamma), dbeta.data_ptr(),
                        sums.data_ptr(), coef.data_ptr())
         else:
             gy = self.grad_map(y)
@@ -1031,8 +1046,21 @@ class Program:
                 torch._foreach_zero_(zl)
             return 0
         bp.calls.append((zero, None, 0))
+        # The two encoder chains of the forward (side_stream / join) are independent in the backward pass too: replayed in
+        # reverse, the forward's join is where the backward forks (the side stream waits for the decoder / attention
+        # backward), the policy chain's backward stays on the main stream, the feature encoder's runs beside it, and the
+        # forward's fork is where they join again. (Gradient buffers, work buffers and weight-gradient targets are
+        # per layer; the operand packs sit at the head of the program, before the fork.)
         for fn in reversed(self.tape):
-            fn()
+            if fn is Program._JOIN:
+                bp.calls.append((Program._FORK, None, 0))
+            elif fn is Program._SIDE_END:
+                bp._sid = 1
+            elif fn is Program._SIDE_BEGIN:
+                bp._sid = 0
+                bp.join()
+            else:
+                fn()
         self.tape = None
         # the prologue was recorded before the list was complete; it reads zl at run time
 
