@@ -574,8 +574,11 @@ class _AttentionModel(_W2CModel):
             # pair's many small launches, not for the n_segnet pair (engine.TWO_STREAMS)
             # ... and for small steps (latency points: at <= 8 agent-frames the <= 64x64 layers of either chain give
             # a 148-SM part 2-32 tiles each, so the two chains fill each other's idle SMs)
+            # ... and for training steps: the element-wise BatchNorm passes, the per-launch tails of the weight-gradient
+            # kernels and the sub-wave layers of one chain leave room the other chain fills (n_segnet pair, 10 frames:
+            # 19.3 -> 18.2 ms per step; the eval-mode step of the same pair loses with two chains)
             small_kernels = (isinstance(self.u_encoder.feature_backbone, resnet_encoder)
-                             or n * b * h * w <= engine.TWO_STREAM_MAX_PIXELS)
+                             or n * b * h * w <= engine.TWO_STREAM_MAX_PIXELS or prog.train)
             with prog.side_stream(auto=small_kernels) as forked:
                 val = _build_encoder(prog, self.u_encoder, "u_encoder", x, b, n, h, w, out=val_out, stem=stem_u,
                                      stack=self._value_stack)
