@@ -65,6 +65,8 @@ def test_tensor_core_and_tma_instructions_present():
     for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "UBLKCP"):
         assert mnemonic in sass, "expected %s in the SASS of libw2c.so" % mnemonic
     assert "HMMA." not in sass.replace("UTCHMMA", ""), "legacy mma.sync path found"
+    # the weight-gradient epilogue adds 16 bytes per reduction (red.global.add.v4.f32), not four scalar atomics
+    assert "REDG.E.ADD.F32x4" in sass, "expected vector reductions in the wgrad epilogue"
 
 
 def test_argument_validation_without_device():
